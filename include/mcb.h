@@ -1,0 +1,144 @@
+/* mcb.h — C ABI of the B200-native marching-cubes polygoniser (libmcb200.so).
+ *
+ * This is the drop-in boundary for the one hot path of raineyeh/Marching-Cube-for-Implicit-Surfaces:
+ *     equation -> field on the grid -> cube classification (+ambiguity) -> scan/compaction -> triangles (+normals)
+ * The reference has no plugin/FFI interface; its boundary is two C++ headers (Source/evaluator.h, Source/marching.h)
+ * consumed by main.cpp:11-20 and drawer.cpp:785-942.  include/evaluator.h and include/marching.h in this repository
+ * keep those class names and public signatures and forward to the functions below; any other host language binds
+ * the same symbols (INTEGRATION.md shows the stubs).  Plain pointers and sizes only: no C++ or torch types cross
+ * this boundary, no exception does either.  Every function returns MCB_OK (0) or a negative mcb_status.
+ *
+ * There is no CPU implementation behind this ABI: every function that computes field values, cases or triangles
+ * runs CUDA kernels on the context's device and fails with MCB_E_NODEVICE / MCB_E_CUDA when it cannot.
+ * The only host-side work is what the reference also does once per equation (tokenising) plus the lowering of the
+ * token list to bytecode.
+ *
+ * Threading: a context may be used from any one thread at a time (the reference calls recalculate() from the GLUT
+ * thread and from its "movie" std::thread, drawer.cpp:135); each call makes the context's device current.
+ */
+#ifndef MCB_H
+#define MCB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB_ABI_VERSION 1
+
+typedef enum {
+    MCB_OK = 0,
+    MCB_E_PARSE = -1,    /* equation rejected (Evaluator::set_equation returning false, evaluator.cpp:15-17) */
+    MCB_E_ARG = -2,      /* argument out of range (the reference's `return false` paths, e.g. marching.cpp:226-238) */
+    MCB_E_CUDA = -3,     /* a CUDA call or kernel failed; mcb_last_error() has the text */
+    MCB_E_NOMEM = -4,    /* device or host allocation failed */
+    MCB_E_STATE = -5,    /* call order: e.g. mcb_get_mesh before mcb_polygonise */
+    MCB_E_CAPACITY = -6, /* equation too large for the bytecode limits, or caller buffer too small */
+    MCB_E_NODEVICE = -7  /* no usable CUDA device: there is no CPU fallback */
+} mcb_status;
+
+typedef struct mcb_ctx mcb_ctx;
+
+/* Result of one polygonisation (one Marching::recalculate(), marching.cpp:308-433 full-grid branch). */
+typedef struct {
+    uint64_t cubes;       /* cubes visited = (k_end-k_begin) * M * M  ("voxels") */
+    uint64_t active;      /* cubes with cube_code not in {0,255} that passed the constraints */
+    uint64_t triangles;   /* triangles emitted */
+    uint64_t ambiguous;   /* active cubes whose code has a redirect entry (marching_lookup.h:329-587) */
+    uint64_t redirected;  /* ... of which the face-centre test chose row 255-code (marching.cpp:545-547) */
+    int32_t M;            /* cubes per axis visited by the reference loop (marching.cpp:375-377) */
+    int32_t k_begin, k_end; /* cube layers of this context's z-slab */
+    float ms_tables;      /* device time of the stages, CUDA events on the context's stream */
+    float ms_eval;
+    float ms_classify;
+    float ms_emit;
+    float ms_total;
+    uint32_t launches;    /* kernels launched by this call */
+    uint32_t reruns;      /* passes repeated because an output buffer had to grow (0 in steady state) */
+} mcb_counts;
+
+/* ---- library / host-only helpers (no GPU needed) ---------------------------------------------------------- */
+
+int mcb_abi_version(void);
+const char* mcb_status_string(int status);
+
+/* Evaluator::tokenize accept/reject (evaluator.cpp:139-237) + the operand-stack check: MCB_OK or MCB_E_PARSE. */
+int mcb_parse(const char* equation);
+/* Token list as text, blank separated, unary minus printed as NEG (evaluator.cpp:165).  Returns MCB_OK,
+ * MCB_E_PARSE, or MCB_E_CAPACITY if `cap` is too small. */
+int mcb_tokens(const char* equation, char* out, size_t cap);
+/* The operation order the reference's two-stack evaluator (evaluator.cpp:22-107) executes, as postfix text:
+ * "x-y+z" -> "x y z + -". */
+int mcb_postfix(const char* equation, char* out, size_t cap);
+/* Bytecode listing; which: 0 = point program, 1 = grid program, 2 = hoisted slot programs. */
+int mcb_disassemble(const char* equation, int which, char* out, size_t cap);
+/* The reference's grid loop on one axis (marching.cpp:372-377): returns M = number of cubes per axis for `step`
+ * and, when coords != NULL and cap >= M+1, the cube origins c[0..M-1] and the far corner c[M] = c[M-1]+step. */
+int mcb_grid_axis(float step, float* coords, int cap);
+/* Balanced split of M cube layers into nranks contiguous z-slabs: layers [*k_begin,*k_end). */
+int mcb_slab_range(int M, int rank, int nranks, int* k_begin, int* k_end);
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+
+/* One context = one Marching object (marching.h:72-157) on one CUDA device.  Defaults follow Marching::Marching
+ * (marching.cpp:23-37): step 0.25, iso 0, scale 1, no constraints, equation "x+y" (evaluator.cpp:6-8). */
+int mcb_create(int device, mcb_ctx** out);
+void mcb_destroy(mcb_ctx* ctx);
+const char* mcb_last_error(const mcb_ctx* ctx);
+/* Use the caller's cudaStream_t (e.g. torch's current stream) instead of the context's own. NULL restores it. */
+int mcb_set_stream(mcb_ctx* ctx, void* cuda_stream);
+
+/* ---- evaluator.h ----------------------------------------------------------------------------------------- */
+
+/* Evaluator::set_equation (evaluator.cpp:15-17).  slot 0 = the surface equation (Marching::set_evaluator,
+ * marching.cpp:140-147); slots 1..3 = left-hand sides of constraints 0..2 (marching.cpp:173-200).
+ * On MCB_E_PARSE the previous equation of that slot stays in force. */
+int mcb_set_equation(mcb_ctx* ctx, int slot, const char* equation);
+/* Evaluator::evaluate (evaluator.cpp:53-107) for n points on the GPU.  xyz = 3n floats, out = n floats, host
+ * memory.  apply_scale != 0 multiplies by the per-axis scale first, i.e. Marching::evaluate (marching.cpp:209-224). */
+int mcb_eval_points(mcb_ctx* ctx, int slot, const float* xyz, float* out, size_t n, int apply_scale);
+
+/* ---- marching.h ------------------------------------------------------------------------------------------ */
+
+/* Marching::set_grid_step_size (marching.cpp:226-238) without its [0.001,0.5] clamp (the C++ class applies it;
+ * 2048^3 needs 2/2048 < 0.001).  Any finite step in (0, 1] with M <= 4094 is accepted. */
+int mcb_set_grid_step(mcb_ctx* ctx, float step);
+/* Restrict this context to cube layers [k_begin,k_end) of [0,M) — its z-slab; the one-vertex halo planes are
+ * recomputed locally.  k_end <= 0 means M.  Reset to the full grid by mcb_set_grid_step. */
+int mcb_set_slab(mcb_ctx* ctx, int k_begin, int k_end);
+int mcb_set_surface_constant(mcb_ctx* ctx, float iso);          /* marching.cpp:149-154 */
+int mcb_set_scaling(mcb_ctx* ctx, float sx, float sy, float sz); /* marching.cpp:240-251 */
+/* Constraint i (0..2): lhs(sx*x,sy*y,sz*z) op rhs with op 0 '>', 1 '<', 2 '>=', 3 '<=' (Comp_Op, marching.h:58);
+ * in_use as Marching::use_constraint (marching.cpp:202-207).  The lhs is slot i+1 of mcb_set_equation.  A cube is
+ * skipped unless all 8 corners satisfy every constraint in use (marching.cpp:255-280, 475-477). */
+int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use);
+/* 0 = positions only; 1 = also per-vertex normals from central-difference field gradients. */
+int mcb_set_normals(mcb_ctx* ctx, int mode);
+
+/* The hot path: Marching::recalculate() (marching.cpp:368-384) for this context's slab, entirely on the GPU.
+ * On return the triangle soup is resident in device memory in the reference's emission order (cube loop order
+ * x fastest, then y, then z; tri_table order inside a cube) and *out holds the counts. */
+int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out);
+
+/* Copy the soup to host memory: pos4 / nrm4 = 3*triangles float4 (x,y,z,1) / (nx,ny,nz,0); either may be NULL.
+ * cap_triangles = capacity of the buffers in triangles. */
+int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles);
+/* Device pointers to the same buffers (valid until the next mcb_polygonise / mcb_destroy). */
+int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4);
+
+/* Parity hooks.  Dense per-cube arrays of the slab in loop order, host memory, `cubes` bytes each (NULL = skip):
+ * cube_code = raw 8-bit sign code (marching.cpp:497-505); table_idx = tri_table row actually used (code or
+ * 255-code); a cube skipped by a constraint reports 0 in both. */
+int mcb_get_cases(mcb_ctx* ctx, uint8_t* cube_code, uint8_t* table_idx);
+/* Field values at the slab's grid vertices, (k_end-k_begin+1) * (M+1) * (M+1) floats, x fastest. */
+int mcb_get_field(mcb_ctx* ctx, float* out);
+/* Compacted active-cube list: record = i | j<<12 | k<<24 | code<<36 | table_idx<<44; tri_offset = index of the
+ * cube's first triangle.  cap = capacity in records. */
+int mcb_get_active(mcb_ctx* ctx, uint64_t* records, uint32_t* tri_offsets, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB_H */

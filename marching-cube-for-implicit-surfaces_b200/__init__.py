@@ -1,0 +1,348 @@
+"""marching-cube-for-implicit-surfaces_b200 — Python face of libmcb200.so (the C ABI in include/mcb.h).
+
+This module is a thin ctypes mirror of the reference's two entry-point classes for the hot path:
+
+    Evaluator  (Source/evaluator.h:24-86)   set_equation / evaluate
+    Marching   (Source/marching.h:72-157)   set_evaluator / set_grid_step_size / set_scaling_* /
+                                            set_surface_constant / set_constraint* / use_constraint* / recalculate /
+                                            get_poly_data
+
+with the same names, argument meaning and bool-return error convention, so that parity tests read like calls into
+the reference.  All computation happens in CUDA kernels behind the C ABI; there is no Python or CPU implementation
+of the path here, and importing the module fails loudly if the native library has not been built.
+
+The directory name contains hyphens, so import it with
+    importlib.import_module("marching-cube-for-implicit-surfaces_b200")
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcb200.so")
+
+MCB_OK, MCB_E_PARSE, MCB_E_ARG, MCB_E_CUDA, MCB_E_NOMEM, MCB_E_STATE, MCB_E_CAPACITY, MCB_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
+
+
+class McbError(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = status
+        super().__init__("mcb status %d (%s) %s" % (status, status_string(status), msg))
+
+
+class Counts(C.Structure):
+    _fields_ = [("cubes", C.c_uint64), ("active", C.c_uint64), ("triangles", C.c_uint64), ("ambiguous", C.c_uint64),
+                ("redirected", C.c_uint64), ("M", C.c_int32), ("k_begin", C.c_int32), ("k_end", C.c_int32),
+                ("ms_tables", C.c_float), ("ms_eval", C.c_float), ("ms_classify", C.c_float), ("ms_emit", C.c_float),
+                ("ms_total", C.c_float), ("launches", C.c_uint32), ("reruns", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmcb200.so is not built: run `python __graft_entry__.py` (or build.py) first — "
+                          "there is no fallback implementation")
+    L = C.CDLL(LIB_PATH)
+    vp, cp, i, f, u64, sz = C.c_void_p, C.c_char_p, C.c_int, C.c_float, C.c_uint64, C.c_size_t
+    sigs = {
+        "mcb_abi_version": ([], i),
+        "mcb_status_string": ([i], cp),
+        "mcb_parse": ([cp], i),
+        "mcb_tokens": ([cp, cp, sz], i),
+        "mcb_postfix": ([cp, cp, sz], i),
+        "mcb_disassemble": ([cp, i, cp, sz], i),
+        "mcb_grid_axis": ([f, vp, i], i),
+        "mcb_slab_range": ([i, i, i, C.POINTER(i), C.POINTER(i)], i),
+        "mcb_create": ([i, C.POINTER(vp)], i),
+        "mcb_destroy": ([vp], None),
+        "mcb_last_error": ([vp], cp),
+        "mcb_set_stream": ([vp, vp], i),
+        "mcb_set_equation": ([vp, i, cp], i),
+        "mcb_eval_points": ([vp, i, vp, vp, sz, i], i),
+        "mcb_set_grid_step": ([vp, f], i),
+        "mcb_set_slab": ([vp, i, i], i),
+        "mcb_set_surface_constant": ([vp, f], i),
+        "mcb_set_scaling": ([vp, f, f, f], i),
+        "mcb_set_constraint": ([vp, i, i, f, i], i),
+        "mcb_set_normals": ([vp, i], i),
+        "mcb_polygonise": ([vp, C.POINTER(Counts)], i),
+        "mcb_get_mesh": ([vp, vp, vp, u64], i),
+        "mcb_get_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp)], i),
+        "mcb_get_cases": ([vp, vp, vp], i),
+        "mcb_get_field": ([vp, vp], i),
+        "mcb_get_active": ([vp, vp, vp, u64], i),
+    }
+    for name, (args, res) in sigs.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export what include/mcb.h declares
+        fn.argtypes = args
+        fn.restype = res
+    return L, sorted(sigs)
+
+
+lib, EXPORTS = _load()
+
+
+def status_string(s):
+    return lib.mcb_status_string(int(s)).decode()
+
+
+def _text(fn, *args, cap=1 << 16):
+    buf = C.create_string_buffer(cap)
+    rc = fn(*args, buf, cap)
+    if rc != MCB_OK:
+        raise McbError(rc)
+    return buf.value.decode()
+
+
+def parse_ok(eq):
+    """Evaluator::tokenize accept/reject (evaluator.cpp:139-237); host-only."""
+    return lib.mcb_parse(eq.encode()) == MCB_OK
+
+
+def tokens(eq):
+    return _text(lib.mcb_tokens, eq.encode())
+
+
+def postfix(eq):
+    """Operation order of the reference's two-stack evaluator as postfix text; host-only."""
+    return _text(lib.mcb_postfix, eq.encode())
+
+
+def disassemble(eq, which=1):
+    return _text(lib.mcb_disassemble, eq.encode(), which)
+
+
+def grid_axis(step):
+    """(M, c[0..M]) of the reference grid loop (marching.cpp:372-377); host-only."""
+    M = lib.mcb_grid_axis(step, None, 0)
+    if M < 0:
+        raise McbError(M)
+    c = np.empty(M + 1, np.float32)
+    lib.mcb_grid_axis(step, c.ctypes.data_as(C.c_void_p), M + 1)
+    return M, c
+
+
+def slab_range(M, rank, nranks):
+    a, b = C.c_int(0), C.c_int(0)
+    rc = lib.mcb_slab_range(M, rank, nranks, C.byref(a), C.byref(b))
+    if rc != MCB_OK:
+        raise McbError(rc)
+    return a.value, b.value
+
+
+class Context:
+    """One mcb_ctx: the device state of one Marching object / one z-slab on one GPU."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        rc = lib.mcb_create(device, C.byref(h))
+        if rc != MCB_OK:
+            raise McbError(rc, "mcb_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.mcb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise McbError(rc, lib.mcb_last_error(self.h).decode())
+        return rc
+
+    def set_stream(self, stream_ptr):
+        self._ck(lib.mcb_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def set_equation(self, eq, slot=0):
+        return lib.mcb_set_equation(self.h, slot, eq.encode())
+
+    def eval_points(self, xyz, slot=0, apply_scale=False):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        out = np.empty(len(xyz), np.float32)
+        self._ck(lib.mcb_eval_points(self.h, slot, xyz.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                     len(xyz), int(apply_scale)))
+        return out
+
+    def set_grid_step(self, step):
+        return lib.mcb_set_grid_step(self.h, step)
+
+    def set_slab(self, k0, k1):
+        self._ck(lib.mcb_set_slab(self.h, k0, k1))
+
+    def set_surface_constant(self, iso):
+        self._ck(lib.mcb_set_surface_constant(self.h, iso))
+
+    def set_scaling(self, sx, sy, sz):
+        self._ck(lib.mcb_set_scaling(self.h, sx, sy, sz))
+
+    def set_constraint(self, i, op, rhs, in_use=True):
+        opi = {">": 0, "<": 1, ">=": 2, "<=": 3}[op] if isinstance(op, str) else int(op)
+        return lib.mcb_set_constraint(self.h, i, opi, rhs, int(in_use))
+
+    def set_normals(self, mode):
+        self._ck(lib.mcb_set_normals(self.h, int(mode)))
+
+    def polygonise(self):
+        c = Counts()
+        self._ck(lib.mcb_polygonise(self.h, C.byref(c)))
+        self.counts = c
+        return c
+
+    def get_mesh(self, normals=True, out_pos=None, out_nrm=None):
+        """Triangle soup on the host: pos[T,3,4] (x,y,z,1) and nrm[T,3,4] (nx,ny,nz,0)."""
+        T = int(self.counts.triangles)
+        pos = out_pos if out_pos is not None else np.empty((T, 3, 4), np.float32)
+        nrm = (out_nrm if out_nrm is not None else np.empty((T, 3, 4), np.float32)) if normals else None
+        self._ck(lib.mcb_get_mesh(self.h, pos.ctypes.data_as(C.c_void_p),
+                                  nrm.ctypes.data_as(C.c_void_p) if nrm is not None else None, pos.shape[0]))
+        return pos[:T], (nrm[:T] if nrm is not None else None)
+
+    def get_mesh_into(self, pos_ptr, nrm_ptr, cap_tris):
+        """Raw-pointer variant (pinned host buffers owned by the caller)."""
+        self._ck(lib.mcb_get_mesh(self.h, C.c_void_p(pos_ptr), C.c_void_p(nrm_ptr) if nrm_ptr else None, cap_tris))
+
+    def get_cases(self):
+        n = int(self.counts.cubes)
+        code = np.empty(n, np.uint8)
+        tidx = np.empty(n, np.uint8)
+        self._ck(lib.mcb_get_cases(self.h, code.ctypes.data_as(C.c_void_p), tidx.ctypes.data_as(C.c_void_p)))
+        return code, tidx
+
+    def get_field(self):
+        c = self.counts
+        n1 = c.M + 1
+        out = np.empty((c.k_end - c.k_begin + 1, n1, n1), np.float32)
+        self._ck(lib.mcb_get_field(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_active(self):
+        A = int(self.counts.active)
+        rec = np.empty(A, np.uint64)
+        off = np.empty(A, np.uint32)
+        self._ck(lib.mcb_get_active(self.h, rec.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), A))
+        return rec, off
+
+
+class Evaluator:
+    """Mirror of the reference's class Evaluator (evaluator.h:55-64).  Evaluation runs on the GPU."""
+
+    def __init__(self, equation=None, device=0):
+        self._ctx = Context(device)  # a fresh context already holds the default "x+y" (evaluator.cpp:6-8)
+        self.equation = "x+y"
+        if equation is not None and not self.set_equation(equation):
+            raise ValueError("parse error")  # Evaluator(string) throws on a parse error (evaluator.cpp:10-13)
+
+    def set_equation(self, s):
+        ok = self._ctx.set_equation(s) == MCB_OK
+        if ok:
+            self.equation = s.replace(" ", "")
+        return ok
+
+    def evaluate(self, x, y, z):
+        return float(self._ctx.eval_points(np.array([[x, y, z]], np.float32))[0])
+
+
+class PolyData:
+    """Poly_Data (marching.h:26-30) as the GPU path produces it: the triangle soup in the reference's emission order.
+    vertex_list / tri_list give the same mesh in indexed form WITHOUT welding (every triangle corner is its own
+    vertex); the reference's tolerance weld (marching.cpp:627-643) is a host-side consumer step, see DESIGN.md."""
+
+    def __init__(self, pos, nrm):
+        self.positions = pos
+        self.normals = nrm
+
+    @property
+    def vertex_list(self):
+        return np.ascontiguousarray(self.positions[:, :, :3]).reshape(-1)
+
+    @property
+    def tri_list(self):
+        return np.arange(self.positions.shape[0] * 3, dtype=np.uint32)
+
+
+class Marching:
+    """Mirror of the reference's class Marching (marching.h:75-122) for the full-grid path."""
+
+    def __init__(self, device=0):
+        self._ctx = Context(device)
+        self._step = 0.25
+        self._eval = None
+        self._poly = PolyData(np.zeros((0, 3, 4), np.float32), None)
+        self.counts = None
+
+    def set_evaluator(self, e):
+        if e is None:
+            return False
+        self._eval = e
+        return True
+
+    def set_grid_step_size(self, v):
+        if not (np.float32(v) >= np.float32(0.001) and v <= 0.5):  # marching.cpp:227
+            return False
+        self._step = float(v)
+        return self._ctx.set_grid_step(v) > 0
+
+    def set_grid_resolution(self, n):
+        """Extension: step 2/n, also below the reference's 0.001 floor (2048^3)."""
+        self._step = 2.0 / n
+        return self._ctx.set_grid_step(self._step) > 0
+
+    def get_grid_size(self):
+        return self._step
+
+    def set_surface_constant(self, c):
+        self._ctx.set_surface_constant(c)
+
+    def set_scaling_x(self, s):
+        self._scale = getattr(self, "_scale", [1.0, 1.0, 1.0]); self._scale[0] = s; self._ctx.set_scaling(*self._scale)
+
+    def set_scaling_y(self, s):
+        self._scale = getattr(self, "_scale", [1.0, 1.0, 1.0]); self._scale[1] = s; self._ctx.set_scaling(*self._scale)
+
+    def set_scaling_z(self, s):
+        self._scale = getattr(self, "_scale", [1.0, 1.0, 1.0]); self._scale[2] = s; self._ctx.set_scaling(*self._scale)
+
+    def set_constraint(self, i, lhs, op, rhs):
+        if i < 0 or i > 2 or op not in (">", "<", ">=", "<="):
+            return False
+        if self._ctx.set_equation(lhs, slot=i + 1) != MCB_OK:
+            return False
+        self._cons = getattr(self, "_cons", {})
+        self._cons[i] = (op, rhs, self._cons.get(i, (None, None, False))[2])
+        return self._ctx.set_constraint(i, op, rhs, self._cons[i][2]) == MCB_OK
+
+    def use_constraint(self, i, use):
+        c = getattr(self, "_cons", {}).get(i)
+        if c is None:
+            return False
+        self._cons[i] = (c[0], c[1], bool(use))
+        return self._ctx.set_constraint(i, c[0], c[1], bool(use)) == MCB_OK and bool(use)
+
+    def set_slab(self, k0, k1):
+        self._ctx.set_slab(k0, k1)
+
+    def set_normals(self, mode):
+        self._ctx.set_normals(mode)
+
+    def recalculate(self, fetch=True):
+        if self._eval is None:
+            return False  # the reference evaluates to 0 everywhere without an evaluator: an empty mesh
+        if self._ctx.set_equation(self._eval.equation) != MCB_OK:
+            return False
+        self.counts = self._ctx.polygonise()
+        if fetch:
+            pos, nrm = self._ctx.get_mesh(normals=True)
+            self._poly = PolyData(pos, nrm)
+        return True
+
+    def get_poly_data(self):
+        return self._poly

@@ -1,0 +1,46 @@
+"""Builds the in-tree native libraries.
+
+  libmcb200.so            the product: C ABI (include/mcb.h) + sm_100a kernels (csrc/*.cu, csrc/*.cpp)
+  (oracle/ is built by oracle/Makefile; see __graft_entry__.build)
+
+nvcc cross-compiles for sm_100a without a GPU.  Flags that matter for parity with the reference's fp32 arithmetic:
+  -fmad=false          no FMA contraction of a*b+c (the oracle is built with -ffp-contract=off)
+  default -prec-div=true -prec-sqrt=true -ftz=false (never --use_fast_math)
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmcb200.so")
+SOURCES = ["mcb_api.cu", "mcb_lower.cpp"]
+HEADERS = ["mcb_kernels.cuh", "mcb_bytecode.h", "mcb_pow.h", "mcb_tables.h", "mcb_tri_words.inc", "mcb_lower.h",
+           os.path.join("..", "..", "include", "mcb.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--shared", "-cudart", "shared"]
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS) or os.path.getmtime(__file__) > t
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libmcb200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,684 @@
+/* libmcb200.so — C ABI (include/mcb.h) over the sm_100a kernels in mcb_kernels.cuh.
+ *
+ * One mcb_ctx owns the device buffers of one z-slab on one GPU and a CUDA stream; every entry point makes the
+ * context's device current, enqueues on that stream and reports failures as negative status codes.  No entry point
+ * computes field values, cases or triangles on the host.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mcb.h"
+#include "mcb_kernels.cuh"
+#include "mcb_lower.h"
+
+using namespace mcbk;
+
+namespace {
+
+struct EqSlot {
+    bool valid = false;
+    mcb::Compiled c;
+    mcb_program point; /* full expression at an arbitrary point */
+    mcb_program grid;  /* full expression on the grid, with hoisted subtrees as table loads */
+    uint32_t* d_slot_code = nullptr;
+    SlotDesc* d_slots = nullptr;
+    float* d_kpool = nullptr;
+    int n_const = 0, n_axis = 0, max_per_axis = 1;
+};
+
+struct Constraint {
+    int op = 0;
+    float rhs = 0.f;
+    bool in_use = false;
+};
+
+} /* namespace */
+
+struct mcb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    EqSlot eq[4];
+    Constraint cons[3];
+    float step = 0.25f;
+    int M = 0;
+    std::vector<float> axis; /* c[0..M] of the reference loop */
+    int kb = 0, ke = 0;
+    float iso = 0.f;
+    float scale[3] = {1.f, 1.f, 1.f};
+    int normals = 1;
+
+    Grid g{};
+    bool grid_dirty = true;
+    float* d_cs = nullptr;
+    float* d_F = nullptr;
+    uint32_t* d_S = nullptr;
+    uint32_t* d_V = nullptr;
+    float* d_tables = nullptr;
+    size_t cap_F = 0, cap_S = 0, cap_V = 0, cap_tables = 0, cap_cs = 0;
+    ClsTables* d_cls = nullptr;
+    Counters* d_ctr = nullptr;
+    Counters* h_ctr = nullptr; /* pinned */
+    ScanState st{};
+    size_t cap_tiles = 0;
+    unsigned long long* d_rec = nullptr;
+    uint32_t* d_trioff = nullptr;
+    unsigned long long cap_active = 0;
+    float4* d_pos = nullptr;
+    float4* d_nrm = nullptr;
+    unsigned long long cap_tris = 0;
+    bool nrm_allocated = false;
+    cudaEvent_t ev[6] = {};
+    mcb_counts last{};
+    bool have_result = false;
+};
+
+namespace {
+
+#define MCB_CK(call)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                   \
+            return e_ == cudaErrorMemoryAllocation ? MCB_E_NOMEM : MCB_E_CUDA;                               \
+        }                                                                                                    \
+    } while (0)
+
+int fail(mcb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+template <class T>
+int ensure(mcb_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (*cap >= need && *p) return MCB_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    MCB_CK(cudaMalloc((void**)p, need * sizeof(T)));
+    *cap = need;
+    return MCB_OK;
+}
+
+/* The reference's grid loop, marching.cpp:372-377: fp32 accumulation, bound rounded from a double expression. */
+std::vector<float> reference_axis(float step) {
+    std::vector<float> c;
+    float lower = -1.0f;
+    float upper = (float)(1.0 + 0.5 * (double)step);
+    for (float v = lower; v <= upper; v += step) {
+        c.push_back(v);
+        if (c.size() > 8192) break;
+    }
+    c.push_back(c.back() + step); /* far corner of the last cube: x_1 = x_0 + step (marching.cpp:458) */
+    return c;
+}
+
+void fill_program(mcb_program& p, const std::vector<uint32_t>& code, const std::vector<float>& k) {
+    std::memset(&p, 0, sizeof p);
+    p.n = (int)code.size();
+    std::copy(code.begin(), code.end(), p.code);
+    std::copy(k.begin(), k.end(), p.k);
+}
+
+void free_slot(EqSlot& s) {
+    if (s.d_slot_code) cudaFree(s.d_slot_code);
+    if (s.d_slots) cudaFree(s.d_slots);
+    if (s.d_kpool) cudaFree(s.d_kpool);
+    s.d_slot_code = nullptr; s.d_slots = nullptr; s.d_kpool = nullptr;
+}
+
+int install_equation(mcb_ctx* ctx, int slot, const char* equation) {
+    mcb::Compiled c;
+    std::string err;
+    int rc = mcb::compile(equation ? equation : "", c, &err);
+    if (rc != MCB_OK) return fail(ctx, rc, err);
+
+    EqSlot ns;
+    ns.c = c;
+    ns.valid = true;
+    std::vector<SlotDesc> descs;
+    for (const mcb::Slot& s : c.slots) {
+        SlotDesc d{s.code_begin, s.code_len, s.axis, s.kindex};
+        descs.push_back(d);
+        if (s.axis < 0) ns.n_const++; else ns.n_axis++;
+    }
+    ns.max_per_axis = std::max(1, std::max(c.n_axis_slots[0], std::max(c.n_axis_slots[1], c.n_axis_slots[2])));
+    if (!descs.empty()) {
+        MCB_CK(cudaMalloc((void**)&ns.d_slot_code, std::max<size_t>(1, c.slot_code.size()) * sizeof(uint32_t)));
+        MCB_CK(cudaMalloc((void**)&ns.d_slots, descs.size() * sizeof(SlotDesc)));
+        MCB_CK(cudaMemcpyAsync(ns.d_slot_code, c.slot_code.data(), c.slot_code.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CK(cudaMemcpyAsync(ns.d_slots, descs.data(), descs.size() * sizeof(SlotDesc), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    MCB_CK(cudaMalloc((void**)&ns.d_kpool, MCB_MAX_K * sizeof(float)));
+    MCB_CK(cudaMemcpyAsync(ns.d_kpool, c.kpool.data(), c.kpool.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (ns.n_const > 0) {
+        /* constant subtrees are folded ON THE DEVICE by the same interpreter that evaluates the field */
+        fold_constants_kernel<<<1, 128, 0, ctx->stream>>>(ns.d_slot_code, ns.d_slots, (int)descs.size(), ns.d_kpool, ns.d_kpool);
+        MCB_CK(cudaGetLastError());
+        MCB_CK(cudaMemcpyAsync(ns.c.kpool.data(), ns.d_kpool, ns.c.kpool.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    fill_program(ns.point, ns.c.point_code, ns.c.kpool);
+    fill_program(ns.grid, ns.c.grid_code, ns.c.kpool);
+    free_slot(ctx->eq[slot]);
+    ctx->eq[slot] = ns;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int setup_grid(mcb_ctx* ctx) {
+    if (!ctx->grid_dirty) return MCB_OK;
+    Grid& g = ctx->g;
+    g.M = ctx->M;
+    g.NV = ctx->M + 3;
+    g.P = (g.NV + 31) / 32 * 32;
+    g.WP = g.P / 32;
+    g.kb = ctx->kb;
+    g.ke = ctx->ke;
+    g.NZ = (g.ke - g.kb) + 3;
+    /* coordinates with the apron: cs[v+1] = c[v]; c[-1] = c[0]-step, c[M+1] = c[M]+step (fp32, like the loop) */
+    std::vector<float> cs((size_t)g.P + 64, 0.f);
+    cs[0] = ctx->axis[0] - ctx->step;
+    for (int v = 0; v <= g.M; v++) cs[v + 1] = ctx->axis[v];
+    cs[g.M + 2] = ctx->axis[g.M] + ctx->step;
+    for (size_t q = g.NV; q < cs.size(); q++) cs[q] = cs[g.NV - 1];
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_cs, &ctx->cap_cs, cs.size())) != MCB_OK) return rc;
+    MCB_CK(cudaMemcpyAsync(ctx->d_cs, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream)); /* cs is a stack vector */
+    const size_t nF = (size_t)g.NZ * g.NV * g.P + 64;
+    const size_t nS = (size_t)g.NZ * g.NV * g.WP + 64;
+    if ((rc = ensure(ctx, &ctx->d_F, &ctx->cap_F, nF)) != MCB_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_S, &ctx->cap_S, nS)) != MCB_OK) return rc;
+    const int WC = (g.M + 31) / 32;
+    const size_t items = (size_t)(g.ke - g.kb) * g.M * WC;
+    const size_t tiles = (items + kClsThreads * kClsItems - 1) / (kClsThreads * kClsItems) + 1;
+    if (tiles > ctx->cap_tiles) {
+        if (ctx->st.flag) { cudaFree(ctx->st.flag); cudaFree(ctx->st.agg_active); cudaFree(ctx->st.agg_tris); cudaFree(ctx->st.inc_active); cudaFree(ctx->st.inc_tris); }
+        ctx->st = ScanState{};
+        ctx->cap_tiles = 0;
+        MCB_CK(cudaMalloc((void**)&ctx->st.flag, tiles * 4));
+        MCB_CK(cudaMalloc((void**)&ctx->st.agg_active, tiles * 4));
+        MCB_CK(cudaMalloc((void**)&ctx->st.agg_tris, tiles * 4));
+        MCB_CK(cudaMalloc((void**)&ctx->st.inc_active, tiles * 8));
+        MCB_CK(cudaMalloc((void**)&ctx->st.inc_tris, tiles * 8));
+        ctx->cap_tiles = tiles;
+    }
+    ctx->grid_dirty = false;
+    return MCB_OK;
+}
+
+int ensure_records(mcb_ctx* ctx, unsigned long long need) {
+    if (ctx->cap_active >= need) return MCB_OK;
+    if (ctx->d_rec) cudaFree(ctx->d_rec);
+    if (ctx->d_trioff) cudaFree(ctx->d_trioff);
+    ctx->d_rec = nullptr; ctx->d_trioff = nullptr; ctx->cap_active = 0;
+    MCB_CK(cudaMalloc((void**)&ctx->d_rec, need * 8));
+    MCB_CK(cudaMalloc((void**)&ctx->d_trioff, need * 4));
+    ctx->cap_active = need;
+    return MCB_OK;
+}
+
+int ensure_soup(mcb_ctx* ctx, unsigned long long need, bool normals) {
+    if (ctx->cap_tris >= need && (!normals || ctx->nrm_allocated)) return MCB_OK;
+    need = std::max(need, ctx->cap_tris);
+    if (ctx->d_pos) cudaFree(ctx->d_pos);
+    if (ctx->d_nrm) cudaFree(ctx->d_nrm);
+    ctx->d_pos = nullptr; ctx->d_nrm = nullptr; ctx->cap_tris = 0; ctx->nrm_allocated = false;
+    MCB_CK(cudaMalloc((void**)&ctx->d_pos, need * 3 * sizeof(float4)));
+    if (normals) {
+        MCB_CK(cudaMalloc((void**)&ctx->d_nrm, need * 3 * sizeof(float4)));
+        ctx->nrm_allocated = true;
+    }
+    ctx->cap_tris = need;
+    return MCB_OK;
+}
+
+int enter(mcb_ctx* ctx) {
+    if (!ctx) return MCB_E_ARG;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, MCB_E_NODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return MCB_OK;
+}
+
+int copy_text(const std::string& s, char* out, size_t cap) {
+    if (!out || cap < s.size() + 1) return MCB_E_CAPACITY;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return MCB_OK;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int mcb_abi_version(void) { return MCB_ABI_VERSION; }
+
+const char* mcb_status_string(int s) {
+    switch (s) {
+        case MCB_OK: return "ok";
+        case MCB_E_PARSE: return "equation rejected";
+        case MCB_E_ARG: return "argument out of range";
+        case MCB_E_CUDA: return "CUDA failure";
+        case MCB_E_NOMEM: return "out of memory";
+        case MCB_E_STATE: return "call out of order";
+        case MCB_E_CAPACITY: return "capacity exceeded";
+        case MCB_E_NODEVICE: return "no CUDA device (there is no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+int mcb_parse(const char* equation) {
+    mcb::Compiled c;
+    return mcb::compile(equation ? equation : "", c, nullptr);
+}
+
+int mcb_tokens(const char* equation, char* out, size_t cap) {
+    std::vector<mcb::Token> t;
+    if (!mcb::tokenize(equation ? equation : "", t, nullptr)) return MCB_E_PARSE;
+    std::string s;
+    for (size_t i = 0; i < t.size(); i++) { if (i) s += ' '; s += t[i].text; }
+    return copy_text(s, out, cap);
+}
+
+int mcb_postfix(const char* equation, char* out, size_t cap) {
+    mcb::Compiled c;
+    int rc = mcb::compile(equation ? equation : "", c, nullptr);
+    if (rc != MCB_OK) return rc;
+    return copy_text(mcb::postfix_text(c.expr), out, cap);
+}
+
+int mcb_disassemble(const char* equation, int which, char* out, size_t cap) {
+    mcb::Compiled c;
+    int rc = mcb::compile(equation ? equation : "", c, nullptr);
+    if (rc != MCB_OK) return rc;
+    std::string s;
+    if (which == 0) s = mcb::disassemble(c.point_code);
+    else if (which == 1) s = mcb::disassemble(c.grid_code);
+    else {
+        for (const mcb::Slot& sl : c.slots) {
+            std::vector<uint32_t> code(c.slot_code.begin() + sl.code_begin, c.slot_code.begin() + sl.code_begin + sl.code_len);
+            char head[64];
+            std::snprintf(head, sizeof head, "%s%d: ", sl.axis < 0 ? "K" : sl.axis == 0 ? "TX" : sl.axis == 1 ? "TY" : "TZ", sl.kindex);
+            s += head + mcb::disassemble(code) + "\n";
+        }
+    }
+    return copy_text(s, out, cap);
+}
+
+int mcb_grid_axis(float step, float* coords, int cap) {
+    if (!(step > 0.f) || !(step <= 1.0f) || !std::isfinite(step)) return MCB_E_ARG;
+    if (2.0 / (double)step > 4094.0) return MCB_E_ARG;
+    std::vector<float> c = reference_axis(step);
+    int M = (int)c.size() - 1;
+    if (M > 4094) return MCB_E_ARG;
+    if (coords && cap >= M + 1) std::copy(c.begin(), c.end(), coords);
+    return M;
+}
+
+int mcb_slab_range(int M, int rank, int nranks, int* k_begin, int* k_end) {
+    if (M <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || !k_begin || !k_end) return MCB_E_ARG;
+    *k_begin = (int)((long long)M * rank / nranks);
+    *k_end = (int)((long long)M * (rank + 1) / nranks);
+    return MCB_OK;
+}
+
+int mcb_create(int device, mcb_ctx** out) {
+    if (!out) return MCB_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MCB_E_NODEVICE;
+    mcb_ctx* ctx = new (std::nothrow) mcb_ctx();
+    if (!ctx) return MCB_E_NOMEM;
+    ctx->device = device;
+    auto bail = [&](int code) { mcb_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(MCB_E_NODEVICE);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(MCB_E_NODEVICE);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MCB_E_CUDA);
+    ctx->stream = ctx->own_stream;
+    for (auto& e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(MCB_E_CUDA);
+    if (cudaMalloc((void**)&ctx->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(MCB_E_NOMEM);
+    if (cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(MCB_E_NOMEM);
+    ClsTables tb;
+    int8_t face[256];
+    mcb_build_ambiguity_faces(face);
+    for (int q = 0; q < 256; q++) {
+        tb.tri[q] = MCB_TRI_WORDS[q];
+        tb.face[q] = face[q];
+        tb.ntri[q] = (uint8_t)mcb_tri_count(MCB_TRI_WORDS[q]);
+    }
+    if (cudaMalloc((void**)&ctx->d_cls, sizeof(ClsTables)) != cudaSuccess) return bail(MCB_E_NOMEM);
+    if (cudaMemcpy(ctx->d_cls, &tb, sizeof tb, cudaMemcpyHostToDevice) != cudaSuccess) return bail(MCB_E_CUDA);
+    if (cudaFuncSetAttribute(eval_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float)) != cudaSuccess)
+        return bail(MCB_E_CUDA);
+    int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
+    if (rc != MCB_OK) return bail(rc);
+    rc = mcb_set_grid_step(ctx, 0.25f); /* Marching::Marching(), marching.cpp:24 */
+    if (rc < 0) return bail(rc);
+    *out = ctx;
+    return MCB_OK;
+}
+
+void mcb_destroy(mcb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->eq) free_slot(s);
+    cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    cudaFree(ctx->st.flag); cudaFree(ctx->st.agg_active); cudaFree(ctx->st.agg_tris); cudaFree(ctx->st.inc_active); cudaFree(ctx->st.inc_tris);
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_trioff); cudaFree(ctx->d_pos); cudaFree(ctx->d_nrm);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* mcb_last_error(const mcb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mcb_set_stream(mcb_ctx* ctx, void* s) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return MCB_OK;
+}
+
+int mcb_set_equation(mcb_ctx* ctx, int slot, const char* equation) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (slot < 0 || slot > 3) return fail(ctx, MCB_E_ARG, "slot must be 0..3");
+    return install_equation(ctx, slot, equation);
+}
+
+int mcb_eval_points(mcb_ctx* ctx, int slot, const float* xyz, float* out, size_t n, int apply_scale) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (slot < 0 || slot > 3 || !ctx->eq[slot].valid) return fail(ctx, MCB_E_STATE, "no equation in that slot");
+    if (n == 0) return MCB_OK;
+    if (!xyz || !out) return fail(ctx, MCB_E_ARG, "null buffer");
+    float *d_in = nullptr, *d_out = nullptr;
+    MCB_CK(cudaMalloc((void**)&d_in, n * 3 * sizeof(float)));
+    cudaError_t e = cudaMalloc((void**)&d_out, n * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(ctx, MCB_E_NOMEM, "cudaMalloc"); }
+    float sx = apply_scale ? ctx->scale[0] : 1.f, sy = apply_scale ? ctx->scale[1] : 1.f, sz = apply_scale ? ctx->scale[2] : 1.f;
+    cudaMemcpyAsync(d_in, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    eval_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->eq[slot].point, d_in, d_out, (long long)n, sx, sy, sz);
+    cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e2 = cudaGetLastError();
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, MCB_E_CUDA, std::string("eval_points: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return MCB_OK;
+}
+
+int mcb_set_grid_step(mcb_ctx* ctx, float step) {
+    if (!ctx) return MCB_E_ARG;
+    int M = mcb_grid_axis(step, nullptr, 0);
+    if (M < 0) return fail(ctx, MCB_E_ARG, "grid step out of range");
+    ctx->axis = reference_axis(step);
+    ctx->step = step;
+    ctx->M = M;
+    ctx->kb = 0;
+    ctx->ke = M;
+    ctx->grid_dirty = true;
+    ctx->have_result = false;
+    return M;
+}
+
+int mcb_set_slab(mcb_ctx* ctx, int k_begin, int k_end) {
+    if (!ctx) return MCB_E_ARG;
+    if (k_end <= 0) k_end = ctx->M;
+    if (k_begin < 0 || k_begin >= k_end || k_end > ctx->M) return fail(ctx, MCB_E_ARG, "slab out of range");
+    ctx->kb = k_begin;
+    ctx->ke = k_end;
+    ctx->grid_dirty = true;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_set_surface_constant(mcb_ctx* ctx, float iso) {
+    if (!ctx) return MCB_E_ARG;
+    ctx->iso = iso;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_set_scaling(mcb_ctx* ctx, float sx, float sy, float sz) {
+    if (!ctx) return MCB_E_ARG;
+    ctx->scale[0] = sx; ctx->scale[1] = sy; ctx->scale[2] = sz;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use) {
+    if (!ctx) return MCB_E_ARG;
+    if (i < 0 || i > 2 || op < 0 || op > 3) return fail(ctx, MCB_E_ARG, "constraint index 0..2, op 0..3");
+    if (in_use && !ctx->eq[i + 1].valid) return fail(ctx, MCB_E_STATE, "constraint has no left-hand side (mcb_set_equation slot i+1)");
+    ctx->cons[i].op = op; ctx->cons[i].rhs = rhs; ctx->cons[i].in_use = in_use != 0;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_set_normals(mcb_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 1) return MCB_E_ARG;
+    ctx->normals = mode;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    EqSlot& eq = ctx->eq[0];
+    if (!eq.valid) return fail(ctx, MCB_E_STATE, "no surface equation");
+    if ((rc = setup_grid(ctx)) != MCB_OK) return rc;
+    Grid& g = ctx->g;
+    g.sx = ctx->scale[0]; g.sy = ctx->scale[1]; g.sz = ctx->scale[2];
+    g.iso = ctx->iso;
+    cudaStream_t s = ctx->stream;
+    uint32_t launches = 0, reruns = 0;
+
+    bool any_constraint = false;
+    for (int i = 0; i < 3; i++) any_constraint |= ctx->cons[i].in_use && ctx->eq[i + 1].valid;
+
+    const size_t ntab = (size_t)3 * eq.max_per_axis * g.P + 64;
+    if ((rc = ensure(ctx, &ctx->d_tables, &ctx->cap_tables, ntab)) != MCB_OK) return rc;
+    if (any_constraint) {
+        const size_t nS = (size_t)g.NZ * g.NV * g.WP + 64;
+        if ((rc = ensure(ctx, &ctx->d_V, &ctx->cap_V, nS)) != MCB_OK) return rc;
+    }
+    if (ctx->cap_active == 0) {
+        unsigned long long guess = std::max<unsigned long long>(1ull << 16, 8ull * g.M * g.M);
+        guess = std::min<unsigned long long>(guess, (unsigned long long)(g.ke - g.kb) * g.M * g.M);
+        if ((rc = ensure_records(ctx, std::max<unsigned long long>(guess, 1024))) != MCB_OK) return rc;
+    }
+    if (ctx->cap_tris == 0 || (ctx->normals && !ctx->nrm_allocated)) {
+        if ((rc = ensure_soup(ctx, std::max<unsigned long long>(2 * ctx->cap_active, 1024), ctx->normals != 0)) != MCB_OK) return rc;
+    }
+
+    MCB_CK(cudaEventRecord(ctx->ev[0], s));
+    /* K0b: per-axis tables of the hoisted single-variable subtrees */
+    if (eq.n_axis > 0) {
+        dim3 grid((g.P + 127) / 128, eq.n_axis);
+        axis_tables_kernel<<<grid, 128, 0, s>>>(eq.d_slot_code, eq.d_slots, eq.n_const, eq.d_kpool, ctx->d_cs, g.NV, g.P,
+                                                eq.max_per_axis, g.sx, g.sy, g.sz, ctx->d_tables);
+        launches++;
+    }
+    MCB_CK(cudaEventRecord(ctx->ev[1], s));
+    /* K1: field + sign bit-plane */
+    {
+        const int rgpp = (g.NV + kEvalRows - 1) / kEvalRows;
+        const long long items = (long long)g.NZ * rgpp * g.WP;
+        const unsigned blocks = (unsigned)((items + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
+        const size_t smem = (size_t)std::max(1, eq.c.grid_depth) * kEvalRows * kEvalThreads * sizeof(float);
+        eval_field_kernel<<<blocks, kEvalThreads, smem, s>>>(eq.grid, g, ctx->d_cs, ctx->d_tables, eq.max_per_axis, ctx->d_F, ctx->d_S, rgpp, items);
+        launches++;
+        if (any_constraint) {
+            const long long words = (long long)g.NZ * g.NV * g.WP;
+            int first = 1;
+            for (int i = 0; i < 3; i++) {
+                if (!(ctx->cons[i].in_use && ctx->eq[i + 1].valid)) continue;
+                eval_constraint_kernel<<<(unsigned)((words + 7) / 8), 256, 0, s>>>(ctx->eq[i + 1].point, g, ctx->d_cs, ctx->cons[i].op,
+                                                                                     ctx->cons[i].rhs, first, ctx->d_V, words);
+                first = 0;
+                launches++;
+            }
+        }
+    }
+    MCB_CK(cudaEventRecord(ctx->ev[2], s));
+    MCB_CK(cudaGetLastError());
+
+    const int WC = (g.M + 31) / 32;
+    const long long items = (long long)(g.ke - g.kb) * g.M * WC;
+    const unsigned tiles = (unsigned)((items + kClsThreads * kClsItems - 1) / (kClsThreads * kClsItems));
+    bool need_classify = true;
+    for (;;) {
+        if (need_classify) {
+            /* K2: classification + ambiguity + single-pass scan + compaction */
+            MCB_CK(cudaMemsetAsync(ctx->st.flag, 0, (size_t)tiles * 4, s));
+            MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
+            classify_compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S,
+                                                                  any_constraint ? ctx->d_V : nullptr, WC, items, ctx->st, ctx->d_ctr,
+                                                                  ctx->d_rec, ctx->d_trioff, ctx->cap_active);
+            launches++;
+            MCB_CK(cudaEventRecord(ctx->ev[3], s));
+        }
+        /* K3: interpolation + coalesced float4 emission */
+        const unsigned eblocks = (unsigned)ctx->sm_count * 8;
+        if (ctx->normals)
+            emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
+        else
+            emit_kernel<false><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, nullptr);
+        launches++;
+        MCB_CK(cudaEventRecord(ctx->ev[4], s));
+        MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        MCB_CK(cudaStreamSynchronize(s));
+        MCB_CK(cudaGetLastError());
+        if (ctx->h_ctr->error) return fail(ctx, MCB_E_CUDA, "decoupled look-back exceeded its spin limit");
+        if (ctx->h_ctr->triangles >= (1ull << 32)) return fail(ctx, MCB_E_CAPACITY, "more than 2^32 triangles in one slab");
+        if (ctx->h_ctr->active > ctx->cap_active) {
+            if ((rc = ensure_records(ctx, ctx->h_ctr->active + ctx->h_ctr->active / 8 + 1024)) != MCB_OK) return rc;
+            need_classify = true;
+            reruns++;
+            if (ctx->h_ctr->triangles > ctx->cap_tris)
+                if ((rc = ensure_soup(ctx, ctx->h_ctr->triangles + ctx->h_ctr->triangles / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
+            continue;
+        }
+        if (ctx->h_ctr->triangles > ctx->cap_tris) {
+            if ((rc = ensure_soup(ctx, ctx->h_ctr->triangles + ctx->h_ctr->triangles / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
+            need_classify = false;
+            reruns++;
+            continue;
+        }
+        break;
+    }
+
+    mcb_counts& c = ctx->last;
+    std::memset(&c, 0, sizeof c);
+    c.cubes = (uint64_t)(g.ke - g.kb) * g.M * g.M;
+    c.active = ctx->h_ctr->active;
+    c.triangles = ctx->h_ctr->triangles;
+    c.ambiguous = ctx->h_ctr->ambiguous;
+    c.redirected = ctx->h_ctr->redirected;
+    c.M = g.M; c.k_begin = g.kb; c.k_end = g.ke;
+    cudaEventElapsedTime(&c.ms_tables, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&c.ms_eval, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&c.ms_classify, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[4]);
+    c.launches = launches;
+    c.reruns = reruns;
+    ctx->have_result = true;
+    if (out) *out = c;
+    return MCB_OK;
+}
+
+int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    const uint64_t T = ctx->last.triangles;
+    if (T > cap_triangles) return fail(ctx, MCB_E_CAPACITY, "mesh buffer too small");
+    if (nrm4 && !ctx->normals) return fail(ctx, MCB_E_STATE, "normals are switched off");
+    if (T == 0) return MCB_OK;
+    if (pos4) MCB_CK(cudaMemcpyAsync(pos4, ctx->d_pos, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nrm4) MCB_CK(cudaMemcpyAsync(nrm4, ctx->d_nrm, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4) {
+    if (!ctx) return MCB_E_ARG;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    if (pos4) *pos4 = (const float*)ctx->d_pos;
+    if (nrm4) *nrm4 = ctx->normals ? (const float*)ctx->d_nrm : nullptr;
+    return MCB_OK;
+}
+
+int mcb_get_cases(mcb_ctx* ctx, uint8_t* cube_code, uint8_t* table_idx) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    const Grid& g = ctx->g;
+    const long long n = (long long)ctx->last.cubes;
+    bool any_constraint = false;
+    for (int i = 0; i < 3; i++) any_constraint |= ctx->cons[i].in_use && ctx->eq[i + 1].valid;
+    uint8_t *d_code = nullptr, *d_tidx = nullptr;
+    MCB_CK(cudaMalloc((void**)&d_code, (size_t)n));
+    if (cudaMalloc((void**)&d_tidx, (size_t)n) != cudaSuccess) { cudaFree(d_code); return fail(ctx, MCB_E_NOMEM, "cudaMalloc"); }
+    dense_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_S, any_constraint ? ctx->d_V : nullptr, d_code, d_tidx, n);
+    if (ctx->last.active)
+        scatter_tidx_kernel<<<(unsigned)((ctx->last.active + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_rec, ctx->last.active, d_tidx);
+    if (cube_code) cudaMemcpyAsync(cube_code, d_code, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (table_idx) cudaMemcpyAsync(table_idx, d_tidx, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e2 = cudaGetLastError();
+    cudaFree(d_code); cudaFree(d_tidx);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, MCB_E_CUDA, std::string("get_cases: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return MCB_OK;
+}
+
+int mcb_get_field(mcb_ctx* ctx, float* out) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    if (!out) return fail(ctx, MCB_E_ARG, "null buffer");
+    const Grid& g = ctx->g;
+    const size_t n1 = (size_t)g.M + 1;
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr(ctx->d_F, (size_t)g.P * sizeof(float), (size_t)g.P, (size_t)g.NV);
+    p.srcPos = make_cudaPos(sizeof(float), 1, 1);
+    p.dstPtr = make_cudaPitchedPtr(out, n1 * sizeof(float), n1, n1);
+    p.dstPos = make_cudaPos(0, 0, 0);
+    p.extent = make_cudaExtent(n1 * sizeof(float), n1, (size_t)(g.ke - g.kb) + 1);
+    p.kind = cudaMemcpyDeviceToHost;
+    MCB_CK(cudaMemcpy3DAsync(&p, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_get_active(mcb_ctx* ctx, uint64_t* records, uint32_t* tri_offsets, uint64_t cap) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    const uint64_t A = ctx->last.active;
+    if (A > cap) return fail(ctx, MCB_E_CAPACITY, "record buffer too small");
+    if (A == 0) return MCB_OK;
+    if (records) MCB_CK(cudaMemcpyAsync(records, ctx->d_rec, A * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tri_offsets) MCB_CK(cudaMemcpyAsync(tri_offsets, ctx->d_trioff, A * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+} /* extern "C" */

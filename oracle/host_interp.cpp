@@ -1,0 +1,76 @@
+/* TEST INFRASTRUCTURE ONLY — runs the product's bytecode on the HOST so that the lowering (mcb_lower.cpp) can be
+ * checked against the compiled reference in the CPU-only test tier (there is no GPU in the build container).
+ * The product never links or calls this; on the GPU the same programs are interpreted by mcb_kernels.cuh.
+ * Built into oracle/libmcoracle_host.so by oracle/Makefile with -ffp-contract=off.
+ */
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../marching-cube-for-implicit-surfaces_b200/csrc/mcb_lower.h"
+#include "../include/mcb.h"
+
+namespace {
+/* folds constant slots with the host build of the same interpreter */
+void fold(mcb::Compiled& c) {
+    for (const mcb::Slot& s : c.slots)
+        if (s.axis < 0)
+            c.kpool[s.kindex] = mcb_interp_scalar(c.slot_code.data() + s.code_begin, s.code_len, c.kpool.data(), 0, 0, 0,
+                                                  nullptr, nullptr, nullptr);
+}
+}  // namespace
+
+extern "C" {
+
+/* which: 0 = point program at n arbitrary points (xyz = 3n floats) */
+int mcoh_eval_points(const char* eq, const float* xyz, float* out, long n) {
+    mcb::Compiled c;
+    int rc = mcb::compile(eq, c, nullptr);
+    if (rc != MCB_OK) return rc;
+    fold(c);
+    for (long i = 0; i < n; i++)
+        out[i] = mcb_interp_scalar(c.point_code.data(), (int)c.point_code.size(), c.kpool.data(), xyz[3 * i], xyz[3 * i + 1],
+                                   xyz[3 * i + 2], nullptr, nullptr, nullptr);
+    return MCB_OK;
+}
+
+/* grid program over the tensor grid cx[nx] x cy[ny] x cz[nz] (already scaled coordinates), x fastest */
+int mcoh_eval_grid(const char* eq, const float* cx, int nx, const float* cy, int ny, const float* cz, int nz, float* out) {
+    mcb::Compiled c;
+    int rc = mcb::compile(eq, c, nullptr);
+    if (rc != MCB_OK) return rc;
+    fold(c);
+    const float* ax[3] = {cx, cy, cz};
+    int an[3] = {nx, ny, nz};
+    std::vector<std::vector<float>> tab[3];
+    for (int a = 0; a < 3; a++) tab[a].assign(c.n_axis_slots[a], std::vector<float>(an[a]));
+    for (const mcb::Slot& s : c.slots) {
+        if (s.axis < 0) continue;
+        for (int i = 0; i < an[s.axis]; i++) {
+            float v = ax[s.axis][i];
+            tab[s.axis][s.kindex][i] = mcb_interp_scalar(c.slot_code.data() + s.code_begin, s.code_len, c.kpool.data(), v, v, v,
+                                                         nullptr, nullptr, nullptr);
+        }
+    }
+    std::vector<float> tx(c.n_axis_slots[0] + 1), ty(c.n_axis_slots[1] + 1), tz(c.n_axis_slots[2] + 1);
+    for (int k = 0; k < nz; k++)
+        for (int j = 0; j < ny; j++)
+            for (int i = 0; i < nx; i++) {
+                for (int s = 0; s < c.n_axis_slots[0]; s++) tx[s] = tab[0][s][i];
+                for (int s = 0; s < c.n_axis_slots[1]; s++) ty[s] = tab[1][s][j];
+                for (int s = 0; s < c.n_axis_slots[2]; s++) tz[s] = tab[2][s][k];
+                out[((size_t)k * ny + j) * nx + i] = mcb_interp_scalar(c.grid_code.data(), (int)c.grid_code.size(), c.kpool.data(),
+                                                                        cx[i], cy[j], cz[k], tx.data(), ty.data(), tz.data());
+            }
+    return MCB_OK;
+}
+
+int mcoh_depths(const char* eq, int* point_depth, int* grid_depth, int* n_point, int* n_grid, int* n_slots) {
+    mcb::Compiled c;
+    int rc = mcb::compile(eq, c, nullptr);
+    if (rc != MCB_OK) return rc;
+    *point_depth = c.point_depth; *grid_depth = c.grid_depth;
+    *n_point = (int)c.point_code.size(); *n_grid = (int)c.grid_code.size(); *n_slots = (int)c.slots.size();
+    return MCB_OK;
+}
+}
