@@ -1,0 +1,69 @@
+"""-m gpu: larger grids.  256^3 (M=257): counts against SURVEY.md Appendix B (made with the unmodified reference) for
+all eight example equations, plus live per-cube comparison against oracle/_ref on a few z-layers.  1024^3: size-
+independent properties (slab additivity, determinism, symmetric-field symmetry)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# SURVEY.md Appendix B, step 2/256, scale 1, iso 0: triangles of the reference's full run
+T257 = {1: 263682, 2: 266244, 3: 153868, 4: 240532, 5: 369792, 6: 186060, 7: 78928, 8: 370672}
+
+
+@pytest.mark.parametrize("n", range(1, 9))
+def test_examples_at_256(mcb, n):
+    from oracle.refbind import EXAMPLE_EQUATIONS
+    c = mcb.Context(0)
+    assert c.set_equation(EXAMPLE_EQUATIONS[n]) == 0
+    assert c.set_grid_step(2.0 / 256) == 257
+    cnt = c.polygonise()
+    assert cnt.triangles == T257[n]
+    c.close()
+
+
+@pytest.mark.parametrize("eq,T", [("x^2+y^2+z^2-0.49", 302792), ("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)", 232128)])
+def test_sphere_torus_at_256(mcb, eq, T):
+    c = mcb.Context(0)
+    assert c.set_equation(eq) == 0
+    assert c.set_grid_step(2.0 / 256) == 257
+    assert c.polygonise().triangles == T
+    c.close()
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_layers_against_live_reference_at_256(mcb, refbind, n):
+    """Per-cube cube_code / table_idx / soup for a handful of z-layers of the 257^3 grid, reference executed live."""
+    from .helpers import same_bits
+    eq = refbind.EXAMPLE_EQUATIONS[n]
+    r = refbind.Ref(eq, 2.0 / 256)
+    c = mcb.Context(0)
+    assert c.set_equation(eq) == 0 and c.set_grid_step(2.0 / 256) == 257
+    for (k0, k1) in [(0, 1), (127, 130), (200, 201), (256, 257)]:
+        c.set_slab(k0, k1)
+        cnt = c.polygonise()
+        code, tidx = c.get_cases()
+        sw = r.sweep(k0, k1, soup=True)
+        assert np.array_equal(code, sw["code"]) and np.array_equal(tidx, sw["table_idx"])
+        assert cnt.triangles == sw["T"]
+        pos, _ = c.get_mesh()
+        assert same_bits(pos[:, :, :3], sw["soup"])
+    c.close()
+
+
+def test_1024_properties(mcb):
+    """1025^3 cubes: determinism, slab additivity and mirror symmetry of the sphere's triangle count."""
+    c = mcb.Context(0)
+    assert c.set_equation("x^2+y^2+z^2-0.49") == 0
+    assert c.set_grid_step(2.0 / 1024) == 1025
+    a = c.polygonise()
+    b = c.polygonise()
+    assert (a.triangles, a.active) == (b.triangles, b.active) and a.cubes == 1025 ** 3
+    assert b.reruns == 0
+    T, A = 0, 0
+    for r in range(4):
+        k0, k1 = mcb.slab_range(1025, r, 4)
+        c.set_slab(k0, k1)
+        s = c.polygonise()
+        T += s.triangles; A += s.active
+    assert (T, A) == (a.triangles, a.active)
+    c.close()

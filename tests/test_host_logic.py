@@ -1,0 +1,191 @@
+"""CPU tier: host logic of the boundary (tokenizer, two-stack lowering, grid loop, slabs, tables, C-ABI exports)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# Evaluator::test()'s nine cases (evaluator.h:67-77) — the only known-answer test the reference ships.
+EVALUATOR_TEST_CASES = [("-(x+ -(y)* -.021)", True), ("(x(y)", False), ("(x)", True), ("(x-)", False), ("(-x)", True),
+                        ("-(-x)", True), ("", False), ("xyz", True), ("xy/z^-.22", True)]
+
+# operation order of the reference's two-stack evaluator (probe-verified against the
+# compiled reference) — NOT conventional precedence.
+POSTFIX_KNOWN = {
+    "x-y+z": "x y z + -",
+    "x/y*z": "x y z * /",
+    "-x^2": "x NEG 2 ^",
+    "x*-y+z": "x y NEG z + *",
+    "x+y*z^2+x": "x y z 2 ^ x + * +",
+    "x-y*z+x": "x y z * x + -",
+    "x*y-z*x+y": "x y * z x * y + -",
+    "x^2-y^2-z^2": "x 2 ^ y 2 ^ z 2 ^ - -",
+    "x^y^z": "x y z ^ ^",
+    "(x)(y)2": "x y 2 * *",
+    "-(x+ -(y)* -.021)": "x y NEG 0.021 NEG * + NEG",
+    "x^2*y^2+x^2*z^2+z^2*y^2+x*y*z": "x 2 ^ y 2 ^ x 2 ^ z 2 ^ z 2 ^ y 2 ^ x y z * * + * + * + *",
+}
+
+
+def test_abi_exports_every_declared_symbol(mcb):
+    hdr = open(os.path.join(ROOT, "include", "mcb.h")).read()
+    declared = set(re.findall(r"\b(mcb_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"mcb_ctx"}
+    lib = C.CDLL(mcb.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libmcb200.so does not export " + name
+    assert set(mcb.EXPORTS) == declared
+    assert mcb.lib.mcb_abi_version() == 1
+
+
+@pytest.mark.parametrize("eq,ok", EVALUATOR_TEST_CASES)
+def test_evaluator_selftest_cases(mcb, eq, ok):
+    assert mcb.parse_ok(eq) == ok
+
+
+def test_tokenizer_matches_reference(mcb, refbind):
+    cases = [e for e, _ in EVALUATOR_TEST_CASES] + ["2..3", "3.x", "x.5", "--x", "x--y", "()", ".", "x)", "a", "X+Y*Z", "x y", "2x",
+                                                     "x(y)", "(x)(y)2", "x^-y", "x*-(y)", "-", "(", "1.2.3", "x+(", "((x))", "x^2^3",
+                                                     "3(x)", "x3", "x 3", ".5.5", "x*/y", "+x", "x++y", "-x-y", "(-)", "-.5x"]
+    for eq in cases:
+        ref_ok = bool(refbind.lib().mcref_parse_ok(eq.encode()))
+        mine = mcb.parse_ok(eq)
+        if ref_ok and not mine:
+            # accepted by the reference tokenizer, refused here: only allowed when the reference would underflow its
+            # operand stack (undefined behaviour), i.e. an operator with a missing operand
+            assert eq in ("x+", "-", "x+(", "(", "x^-") or eq.rstrip()[-1] in "+-*/^(" or eq == "-", eq
+        else:
+            assert mine == ref_ok, eq
+
+
+@pytest.mark.parametrize("eq,pf", sorted(POSTFIX_KNOWN.items()))
+def test_two_stack_operation_order(mcb, eq, pf):
+    assert mcb.postfix(eq) == pf
+
+
+def test_implicit_multiplication_tokens(mcb):
+    assert mcb.tokens("xyz") == "x * y * z"
+    assert mcb.tokens("2x(y)3") == "2 * x * ( y ) * 3"
+    assert mcb.tokens("x*-y") == "x * NEG y"
+    assert mcb.tokens("xy/z^-.22") == "x * y / z ^ NEG .22"
+
+
+def test_grid_loop_matches_reference(mcb, refbind):
+    for step in (0.5, 0.25, 0.2, 0.1, 0.05, 0.01, 0.001, 2.0 / 256, 2.0 / 1024, 0.0123, 0.3):
+        r = refbind.Ref("x", step)
+        Mr, cr = r.coords()
+        M, c = mcb.grid_axis(step)
+        assert M == Mr and np.array_equal(c.view(np.uint32), cr.view(np.uint32)), step
+
+
+def test_grid_loop_known_counts(mcb):
+    # SURVEY.md Appendix A.3 (probe of the reference loop)
+    for step, M in [(0.5, 5), (0.25, 9), (0.2, 11), (0.1, 21), (0.05, 41), (0.01, 201), (0.001, 2001), (2.0 / 256, 257),
+                    (2.0 / 1024, 1025), (2.0 / 2048, 2049)]:
+        assert mcb.grid_axis(step)[0] == M
+    with pytest.raises(mcb.McbError):
+        mcb.grid_axis(0.0)
+
+
+def test_slab_ranges_partition(mcb):
+    for M in (9, 257, 1025, 2049):
+        for n in (1, 2, 3, 4, 8):
+            edges = [mcb.slab_range(M, r, n) for r in range(n)]
+            assert edges[0][0] == 0 and edges[-1][1] == M
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(n - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _packed_rows():
+    txt = open(os.path.join(ROOT, "marching-cube-for-implicit-surfaces_b200", "csrc", "mcb_tri_words.inc")).read()
+    words = [int(w, 16) for w in re.findall(r"0x([0-9a-f]{16})ull", txt)]
+    assert len(words) == 256
+    rows = []
+    for w in words:
+        r = [(w >> (4 * f)) & 0xF for f in range(16)]
+        rows.append([v if v != 0xF else -1 for v in r])
+    return np.array(rows, np.int32)
+
+
+def test_packed_triangle_table_equals_reference(refbind):
+    tri, _, edge = refbind.tables()
+    assert np.array_equal(_packed_rows(), tri)
+    assert edge.tolist() == [[0, 1], [1, 2], [2, 3], [3, 0], [4, 5], [5, 6], [6, 7], [7, 4], [0, 4], [1, 5], [2, 6], [3, 7]]
+
+
+def test_triangle_table_invariants():
+    rows = _packed_rows()
+    hist = np.bincount([(r != -1).sum() // 3 for r in rows], minlength=6)
+    assert hist.tolist() == [2, 16, 50, 80, 76, 32]
+    EA = [0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3]
+    EB = [1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7]
+    for code, r in enumerate(rows):
+        for e in r[r != -1]:
+            assert ((code >> EA[e]) ^ (code >> EB[e])) & 1, "row references a non-crossing edge"
+
+
+def test_ambiguity_faces_equal_reference(mcb, refbind, golden):
+    """The derived face-per-code table (mcb_tables.h) against the table the reference ships, all 256 rows."""
+    _, amb, _ = refbind.tables()
+    FACE = [(0, 1, 2, 3), (1, 2, 6, 5), (4, 5, 6, 7), (0, 3, 7, 4), (3, 2, 6, 7), (0, 1, 5, 4)]
+    for code in range(256):
+        f = -1
+        for fi in (0, 1, 2, 3, 5, 4):
+            b = [(code >> v) & 1 for v in FACE[fi]]
+            if b[0] == b[2] and b[1] == b[3] and b[0] != b[1]:
+                f = fi
+        if f < 0:
+            assert amb[code][0] == -1
+        else:
+            assert amb[code].tolist() == [255 - code] + list(FACE[f])
+    assert int((amb[:, 0] >= 0).sum()) == 120
+
+
+def test_lowering_bit_exact_on_host(mcb, refbind):
+    """The bytecode the GPU interprets, run by the host build of the same interpreter (oracle/host_interp.cpp), against
+    Evaluator::evaluate of the compiled reference: random points and a tensor grid (exercises folding + hoisting)."""
+    so = os.path.join(ROOT, "oracle", "libmcoracle_host.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/libmcoracle_host.so not built")
+    H = C.CDLL(so)
+    H.mcoh_eval_points.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_long]
+    H.mcoh_eval_grid.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(1)
+    pts = (rng.random((4000, 3), dtype=np.float32) * 4 - 2).astype(np.float32)
+    pts[:32] = 0
+    cx = np.linspace(-1.1, 1.2, 19, dtype=np.float32)
+    cy = np.linspace(-0.9, 1.3, 13, dtype=np.float32)
+    cz = np.linspace(-1, 1, 7, dtype=np.float32)
+    Z, Y, X = np.meshgrid(cz, cy, cx, indexing="ij")
+    gp = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
+    eqs = list(refbind.EXAMPLE_EQUATIONS.values()) + [refbind.SPHERE, refbind.TORUS, refbind.GYR34, refbind.GYR78] + \
+        list(POSTFIX_KNOWN) + ["x^0.5+y", "x/y", "1/(x*y*z)", "x^-2", "-x^0.5", "2^x+y^z", "x^y", "(1/3)^2*x+(1/3)*y", "3", "1+2*3"]
+    for eq in eqs:
+        ref = refbind.Ref(eq)
+        out = np.empty(len(pts), np.float32)
+        assert H.mcoh_eval_points(eq.encode(), pts.ctypes.data, out.ctypes.data, len(pts)) == 0
+        r = ref.eval_points(pts)
+        assert np.all((r.view(np.uint32) == out.view(np.uint32)) | (np.isnan(r) & np.isnan(out))), eq
+        g = np.empty(len(gp), np.float32)
+        assert H.mcoh_eval_grid(eq.encode(), cx.ctypes.data, len(cx), cy.ctypes.data, len(cy), cz.ctypes.data, len(cz), g.ctypes.data) == 0
+        rg = ref.eval_points(gp)
+        assert np.all((rg.view(np.uint32) == g.view(np.uint32)) | (np.isnan(rg) & np.isnan(g))), eq
+
+
+def test_no_device_is_a_loud_failure(mcb):
+    """Without a GPU the product refuses to work (no CPU fallback); with one, creation succeeds."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        mcb.Context(0).close()
+    else:
+        with pytest.raises(mcb.McbError) as ei:
+            mcb.Context(0)
+        assert ei.value.status == mcb.MCB_E_NODEVICE
