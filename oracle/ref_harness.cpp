@@ -200,19 +200,19 @@ long mcref_sweep(mcref* h, int k0, int k1, uint8_t* code, uint8_t* tidx, uint8_t
     return T;
 }
 
-/* CPU baseline: nthreads independent Evaluator+Marching pairs (they share no state), each running the
- * reference's calculate_step + add_step_to_poly_data over its own contiguous range of cube layers of
- * [k0,k1).  Returns wall seconds; *cubes / *tris = totals.  nthreads==1 and the full range is exactly
- * the work of Marching::recalculate()'s full-grid branch. */
-double mcref_timed_sweep_mt(const char* eq, float step, float sx, float sy, float sz, float iso, int k0, int k1,
-                            int nthreads, long* cubes, long* tris) {
+/* CPU baseline: nthreads independent Evaluator+Marching pairs (they share no state), each running the reference's
+ * calculate_step + add_step_to_poly_data over its own contiguous share of `nrows` cube rows starting at row0
+ * (row = k*M + j, M cubes each, loop order).  Returns wall seconds; *cubes / *tris = totals.  nthreads==1 with
+ * row0=0, nrows=M*M is exactly the work of Marching::recalculate()'s full-grid branch (marching.cpp:368-384). */
+double mcref_timed_rows_mt(const char* eq, float step, float sx, float sy, float sz, float iso, long row0, long nrows,
+                           int nthreads, long* cubes, long* tris) {
     std::vector<float> c = ref_axis(step);
-    int M = (int)c.size();
-    if (k0 < 0) k0 = 0;
-    if (k1 > M) k1 = M;
+    long M = (long)c.size();
+    if (row0 < 0) row0 = 0;
+    if (row0 > M * M) row0 = M * M;
+    if (row0 + nrows > M * M) nrows = M * M - row0;
     if (nthreads < 1) nthreads = 1;
-    int L = k1 - k0;
-    if (nthreads > L) nthreads = L > 0 ? L : 1;
+    if (nthreads > nrows) nthreads = nrows > 0 ? (int)nrows : 1;
     std::vector<long> t_tris(nthreads, 0);
     std::vector<mcref*> hs(nthreads);
     for (int t = 0; t < nthreads; t++) {
@@ -225,16 +225,17 @@ double mcref_timed_sweep_mt(const char* eq, float step, float sx, float sy, floa
     auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++) {
-        int a = k0 + (int)((long)L * t / nthreads), b = k0 + (int)((long)L * (t + 1) / nthreads);
+        long a = row0 + nrows * t / nthreads, b = row0 + nrows * (t + 1) / nthreads;
         th.emplace_back([&, t, a, b]() {
             Marching& m = hs[t]->march;
             m.reset_all_data();
-            for (int k = a; k < b; k++)
-                for (int j = 0; j < M; j++)
-                    for (int i = 0; i < M; i++) {
-                        m.calculate_step(c[i], c[j], c[k]);
-                        m.add_step_to_poly_data();
-                    }
+            for (long r = a; r < b; r++) {
+                const float z0 = c[r / M], y0 = c[r % M];
+                for (long i = 0; i < M; i++) {
+                    m.calculate_step(c[i], y0, z0);
+                    m.add_step_to_poly_data();
+                }
+            }
             t_tris[t] = (long)m.poly_data.tri_list.size() / 3;
         });
     }
@@ -242,7 +243,7 @@ double mcref_timed_sweep_mt(const char* eq, float step, float sx, float sy, floa
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     long T = 0;
     for (int t = 0; t < nthreads; t++) { T += t_tris[t]; delete hs[t]; }
-    if (cubes) *cubes = (long)L * M * M;
+    if (cubes) *cubes = nrows * M;
     if (tris) *tris = T;
     return sec;
 }

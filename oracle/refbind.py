@@ -69,9 +69,9 @@ def lib():
         L.mcref_sweep.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcref_sweep.restype = C.c_long
-        L.mcref_timed_sweep_mt.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                           C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-        L.mcref_timed_sweep_mt.restype = C.c_double
+        L.mcref_timed_rows_mt.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                          C.c_long, C.c_long, C.c_int, C.c_void_p, C.c_void_p]
+        L.mcref_timed_rows_mt.restype = C.c_double
         L.mcref_timed_recalculate.argtypes = [C.c_void_p]
         L.mcref_timed_recalculate.restype = C.c_double
         L.mcref_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -178,10 +178,11 @@ class Ref:
         return out
 
 
-def timed_sweep_mt(eq, step, scale=(1.0, 1.0, 1.0), iso=0.0, k0=0, k1=1 << 30, nthreads=1):
+def timed_rows_mt(eq, step, scale=(1.0, 1.0, 1.0), iso=0.0, row0=0, nrows=1 << 40, nthreads=1):
+    """Reference CPU baseline over cube rows [row0,row0+nrows) (row = k*M+j); returns (seconds, cubes, triangles)."""
     cubes, tris = C.c_long(0), C.c_long(0)
-    sec = lib().mcref_timed_sweep_mt(eq.encode(), step, scale[0], scale[1], scale[2], iso, k0, k1, nthreads,
-                                     C.byref(cubes), C.byref(tris))
+    sec = lib().mcref_timed_rows_mt(eq.encode(), step, scale[0], scale[1], scale[2], iso, row0, nrows, nthreads,
+                                    C.byref(cubes), C.byref(tris))
     return sec, cubes.value, tris.value
 
 
