@@ -519,10 +519,10 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     /* K1: field + sign bit-plane */
     {
         const int rgpp = (g.NV + kEvalRows - 1) / kEvalRows;
-        const long long items = (long long)g.NZ * rgpp * g.WP;
-        const unsigned blocks = (unsigned)((items + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
+        const unsigned items = (unsigned)rgpp * (unsigned)g.WP; /* (row group, word) pairs per z-plane */
+        const dim3 blocks((items + kEvalThreads / 32 - 1) / (kEvalThreads / 32), (unsigned)g.NZ);
         const size_t smem = (size_t)std::max(1, eq.c.grid_depth) * kEvalRows * kEvalThreads * sizeof(float);
-        eval_field_kernel<<<blocks, kEvalThreads, smem, s>>>(eq.grid, g, ctx->d_cs, ctx->d_tables, eq.max_per_axis, ctx->d_F, ctx->d_S, rgpp, items);
+        eval_field_kernel<<<blocks, kEvalThreads, smem, s>>>(eq.grid, g, ctx->d_cs, ctx->d_tables, eq.max_per_axis, ctx->d_F, ctx->d_S, items);
         launches++;
         if (any_constraint) {
             const long long words = (long long)g.NZ * g.NV * g.WP;

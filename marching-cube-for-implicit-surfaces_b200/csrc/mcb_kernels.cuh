@@ -22,10 +22,10 @@
 
 namespace mcbk {
 
-constexpr int kEvalThreads = 256;   /* 8 warps; each warp: 32 x-columns x 4 y-rows */
-constexpr int kEvalRows = 4;
+constexpr int kEvalThreads = 128;   /* 4 warps; each warp: 32 x-columns x kEvalRows y-rows of one z-plane */
+constexpr int kEvalRows = 8;
 constexpr int kClsThreads = 256;
-constexpr int kClsItems = 2;        /* 32-cube words per thread in classify */
+constexpr int kClsItems = 8;        /* consecutive 32-cube words per thread in classify */
 constexpr int kEmitThreads = 128;   /* = active cubes per emit chunk */
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -96,15 +96,14 @@ __device__ __noinline__ float powf_call(float a, float b) { return mcb_powf(a, b
 __global__ void __launch_bounds__(kEvalThreads)
 eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ cs,
                   const float* __restrict__ tables, int max_slots_per_axis, float* __restrict__ F,
-                  uint32_t* __restrict__ S, int rowgroups_per_plane, long long total_items) {
+                  uint32_t* __restrict__ S, unsigned items_per_plane) {
     extern __shared__ float stack_smem[]; /* [depth][kEvalRows][kEvalThreads] */
     const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * (kEvalThreads / 32) + (threadIdx.x >> 5);
-    if (item >= total_items) return; /* whole warp exits together */
-    const int w = (int)(item % g.WP);
-    const long long rg = item / g.WP;
-    const int yq = (int)(rg % rowgroups_per_plane);
-    const int pz = (int)(rg / rowgroups_per_plane);
+    const unsigned item = blockIdx.x * (kEvalThreads / 32) + (threadIdx.x >> 5); /* (row group, word) of plane blockIdx.y */
+    if (item >= items_per_plane) return; /* whole warp exits together */
+    const int w = (int)(item % (unsigned)g.WP);
+    const int yq = (int)(item / (unsigned)g.WP);
+    const int pz = (int)blockIdx.y;
     const int x = w * 32 + lane;
     const int y0 = yq * kEvalRows;
 
@@ -163,7 +162,7 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
                 case MCB_OP_PUSH_TY: {
                     const float* ty = taby + (size_t)arg * g.P + y0;
 #pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = __ldg(ty + e); /* tables are padded to P >= NV+3 */
+                    for (int e = 0; e < kEvalRows; e++) t0[e] = __ldg(ty + e); /* tables are padded past NV+kEvalRows */
                     break;
                 }
                 default: { /* MCB_OP_PUSH_TZ (MCB_OP_END never appears inside a program) */
@@ -218,14 +217,15 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
         }
     }
 
-    const size_t plane = (size_t)pz * g.NV;
+    const size_t row0 = (size_t)pz * g.NV + y0;
+    float* fp = F + row0 * g.P + x;
+    uint32_t* sp_bits = S + row0 * g.WP + w;
 #pragma unroll
     for (int e = 0; e < kEvalRows; e++) {
-        const int y = y0 + e;
-        const bool in = (y < g.NV); /* uniform per warp */
-        if (in && x < g.P) F[(plane + y) * g.P + x] = t0[e];
+        const bool in = (y0 + e < g.NV); /* uniform per warp */
+        if (in) fp[(size_t)e * g.P] = t0[e]; /* x < P always: P is the padded pitch */
         const unsigned bits = __ballot_sync(0xffffffffu, in && x < g.NV && t0[e] > g.iso);
-        if (in && lane == e) S[(plane + y) * g.WP + w] = bits;
+        if (in && lane == e) sp_bits[e * g.WP] = bits;
     }
 }
 
@@ -273,30 +273,32 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return *(const volatile unsigned long long*)p;
 }
 
-struct ClsTables { /* built once per context on the host (mcb_tables.h), staged in shared memory per block */
+struct ClsTables { /* built once per context on the host (mcb_tables.h); read through the read-only path */
     uint64_t tri[256];
     int8_t face[256];
     uint8_t ntri[256];
 };
 
-/* corner sign words of the 32 cubes of one item: bit b of c[v] = sign of corner v of cube 32w+b */
-__device__ __forceinline__ void load_corner_words(const uint32_t* __restrict__ B, const Grid& g, int kz, int j, int w,
-                                                  uint32_t c[8]) {
+/* the four sign-word rows a cube row touches: (y, z), (y+1, z), (y, z+1), (y+1, z+1) */
+struct RowPtrs {
+    const uint32_t* r[4];
+};
+__device__ __forceinline__ RowPtrs cube_row_ptrs(const uint32_t* __restrict__ B, const Grid& g, int kz, int j) {
     /* cube (i,j,kz) corner (dx,dy,dz) = vertex index (i+1+dx, j+1+dy, plane kz+1+dz) */
-    const size_t r00 = ((size_t)(kz + 1) * g.NV + (j + 1)) * g.WP;
-    const size_t r10 = r00 + g.WP;
-    const size_t r01 = r00 + (size_t)g.NV * g.WP;
-    const size_t r11 = r01 + g.WP;
-    const bool hi_ok = (w + 1 < g.WP);
-    uint32_t lo, hi;
-    lo = __ldg(B + r00 + w); hi = hi_ok ? __ldg(B + r00 + w + 1) : 0u;
-    c[0] = __funnelshift_r(lo, hi, 1); c[1] = __funnelshift_r(lo, hi, 2);
-    lo = __ldg(B + r10 + w); hi = hi_ok ? __ldg(B + r10 + w + 1) : 0u;
-    c[3] = __funnelshift_r(lo, hi, 1); c[2] = __funnelshift_r(lo, hi, 2);
-    lo = __ldg(B + r01 + w); hi = hi_ok ? __ldg(B + r01 + w + 1) : 0u;
-    c[4] = __funnelshift_r(lo, hi, 1); c[5] = __funnelshift_r(lo, hi, 2);
-    lo = __ldg(B + r11 + w); hi = hi_ok ? __ldg(B + r11 + w + 1) : 0u;
-    c[7] = __funnelshift_r(lo, hi, 1); c[6] = __funnelshift_r(lo, hi, 2);
+    RowPtrs p;
+    p.r[0] = B + ((size_t)(kz + 1) * g.NV + (j + 1)) * g.WP;
+    p.r[1] = p.r[0] + g.WP;
+    p.r[2] = p.r[0] + (size_t)g.NV * g.WP;
+    p.r[3] = p.r[2] + g.WP;
+    return p;
+}
+/* corner sign words of the 32 cubes of word w: bit b of c[v] = sign of corner v of cube 32w+b.
+ * lo[] = words w of the four rows (carried from the previous item when possible), hi[] = words w+1. */
+__device__ __forceinline__ void corner_words(const uint32_t lo[4], const uint32_t hi[4], uint32_t c[8]) {
+    c[0] = __funnelshift_r(lo[0], hi[0], 1); c[1] = __funnelshift_r(lo[0], hi[0], 2);
+    c[3] = __funnelshift_r(lo[1], hi[1], 1); c[2] = __funnelshift_r(lo[1], hi[1], 2);
+    c[4] = __funnelshift_r(lo[2], hi[2], 1); c[5] = __funnelshift_r(lo[2], hi[2], 2);
+    c[7] = __funnelshift_r(lo[3], hi[3], 1); c[6] = __funnelshift_r(lo[3], hi[3], 2);
 }
 
 __device__ __forceinline__ int code_of(const uint32_t c[8], int b) {
@@ -324,65 +326,93 @@ __device__ __noinline__ bool ambiguity_redirects(const mcb_program& prog, const 
 
 __global__ void __launch_bounds__(kClsThreads)
 classify_compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
-                        const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V, int WC /* words per cube row */,
+                        const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S,
+                        const uint32_t* __restrict__ V, int WC /* words per cube row */,
                         long long total_items, ScanState st, Counters* __restrict__ ctr,
                         unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
                         unsigned long long cap_active) {
-    __shared__ ClsTables tb;
     __shared__ uint32_t warp_a[kClsThreads / 32], warp_t[kClsThreads / 32];
     __shared__ unsigned long long base_a_s, base_t_s;
     __shared__ uint32_t tile_s;
 
-    for (int q = threadIdx.x; q < 256; q += kClsThreads) {
-        tb.tri[q] = gtb->tri[q];
-        tb.face[q] = gtb->face[q];
-        tb.ntri[q] = gtb->ntri[q];
-    }
     if (threadIdx.x == 0) tile_s = atomicAdd(&ctr->tile_ticket, 1u);
     __syncthreads();
     const uint32_t tile = tile_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    /* this thread's kClsItems consecutive items start at (kz0, j0, w0) */
+    const long long item0 = ((long long)tile * kClsThreads + threadIdx.x) * kClsItems;
+    int nitems = 0, kz0 = 0, j0 = 0, w0 = 0;
+    if (item0 < total_items) {
+        const long long left = total_items - item0;
+        nitems = left < kClsItems ? (int)left : kClsItems;
+        const long long row = item0 / WC;
+        w0 = (int)(item0 - row * WC);
+        kz0 = (int)(row / g.M);
+        j0 = (int)(row - (long long)kz0 * g.M);
+    }
+
     /* ---- phase 1: masks and counts -------------------------------------------------------------------------- */
     uint32_t act[kClsItems], red[kClsItems];
     uint32_t n_act = 0, n_tri = 0, n_amb = 0, n_red = 0;
-    const long long item0 = ((long long)tile * kClsThreads + threadIdx.x) * kClsItems;
+    {
+        int kz = kz0, j = j0, w = w0;
+        RowPtrs rp = cube_row_ptrs(S, g, kz, j);
+        uint32_t lo[4], hi[4];
 #pragma unroll
-    for (int q = 0; q < kClsItems; q++) {
-        act[q] = 0; red[q] = 0;
-        const long long item = item0 + q;
-        if (item >= total_items) continue;
-        const int w = (int)(item % WC);
-        const long long row = item / WC;
-        const int j = (int)(row % g.M);
-        const int kz = (int)(row / g.M);
-        uint32_t c[8];
-        load_corner_words(S, g, kz, j, w, c);
-        const uint32_t any = c[0] | c[1] | c[2] | c[3] | c[4] | c[5] | c[6] | c[7];
-        const uint32_t all = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
-        const int ncubes = g.M - w * 32; /* cubes of this word inside the row */
-        uint32_t m = any & ~all & (ncubes >= 32 ? 0xffffffffu : ((1u << ncubes) - 1u));
-        if (V != nullptr && m) {
-            uint32_t v[8];
-            load_corner_words(V, g, kz, j, w, v);
-            m &= v[0] & v[1] & v[2] & v[3] & v[4] & v[5] & v[6] & v[7];
-        }
-        act[q] = m;
-        n_act += __popc(m);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            int code = code_of(c, b);
-            const int face = tb.face[code];
-            if (face >= 0) {
-                n_amb++;
-                if (ambiguity_redirects(point_prog, g, cs, face, w * 32 + b, j, kz + g.kb)) {
-                    code = 255 - code;
-                    red[q] |= 1u << b;
-                    n_red++;
+        for (int r = 0; r < 4; r++) lo[r] = nitems ? __ldg(rp.r[r] + w) : 0u;
+#pragma unroll
+        for (int q = 0; q < kClsItems; q++) {
+            act[q] = 0; red[q] = 0;
+            if (q < nitems) {
+                const bool hi_ok = (w + 1 < g.WP);
+#pragma unroll
+                for (int r = 0; r < 4; r++) hi[r] = hi_ok ? __ldg(rp.r[r] + w + 1) : 0u;
+                uint32_t c[8];
+                corner_words(lo, hi, c);
+                const uint32_t any = c[0] | c[1] | c[2] | c[3] | c[4] | c[5] | c[6] | c[7];
+                const uint32_t all = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
+                const int ncubes = g.M - w * 32; /* cubes of this word inside the row */
+                uint32_t m = any & ~all & (ncubes >= 32 ? 0xffffffffu : ((1u << ncubes) - 1u));
+                if (V != nullptr && m) { /* constraints: all 8 corners must be valid (marching.cpp:475-477) */
+                    const RowPtrs vp = cube_row_ptrs(V, g, kz, j);
+                    uint32_t vlo[4], vhi[4], v[8];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) { vlo[r] = __ldg(vp.r[r] + w); vhi[r] = hi_ok ? __ldg(vp.r[r] + w + 1) : 0u; }
+                    corner_words(vlo, vhi, v);
+                    m &= v[0] & v[1] & v[2] & v[3] & v[4] & v[5] & v[6] & v[7];
+                }
+                act[q] = m;
+                n_act += __popc(m);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    int code = code_of(c, b);
+                    const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
+                    if (face >= 0) {
+                        n_amb++;
+                        if (ambiguity_redirects(point_prog, g, cs, face, w * 32 + b, j, kz + g.kb)) {
+                            code = 255 - code;
+                            red[q] |= 1u << b;
+                            n_red++;
+                        }
+                    }
+                    n_tri += __ldg(gtb->ntri + code);
+                }
+                /* advance to the next item in loop order */
+                if (++w == WC) {
+                    w = 0;
+                    if (++j == g.M) { j = 0; kz++; }
+                    rp = cube_row_ptrs(S, g, kz, j);
+                    if (q + 1 < nitems) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) lo[r] = __ldg(rp.r[r]);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) lo[r] = hi[r];
                 }
             }
-            n_tri += tb.ntri[code];
         }
     }
 
@@ -394,12 +424,11 @@ classify_compact_kernel(const __grid_constant__ mcb_program point_prog, const Gr
         if (lane >= d) { inc_a += ua; inc_t += ut; }
     }
     if (lane == 31) { warp_a[warp] = inc_a; warp_t[warp] = inc_t; }
-    /* statistics: one atomic per warp, only when needed */
-    {
+    if (__any_sync(0xffffffffu, n_amb != 0)) { /* statistics: one atomic per warp, only when needed */
         uint32_t sa = n_amb, sr = n_red;
 #pragma unroll
         for (int d = 16; d; d >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, d); sr += __shfl_xor_sync(0xffffffffu, sr, d); }
-        if (lane == 0 && sa) { atomicAdd(&ctr->ambiguous, (unsigned long long)sa); if (sr) atomicAdd(&ctr->redirected, (unsigned long long)sr); }
+        if (lane == 0) { atomicAdd(&ctr->ambiguous, (unsigned long long)sa); if (sr) atomicAdd(&ctr->redirected, (unsigned long long)sr); }
     }
     __syncthreads();
     uint32_t wbase_a = 0, wbase_t = 0, tot_a = 0, tot_t = 0;
@@ -453,35 +482,39 @@ classify_compact_kernel(const __grid_constant__ mcb_program point_prog, const Gr
             }
         }
     }
+    if (tot_a == 0) return; /* nothing to write in this tile (uniform per block) */
     __syncthreads();
 
     /* ---- phase 2: write the compacted records in loop order ------------------------------------------------- */
+    if (n_act == 0) return;
     unsigned long long oa = base_a_s + excl_a, ot = base_t_s + excl_t;
+    int kz = kz0, j = j0, w = w0;
 #pragma unroll
     for (int q = 0; q < kClsItems; q++) {
         uint32_t m = act[q];
-        if (!m) continue;
-        const long long item = item0 + q;
-        const int w = (int)(item % WC);
-        const long long row = item / WC;
-        const int j = (int)(row % g.M);
-        const int kz = (int)(row / g.M);
-        uint32_t c[8];
-        load_corner_words(S, g, kz, j, w, c);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int code = code_of(c, b);
-            const int tidx = (red[q] >> b) & 1u ? 255 - code : code;
-            if (oa < cap_active) {
-                rec[oa] = (unsigned long long)(w * 32 + b) | ((unsigned long long)j << 12) |
-                          ((unsigned long long)(kz + g.kb) << 24) | ((unsigned long long)code << 36) |
-                          ((unsigned long long)tidx << 44);
-                trioff[oa] = (uint32_t)ot;
+        if (m) {
+            const RowPtrs rp = cube_row_ptrs(S, g, kz, j);
+            const bool hi_ok = (w + 1 < g.WP);
+            uint32_t lo[4], hi[4], c[8];
+#pragma unroll
+            for (int r = 0; r < 4; r++) { lo[r] = __ldg(rp.r[r] + w); hi[r] = hi_ok ? __ldg(rp.r[r] + w + 1) : 0u; }
+            corner_words(lo, hi, c);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int code = code_of(c, b);
+                const int tidx = (red[q] >> b) & 1u ? 255 - code : code;
+                if (oa < cap_active) {
+                    rec[oa] = (unsigned long long)(w * 32 + b) | ((unsigned long long)j << 12) |
+                              ((unsigned long long)(kz + g.kb) << 24) | ((unsigned long long)code << 36) |
+                              ((unsigned long long)tidx << 44);
+                    trioff[oa] = (uint32_t)ot;
+                }
+                oa++;
+                ot += __ldg(gtb->ntri + tidx);
             }
-            oa++;
-            ot += tb.ntri[tidx];
         }
+        if (++w == WC) { w = 0; if (++j == g.M) { j = 0; kz++; } }
     }
 }
 
