@@ -172,14 +172,13 @@ def run_ours(args):
     k0, k1 = mcb.slab_range(M, rank, world)
     ctx.set_slab(k0, k1)
     ctx.set_normals(1)
-    counts_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
-    gathered = torch.zeros(world, dtype=torch.int64, device="cuda")
+    slabs = importlib.import_module(PKG + ".slabs")
+    placement = {}
 
     def step_fn():
         c = ctx.polygonise()
-        if world > 1:  # the path's only exchange: per-slab triangle counts -> global output offsets
-            counts_dev.fill_(int(c.triangles))
-            dist.all_gather_into_tensor(gathered, counts_dev)
+        if world > 1:  # the path's only exchange: per-slab triangle counts -> global output offsets (NCCL all-gather)
+            placement["offset"], placement["total"], _ = slabs.exchange_counts(c.triangles, device=torch.device("cuda", local))
         return c
 
     def sync_all():

@@ -1,0 +1,290 @@
+/* Drop-in for the reference's Source/marching.h (class Marching, marching.h:72-157) on top of the C ABI (mcb.h).
+ *
+ * The public surface — Step_Data, Poly_Data, xyz, Constraint's comparison names, and every public method of Marching —
+ * keeps the reference's names, signatures and bool-return conventions, so main.cpp:11-20, drawer.cpp:785-942 and
+ * normal.h compile against this header.  recalculate() (marching.cpp:308-433, full-grid branch :368-384) runs on the
+ * GPU: field + sign planes -> classify/scan/compact -> emit; the triangle soup comes back in the reference's emission
+ * order and fills Poly_Data.
+ *
+ * Poly_Data::vertex_list / tri_list: by default the soup is welded on the host exactly like add_point
+ * (marching.cpp:627-643; std::set with the tolerance comparator of marching.h:38-54, first-inserted coordinates win),
+ * because that is what the GL drawer and normal.h expect.  This weld is a host-side consumer of the GPU output, not
+ * a CPU implementation of the path; set_weld(false) skips it and hands out the soup with a trivial index list.
+ *
+ * Not carried over (GUI teaching aids): seed mode, step-by-step mode and the unused
+ * repeating-surface mode.  Their setters exist and keep their return values, but recalculate() always polygonises
+ * the full grid.  load/save of .ply use plain files ("mesh.ply" or $MCB_MESH_FILE) instead of Win32 dialogs.
+ *
+ * Extensions: set_grid_resolution(n) (step 2/n without the 0.001 floor), set_slab(k0,k1) for z-slab
+ * sharding, set_normals(bool), get_normals() (central-difference gradient normals per soup vertex), last_counts().
+ */
+#pragma once
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "evaluator.h"
+#include "mcb.h"
+
+struct Step_Data {
+    int step_i;                         /* -2 not started, -1 finished (step-by-step mode is not carried over) */
+    std::vector<float> corner_coords;   /* 24 */
+    std::vector<float> corner_values;   /* 8 */
+    std::vector<float> intersect_coord;
+    std::vector<int> tri_vlist;
+    std::vector<int> edge_list;
+    float surf_constant;
+};
+
+struct Poly_Data {
+    std::vector<float> vertex_list;       /* xyz per vertex */
+    std::vector<unsigned int> tri_list;   /* 3 indices per triangle */
+    Step_Data step_data;
+};
+
+/* point with the reference's tolerance ordering (marching.h:33-55): |d| < 1e-6 per axis counts as equal */
+struct xyz {
+    float x, y, z;
+    int idx;
+    xyz() : x(NAN), y(NAN), z(NAN), idx(-1) {}
+    xyz(float a, float b, float c, int i) : x(a), y(b), z(c), idx(i) {}
+    xyz(float a, float b, float c) : x(a), y(b), z(c), idx(-1) {}
+    bool close_enough(float a, float b) const { return std::fabs(a - b) < 0.000001; }
+    bool operator<(const xyz& r) const {
+        if (!close_enough(x, r.x)) return x < r.x;
+        if (!close_enough(y, r.y)) return y < r.y;
+        if (!close_enough(z, r.z)) return z < r.z;
+        return false;
+    }
+};
+
+enum Comp_Op { GT, LT, GE, LE, NAO };
+
+class Marching {
+public:
+    Marching()
+        : ctx_(nullptr), evaluator_(nullptr), step_(0.25f), iso_(0.f), sx_(1.f), sy_(1.f), sz_(1.f), weld_(true),
+          normals_(true), seed_mode_(false), step_mode_(false), repeat_(false), repeat_step_(0.f) {
+        seed_[0] = seed_[1] = seed_[2] = 0.f;
+        poly_data.step_data.corner_coords.resize(24);
+        poly_data.step_data.corner_values.resize(8);
+        poly_data.step_data.step_i = -2;
+        poly_data.step_data.surf_constant = 0.f;
+        for (int i = 0; i < 3; i++) { cons_valid_[i] = cons_use_[i] = false; cons_op_[i] = NAO; cons_rhs_[i] = 0.f; }
+        counts_ = mcb_counts();
+    }
+    ~Marching() { if (ctx_) mcb_destroy(ctx_); }
+    Marching(const Marching&) = delete;
+    Marching& operator=(const Marching&) = delete;
+
+    bool set_evaluator(Evaluator* e) { if (!e) return false; evaluator_ = e; return true; } /* borrowed, marching.cpp:140-147 */
+    Poly_Data const* get_poly_data() { return &poly_data; }
+    std::deque<xyz> const* get_seed_queue() { return &seed_queue_; }
+
+    bool recalculate() {
+        if (!ensure_ctx()) return false;
+        reset_all_data();
+        if (!evaluator_) return true; /* Marching::evaluate returns 0 without an evaluator: nothing is above iso */
+        if (mcb_set_equation(ctx_, 0, evaluator_->equation().c_str()) != MCB_OK) return false;
+        mcb_set_surface_constant(ctx_, iso_);
+        mcb_set_scaling(ctx_, sx_, sy_, sz_);
+        mcb_set_normals(ctx_, normals_ ? 1 : 0);
+        for (int i = 0; i < 3; i++)
+            mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
+        if (mcb_polygonise(ctx_, &counts_) != MCB_OK) return false;
+        const size_t T = (size_t)counts_.triangles;
+        soup_.resize(T * 12);
+        if (normals_) normals_soup_.resize(T * 12); else normals_soup_.clear();
+        if (T && mcb_get_mesh(ctx_, soup_.data(), normals_ ? normals_soup_.data() : nullptr, T) != MCB_OK) return false;
+        fill_poly_data();
+        poly_data.step_data.step_i = -1;
+        return true;
+    }
+
+    void reset_all_data() {
+        poly_data.tri_list.clear(); poly_data.vertex_list.clear();
+        poly_data.step_data.intersect_coord.clear(); poly_data.step_data.tri_vlist.clear(); poly_data.step_data.edge_list.clear();
+        seed_queue_.clear();
+        reset_step();
+    }
+
+    bool set_grid_step_size(float v) { /* [0.001, 0.5], marching.cpp:226-238 */
+        if (v >= 0.001 && v <= .5) {
+            if (v != step_) { step_ = v; reset_step(); }
+            return true;
+        }
+        return false;
+    }
+    bool set_grid_resolution(int n) { if (n < 2 || n > 4094) return false; step_ = 2.0f / (float)n; reset_step(); return true; }
+    float get_grid_size() { return step_; }
+
+    void step_by_step_mode(bool b) { step_mode_ = b; reset_step(); }
+    void reset_step() { poly_data.step_data.step_i = -2; }
+    void set_surface_constant(float c) { if (iso_ != c) { iso_ = c; reset_step(); } }
+
+    void seed_mode(bool b) { seed_mode_ = b; reset_step(); }
+    bool set_seed(float x, float y, float z) {
+        if (x <= 1 && x >= -1 && y >= -1 && y <= 1 && z >= -1 && z <= 1) { seed_[0] = x; seed_[1] = y; seed_[2] = z; reset_step(); return true; }
+        return false;
+    }
+    void get_seed(float* x, float* y, float* z) { *x = seed_[0]; *y = seed_[1]; *z = seed_[2]; }
+
+    bool set_surface_repeat_step_distance(float l) { if (l <= 0) return false; repeat_step_ = l; reset_step(); return true; }
+    bool repeating_surface_mode(bool b) { repeat_ = b; reset_step(); return true; }
+
+    bool set_constraint0(std::string lhs, std::string op, float rhs) { return set_constraint(0, lhs, op, rhs); }
+    bool set_constraint1(std::string lhs, std::string op, float rhs) { return set_constraint(1, lhs, op, rhs); }
+    bool set_constraint2(std::string lhs, std::string op, float rhs) { return set_constraint(2, lhs, op, rhs); }
+    bool set_constraint(int i, std::string lhs, std::string op, float rhs) { /* marching.cpp:173-200 (with the missing `return true`) */
+        if (i < 0 || i > 2) return false;
+        Comp_Op o;
+        if (op == "<=") o = LE; else if (op == ">=") o = GE; else if (op == "<") o = LT; else if (op == ">") o = GT; else return false;
+        if (!ensure_ctx()) return false;
+        if (mcb_set_equation(ctx_, i + 1, lhs.c_str()) != MCB_OK) return false;
+        cons_valid_[i] = true; cons_op_[i] = o; cons_rhs_[i] = rhs;
+        reset_step();
+        return true;
+    }
+    bool use_constraint0(bool b) { return use_constraint(0, b); }
+    bool use_constraint1(bool b) { return use_constraint(1, b); }
+    bool use_constraint2(bool b) { return use_constraint(2, b); }
+    bool use_constraint(int i, bool use) { if (i < 0 || i > 2) return false; reset_step(); return cons_use_[i] = use; } /* marching.cpp:202-207 */
+
+    void set_scaling_x(float s) { sx_ = s; reset_step(); }
+    void set_scaling_y(float s) { sy_ = s; reset_step(); }
+    void set_scaling_z(float s) { sz_ = s; reset_step(); }
+
+    /* ASCII PLY in the reference's format (marching.cpp:821-850: "element face %d " keeps its trailing blank, %f coordinates) */
+    bool save_poly_to_file() {
+        if (poly_data.vertex_list.empty()) return false;
+        FILE* fp = std::fopen(mesh_file(), "w");
+        if (!fp) return false;
+        const int nv = (int)(poly_data.vertex_list.size() / 3), nt = (int)(poly_data.tri_list.size() / 3);
+        std::fprintf(fp, "ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n", nv);
+        std::fprintf(fp, "element face %d \nproperty list uchar int vertex_indices\nend_header\n", nt);
+        for (int i = 0; i < nv; i++)
+            std::fprintf(fp, "%f %f %f\n", poly_data.vertex_list[3 * i], poly_data.vertex_list[3 * i + 1], poly_data.vertex_list[3 * i + 2]);
+        for (int i = 0; i < nt; i++)
+            std::fprintf(fp, "%u %u %u %u\n", 3u, poly_data.tri_list[3 * i], poly_data.tri_list[3 * i + 1], poly_data.tri_list[3 * i + 2]);
+        std::fclose(fp);
+        return true;
+    }
+    bool load_poly_from_file() {
+        reset_all_data();
+        FILE* fp = std::fopen(mesh_file(), "r");
+        if (!fp) return false;
+        int nv = 0, nt = 0;
+        char line[256];
+        bool header_done = false;
+        while (!header_done && std::fgets(line, sizeof line, fp)) {
+            std::sscanf(line, "element vertex %d", &nv);
+            std::sscanf(line, "element face %d", &nt);
+            if (std::string(line).rfind("end_header", 0) == 0) header_done = true;
+        }
+        bool ok = header_done;
+        for (int i = 0; ok && i < nv; i++) {
+            float x, y, z;
+            ok = std::fscanf(fp, "%f %f %f", &x, &y, &z) == 3;
+            if (ok) { poly_data.vertex_list.push_back(x); poly_data.vertex_list.push_back(y); poly_data.vertex_list.push_back(z); }
+        }
+        for (int i = 0; ok && i < nt; i++) {
+            unsigned n, a, b, c;
+            ok = std::fscanf(fp, "%u %u %u %u", &n, &a, &b, &c) == 4 && n == 3;
+            if (ok) { poly_data.tri_list.push_back(a); poly_data.tri_list.push_back(b); poly_data.tri_list.push_back(c); }
+        }
+        std::fclose(fp);
+        return ok;
+    }
+
+    /* ---- extensions ---- */
+    void set_weld(bool b) { weld_ = b; }
+    void set_normals(bool b) { normals_ = b; }
+    bool set_slab(int k_begin, int k_end) { slab_[0] = k_begin; slab_[1] = k_end; have_slab_ = true; return true; }
+    const mcb_counts& last_counts() const { return counts_; }
+    /* triangle soup of the last recalculate(): 3 float4 per triangle, (x,y,z,1) and (nx,ny,nz,0) */
+    const std::vector<float>& get_soup() const { return soup_; }
+    const std::vector<float>& get_normals() const { return normals_soup_; }
+
+private:
+    bool ensure_ctx() {
+        if (!ctx_) {
+            const char* d = std::getenv("MCB_DEVICE");
+            if (mcb_create(d ? std::atoi(d) : 0, &ctx_) != MCB_OK) { ctx_ = nullptr; return false; }
+        }
+        if (mcb_set_grid_step(ctx_, step_) < 0) return false;
+        if (have_slab_ && mcb_set_slab(ctx_, slab_[0], slab_[1]) != MCB_OK) return false;
+        return true;
+    }
+    void fill_poly_data() {
+        const size_t nv = soup_.size() / 4;
+        if (!weld_) {
+            poly_data.vertex_list.resize(nv * 3);
+            poly_data.tri_list.resize(nv);
+            for (size_t v = 0; v < nv; v++) {
+                for (int a = 0; a < 3; a++) poly_data.vertex_list[3 * v + a] = soup_[4 * v + a];
+                poly_data.tri_list[v] = (unsigned)v;
+            }
+            return;
+        }
+        /* add_step_to_poly_data / add_point (marching.cpp:599-643).  The reference adds a cube's vertices in
+         * ascending-edge order before its triangles; a vertex that first appears later in the triangle list would
+         * get a different index, so the per-cube edge order is recovered from the soup: the triangles of one cube
+         * are consecutive and its distinct corners are inserted in edge order via the records' triangle rows. */
+        std::set<xyz> vertex_set;
+        std::vector<uint64_t> rec((size_t)counts_.active);
+        std::vector<uint32_t> off((size_t)counts_.active);
+        if (!rec.empty() && mcb_get_active(ctx_, rec.data(), off.data(), rec.size()) != MCB_OK) return;
+        for (size_t c = 0; c < rec.size(); c++) {
+            const uint32_t t0 = off[c], t1 = (c + 1 < rec.size()) ? off[c + 1] : (uint32_t)counts_.triangles;
+            /* distinct edge -> first soup slot holding it, visited in ascending edge order */
+            int slot_of_edge[12];
+            for (int e = 0; e < 12; e++) slot_of_edge[e] = -1;
+            const uint64_t row = tri_row((int)((rec[c] >> 44) & 0xFF));
+            for (uint32_t t = t0; t < t1; t++)
+                for (int v = 0; v < 3; v++) {
+                    const int e = (int)((row >> (4 * (3 * (t - t0) + v))) & 0xF);
+                    if (slot_of_edge[e] < 0) slot_of_edge[e] = (int)(3 * t + v);
+                }
+            int vid[12];
+            for (int e = 0; e < 12; e++) {
+                vid[e] = -1;
+                if (slot_of_edge[e] < 0) continue;
+                const float* p = &soup_[4 * (size_t)slot_of_edge[e]];
+                if (std::isnan(p[0])) continue;
+                const int new_i = (int)(poly_data.vertex_list.size() / 3);
+                const int found = vertex_set.insert(xyz(p[0], p[1], p[2], new_i)).first->idx;
+                if (found == new_i) { poly_data.vertex_list.push_back(p[0]); poly_data.vertex_list.push_back(p[1]); poly_data.vertex_list.push_back(p[2]); }
+                vid[e] = found;
+            }
+            for (uint32_t t = t0; t < t1; t++)
+                for (int v = 0; v < 3; v++)
+                    poly_data.tri_list.push_back((unsigned)vid[(row >> (4 * (3 * (t - t0) + v))) & 0xF]);
+        }
+    }
+    static uint64_t tri_row(int idx); /* packed triangle table row (defined in libmcb200.so: mcb_tri_row) */
+    static const char* mesh_file() { const char* f = std::getenv("MCB_MESH_FILE"); return f ? f : "mesh.ply"; }
+
+    mcb_ctx* ctx_;
+    Evaluator* evaluator_;
+    float step_, iso_, sx_, sy_, sz_;
+    bool weld_, normals_, seed_mode_, step_mode_, repeat_;
+    float repeat_step_;
+    float seed_[3];
+    bool cons_valid_[3], cons_use_[3];
+    Comp_Op cons_op_[3];
+    float cons_rhs_[3];
+    int slab_[2] = {0, 0};
+    bool have_slab_ = false;
+    Poly_Data poly_data;
+    std::deque<xyz> seed_queue_;
+    std::vector<float> soup_, normals_soup_;
+    mcb_counts counts_;
+};
+
+extern "C" uint64_t mcb_tri_row(int table_idx);
+inline uint64_t Marching::tri_row(int idx) { return mcb_tri_row(idx); }

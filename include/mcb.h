@@ -77,6 +77,8 @@ int mcb_disassemble(const char* equation, int which, char* out, size_t cap);
 /* The reference's grid loop on one axis (marching.cpp:372-377): returns M = number of cubes per axis for `step`
  * and, when coords != NULL and cap >= M+1, the cube origins c[0..M-1] and the far corner c[M] = c[M-1]+step. */
 int mcb_grid_axis(float step, float* coords, int cap);
+/* Row `table_idx` of the packed triangle table: sixteen 4-bit edge indices, 0xF terminated (marching_lookup.h:64-320). */
+uint64_t mcb_tri_row(int table_idx);
 /* Balanced split of M cube layers into nranks contiguous z-slabs: layers [*k_begin,*k_end). */
 int mcb_slab_range(int M, int rank, int nranks, int* k_begin, int* k_end);
 

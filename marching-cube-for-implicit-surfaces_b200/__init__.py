@@ -55,6 +55,7 @@ def _load():
         "mcb_postfix": ([cp, cp, sz], i),
         "mcb_disassemble": ([cp, i, cp, sz], i),
         "mcb_grid_axis": ([f, vp, i], i),
+        "mcb_tri_row": ([i], u64),
         "mcb_slab_range": ([i, i, i, C.POINTER(i), C.POINTER(i)], i),
         "mcb_create": ([i, C.POINTER(vp)], i),
         "mcb_destroy": ([vp], None),

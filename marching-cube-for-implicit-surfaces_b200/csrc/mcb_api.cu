@@ -322,6 +322,8 @@ int mcb_grid_axis(float step, float* coords, int cap) {
     return M;
 }
 
+uint64_t mcb_tri_row(int table_idx) { return (table_idx >= 0 && table_idx < 256) ? MCB_TRI_WORDS[table_idx] : ~0ull; }
+
 int mcb_slab_range(int M, int rank, int nranks, int* k_begin, int* k_end) {
     if (M <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || !k_begin || !k_end) return MCB_E_ARG;
     *k_begin = (int)((long long)M * rank / nranks);

@@ -1,0 +1,60 @@
+"""z-slab sharding of the grid over ranks (BASELINE.json configs[4]).
+
+The reference emits triangles in cube-loop order with z slowest (marching.cpp:375-383), so cutting the M cube layers
+into contiguous z-slabs and concatenating the slabs' outputs in rank order reproduces the single-device output
+exactly.  Each rank recomputes its one-vertex halo plane (the field is analytic), so the ONLY exchange on the path is
+the all-gather of one integer per rank — the slab's triangle count — whose exclusive prefix is the slab's offset in the
+global triangle list.  One process per GPU; the collective goes through torch.distributed (NCCL over NVLink on the
+GPU box, gloo in the CPU test tier).
+"""
+import torch
+import torch.distributed as dist
+
+
+def slab_of(M, rank, world):
+    """Cube layers [k0,k1) of rank `rank` — same arithmetic as mcb_slab_range in the C ABI."""
+    return (M * rank) // world, (M * (rank + 1)) // world
+
+
+def exchange_counts(local_triangles, device=None, group=None):
+    """All-gather of the per-slab triangle counts.  Returns (offset_of_this_rank, total, counts_per_rank)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, int(local_triangles), [int(local_triangles)]
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor([int(local_triangles)], dtype=torch.int64, device=device)
+    allc = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    counts = [int(x) for x in allc.tolist()]
+    return sum(counts[:rank]), sum(counts), counts
+
+
+def gather_soup_to_rank0(local_soup, offset, total, group=None):
+    """Optional (NOT part of the timed path): place every slab's soup at its global offset on rank 0.
+    local_soup: [T_r, 3, C] tensor.  Returns the [total, 3, C] tensor on rank 0, None elsewhere."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_soup
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    shape_tail = tuple(local_soup.shape[1:])
+    if rank == 0:
+        out = torch.empty((total,) + shape_tail, dtype=local_soup.dtype, device=local_soup.device)
+        out[offset:offset + local_soup.shape[0]] = local_soup
+        counts = torch.empty(world, dtype=torch.int64, device=local_soup.device)
+    else:
+        out, counts = None, None
+    sizes = torch.tensor([local_soup.shape[0]], dtype=torch.int64, device=local_soup.device)
+    gathered = [torch.empty_like(sizes) for _ in range(world)] if rank == 0 else None
+    dist.gather(sizes, gathered, dst=0, group=group)
+    if rank == 0:
+        pos = int(local_soup.shape[0]) + offset
+        for r in range(1, world):
+            n = int(gathered[r].item())
+            if n:
+                dist.recv(out[pos:pos + n], src=r, group=group)
+            pos += n
+        return out
+    if local_soup.shape[0]:
+        dist.send(local_soup.contiguous(), dst=0, group=group)
+    return None
