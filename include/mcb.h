@@ -72,7 +72,8 @@ int mcb_tokens(const char* equation, char* out, size_t cap);
 /* The operation order the reference's two-stack evaluator (evaluator.cpp:22-107) executes, as postfix text:
  * "x-y+z" -> "x y z + -". */
 int mcb_postfix(const char* equation, char* out, size_t cap);
-/* Bytecode listing; which: 0 = point program, 1 = grid program, 2 = hoisted slot programs. */
+/* Bytecode listing; which: 0 = point program, 1 = grid program (postfix), 2 = hoisted slot programs,
+ * 3 = grid program in the fused accumulator form the grid kernel executes. */
 int mcb_disassemble(const char* equation, int which, char* out, size_t cap);
 /* The reference's grid loop on one axis (marching.cpp:372-377): returns M = number of cubes per axis for `step`
  * and, when coords != NULL and cap >= M+1, the cube origins c[0..M-1] and the far corner c[M] = c[M-1]+step. */

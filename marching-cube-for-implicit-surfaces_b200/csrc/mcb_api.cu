@@ -26,7 +26,7 @@ struct EqSlot {
     bool valid = false;
     mcb::Compiled c;
     mcb_program point; /* full expression at an arbitrary point */
-    mcb_program grid;  /* full expression on the grid, with hoisted subtrees as table loads */
+    mcb_program grid;  /* full expression on the grid, hoisted subtrees as table operands, fused accumulator form */
     uint32_t* d_slot_code = nullptr;
     SlotDesc* d_slots = nullptr;
     float* d_kpool = nullptr;
@@ -68,7 +68,11 @@ struct mcb_ctx {
     ClsTables* d_cls = nullptr;
     Counters* d_ctr = nullptr;
     Counters* h_ctr = nullptr; /* pinned */
-    ScanState st{};
+    unsigned long long* d_status = nullptr; /* one look-back status word per classify tile */
+    uint16_t* d_tile_list = nullptr;        /* classify -> compact scratch: active items per tile, their counts */
+    uint16_t* d_tile_cnt = nullptr;
+    uint32_t* d_tile_nz = nullptr;
+    size_t cap_tile_entries = 0;
     size_t cap_tiles = 0;
     unsigned long long* d_rec = nullptr;
     uint32_t* d_trioff = nullptr;
@@ -166,11 +170,28 @@ int install_equation(mcb_ctx* ctx, int slot, const char* equation) {
     }
     MCB_CK(cudaStreamSynchronize(ctx->stream));
     fill_program(ns.point, ns.c.point_code, ns.c.kpool);
-    fill_program(ns.grid, ns.c.grid_code, ns.c.kpool);
+    fill_program(ns.grid, ns.c.grid_fused, ns.c.kpool);
     free_slot(ctx->eq[slot]);
     ctx->eq[slot] = ns;
     ctx->have_result = false;
     return MCB_OK;
+}
+
+/* Tiling of the classify pass: runs of whole cube rows, at most kClsItemCap items, at least ~4 tiles per SM
+ * (classify). */
+ClsGeom classify_geometry(const mcb_ctx* ctx, const Grid& g, unsigned* tiles) {
+    ClsGeom cg;
+    cg.WC = (uint32_t)((g.M + 31) / 32);
+    cg.total_rows = (uint32_t)(g.ke - g.kb) * (uint32_t)g.M;
+    const uint32_t cap_rows = (uint32_t)kClsItemCap / cg.WC;
+    const uint32_t target = (uint32_t)ctx->sm_count * 4u;
+    cg.tile_rows = std::min(cap_rows, std::max(1u, (cg.total_rows + target - 1) / target));
+    cg.nstrips = std::max(1u, (uint32_t)kClsThreads / cg.WC);
+    cg.strip_rows = (cg.tile_rows + cg.nstrips - 1) / cg.nstrips;
+    cg.inv_wc = cg.WC == 1 ? 0u : (uint32_t)((1ull << 32) / cg.WC + ((1ull << 32) % cg.WC ? 1 : 0));
+    cg.inv_m = g.M == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned)g.M + ((1ull << 32) % (unsigned)g.M ? 1 : 0));
+    *tiles = (cg.total_rows + cg.tile_rows - 1) / cg.tile_rows;
+    return cg;
 }
 
 int setup_grid(mcb_ctx* ctx) {
@@ -197,19 +218,27 @@ int setup_grid(mcb_ctx* ctx) {
     const size_t nS = (size_t)g.NZ * g.NV * g.WP + 64;
     if ((rc = ensure(ctx, &ctx->d_F, &ctx->cap_F, nF)) != MCB_OK) return rc;
     if ((rc = ensure(ctx, &ctx->d_S, &ctx->cap_S, nS)) != MCB_OK) return rc;
-    const int WC = (g.M + 31) / 32;
-    const size_t items = (size_t)(g.ke - g.kb) * g.M * WC;
-    const size_t tiles = (items + kClsThreads * kClsItems - 1) / (kClsThreads * kClsItems) + 1;
+    unsigned tiles_now = 0;
+    const ClsGeom cg0 = classify_geometry(ctx, g, &tiles_now);
+    const size_t tiles = (size_t)tiles_now + 1;
     if (tiles > ctx->cap_tiles) {
-        if (ctx->st.flag) { cudaFree(ctx->st.flag); cudaFree(ctx->st.agg_active); cudaFree(ctx->st.agg_tris); cudaFree(ctx->st.inc_active); cudaFree(ctx->st.inc_tris); }
-        ctx->st = ScanState{};
+        if (ctx->d_status) cudaFree(ctx->d_status);
+        if (ctx->d_tile_nz) cudaFree(ctx->d_tile_nz);
+        ctx->d_status = nullptr; ctx->d_tile_nz = nullptr;
         ctx->cap_tiles = 0;
-        MCB_CK(cudaMalloc((void**)&ctx->st.flag, tiles * 4));
-        MCB_CK(cudaMalloc((void**)&ctx->st.agg_active, tiles * 4));
-        MCB_CK(cudaMalloc((void**)&ctx->st.agg_tris, tiles * 4));
-        MCB_CK(cudaMalloc((void**)&ctx->st.inc_active, tiles * 8));
-        MCB_CK(cudaMalloc((void**)&ctx->st.inc_tris, tiles * 8));
+        MCB_CK(cudaMalloc((void**)&ctx->d_status, tiles * 8));
+        MCB_CK(cudaMalloc((void**)&ctx->d_tile_nz, tiles * 4));
         ctx->cap_tiles = tiles;
+    }
+    const size_t entries = tiles * (size_t)cg0.tile_rows * cg0.WC; /* worst case: every item active */
+    if (entries > ctx->cap_tile_entries) {
+        if (ctx->d_tile_list) cudaFree(ctx->d_tile_list);
+        if (ctx->d_tile_cnt) cudaFree(ctx->d_tile_cnt);
+        ctx->d_tile_list = nullptr; ctx->d_tile_cnt = nullptr;
+        ctx->cap_tile_entries = 0;
+        MCB_CK(cudaMalloc((void**)&ctx->d_tile_list, entries * 2));
+        MCB_CK(cudaMalloc((void**)&ctx->d_tile_cnt, entries * 2));
+        ctx->cap_tile_entries = entries;
     }
     ctx->grid_dirty = false;
     return MCB_OK;
@@ -301,6 +330,7 @@ int mcb_disassemble(const char* equation, int which, char* out, size_t cap) {
     std::string s;
     if (which == 0) s = mcb::disassemble(c.point_code);
     else if (which == 1) s = mcb::disassemble(c.grid_code);
+    else if (which == 3) s = mcb::disassemble_fused(c.grid_fused);
     else {
         for (const mcb::Slot& sl : c.slots) {
             std::vector<uint32_t> code(c.slot_code.begin() + sl.code_begin, c.slot_code.begin() + sl.code_begin + sl.code_len);
@@ -363,6 +393,8 @@ int mcb_create(int device, mcb_ctx** out) {
     if (cudaFuncSetAttribute(eval_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float)) != cudaSuccess)
         return bail(MCB_E_CUDA);
+    if (cudaFuncSetAttribute(classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClsSmemBytes) != cudaSuccess)
+        return bail(MCB_E_CUDA);
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
     rc = mcb_set_grid_step(ctx, 0.25f); /* Marching::Marching(), marching.cpp:24 */
@@ -379,7 +411,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    cudaFree(ctx->st.flag); cudaFree(ctx->st.agg_active); cudaFree(ctx->st.agg_tris); cudaFree(ctx->st.inc_active); cudaFree(ctx->st.inc_tris);
+    cudaFree(ctx->d_status); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_tile_nz);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_trioff); cudaFree(ctx->d_pos); cudaFree(ctx->d_nrm);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -520,11 +552,20 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     MCB_CK(cudaEventRecord(ctx->ev[1], s));
     /* K1: field + sign bit-plane */
     {
-        const int rgpp = (g.NV + kEvalRows - 1) / kEvalRows;
-        const unsigned items = (unsigned)rgpp * (unsigned)g.WP; /* (row group, word) pairs per z-plane */
-        const dim3 blocks((items + kEvalThreads / 32 - 1) / (kEvalThreads / 32), (unsigned)g.NZ);
-        const size_t smem = (size_t)std::max(1, eq.c.grid_depth) * kEvalRows * kEvalThreads * sizeof(float);
-        eval_field_kernel<<<blocks, kEvalThreads, smem, s>>>(eq.grid, g, ctx->d_cs, ctx->d_tables, eq.max_per_axis, ctx->d_F, ctx->d_S, items);
+        const int rgpp = (g.NV + kEvalRows - 1) / kEvalRows; /* row groups per plane */
+        const dim3 blocks((unsigned)g.WP, (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)), (unsigned)g.NZ);
+        const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
+        /* resolve the table operands for this grid: argument = float offset of the table row inside d_tables */
+        mcb_program launch = eq.grid;
+        for (int pc = 0; pc < launch.n; pc++) {
+            const uint32_t wd = launch.code[pc], src = MCB_FINSN_SRC(wd);
+            if (MCB_FINSN_OP(wd) == MCB_F_NEG || src == MCB_SRC_K || src == MCB_SRC_POP) continue;
+            if (src < MCB_SRC_TX) return fail(ctx, MCB_E_STATE, "internal: raw coordinate operand in a grid program");
+            const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + MCB_FINSN_ARG(wd)) * g.P;
+            if (off >= (1u << 24)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
+            launch.code[pc] = MCB_FINSN(MCB_FINSN_OP(wd), src, (uint32_t)off);
+        }
+        eval_field_kernel<<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
         launches++;
         if (any_constraint) {
             const long long words = (long long)g.NZ * g.NV * g.WP;
@@ -541,19 +582,20 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     MCB_CK(cudaEventRecord(ctx->ev[2], s));
     MCB_CK(cudaGetLastError());
 
-    const int WC = (g.M + 31) / 32;
-    const long long items = (long long)(g.ke - g.kb) * g.M * WC;
-    const unsigned tiles = (unsigned)((items + kClsThreads * kClsItems - 1) / (kClsThreads * kClsItems));
+    unsigned tiles = 0;
+    const ClsGeom cg = classify_geometry(ctx, g, &tiles);
     bool need_classify = true;
     for (;;) {
         if (need_classify) {
-            /* K2: classification + ambiguity + single-pass scan + compaction */
-            MCB_CK(cudaMemsetAsync(ctx->st.flag, 0, (size_t)tiles * 4, s));
+            /* K2: classification + ambiguity (per tile, independent) -> look-back scan + compaction */
             MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
-            classify_compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S,
-                                                                  any_constraint ? ctx->d_V : nullptr, WC, items, ctx->st, ctx->d_ctr,
-                                                                  ctx->d_rec, ctx->d_trioff, ctx->cap_active);
-            launches++;
+            const ClsScratch sc{ctx->d_tile_list, ctx->d_tile_cnt, ctx->d_tile_nz, cg.tile_rows * cg.WC};
+            const uint32_t* dV = any_constraint ? ctx->d_V : nullptr;
+            classify_kernel<<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
+                                                                      ctx->d_status, ctx->d_ctr);
+            compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,
+                                                         ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active);
+            launches += 2;
             MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
         /* K3: interpolation + coalesced float4 emission */
@@ -567,8 +609,8 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
         MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         MCB_CK(cudaStreamSynchronize(s));
         MCB_CK(cudaGetLastError());
-        if (ctx->h_ctr->error) return fail(ctx, MCB_E_CUDA, "decoupled look-back exceeded its spin limit");
-        if (ctx->h_ctr->triangles >= (1ull << 32)) return fail(ctx, MCB_E_CAPACITY, "more than 2^32 triangles in one slab");
+        if (ctx->h_ctr->error == 2 || ctx->h_ctr->triangles >= (1ull << 31))
+            return fail(ctx, MCB_E_CAPACITY, "2^31 or more triangles in one slab: split the grid into more z-slabs");
         if (ctx->h_ctr->active > ctx->cap_active) {
             if ((rc = ensure_records(ctx, ctx->h_ctr->active + ctx->h_ctr->active / 8 + 1024)) != MCB_OK) return rc;
             need_classify = true;

@@ -101,4 +101,69 @@ MCB_BC_FN float mcb_interp_scalar(const uint32_t* code, int n, const float* k, f
     return st[0];
 }
 
+/* ---- fused ("accumulator") form of a grid program -----------------------------------------------------------
+ * The grid kernel does not run the postfix words above directly.  mcb::fuse() (mcb_lower.cpp) rewrites them so
+ * that a push which is immediately consumed by a binary operator becomes that operator's second operand:
+ *      word = fop | src << 4 | arg << 8
+ * The machine state is an accumulator `acc` (= the top of the operand stack, in registers) and a memory stack
+ * holding the deeper levels.  `v` is the operand named by src:
+ *      src X,Y,Z     scaled coordinate of the vertex            src K       constant pool entry arg
+ *      src TX,TY,TZ  axis table arg at the vertex's index       src POP     pop the memory stack
+ *      fop LOAD      acc = v                                    fop PUSH    spill acc to the memory stack; acc = v
+ *      fop ADD, MUL  acc = acc (op) v                           fop NEG     acc = -acc  (src unused)
+ *      fop SUB/DIV/POW  acc = acc (op) v                        fop RSUB/RDIV/RPOW  acc = v (op) acc
+ * Every fp32 operation and the role of each operand are those of the postfix program; only pushes and pops of
+ * the operand stack disappear.  `x^2+y^2+z^2-0.49` (grid form TX0 TY0 TZ0 K0 - + +) becomes
+ *      LOAD TZ0; SUB K0; ADD TY0; ADD TX0 — 4 words and no memory-stack traffic at all.
+ */
+enum { MCB_SRC_X = 0, MCB_SRC_Y, MCB_SRC_Z, MCB_SRC_K, MCB_SRC_TX, MCB_SRC_TY, MCB_SRC_TZ, MCB_SRC_POP };
+enum {
+    MCB_F_LOAD = 0, MCB_F_PUSH, MCB_F_ADD, MCB_F_SUB, MCB_F_RSUB, MCB_F_MUL, MCB_F_DIV, MCB_F_RDIV, MCB_F_POW,
+    MCB_F_RPOW, MCB_F_NEG, MCB_F_COUNT
+};
+#define MCB_FINSN(fop, src, arg) ((uint32_t)(fop) | ((uint32_t)(src) << 4) | ((uint32_t)(arg) << 8))
+#define MCB_FINSN_OP(w) ((w) & 0xFu)
+#define MCB_FINSN_SRC(w) (((w) >> 4) & 0xFu)
+#define MCB_FINSN_ARG(w) ((w) >> 8)
+
+MCB_BC_FN float mcb_fop(uint32_t fop, float acc, float v) {
+    switch (fop) {
+        case MCB_F_ADD: return acc + v;
+        case MCB_F_SUB: return acc - v;
+        case MCB_F_RSUB: return v - acc;
+        case MCB_F_MUL: return acc * v;
+        case MCB_F_DIV: return acc / v;
+        case MCB_F_RDIV: return v / acc;
+        case MCB_F_POW: return mcb_powf(acc, v);
+        case MCB_F_RPOW: return mcb_powf(v, acc);
+        default: return v; /* LOAD, PUSH */
+    }
+}
+
+/* Scalar interpreter of the fused form (host-side checks of mcb::fuse(); the grid kernel has its own). */
+MCB_BC_FN float mcb_interp_fused_scalar(const uint32_t* code, int n, const float* k, float x, float y, float z,
+                                        const float* tx, const float* ty, const float* tz) {
+    float st[MCB_MAX_STACK];
+    int sp = 0;
+    float acc = 0.f;
+    for (int pc = 0; pc < n; pc++) {
+        uint32_t w = code[pc], fop = MCB_FINSN_OP(w), src = MCB_FINSN_SRC(w), arg = MCB_FINSN_ARG(w);
+        if (fop == MCB_F_NEG) { acc = -acc; continue; }
+        if (fop == MCB_F_PUSH) st[sp++] = acc;
+        float v;
+        switch (src) {
+            case MCB_SRC_X: v = x; break;
+            case MCB_SRC_Y: v = y; break;
+            case MCB_SRC_Z: v = z; break;
+            case MCB_SRC_K: v = k[arg]; break;
+            case MCB_SRC_TX: v = tx[arg]; break;
+            case MCB_SRC_TY: v = ty[arg]; break;
+            case MCB_SRC_TZ: v = tz[arg]; break;
+            default: v = st[--sp]; break;
+        }
+        acc = mcb_fop(fop, acc, v);
+    }
+    return acc;
+}
+
 #endif /* MCB_BYTECODE_H */

@@ -23,11 +23,9 @@
 namespace mcbk {
 
 constexpr int kEvalThreads = 128;   /* 4 warps; each warp: 32 x-columns x kEvalRows y-rows of one z-plane */
-constexpr int kEvalRows = 8;
+constexpr int kEvalRows = 16;
 constexpr int kClsThreads = 256;
-constexpr int kClsItems = 8;        /* consecutive 32-cube words per thread in classify */
 constexpr int kEmitThreads = 128;   /* = active cubes per emit chunk */
-constexpr uint32_t kSpinLimit = 1u << 26;
 
 struct Grid {
     int M;        /* cubes per axis */
@@ -46,7 +44,7 @@ struct Counters {
     unsigned long long ambiguous;
     unsigned long long redirected;
     unsigned int tile_ticket;
-    unsigned int error; /* 1 = look-back spin limit hit */
+    unsigned int error; /* 2 = 2^31 or more triangles in the slab */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -84,150 +82,152 @@ __global__ void axis_tables_kernel(const uint32_t* __restrict__ slot_code, const
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K1  eval_field: the bytecode interpreter over the grid.
- *     A warp owns 32 consecutive x-columns x kEvalRows consecutive y-rows of one z-plane; a lane keeps the 4 row
- *     values of the top of the operand stack in registers and the deeper levels in shared memory
- *     ([level][row][thread], conflict-free).  Every lane executes the same instruction word, fetched from the
- *     kernel-parameter block (constant bank).  Outputs: F (coalesced 128 B per warp store) and the sign bit-plane
- *     S (one ballot per row) — the comparison against iso is fused here so that classification never has to read
- *     the 4 B/vertex field again.
+ *     A warp owns 32 consecutive x-columns x kEvalRows consecutive y-rows of one z-plane.  Every lane executes the
+ *     same fused instruction word (mcb_bytecode.h), fetched from the kernel-parameter block (constant bank), so
+ *     there is no divergence; the cost of fetching/decoding a word is shared by the kEvalRows vertices a lane
+ *     carries.  The accumulator (top of the operand stack) lives in kEvalRows registers; an operator's other
+ *     operand comes straight from its source — a coordinate, a constant-bank constant, an axis table (L1-resident)
+ *     or, only for products of two compound subtrees, the shared-memory stack ([level][row][thread], conflict
+ *     free).  Operands that are the same for all rows of a lane (x, z, constants, x/z tables) are applied from one
+ *     register.  Outputs: F (evict-first 128 B per warp row store: the field is far larger than L2 and is only
+ *     revisited around the surface) and the sign bit-plane S (one ballot per row) — the comparison against iso is
+ *     fused here so that classification never reads the 4 B/vertex field.
  * ------------------------------------------------------------------------------------------------------------- */
 __device__ __noinline__ float powf_call(float a, float b) { return mcb_powf(a, b); } /* one copy, register args */
 
-__global__ void __launch_bounds__(kEvalThreads)
-eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ cs,
-                  const float* __restrict__ tables, int max_slots_per_axis, float* __restrict__ F,
-                  uint32_t* __restrict__ S, unsigned items_per_plane) {
-    extern __shared__ float stack_smem[]; /* [depth][kEvalRows][kEvalThreads] */
-    const int lane = threadIdx.x & 31;
-    const unsigned item = blockIdx.x * (kEvalThreads / 32) + (threadIdx.x >> 5); /* (row group, word) of plane blockIdx.y */
-    if (item >= items_per_plane) return; /* whole warp exits together */
-    const int w = (int)(item % (unsigned)g.WP);
-    const int yq = (int)(item / (unsigned)g.WP);
-    const int pz = (int)blockIdx.y;
-    const int x = w * 32 + lane;
-    const int y0 = yq * kEvalRows;
-
-    const float X = g.sx * cs[x < g.NV ? x : g.NV - 1];
-    float Y[kEvalRows];
-#pragma unroll
-    for (int e = 0; e < kEvalRows; e++) {
-        int y = y0 + e < g.NV ? y0 + e : g.NV - 1;
-        Y[e] = g.sy * cs[y];
+template <int FOP>
+__device__ __forceinline__ float fused_op(float acc, float v) {
+    switch (FOP) {
+        case MCB_F_ADD: return acc + v;
+        case MCB_F_SUB: return acc - v;
+        case MCB_F_RSUB: return v - acc;
+        case MCB_F_MUL: return acc * v;
+        case MCB_F_DIV: return acc / v;
+        case MCB_F_RDIV: return v / acc;
+        case MCB_F_POW: return powf_call(acc, v);
+        case MCB_F_RPOW: return powf_call(v, acc);
+        default: return v; /* MCB_F_LOAD, MCB_F_PUSH */
     }
-    const float Z = g.sz * cs[pz + (g.kb)]; /* plane pz holds vertex kb-1+pz -> cs index kb+pz */
-    const float* tabx = tables + (size_t)0 * max_slots_per_axis * g.P;
-    const float* taby = tables + (size_t)1 * max_slots_per_axis * g.P;
-    const float* tabz = tables + (size_t)2 * max_slots_per_axis * g.P;
-    const int zi = pz + g.kb;
+}
 
-    float t0[kEvalRows];
+struct EvalLane { /* what an operand fetch needs besides the instruction argument */
+    const float* __restrict__ tables;
+    int x, y0, zi;
+};
+constexpr int kEvalLevel = kEvalRows * kEvalThreads; /* floats per memory-stack level */
+
+/* One fused instruction, fully specialised on (operation, operand source): straight-line code, no inner dispatch. */
+template <int FOP, int SRC>
+__device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, const uint32_t arg, const mcb_program& prog,
+                                          const EvalLane& L) {
+    if (FOP == MCB_F_PUSH) {
 #pragma unroll
-    for (int e = 0; e < kEvalRows; e++) t0[e] = 0.f;
+        for (int e = 0; e < kEvalRows; e++) sp[e * kEvalThreads] = acc[e];
+        sp += kEvalLevel;
+    }
+    if (SRC == MCB_SRC_POP) {
+        sp -= kEvalLevel;
+#pragma unroll
+        for (int e = 0; e < kEvalRows; e++) acc[e] = fused_op<FOP>(acc[e], sp[e * kEvalThreads]);
+    } else if (SRC == MCB_SRC_TY) { /* rows y0..y0+kEvalRows-1 of a table: 16-byte aligned, same address in every lane */
+        const float4* ty = reinterpret_cast<const float4*>(L.tables + arg + L.y0);
+#pragma unroll
+        for (int e = 0; e < kEvalRows; e += 4) {
+            const float4 t = __ldg(ty + (e >> 2));
+            acc[e] = fused_op<FOP>(acc[e], t.x);
+            acc[e + 1] = fused_op<FOP>(acc[e + 1], t.y);
+            acc[e + 2] = fused_op<FOP>(acc[e + 2], t.z);
+            acc[e + 3] = fused_op<FOP>(acc[e + 3], t.w);
+        }
+    } else { /* one value for all rows of the lane */
+        const float u = SRC == MCB_SRC_K ? prog.k[arg] : __ldg(L.tables + arg + (SRC == MCB_SRC_TX ? L.x : L.zi));
+#pragma unroll
+        for (int e = 0; e < kEvalRows; e++) acc[e] = fused_op<FOP>(acc[e], u);
+    }
+}
+
+/* `prog` is the fused grid program with its table operands already resolved by the host for this launch:
+ * for src TX/TY/TZ the argument is the float offset of the table row inside `tables` ((axis*slots + slot) * P),
+ * so an operand fetch is one address add and one load.  Grid programs contain no raw X/Y/Z operands: bare
+ * variables are axis tables too (mcb_lower.cpp).  The low byte of an instruction word (operation | source << 4)
+ * indexes one jump table whose targets are the straight-line bodies above. */
+#define MCB_STEP(FOP, SRC) \
+    case MCB_FINSN(FOP, SRC, 0): eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
+#define MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_K) MCB_STEP(FOP, MCB_SRC_TX) MCB_STEP(FOP, MCB_SRC_TY) MCB_STEP(FOP, MCB_SRC_TZ)
+#define MCB_STEP_ALL(FOP) MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_POP)
+
+__global__ void __launch_bounds__(kEvalThreads)
+eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
+                  float* __restrict__ F, uint32_t* __restrict__ S, int row_groups) {
+    extern __shared__ float stack_smem[]; /* [level][kEvalRows][kEvalThreads] */
+    const int lane = threadIdx.x & 31;
+    const int w = (int)blockIdx.x;                                             /* 32-vertex word of the row */
+    const int yq = (int)blockIdx.y * (kEvalThreads / 32) + (threadIdx.x >> 5); /* row group */
+    const int pz = (int)blockIdx.z;                                            /* plane: vertex kb-1+pz */
+    if (yq >= row_groups) return; /* whole warp exits together; the kernel has no block-wide barrier */
+    EvalLane L;
+    L.tables = tables;
+    L.x = w * 32 + lane;
+    L.y0 = yq * kEvalRows;
+    L.zi = pz + g.kb; /* index into the z tables */
+
+    float acc[kEvalRows];
+#pragma unroll
+    for (int e = 0; e < kEvalRows; e++) acc[e] = 0.f;
     float* sp = stack_smem + threadIdx.x; /* next free level */
-    constexpr int kLevel = kEvalRows * kEvalThreads;
 
 #pragma unroll 1
     for (int pc = 0; pc < prog.n; pc++) {
         const uint32_t insn = prog.code[pc];
-        const uint32_t op = MCB_INSN_OP(insn), arg = MCB_INSN_ARG(insn);
-        if (op <= MCB_OP_PUSH_TZ) { /* pushes: spill the cached top, load the new one */
+        const uint32_t arg = MCB_FINSN_ARG(insn);
+        switch (insn & 0xffu) {
+            MCB_STEP_LEAF(MCB_F_LOAD)
+            MCB_STEP_LEAF(MCB_F_PUSH)
+            MCB_STEP_ALL(MCB_F_ADD)
+            MCB_STEP_ALL(MCB_F_SUB)
+            MCB_STEP_ALL(MCB_F_RSUB)
+            MCB_STEP_ALL(MCB_F_MUL)
+            MCB_STEP_ALL(MCB_F_DIV)
+            MCB_STEP_ALL(MCB_F_RDIV)
+            MCB_STEP_ALL(MCB_F_POW)
+            MCB_STEP_ALL(MCB_F_RPOW)
+            default: /* MCB_F_NEG */
 #pragma unroll
-            for (int e = 0; e < kEvalRows; e++) sp[e * kEvalThreads] = t0[e];
-            sp += kLevel;
-            switch (op) {
-                case MCB_OP_PUSH_X:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = X;
-                    break;
-                case MCB_OP_PUSH_Y:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = Y[e];
-                    break;
-                case MCB_OP_PUSH_Z:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = Z;
-                    break;
-                case MCB_OP_PUSH_K: {
-                    float kv = prog.k[arg];
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = kv;
-                    break;
-                }
-                case MCB_OP_PUSH_TX: {
-                    float tv = __ldg(tabx + (size_t)arg * g.P + x);
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = tv;
-                    break;
-                }
-                case MCB_OP_PUSH_TY: {
-                    const float* ty = taby + (size_t)arg * g.P + y0;
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = __ldg(ty + e); /* tables are padded past NV+kEvalRows */
-                    break;
-                }
-                default: { /* MCB_OP_PUSH_TZ (MCB_OP_END never appears inside a program) */
-                    float tv = __ldg(tabz + (size_t)arg * g.P + zi);
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = tv;
-                    break;
-                }
-            }
-        } else if (op == MCB_OP_NEG) {
-#pragma unroll
-            for (int e = 0; e < kEvalRows; e++) t0[e] = -t0[e];
-        } else {
-            sp -= kLevel;
-            float s2[kEvalRows];
-#pragma unroll
-            for (int e = 0; e < kEvalRows; e++) s2[e] = sp[e * kEvalThreads];
-            switch (op) {
-                case MCB_OP_ADD:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = s2[e] + t0[e];
-                    break;
-                case MCB_OP_SUB:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = s2[e] - t0[e];
-                    break;
-                case MCB_OP_RSUB:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = t0[e] - s2[e];
-                    break;
-                case MCB_OP_MUL:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = s2[e] * t0[e];
-                    break;
-                case MCB_OP_DIV:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = s2[e] / t0[e];
-                    break;
-                case MCB_OP_RDIV:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = t0[e] / s2[e];
-                    break;
-                case MCB_OP_POW:
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = powf_call(s2[e], t0[e]);
-                    break;
-                default: /* MCB_OP_RPOW */
-#pragma unroll
-                    for (int e = 0; e < kEvalRows; e++) t0[e] = powf_call(t0[e], s2[e]);
-                    break;
-            }
+                for (int e = 0; e < kEvalRows; e++) acc[e] = -acc[e];
+                break;
         }
     }
 
-    const size_t row0 = (size_t)pz * g.NV + y0;
-    float* fp = F + row0 * g.P + x;
-    uint32_t* sp_bits = S + row0 * g.WP + w;
+    const int x = L.x, y0 = L.y0;
+    const unsigned row0 = (unsigned)pz * (unsigned)g.NV + (unsigned)y0;
+    float* fp = F + (size_t)row0 * g.P + x; /* x < P always: P is the padded pitch */
+    const bool xin = x < g.NV;
+    uint32_t mine = 0;
+    if (y0 + kEvalRows <= g.NV) { /* uniform per warp; false only for the last row group of a plane */
 #pragma unroll
-    for (int e = 0; e < kEvalRows; e++) {
-        const bool in = (y0 + e < g.NV); /* uniform per warp */
-        if (in) fp[(size_t)e * g.P] = t0[e]; /* x < P always: P is the padded pitch */
-        const unsigned bits = __ballot_sync(0xffffffffu, in && x < g.NV && t0[e] > g.iso);
-        if (in && lane == e) sp_bits[e * g.WP] = bits;
+        for (int e = 0; e < kEvalRows; e++) {
+            __stcs(fp, acc[e]);
+            fp += g.P;
+        }
+#pragma unroll
+        for (int e = 0; e < kEvalRows; e++) {
+            const unsigned bits = __ballot_sync(0xffffffffu, xin && acc[e] > g.iso);
+            if (lane == e) mine = bits;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < kEvalRows; e++) {
+            const bool in = (y0 + e < g.NV);
+            if (in) __stcs(fp + (unsigned)(e * g.P), acc[e]);
+            const unsigned bits = __ballot_sync(0xffffffffu, in && xin && acc[e] > g.iso);
+            if (lane == e) mine = bits;
+        }
     }
+    if (lane < kEvalRows && y0 + lane < g.NV) S[(size_t)(row0 + lane) * g.WP + w] = mine;
 }
+#undef MCB_STEP
+#undef MCB_STEP_LEAF
+#undef MCB_STEP_ALL
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
 __global__ void __launch_bounds__(256)
@@ -252,25 +252,53 @@ eval_constraint_kernel(const __grid_constant__ mcb_program prog, const Grid g, c
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
- * K2  classify_compact: sign bit-planes -> cube codes -> ambiguity redirect -> per-cube triangle counts ->
- *     single-pass device-wide exclusive scan (decoupled look-back) of (active cubes, triangles) -> compacted,
- *     loop-ordered active-cube records with their triangle offsets.
+ * K2  classify + compact: sign bit-planes -> cube codes -> ambiguity redirect -> per-cube triangle counts ->
+ *     device-wide exclusive scan (decoupled look-back) of (active cubes, triangles) -> compacted, loop-ordered
+ *     active-cube records with their triangle offsets.
  *
- *     Work item = one 32-cube word of a cube row; items are numbered in the reference's loop order
- *     (z slowest, then y, then x), a tile is kClsThreads*kClsItems consecutive items, and tiles take their
- *     number from an atomic ticket so that a tile only ever waits for tiles that already started.
+ *     Work item = one 32-cube word of a cube row; items are numbered in the reference's loop order (z slowest,
+ *     then y, then x).  A tile is a run of whole cube rows (<= kClsItemCap items).
+ *
+ *     classify_kernel (one block per tile, no dependency between tiles):
+ *       A  every thread walks one word column down a strip of rows, carrying the sign words of the vertex row it
+ *          shares with the next cube row (4 loads and ~30 instructions per 32 cubes), and sets a bit in a
+ *          shared-memory bitmap for every item that has an active cube.  This is the only work done per voxel;
+ *          everything below is proportional to the surface.
+ *       B  the bitmap is turned into the list of active items in loop order (popc + block scan);
+ *       C1 one lane per ACTIVE item: rebuild its corner words, per cube code -> ambiguity face test
+ *          (marching.cpp:521-549) -> triangle count.  The list, the per-item counts and the tile aggregate go to
+ *          global scratch; the aggregate is the tile's look-back status word
+ *              [63:62] 0 = nothing yet, 1 = tile aggregate, 2 = inclusive prefix  [61:31] triangles  [30:0] active
+ *     compact_kernel (tiles by atomic ticket):
+ *       S  warp 0 runs the decoupled look-back over the status words (single 8-byte accesses, no fence between
+ *          value and flag) and publishes the tile's inclusive prefix at once — all the expensive, data-dependent
+ *          work (face-centre evaluations) happened in classify_kernel, so a slow tile never stalls the chain;
+ *          the other warps meanwhile scan the tile's per-item counts in chunks of 32;
+ *       C2 one lane per active item: packed shuffle scan inside the chunk, then the records are written in loop
+ *          order at tile base + chunk base + lane offset.
  * ------------------------------------------------------------------------------------------------------------- */
-struct ScanState {
-    uint32_t* flag;       /* 0 = nothing, 1 = aggregate published, 2 = inclusive prefix published */
-    uint32_t* agg_active;
-    uint32_t* agg_tris;
-    unsigned long long* inc_active;
-    unsigned long long* inc_tris;
-};
+constexpr int kClsWarps = kClsThreads / 32;
+constexpr int kClsItemCap = 16384; /* items per tile: bitmap 2 KB, active-item list and counts 2 x 32 KB */
+constexpr int kClsChunkCap = kClsItemCap / 32;
+constexpr size_t kClsSmemBytes = (size_t)kClsChunkCap * 4 + (size_t)kClsItemCap * 2; /* bitmap + list */
 
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+struct ClsGeom {
+    uint32_t WC;         /* 32-cube words per cube row */
+    uint32_t total_rows; /* (ke-kb) * M cube rows in the slab */
+    uint32_t tile_rows;  /* cube rows per tile; tile_rows * WC <= kClsItemCap */
+    uint32_t nstrips;    /* kClsThreads / WC row strips walked in parallel in phase A */
+    uint32_t strip_rows; /* ceil(tile_rows / nstrips) */
+    uint32_t inv_wc;     /* ceil(2^32 / WC), 0 when WC == 1 */
+    uint32_t inv_m;      /* ceil(2^32 / M),  0 when M == 1 */
+};
+/* floor(n / d) for n * d < 2^32 (tile-local indices), inv = ceil(2^32 / d) */
+__device__ __forceinline__ uint32_t div_small(uint32_t n, uint32_t inv) { return inv ? __umulhi(n, inv) : n; }
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
     return *(const volatile unsigned long long*)p;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    *(volatile unsigned long long*)p = v;
 }
 
 struct ClsTables { /* built once per context on the host (mcb_tables.h); read through the read-only path */
@@ -279,26 +307,21 @@ struct ClsTables { /* built once per context on the host (mcb_tables.h); read th
     uint8_t ntri[256];
 };
 
-/* the four sign-word rows a cube row touches: (y, z), (y+1, z), (y, z+1), (y+1, z+1) */
-struct RowPtrs {
-    const uint32_t* r[4];
-};
-__device__ __forceinline__ RowPtrs cube_row_ptrs(const uint32_t* __restrict__ B, const Grid& g, int kz, int j) {
-    /* cube (i,j,kz) corner (dx,dy,dz) = vertex index (i+1+dx, j+1+dy, plane kz+1+dz) */
-    RowPtrs p;
-    p.r[0] = B + ((size_t)(kz + 1) * g.NV + (j + 1)) * g.WP;
-    p.r[1] = p.r[0] + g.WP;
-    p.r[2] = p.r[0] + (size_t)g.NV * g.WP;
-    p.r[3] = p.r[2] + g.WP;
-    return p;
+/* Sign words of one vertex row as seen by the 32 cubes of an item: the vertex x-index of corner dx of cube i is
+ * i+1+dx (apron), hence the funnel shifts by 1 and 2.  r[0], r[1] = corners dx=0,1 on plane z; r[2], r[3] on z+1.
+ * All indices fit 32 bits (NZ*NV*WP < 2^32 for M <= 4094). */
+__device__ __forceinline__ void vertex_row_words(const uint32_t* __restrict__ B, uint32_t idx, uint32_t plane, uint32_t r[4]) {
+    const uint32_t* p0 = B + idx;
+    const uint32_t* p1 = B + (idx + plane);
+    const uint32_t a0 = __ldg(p0), a1 = __ldg(p0 + 1);
+    const uint32_t b0 = __ldg(p1), b1 = __ldg(p1 + 1);
+    r[0] = __funnelshift_r(a0, a1, 1); r[1] = __funnelshift_r(a0, a1, 2);
+    r[2] = __funnelshift_r(b0, b1, 1); r[3] = __funnelshift_r(b0, b1, 2);
 }
-/* corner sign words of the 32 cubes of word w: bit b of c[v] = sign of corner v of cube 32w+b.
- * lo[] = words w of the four rows (carried from the previous item when possible), hi[] = words w+1. */
+/* corner words c[v] (bit b = sign of corner v of cube 32w+b) from the two vertex rows of a cube row */
 __device__ __forceinline__ void corner_words(const uint32_t lo[4], const uint32_t hi[4], uint32_t c[8]) {
-    c[0] = __funnelshift_r(lo[0], hi[0], 1); c[1] = __funnelshift_r(lo[0], hi[0], 2);
-    c[3] = __funnelshift_r(lo[1], hi[1], 1); c[2] = __funnelshift_r(lo[1], hi[1], 2);
-    c[4] = __funnelshift_r(lo[2], hi[2], 1); c[5] = __funnelshift_r(lo[2], hi[2], 2);
-    c[7] = __funnelshift_r(lo[3], hi[3], 1); c[6] = __funnelshift_r(lo[3], hi[3], 2);
+    c[0] = lo[0]; c[1] = lo[1]; c[4] = lo[2]; c[5] = lo[3];
+    c[3] = hi[0]; c[2] = hi[1]; c[7] = hi[2]; c[6] = hi[3];
 }
 
 __device__ __forceinline__ int code_of(const uint32_t c[8], int b) {
@@ -324,106 +347,166 @@ __device__ __noinline__ bool ambiguity_redirects(const mcb_program& prog, const 
     return mid > g.iso;
 }
 
-__global__ void __launch_bounds__(kClsThreads)
-classify_compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
-                        const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S,
-                        const uint32_t* __restrict__ V, int WC /* words per cube row */,
-                        long long total_items, ScanState st, Counters* __restrict__ ctr,
-                        unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
-                        unsigned long long cap_active) {
-    __shared__ uint32_t warp_a[kClsThreads / 32], warp_t[kClsThreads / 32];
-    __shared__ unsigned long long base_a_s, base_t_s;
-    __shared__ uint32_t tile_s;
+__device__ __forceinline__ uint32_t column_mask(const Grid& g, uint32_t w) { /* cubes of word w inside the row */
+    const int ncubes = g.M - (int)w * 32;
+    return ncubes >= 32 ? 0xffffffffu : ((1u << ncubes) - 1u);
+}
+__device__ __forceinline__ uint32_t active_mask(const uint32_t c[8], uint32_t colmask) {
+    const uint32_t any = c[0] | c[1] | c[2] | c[3] | c[4] | c[5] | c[6] | c[7];
+    const uint32_t all = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
+    return any & ~all & colmask;
+}
+/* constraints: all 8 corners of a cube must be valid (marching.cpp:475-477) */
+__device__ __forceinline__ uint32_t valid_mask(const uint32_t* __restrict__ V, uint32_t idx, uint32_t WP, uint32_t plane) {
+    uint32_t lo[4], hi[4];
+    vertex_row_words(V, idx, plane, lo);
+    vertex_row_words(V, idx + WP, plane, hi);
+    return lo[0] & lo[1] & lo[2] & lo[3] & hi[0] & hi[1] & hi[2] & hi[3];
+}
 
-    if (threadIdx.x == 0) tile_s = atomicAdd(&ctr->tile_ticket, 1u);
+/* an active item revisited: position, corner words, active mask */
+struct ItemView {
+    uint32_t w, j, kz, m;
+    uint32_t c[8];
+};
+__device__ __forceinline__ void view_item(ItemView& it, uint32_t item_local, uint32_t j0, uint32_t kz0, const ClsGeom& q,
+                                          const Grid& g, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
+                                          uint32_t plane) {
+    const uint32_t r = div_small(item_local, q.inv_wc);
+    it.w = item_local - r * q.WC;
+    const uint32_t jj = j0 + r, dk = div_small(jj, q.inv_m);
+    it.j = jj - dk * (uint32_t)g.M;
+    it.kz = kz0 + dk;
+    const uint32_t idx = ((it.kz + 1u) * (uint32_t)g.NV + (it.j + 1u)) * (uint32_t)g.WP + it.w;
+    uint32_t lo[4], hi[4];
+    vertex_row_words(S, idx, plane, lo);
+    vertex_row_words(S, idx + (uint32_t)g.WP, plane, hi);
+    corner_words(lo, hi, it.c);
+    it.m = active_mask(it.c, column_mask(g, it.w));
+    if (V != nullptr && it.m) it.m &= valid_mask(V, idx, (uint32_t)g.WP, plane);
+}
+
+struct ClsScratch {        /* global scratch handed from classify_kernel to compact_kernel */
+    uint16_t* list;        /* [tiles][tile_items]  active items of the tile, loop order (tile-local item index) */
+    uint16_t* cnt;         /* [tiles][tile_items]  active cubes | triangles << 6 of list entry k */
+    uint32_t* nz;          /* [tiles]              number of list entries */
+    uint32_t tile_items;   /* tile_rows * WC */
+};
+
+__global__ void __launch_bounds__(kClsThreads, 3)
+classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
+                const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
+                const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status, Counters* __restrict__ ctr) {
+    extern __shared__ uint32_t cls_smem[];
+    uint32_t* bitmap = cls_smem;                                          /* [kClsChunkCap] one bit per item */
+    uint16_t* list = reinterpret_cast<uint16_t*>(cls_smem + kClsChunkCap); /* [kClsItemCap] active items, loop order */
+    __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];
+
+    for (int i = threadIdx.x; i < kClsChunkCap; i += kClsThreads) bitmap[i] = 0u;
     __syncthreads();
-    const uint32_t tile = tile_s;
+    const uint32_t tile = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t WP = (uint32_t)g.WP, plane = (uint32_t)g.NV * WP, M = (uint32_t)g.M;
+    const uint32_t row0 = tile * q.tile_rows;
+    const uint32_t rows = min(q.tile_rows, q.total_rows - row0);
+    const uint32_t kz0 = row0 / M, j0 = row0 - kz0 * M;
 
-    /* this thread's kClsItems consecutive items start at (kz0, j0, w0) */
-    const long long item0 = ((long long)tile * kClsThreads + threadIdx.x) * kClsItems;
-    int nitems = 0, kz0 = 0, j0 = 0, w0 = 0;
-    if (item0 < total_items) {
-        const long long left = total_items - item0;
-        nitems = left < kClsItems ? (int)left : kClsItems;
-        const long long row = item0 / WC;
-        w0 = (int)(item0 - row * WC);
-        kz0 = (int)(row / g.M);
-        j0 = (int)(row - (long long)kz0 * g.M);
-    }
-
-    /* ---- phase 1: masks and counts -------------------------------------------------------------------------- */
-    uint32_t act[kClsItems], red[kClsItems];
-    uint32_t n_act = 0, n_tri = 0, n_amb = 0, n_red = 0;
+    /* ---- A: one bit per item ------------------------------------------------------------------------------- */
     {
-        int kz = kz0, j = j0, w = w0;
-        RowPtrs rp = cube_row_ptrs(S, g, kz, j);
-        uint32_t lo[4], hi[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) lo[r] = nitems ? __ldg(rp.r[r] + w) : 0u;
-#pragma unroll
-        for (int q = 0; q < kClsItems; q++) {
-            act[q] = 0; red[q] = 0;
-            if (q < nitems) {
-                const bool hi_ok = (w + 1 < g.WP);
-#pragma unroll
-                for (int r = 0; r < 4; r++) hi[r] = hi_ok ? __ldg(rp.r[r] + w + 1) : 0u;
-                uint32_t c[8];
-                corner_words(lo, hi, c);
-                const uint32_t any = c[0] | c[1] | c[2] | c[3] | c[4] | c[5] | c[6] | c[7];
-                const uint32_t all = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
-                const int ncubes = g.M - w * 32; /* cubes of this word inside the row */
-                uint32_t m = any & ~all & (ncubes >= 32 ? 0xffffffffu : ((1u << ncubes) - 1u));
-                if (V != nullptr && m) { /* constraints: all 8 corners must be valid (marching.cpp:475-477) */
-                    const RowPtrs vp = cube_row_ptrs(V, g, kz, j);
-                    uint32_t vlo[4], vhi[4], v[8];
-#pragma unroll
-                    for (int r = 0; r < 4; r++) { vlo[r] = __ldg(vp.r[r] + w); vhi[r] = hi_ok ? __ldg(vp.r[r] + w + 1) : 0u; }
-                    corner_words(vlo, vhi, v);
-                    m &= v[0] & v[1] & v[2] & v[3] & v[4] & v[5] & v[6] & v[7];
+        const uint32_t strip = div_small(threadIdx.x, q.inv_wc), w = threadIdx.x - strip * q.WC;
+        uint32_t r = strip * q.strip_rows;
+        const uint32_t r_end = strip < q.nstrips ? min(r + q.strip_rows, rows) : 0u;
+        if (r < r_end) {
+            const uint32_t colmask = column_mask(g, w);
+            uint32_t kz = kz0 + (j0 + r) / M, j = (j0 + r) - (kz - kz0) * M;
+            uint32_t item = r * q.WC + w;
+            while (r < r_end) {
+                uint32_t idx = ((kz + 1u) * (uint32_t)g.NV + (j + 1u)) * WP + w;
+                uint32_t lo[4];
+                vertex_row_words(S, idx, plane, lo);
+                uint32_t any_lo = lo[0] | lo[1] | lo[2] | lo[3], all_lo = lo[0] & lo[1] & lo[2] & lo[3];
+                const uint32_t n = min(r_end - r, M - j); /* rows left in this strip and in this plane */
+#pragma unroll 4
+                for (uint32_t t = 0; t < n; t++) {
+                    uint32_t hi[4];
+                    vertex_row_words(S, idx + WP, plane, hi);
+                    const uint32_t any_hi = hi[0] | hi[1] | hi[2] | hi[3], all_hi = hi[0] & hi[1] & hi[2] & hi[3];
+                    uint32_t m = (any_lo | any_hi) & ~(all_lo & all_hi) & colmask;
+                    if (V != nullptr && m) m &= valid_mask(V, idx, WP, plane);
+                    if (m) atomicOr(&bitmap[item >> 5], 1u << (item & 31u));
+                    any_lo = any_hi; all_lo = all_hi;
+                    idx += WP;
+                    item += q.WC;
                 }
-                act[q] = m;
-                n_act += __popc(m);
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    int code = code_of(c, b);
-                    const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
-                    if (face >= 0) {
-                        n_amb++;
-                        if (ambiguity_redirects(point_prog, g, cs, face, w * 32 + b, j, kz + g.kb)) {
-                            code = 255 - code;
-                            red[q] |= 1u << b;
-                            n_red++;
-                        }
-                    }
-                    n_tri += __ldg(gtb->ntri + code);
-                }
-                /* advance to the next item in loop order */
-                if (++w == WC) {
-                    w = 0;
-                    if (++j == g.M) { j = 0; kz++; }
-                    rp = cube_row_ptrs(S, g, kz, j);
-                    if (q + 1 < nitems) {
-#pragma unroll
-                        for (int r = 0; r < 4; r++) lo[r] = __ldg(rp.r[r]);
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) lo[r] = hi[r];
-                }
+                r += n;
+                j = 0; kz++; /* only reached again when the strip continues on the next plane */
             }
         }
     }
+    __syncthreads();
 
-    /* ---- block-wide exclusive scan of (n_act, n_tri): shuffles inside a warp, shared memory across warps ---- */
-    uint32_t inc_a = n_act, inc_t = n_tri;
+    /* ---- B: bitmap -> list of active items in loop order ------------------------------------------------------ */
+    uint32_t nz;
+    {
+        constexpr int kPer = kClsChunkCap / kClsThreads; /* bitmap words per thread */
+        uint32_t wd[kPer], mine = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t ua = __shfl_up_sync(0xffffffffu, inc_a, d), ut = __shfl_up_sync(0xffffffffu, inc_t, d);
-        if (lane >= d) { inc_a += ua; inc_t += ut; }
+        for (int i = 0; i < kPer; i++) { wd[i] = bitmap[threadIdx.x * kPer + i]; mine += __popc(wd[i]); }
+        uint32_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_x[warp] = inc;
+        __syncthreads();
+        uint32_t base = inc - mine;
+        nz = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kClsWarps; w2++) { if (w2 < warp) base += warp_x[w2]; nz += warp_x[w2]; }
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            uint32_t b = wd[i];
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                list[base++] = (uint16_t)((threadIdx.x * kPer + i) * 32 + bit);
+            }
+        }
     }
-    if (lane == 31) { warp_a[warp] = inc_a; warp_t[warp] = inc_t; }
+    __syncthreads();
+
+    /* ---- C1: per active item: cube codes, ambiguity, triangle counts ------------------------------------------ */
+    uint16_t* glist = sc.list + (size_t)tile * sc.tile_items;
+    uint16_t* gcnt = sc.cnt + (size_t)tile * sc.tile_items;
+    uint32_t n_amb = 0, n_red = 0, sum_a = 0, sum_t = 0;
+    for (uint32_t kb = (uint32_t)warp * 32u; kb < nz; kb += kClsThreads) {
+        const uint32_t k = kb + (uint32_t)lane;
+        if (k < nz) {
+            const uint32_t item_local = list[k];
+            ItemView it;
+            view_item(it, item_local, j0, kz0, q, g, S, V, plane);
+            const uint32_t na = __popc(it.m);
+            uint32_t nt = 0, mm = it.m;
+            while (mm) {
+                const int b = __ffs(mm) - 1;
+                mm &= mm - 1;
+                int code = code_of(it.c, b);
+                const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
+                if (face >= 0) {
+                    n_amb++;
+                    if (ambiguity_redirects(point_prog, g, cs, face, (int)it.w * 32 + b, (int)it.j, (int)it.kz + g.kb)) {
+                        code = 255 - code;
+                        n_red++;
+                    }
+                }
+                nt += __ldg(gtb->ntri + code);
+            }
+            glist[k] = (uint16_t)item_local;
+            gcnt[k] = (uint16_t)(na | (nt << 6)); /* na <= 32, nt <= 160 */
+            sum_a += na; sum_t += nt;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { sum_a += __shfl_xor_sync(0xffffffffu, sum_a, d); sum_t += __shfl_xor_sync(0xffffffffu, sum_t, d); }
+    if (lane == 0) { warp_x[warp] = sum_a; warp_y[warp] = sum_t; }
     if (__any_sync(0xffffffffu, n_amb != 0)) { /* statistics: one atomic per warp, only when needed */
         uint32_t sa = n_amb, sr = n_red;
 #pragma unroll
@@ -431,90 +514,145 @@ classify_compact_kernel(const __grid_constant__ mcb_program point_prog, const Gr
         if (lane == 0) { atomicAdd(&ctr->ambiguous, (unsigned long long)sa); if (sr) atomicAdd(&ctr->redirected, (unsigned long long)sr); }
     }
     __syncthreads();
-    uint32_t wbase_a = 0, wbase_t = 0, tot_a = 0, tot_t = 0;
+    if (threadIdx.x == 0) {
+        unsigned long long ta = 0, tt = 0;
 #pragma unroll
-    for (int q = 0; q < kClsThreads / 32; q++) {
-        if (q < warp) { wbase_a += warp_a[q]; wbase_t += warp_t[q]; }
-        tot_a += warp_a[q]; tot_t += warp_t[q];
+        for (int w2 = 0; w2 < kClsWarps; w2++) { ta += warp_x[w2]; tt += warp_y[w2]; }
+        sc.nz[tile] = nz;
+        status[tile] = (1ull << 62) | (tt << 31) | ta; /* tile aggregate: < 2^19 cubes, < 2^22 triangles */
     }
-    const uint32_t excl_a = wbase_a + inc_a - n_act, excl_t = wbase_t + inc_t - n_tri;
+}
 
-    /* ---- decoupled look-back (warp 0) ----------------------------------------------------------------------- */
+__global__ void __launch_bounds__(kClsThreads)
+compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
+               const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
+               const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status,
+               Counters* __restrict__ ctr, unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
+               unsigned long long cap_active) {
+    __shared__ uint32_t chunk_a[kClsChunkCap], chunk_t[kClsChunkCap]; /* per 32 list entries */
+    __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];
+    __shared__ unsigned long long base_a_s, base_t_s;
+    __shared__ uint32_t tile_s;
+
+    if (threadIdx.x == 0) tile_s = atomicAdd(&ctr->tile_ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nz = sc.nz[tile];
+    const uint16_t* __restrict__ glist = sc.list + (size_t)tile * sc.tile_items;
+    const uint16_t* __restrict__ gcnt = sc.cnt + (size_t)tile * sc.tile_items;
+    const uint32_t row0 = tile * q.tile_rows;
+    const uint32_t rows = min(q.tile_rows, q.total_rows - row0);
+
+    /* ---- S: look-back (warp 0) while every warp reduces its chunks of the per-item counts ---------------------- */
     if (warp == 0) {
+        constexpr unsigned long long kField = 0x7fffffffull;
+        const unsigned long long own = ld_status(status + tile);
         unsigned long long pa = 0, pt = 0;
         if (tile > 0) {
-            if (lane == 0) {
-                st.agg_active[tile] = tot_a; st.agg_tris[tile] = tot_t;
-                __threadfence();
-                *(volatile uint32_t*)(st.flag + tile) = 1u;
-            }
             long long basei = (long long)tile - 1;
-            uint32_t spins = 0;
-            bool done = false;
-            while (!done) {
+            for (;;) {
                 const long long idx = basei - lane;
-                uint32_t f = idx >= 0 ? ld_volatile_u32(st.flag + idx) : 2u;
-                while (__any_sync(0xffffffffu, f == 0u)) {
-                    if (f == 0u) f = ld_volatile_u32(st.flag + idx);
-                    if (++spins > kSpinLimit) { if (lane == 0) atomicExch(&ctr->error, 1u); f = 2u; }
-                }
-                __threadfence();
-                const uint32_t pmask = __ballot_sync(0xffffffffu, f == 2u);
+                const unsigned long long sv = idx >= 0 ? ld_status(status + idx) : (2ull << 62);
+                /* every status word is at least an aggregate: classify_kernel finished before this kernel started */
+                const uint32_t pmask = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
                 const int first = pmask ? __ffs(pmask) - 1 : 32;
                 unsigned long long va = 0, vt = 0;
-                if (lane < first) { va = ld_volatile_u32(st.agg_active + idx); vt = ld_volatile_u32(st.agg_tris + idx); }
-                else if (lane == first && idx >= 0) { va = ld_volatile_u64(st.inc_active + idx); vt = ld_volatile_u64(st.inc_tris + idx); }
+                if (lane <= first) { va = sv & kField; vt = (sv >> 31) & kField; } /* aggregates up to, and including, the first inclusive prefix */
 #pragma unroll
                 for (int d = 16; d; d >>= 1) { va += __shfl_xor_sync(0xffffffffu, va, d); vt += __shfl_xor_sync(0xffffffffu, vt, d); }
                 pa += va; pt += vt;
-                done = pmask != 0u;
+                if (pmask) break;
                 basei -= 32;
             }
         }
         if (lane == 0) {
-            st.inc_active[tile] = pa + tot_a; st.inc_tris[tile] = pt + tot_t;
-            __threadfence();
-            *(volatile uint32_t*)(st.flag + tile) = 2u;
+            const unsigned long long ia = pa + (own & kField), it = pt + ((own >> 31) & kField);
+            if (it > kField) atomicExch(&ctr->error, 2u); /* >= 2^31 triangles in one slab: beyond any output buffer */
+            st_status(status + tile, (2ull << 62) | ((it & kField) << 31) | (ia & kField));
             base_a_s = pa; base_t_s = pt;
-            if ((long long)(tile + 1) * kClsThreads * kClsItems >= total_items) { /* last tile: grand totals */
-                ctr->active = pa + tot_a;
-                ctr->triangles = pt + tot_t;
+            if (row0 + rows >= q.total_rows) { /* last tile: grand totals */
+                ctr->active = ia;
+                ctr->triangles = it;
             }
         }
     }
-    if (tot_a == 0) return; /* nothing to write in this tile (uniform per block) */
+    if (nz == 0) return; /* uniform per block */
+    for (uint32_t kb = (uint32_t)warp * 32u; kb < nz; kb += kClsThreads) {
+        const uint32_t k = kb + (uint32_t)lane;
+        const uint32_t c = k < nz ? (uint32_t)gcnt[k] : 0u;
+        uint32_t na = c & 63u, nt = c >> 6;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, d); nt += __shfl_xor_sync(0xffffffffu, nt, d); }
+        if (lane == 0) { chunk_a[kb >> 5] = na; chunk_t[kb >> 5] = nt; }
+    }
+    __syncthreads();
+    { /* exclusive scan of the chunk totals, in place */
+        constexpr int kPer = kClsChunkCap / kClsThreads;
+        const uint32_t nchunks = (nz + 31u) >> 5;
+        uint32_t a[kPer], t[kPer], sa = 0, st = 0;
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const uint32_t c = threadIdx.x * kPer + i;
+            a[i] = c < nchunks ? chunk_a[c] : 0u;
+            t[i] = c < nchunks ? chunk_t[c] : 0u;
+            sa += a[i]; st += t[i];
+        }
+        uint32_t ia = sa, it = st;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ua = __shfl_up_sync(0xffffffffu, ia, d), ut = __shfl_up_sync(0xffffffffu, it, d);
+            if (lane >= d) { ia += ua; it += ut; }
+        }
+        if (lane == 31) { warp_x[warp] = ia; warp_y[warp] = it; }
+        __syncthreads();
+        uint32_t ba = ia - sa, bt = it - st;
+#pragma unroll
+        for (int w2 = 0; w2 < kClsWarps; w2++)
+            if (w2 < warp) { ba += warp_x[w2]; bt += warp_y[w2]; }
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const uint32_t c = threadIdx.x * kPer + i;
+            if (c < nchunks) { chunk_a[c] = ba; chunk_t[c] = bt; }
+            ba += a[i]; bt += t[i];
+        }
+    }
     __syncthreads();
 
-    /* ---- phase 2: write the compacted records in loop order ------------------------------------------------- */
-    if (n_act == 0) return;
-    unsigned long long oa = base_a_s + excl_a, ot = base_t_s + excl_t;
-    int kz = kz0, j = j0, w = w0;
+    /* ---- C2: write the compacted records in loop order -------------------------------------------------------- */
+    const uint32_t WP = (uint32_t)g.WP, plane = (uint32_t)g.NV * WP, M = (uint32_t)g.M;
+    const uint32_t kz0 = row0 / M, j0 = row0 - kz0 * M;
+    const unsigned long long tile_a = base_a_s, tile_t = base_t_s;
+    for (uint32_t kb = (uint32_t)warp * 32u; kb < nz; kb += kClsThreads) {
+        const uint32_t k = kb + (uint32_t)lane;
+        const uint32_t c = k < nz ? (uint32_t)gcnt[k] : 0u;
+        const uint32_t mine = (c & 63u) | ((c >> 6) << 16);
+        uint32_t inc = mine; /* <= 32 | 160 << 16 per lane: a chunk's sum stays below 2^16 per field */
 #pragma unroll
-    for (int q = 0; q < kClsItems; q++) {
-        uint32_t m = act[q];
-        if (m) {
-            const RowPtrs rp = cube_row_ptrs(S, g, kz, j);
-            const bool hi_ok = (w + 1 < g.WP);
-            uint32_t lo[4], hi[4], c[8];
-#pragma unroll
-            for (int r = 0; r < 4; r++) { lo[r] = __ldg(rp.r[r] + w); hi[r] = hi_ok ? __ldg(rp.r[r] + w + 1) : 0u; }
-            corner_words(lo, hi, c);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const int code = code_of(c, b);
-                const int tidx = (red[q] >> b) & 1u ? 255 - code : code;
-                if (oa < cap_active) {
-                    rec[oa] = (unsigned long long)(w * 32 + b) | ((unsigned long long)j << 12) |
-                              ((unsigned long long)(kz + g.kb) << 24) | ((unsigned long long)code << 36) |
-                              ((unsigned long long)tidx << 44);
-                    trioff[oa] = (uint32_t)ot;
-                }
-                oa++;
-                ot += __ldg(gtb->ntri + tidx);
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (k >= nz) continue;
+        unsigned long long oa = tile_a + chunk_a[kb >> 5] + ((inc - mine) & 0xffffu);
+        unsigned long long ot = tile_t + chunk_t[kb >> 5] + ((inc - mine) >> 16);
+        ItemView it;
+        view_item(it, glist[k], j0, kz0, q, g, S, V, plane);
+        uint32_t m = it.m;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int code = code_of(it.c, b);
+            int tidx = code;
+            const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
+            if (face >= 0 && ambiguity_redirects(point_prog, g, cs, face, (int)it.w * 32 + b, (int)it.j, (int)it.kz + g.kb))
+                tidx = 255 - code;
+            if (oa < cap_active) {
+                rec[oa] = (unsigned long long)(it.w * 32 + b) | ((unsigned long long)it.j << 12) |
+                          ((unsigned long long)(it.kz + g.kb) << 24) | ((unsigned long long)code << 36) |
+                          ((unsigned long long)tidx << 44);
+                trioff[oa] = (uint32_t)ot;
             }
+            oa++;
+            ot += __ldg(gtb->ntri + tidx);
         }
-        if (++w == WC) { w = 0; if (++j == g.M) { j = 0; kz++; } }
     }
 }
 

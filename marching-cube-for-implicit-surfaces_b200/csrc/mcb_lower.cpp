@@ -238,7 +238,12 @@ struct Lowerer {
     /* maximal constant subtrees and maximal single-variable subtrees */
     void find_slots(int n, bool inside_axis) {
         const Node& nd = e.nodes[n];
-        if (leaf(nd)) return;
+        if (leaf(nd)) {
+            /* a bare variable outside any hoisted subtree is the trivial one-variable subtree: the grid kernel then
+             * reads the scaled coordinate from an axis table like every other per-axis value */
+            if (nd.kind != 'c' && !inside_axis && !axis_slot.count(n)) { int s = (int)axis_slot.size(); axis_slot[n] = s; }
+            return;
+        }
         if (nd.mask == 0) {
             if (!const_slot.count(n)) { int s = (int)const_slot.size(); const_slot[n] = s; }
             return;
@@ -278,12 +283,6 @@ struct Lowerer {
     void gen(int n, Mode mode, int self, std::vector<uint32_t>& code, std::map<int, int>& memo) {
         const Node& nd = e.nodes[n];
         if (n != self || leaf(nd)) {
-            if (nd.kind == 'x') { code.push_back(MCB_INSN(MCB_OP_PUSH_X, 0)); return; }
-            if (nd.kind == 'y') { code.push_back(MCB_INSN(MCB_OP_PUSH_Y, 0)); return; }
-            if (nd.kind == 'z') { code.push_back(MCB_INSN(MCB_OP_PUSH_Z, 0)); return; }
-            if (nd.kind == 'c') { code.push_back(MCB_INSN(MCB_OP_PUSH_K, literal(nd.value))); return; }
-            auto cs = const_slot.find(n);
-            if (mode != LITERAL && cs != const_slot.end()) { code.push_back(MCB_INSN(MCB_OP_PUSH_K, out.n_literals + cs->second)); return; }
             if (mode == GRID) {
                 auto as = axis_slot.find(n);
                 if (as != axis_slot.end()) {
@@ -292,6 +291,12 @@ struct Lowerer {
                     return;
                 }
             }
+            if (nd.kind == 'x') { code.push_back(MCB_INSN(MCB_OP_PUSH_X, 0)); return; }
+            if (nd.kind == 'y') { code.push_back(MCB_INSN(MCB_OP_PUSH_Y, 0)); return; }
+            if (nd.kind == 'z') { code.push_back(MCB_INSN(MCB_OP_PUSH_Z, 0)); return; }
+            if (nd.kind == 'c') { code.push_back(MCB_INSN(MCB_OP_PUSH_K, literal(nd.value))); return; }
+            auto cs = const_slot.find(n);
+            if (mode != LITERAL && cs != const_slot.end()) { code.push_back(MCB_INSN(MCB_OP_PUSH_K, out.n_literals + cs->second)); return; }
         }
         if (nd.kind == 'N') {
             gen(nd.a, mode, self, code, memo);
@@ -365,6 +370,7 @@ struct Lowerer {
             std::map<int, int> memo;
             gen(e.root, GRID, -1, out.grid_code, memo);
             out.grid_depth = depth_of(out.grid_code, 0, out.grid_code.size());
+            out.grid_fused_depth = fuse(out.grid_code, out.grid_fused);
         }
         if (out.point_code.size() > MCB_MAX_CODE || out.grid_code.size() > MCB_MAX_CODE ||
             out.slot_code.size() > 4 * MCB_MAX_CODE || out.kpool.size() > MCB_MAX_K ||
@@ -394,6 +400,64 @@ int compile(const std::string& eq, Compiled& out, std::string* err) {
     int rc = lw.run();
     if (rc != MCB_OK && err) *err = "equation too large for the bytecode limits (MCB_MAX_CODE/MCB_MAX_K/MCB_MAX_SLOTS/MCB_MAX_STACK)";
     return rc;
+}
+
+/* Postfix -> fused accumulator form (mcb_bytecode.h).  A push directly followed by a binary operator becomes that
+ * operator's operand; the other pushes keep spilling the accumulator, except the very first value of the program,
+ * which is a plain load.  Returns the number of memory-stack levels the fused program needs. */
+int fuse(const std::vector<uint32_t>& postfix, std::vector<uint32_t>& fused) {
+    fused.clear();
+    auto is_push = [](uint32_t op) { return op >= MCB_OP_PUSH_X && op <= MCB_OP_PUSH_TZ; };
+    auto is_bin = [](uint32_t op) { return op >= MCB_OP_ADD && op <= MCB_OP_RPOW; };
+    static const int direct[] = {MCB_F_ADD, MCB_F_SUB, MCB_F_RSUB, MCB_F_MUL, MCB_F_DIV, MCB_F_RDIV, MCB_F_POW, MCB_F_RPOW};
+    static const int popped[] = {MCB_F_ADD, MCB_F_RSUB, MCB_F_SUB, MCB_F_MUL, MCB_F_RDIV, MCB_F_DIV, MCB_F_RPOW, MCB_F_POW};
+    int depth = 0, mem = 0, mem_max = 0; /* depth: values on the operand stack (accumulator included) */
+    for (size_t i = 0; i < postfix.size(); i++) {
+        const uint32_t w = postfix[i], op = MCB_INSN_OP(w), arg = MCB_INSN_ARG(w);
+        if (op == MCB_OP_END) break;
+        if (is_push(op)) {
+            const uint32_t src = op - MCB_OP_PUSH_X; /* PUSH_X..PUSH_TZ map onto MCB_SRC_X..MCB_SRC_TZ in order */
+            const uint32_t nop = i + 1 < postfix.size() ? MCB_INSN_OP(postfix[i + 1]) : (uint32_t)MCB_OP_END;
+            if (depth >= 1 && is_bin(nop)) { /* acc = second, leaf = top */
+                fused.push_back(MCB_FINSN(direct[nop - MCB_OP_ADD], src, arg));
+                i++;
+            } else if (depth == 0) {
+                fused.push_back(MCB_FINSN(MCB_F_LOAD, src, arg));
+                depth = 1;
+            } else {
+                fused.push_back(MCB_FINSN(MCB_F_PUSH, src, arg));
+                depth++;
+                mem_max = std::max(mem_max, ++mem);
+            }
+        } else if (op == MCB_OP_NEG) {
+            fused.push_back(MCB_FINSN(MCB_F_NEG, 0, 0));
+        } else { /* binary operator on two stacked values: acc = top, popped = second */
+            fused.push_back(MCB_FINSN(popped[op - MCB_OP_ADD], MCB_SRC_POP, 0));
+            depth--;
+            mem--;
+        }
+    }
+    return mem_max;
+}
+
+std::string disassemble_fused(const std::vector<uint32_t>& code) {
+    static const char* fops[] = {"LOAD", "PUSH", "ADD", "SUB", "RSUB", "MUL", "DIV", "RDIV", "POW", "RPOW", "NEG"};
+    static const char* srcs[] = {"X", "Y", "Z", "K", "TX", "TY", "TZ", "POP"};
+    std::string s;
+    char buf[48];
+    for (uint32_t w : code) {
+        uint32_t fop = MCB_FINSN_OP(w), src = MCB_FINSN_SRC(w);
+        if (!s.empty()) s += "; ";
+        s += fop < MCB_F_COUNT ? fops[fop] : "?";
+        if (fop == MCB_F_NEG) continue;
+        s += ' ';
+        s += src <= MCB_SRC_POP ? srcs[src] : "?";
+        if (src >= MCB_SRC_K && src <= MCB_SRC_TZ) {
+            std::snprintf(buf, sizeof buf, "%u", MCB_FINSN_ARG(w));
+            s += buf;
+        }
+    }
+    return s;
 }
 
 std::string disassemble(const std::vector<uint32_t>& code) {

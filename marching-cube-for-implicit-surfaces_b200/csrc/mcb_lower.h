@@ -71,6 +71,8 @@ struct Compiled {
     Expr expr;
     std::vector<uint32_t> point_code; /* full expression, arbitrary (x,y,z); uses PUSH_K but no tables */
     std::vector<uint32_t> grid_code;  /* full expression on the grid; uses PUSH_K and PUSH_T* */
+    std::vector<uint32_t> grid_fused; /* grid_code in the fused accumulator form the grid kernel runs */
+    int grid_fused_depth = 0;         /* memory-stack levels grid_fused needs */
     std::vector<uint32_t> slot_code;  /* programs of all slots, concatenated */
     std::vector<Slot> slots;          /* constant slots first, then axis slots */
     std::vector<float> kpool;         /* literals (exact strtof bits); folded slots are filled in by the device */
@@ -83,6 +85,10 @@ struct Compiled {
 int compile(const std::string& eq, Compiled& out, std::string* err);
 
 std::string disassemble(const std::vector<uint32_t>& code);
+
+/* postfix words -> fused accumulator words (mcb_bytecode.h); returns the memory-stack depth of the result */
+int fuse(const std::vector<uint32_t>& postfix, std::vector<uint32_t>& fused);
+std::string disassemble_fused(const std::vector<uint32_t>& code);
 
 } /* namespace mcb */
 

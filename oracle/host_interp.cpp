@@ -59,8 +59,13 @@ int mcoh_eval_grid(const char* eq, const float* cx, int nx, const float* cy, int
                 for (int s = 0; s < c.n_axis_slots[0]; s++) tx[s] = tab[0][s][i];
                 for (int s = 0; s < c.n_axis_slots[1]; s++) ty[s] = tab[1][s][j];
                 for (int s = 0; s < c.n_axis_slots[2]; s++) tz[s] = tab[2][s][k];
-                out[((size_t)k * ny + j) * nx + i] = mcb_interp_scalar(c.grid_code.data(), (int)c.grid_code.size(), c.kpool.data(),
-                                                                        cx[i], cy[j], cz[k], tx.data(), ty.data(), tz.data());
+                /* the fused accumulator form is what the grid kernel runs; the postfix form must agree with it */
+                const float fused = mcb_interp_fused_scalar(c.grid_fused.data(), (int)c.grid_fused.size(), c.kpool.data(),
+                                                            cx[i], cy[j], cz[k], tx.data(), ty.data(), tz.data());
+                const float postfix = mcb_interp_scalar(c.grid_code.data(), (int)c.grid_code.size(), c.kpool.data(),
+                                                        cx[i], cy[j], cz[k], tx.data(), ty.data(), tz.data());
+                if (std::memcmp(&fused, &postfix, 4) != 0 && !(fused != fused && postfix != postfix)) return -100;
+                out[((size_t)k * ny + j) * nx + i] = fused;
             }
     return MCB_OK;
 }
