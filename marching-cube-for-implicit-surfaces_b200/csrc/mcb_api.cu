@@ -393,8 +393,6 @@ int mcb_create(int device, mcb_ctx** out) {
     if (cudaFuncSetAttribute(eval_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float)) != cudaSuccess)
         return bail(MCB_E_CUDA);
-    if (cudaFuncSetAttribute(classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClsSmemBytes) != cudaSuccess)
-        return bail(MCB_E_CUDA);
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
     rc = mcb_set_grid_step(ctx, 0.25f); /* Marching::Marching(), marching.cpp:24 */
@@ -591,15 +589,19 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
             const ClsScratch sc{ctx->d_tile_list, ctx->d_tile_cnt, ctx->d_tile_nz, cg.tile_rows * cg.WC};
             const uint32_t* dV = any_constraint ? ctx->d_V : nullptr;
-            classify_kernel<<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
-                                                                      ctx->d_status, ctx->d_ctr);
+            if (dV)
+                classify_kernel<true><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
+                                                                                ctx->d_status, ctx->d_ctr);
+            else
+                classify_kernel<false><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
+                                                                                 ctx->d_status, ctx->d_ctr);
             compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,
                                                          ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active);
             launches += 2;
             MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
         /* K3: interpolation + coalesced float4 emission */
-        const unsigned eblocks = (unsigned)ctx->sm_count * 8;
+        const unsigned eblocks = (unsigned)ctx->sm_count * 4;
         if (ctx->normals)
             emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
         else

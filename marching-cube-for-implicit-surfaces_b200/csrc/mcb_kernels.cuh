@@ -25,7 +25,8 @@ namespace mcbk {
 constexpr int kEvalThreads = 128;   /* 4 warps; each warp: 32 x-columns x kEvalRows y-rows of one z-plane */
 constexpr int kEvalRows = 16;
 constexpr int kClsThreads = 256;
-constexpr int kEmitThreads = 128;   /* = active cubes per emit chunk */
+constexpr int kEmitCubes = 128;     /* active cubes per emit chunk */
+constexpr int kEmitThreads = 256;   /* threads working on one chunk */
 
 struct Grid {
     int M;        /* cubes per axis */
@@ -278,7 +279,7 @@ eval_constraint_kernel(const __grid_constant__ mcb_program prog, const Grid g, c
  *          order at tile base + chunk base + lane offset.
  * ------------------------------------------------------------------------------------------------------------- */
 constexpr int kClsWarps = kClsThreads / 32;
-constexpr int kClsItemCap = 16384; /* items per tile: bitmap 2 KB, active-item list and counts 2 x 32 KB */
+constexpr int kClsItemCap = 8192; /* items per tile: bitmap 1 KB + active-item list 16 KB of shared memory */
 constexpr int kClsChunkCap = kClsItemCap / 32;
 constexpr size_t kClsSmemBytes = (size_t)kClsChunkCap * 4 + (size_t)kClsItemCap * 2; /* bitmap + list */
 
@@ -393,7 +394,8 @@ struct ClsScratch {        /* global scratch handed from classify_kernel to comp
     uint32_t tile_items;   /* tile_rows * WC */
 };
 
-__global__ void __launch_bounds__(kClsThreads, 3)
+template <bool HAS_V>
+__global__ void __launch_bounds__(kClsThreads, 4)
 classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
                 const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
                 const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status, Counters* __restrict__ ctr) {
@@ -432,7 +434,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
                     vertex_row_words(S, idx + WP, plane, hi);
                     const uint32_t any_hi = hi[0] | hi[1] | hi[2] | hi[3], all_hi = hi[0] & hi[1] & hi[2] & hi[3];
                     uint32_t m = (any_lo | any_hi) & ~(all_lo & all_hi) & colmask;
-                    if (V != nullptr && m) m &= valid_mask(V, idx, WP, plane);
+                    if (HAS_V && m) m &= valid_mask(V, idx, WP, plane);
                     if (m) atomicOr(&bitmap[item >> 5], 1u << (item & 31u));
                     any_lo = any_hi; all_lo = all_hi;
                     idx += WP;
@@ -448,10 +450,14 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
     /* ---- B: bitmap -> list of active items in loop order ------------------------------------------------------ */
     uint32_t nz;
     {
-        constexpr int kPer = kClsChunkCap / kClsThreads; /* bitmap words per thread */
+        constexpr int kPer = (kClsChunkCap + kClsThreads - 1) / kClsThreads; /* bitmap words per thread */
         uint32_t wd[kPer], mine = 0;
 #pragma unroll
-        for (int i = 0; i < kPer; i++) { wd[i] = bitmap[threadIdx.x * kPer + i]; mine += __popc(wd[i]); }
+        for (int i = 0; i < kPer; i++) {
+            const int wi = threadIdx.x * kPer + i;
+            wd[i] = wi < kClsChunkCap ? bitmap[wi] : 0u;
+            mine += __popc(wd[i]);
+        }
         uint32_t inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
@@ -588,7 +594,7 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
     }
     __syncthreads();
     { /* exclusive scan of the chunk totals, in place */
-        constexpr int kPer = kClsChunkCap / kClsThreads;
+        constexpr int kPer = (kClsChunkCap + kClsThreads - 1) / kClsThreads;
         const uint32_t nchunks = (nz + 31u) >> 5;
         uint32_t a[kPer], t[kPer], sa = 0, st = 0;
 #pragma unroll
@@ -657,12 +663,19 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
- * K3  emit: one thread interpolates the <=12 edge vertices (and normals) of one active cube into shared memory,
- *     then the block writes the chunk's contiguous output range with one float4 per thread per store.
+ * K3  emit: a block of kEmitThreads threads takes kEmitCubes consecutive active cubes.
+ *       1  one thread per cube reads its record, derives the crossing-edge set from the raw cube code
+ *          (marching.cpp:563-566) and appends one work entry per crossing edge to a shared-memory list (block scan);
+ *       2  one thread per crossing EDGE (dense lanes, no divergence over which edges cross): the two corner values,
+ *          central-difference gradients at both corners, Marching::interp for the position, gradient blend for
+ *          the normal -> shared memory, slot [cube][edge];
+ *       3  the block writes the chunk's contiguous output range, one float4 position (+ one float4 normal) per
+ *          thread per step: fully coalesced 16-byte stores in the reference's emission order.
  * ------------------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ float interp_ref(float xs, float xe, float vs, float ve, float iso) {
-    /* Marching::interp, marching.cpp:437-446 */
-    float v = ((iso - vs) / (ve - vs)) * (xe - xs);
+__device__ __forceinline__ float interp_ref(float xs, float xe, float t) {
+    /* Marching::interp, marching.cpp:437-446, with t = (c - v_s) / (v_e - v_s) computed once: the reference calls it
+     * three times per edge with the same field values, so the quotient has the same bits every time */
+    const float v = t * (xe - xs);
     if (isinf(v) || isnan(v)) return (float)((double)xs + 0.5 * (double)(xe - xs));
     return xs + v;
 }
@@ -670,75 +683,102 @@ __device__ __forceinline__ float interp_ref(float xs, float xe, float vs, float 
 constexpr int kEdgeStride = 37; /* 12 edges x 3 floats, +1 to spread banks */
 
 template <bool NORMALS>
-__global__ void __launch_bounds__(kEmitThreads)
+__global__ void __launch_bounds__(kEmitThreads, 4)
 emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict__ F,
             const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ trioff,
             const Counters* __restrict__ ctr, unsigned long long cap_active, unsigned long long cap_tris,
             float4* __restrict__ pos, float4* __restrict__ nrm) {
-    __shared__ float epos[kEmitThreads * kEdgeStride];
-    __shared__ float enrm[NORMALS ? kEmitThreads * kEdgeStride : 1];
-    __shared__ uint32_t off_s[kEmitThreads + 1];
-    __shared__ uint64_t triw_s[kEmitThreads];
+    __shared__ float epos[kEmitCubes * kEdgeStride];
+    __shared__ float enrm[NORMALS ? kEmitCubes * kEdgeStride : 1];
+    __shared__ uint32_t off_s[kEmitCubes + 1];
+    __shared__ uint64_t triw_s[kEmitCubes];
+    __shared__ uint32_t ijk_s[kEmitCubes];   /* i | j << 12 (k kept apart: 3 x 12 bits do not fit with the code) */
+    __shared__ uint16_t kc_s[kEmitCubes * 2]; /* k, raw cube code */
+    __shared__ uint16_t work_s[kEmitCubes * 12]; /* local cube << 4 | edge, one per crossing edge */
+    __shared__ uint32_t warp_s[kEmitThreads / 32];
 
     unsigned long long A = ctr->active, T = ctr->triangles;
     if (A > cap_active) A = cap_active; /* the host re-runs with larger buffers when counts exceed capacity */
-    const unsigned long long nchunks = (A + kEmitThreads - 1) / kEmitThreads;
+    const unsigned long long nchunks = (A + kEmitCubes - 1) / kEmitCubes;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
 
     for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         __syncthreads();
-        const unsigned long long c0 = chunk * kEmitThreads;
-        const int n = (int)((A - c0) < (unsigned long long)kEmitThreads ? (A - c0) : kEmitThreads);
-        const int t = threadIdx.x;
+        const unsigned long long c0 = chunk * kEmitCubes;
+        const int n = (int)((A - c0) < (unsigned long long)kEmitCubes ? (A - c0) : kEmitCubes);
+
+        /* ---- 1: records -> per-cube state and the edge work list ---- */
+        uint32_t emask = 0;
         if (t < n) {
             const unsigned long long r = rec[c0 + t];
-            const int i = (int)(r & 0xFFF), j = (int)((r >> 12) & 0xFFF), k = (int)((r >> 24) & 0xFFF);
             const int code = (int)((r >> 36) & 0xFF), tidx = (int)((r >> 44) & 0xFF);
             off_s[t] = trioff[c0 + t];
             triw_s[t] = mcb_tri_word(tidx);
-            const int vx = i + 1, vy = j + 1, vz = k + 1;   /* indices into cs */
-            const int pz = k - g.kb + 1;                     /* local plane of corner dz=0 */
-            const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
-            const float* f0 = F + (size_t)pz * planep + (size_t)vy * rowp + vx;
-            float val[8], gx[8], gy[8], gz[8];
+            ijk_s[t] = (uint32_t)(r & 0xFFFFFF);
+            kc_s[2 * t] = (uint16_t)((r >> 24) & 0xFFF);
+            kc_s[2 * t + 1] = (uint16_t)code;
 #pragma unroll
-            for (int v = 0; v < 8; v++) {
-                const int o = mcb_corner_ofs(v);
-                const int dx = o & 1, dy = (o >> 1) & 1, dz = (o >> 2) & 1;
-                const float* p = f0 + dz * planep + dy * rowp + dx;
-                val[v] = __ldg(p);
-                if (NORMALS) { /* central differences at the grid vertex, DESIGN.md §normals */
-                    gx[v] = (__ldg(p + 1) - __ldg(p - 1)) / (cs[vx + dx + 1] - cs[vx + dx - 1]);
-                    gy[v] = (__ldg(p + rowp) - __ldg(p - rowp)) / (cs[vy + dy + 1] - cs[vy + dy - 1]);
-                    gz[v] = (__ldg(p + planep) - __ldg(p - planep)) / (cs[vz + dz + 1] - cs[vz + dz - 1]);
-                }
-            }
-            const float cx[2] = {cs[vx], cs[vx + 1]}, cy[2] = {cs[vy], cs[vy + 1]}, cz[2] = {cs[vz], cs[vz + 1]};
-            float* ep = epos + t * kEdgeStride;
-            float* en = enrm + (NORMALS ? t * kEdgeStride : 0);
-#pragma unroll
-            for (int e = 0; e < 12; e++) {
-                const int a = mcb_edge_a(e), b = mcb_edge_b(e);
-                if ((((code >> a) ^ (code >> b)) & 1) == 0) continue; /* marching.cpp:563-566 */
-                const int oa = mcb_corner_ofs(a), ob = mcb_corner_ofs(b);
-                const float f1 = val[a], f2 = val[b];
-                ep[3 * e + 0] = interp_ref(cx[oa & 1], cx[ob & 1], f1, f2, g.iso);
-                ep[3 * e + 1] = interp_ref(cy[(oa >> 1) & 1], cy[(ob >> 1) & 1], f1, f2, g.iso);
-                ep[3 * e + 2] = interp_ref(cz[(oa >> 2) & 1], cz[(ob >> 2) & 1], f1, f2, g.iso);
-                if (NORMALS) {
-                    float tt = (g.iso - f1) / (f2 - f1);
-                    if (isinf(tt) || isnan(tt)) tt = 0.5f;
-                    float nx = gx[a] + tt * (gx[b] - gx[a]);
-                    float ny = gy[a] + tt * (gy[b] - gy[a]);
-                    float nz = gz[a] + tt * (gz[b] - gz[a]);
-                    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
-                    en[3 * e + 0] = nx * inv; en[3 * e + 1] = ny * inv; en[3 * e + 2] = nz * inv;
-                }
-            }
+            for (int e = 0; e < 12; e++)
+                emask |= (uint32_t)(((code >> mcb_edge_a(e)) ^ (code >> mcb_edge_b(e))) & 1) << e;
         }
+        const uint32_t nv = __popc(emask);
+        uint32_t inc = nv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_s[warp] = inc;
         __syncthreads();
+        uint32_t wbase = inc - nv, total_v = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kEmitThreads / 32; w2++) { if (w2 < warp) wbase += warp_s[w2]; total_v += warp_s[w2]; }
+        while (emask) {
+            const int e = __ffs(emask) - 1;
+            emask &= emask - 1;
+            work_s[wbase++] = (uint16_t)((t << 4) | e);
+        }
         if (t == 0) /* end of the chunk's output range; a capacity-truncated run is repeated by the host anyway */
             off_s[n] = (c0 + n < A) ? trioff[c0 + n] : (A == ctr->active ? (uint32_t)T : off_s[n - 1]);
         __syncthreads();
+
+        /* ---- 2: one thread per crossing edge ---- */
+        for (uint32_t q = t; q < total_v; q += kEmitThreads) {
+            const uint32_t wk = work_s[q];
+            const int lc = (int)(wk >> 4), e = (int)(wk & 15u);
+            const uint32_t ij = ijk_s[lc];
+            const int i = (int)(ij & 0xFFF), j = (int)(ij >> 12), k = (int)kc_s[2 * lc];
+            const int a = mcb_edge_a(e), b = mcb_edge_b(e);
+            const int oa = mcb_corner_ofs(a), ob = mcb_corner_ofs(b);
+            /* vertex indices into cs (apron: +1) and local plane of the two end points */
+            const int xa = i + 1 + (oa & 1), ya = j + 1 + ((oa >> 1) & 1), za = k + 1 + ((oa >> 2) & 1);
+            const int xb = i + 1 + (ob & 1), yb = j + 1 + ((ob >> 1) & 1), zb = k + 1 + ((ob >> 2) & 1);
+            const float* pa = F + (size_t)(za - g.kb) * planep + (size_t)ya * rowp + xa;
+            const float* pb = F + (size_t)(zb - g.kb) * planep + (size_t)yb * rowp + xb;
+            const float f1 = __ldg(pa), f2 = __ldg(pb);
+            const float tq = (g.iso - f1) / (f2 - f1);
+            float* ep = epos + lc * kEdgeStride + 3 * e;
+            ep[0] = interp_ref(cs[xa], cs[xb], tq);
+            ep[1] = interp_ref(cs[ya], cs[yb], tq);
+            ep[2] = interp_ref(cs[za], cs[zb], tq);
+            if (NORMALS) { /* central differences at the two grid vertices, blended along the edge (normals) */
+                const float gxa = (__ldg(pa + 1) - __ldg(pa - 1)) / (cs[xa + 1] - cs[xa - 1]);
+                const float gya = (__ldg(pa + rowp) - __ldg(pa - rowp)) / (cs[ya + 1] - cs[ya - 1]);
+                const float gza = (__ldg(pa + planep) - __ldg(pa - planep)) / (cs[za + 1] - cs[za - 1]);
+                const float gxb = (__ldg(pb + 1) - __ldg(pb - 1)) / (cs[xb + 1] - cs[xb - 1]);
+                const float gyb = (__ldg(pb + rowp) - __ldg(pb - rowp)) / (cs[yb + 1] - cs[yb - 1]);
+                const float gzb = (__ldg(pb + planep) - __ldg(pb - planep)) / (cs[zb + 1] - cs[zb - 1]);
+                float tt = tq;
+                if (isinf(tt) || isnan(tt)) tt = 0.5f;
+                const float nx = gxa + tt * (gxb - gxa);
+                const float ny = gya + tt * (gyb - gya);
+                const float nz = gza + tt * (gzb - gza);
+                const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+                float* en = enrm + lc * kEdgeStride + 3 * e;
+                en[0] = nx * inv; en[1] = ny * inv; en[2] = nz * inv;
+            }
+        }
+        __syncthreads();
+
+        /* ---- 3: coalesced float4 emission ---- */
         const unsigned long long v_begin = 3ull * off_s[0], v_end = 3ull * off_s[n];
         for (unsigned long long ov = v_begin + t; ov < v_end; ov += kEmitThreads) {
             const uint32_t tri = (uint32_t)(ov / 3);
@@ -752,10 +792,10 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
             const int e = (int)((triw_s[lo] >> (4 * (3 * lt + corner))) & 0xF);
             if (tri < cap_tris) {
                 const float* ep = epos + lo * kEdgeStride + 3 * e;
-                pos[ov] = make_float4(ep[0], ep[1], ep[2], 1.0f);
+                __stcs(pos + ov, make_float4(ep[0], ep[1], ep[2], 1.0f));
                 if (NORMALS) {
                     const float* en = enrm + lo * kEdgeStride + 3 * e;
-                    nrm[ov] = make_float4(en[0], en[1], en[2], 0.0f);
+                    __stcs(nrm + ov, make_float4(en[0], en[1], en[2], 0.0f));
                 }
             }
         }
