@@ -258,14 +258,24 @@ def run_ours(args):
         per = {k: v / args.steps for k, v in stage.items()}
         kern = {
             # algorithmic bytes per launch, SURVEY.md §8(d) / DESIGN.md §roofline
-            "eval_field": {"ms": per["ms_eval"], "bytes": 4.0 * V + V / 8.0},
-            "classify_compact": {"ms": per["ms_classify"], "bytes": 4.0 * V / 32.0 + 12.0 * A_r},
-            "emit": {"ms": per["ms_emit"], "bytes": 12.0 * A_r + 32.0 * A_r + 96.0 * T_r},
+            "eval_field": {"ms": per["ms_eval"], "bytes": 4.0 * V + V / 8.0,
+                           "what": "4 B field + 1 bit sign per grid vertex written"},
+            "classify+compact": {"ms": per["ms_classify"], "bytes": V / 8.0 + 12.0 * A_r,
+                                 "what": "1 bit per vertex read + 12 B per active cube written (our layout; SURVEY's 4V+C accounting is in classify_scan_emit_vs_survey_bytes)"},
+            "emit": {"ms": per["ms_emit"], "bytes": 12.0 * A_r + 32.0 * A_r + 96.0 * T_r,
+                     "what": "12 B record + 8 corner values per active cube read, 96 B per triangle written"},
         }
         for k, d in kern.items():
             d["GBps"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else None
             d["frac_of_hbm_peak"] = d["GBps"] / hbm if d["GBps"] else None
         dom = max(kern, key=lambda k: kern[k]["ms"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("%s@%d" % (args.workload, n), {}).get(dom)
+            except Exception:
+                traffic = None
         survey_bytes = 6.0 * C_r + 40.0 * A_r + 96.0 * T_r  # SURVEY.md §8(d) classify+scan+emit accounting
         pipe_ms = per["ms_classify"] + per["ms_emit"]
         out = {
@@ -277,7 +287,7 @@ def run_ours(args):
                 "l2": "inputs larger than L2 (field %.2f GB per GPU)" % (4.0 * (M + 3) ** 2 * (Ml + 3) / 1e9),
                 "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": hbm, "unit": "GB/s",
-                         "frac": kern[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                         "frac": kern[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                          "kernels": kern,
                          "classify_scan_emit_vs_survey_bytes": {"bytes": survey_bytes, "ms": pipe_ms,
                                                                 "GBps": survey_bytes / (pipe_ms * 1e-3) / 1e9,
