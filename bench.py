@@ -218,36 +218,58 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = cubes / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: through the reference-facing call with HOST buffers: equation text in, mesh out -------------------
-    cap = int(c.triangles) + 1024
-    pos_h = torch.empty((cap, 3, 4), dtype=torch.float32).pin_memory()
-    nrm_h = torch.empty((cap, 3, 4), dtype=torch.float32).pin_memory()
+    # ---- e2e: through the reference-facing call with HOST buffers: equation text in, Poly_Data out ----------------
+    # Marching::recalculate() leaves a welded, indexed mesh in Poly_Data (vertex_list + tri_list, marching.h:26-30);
+    # that is what comes back here (MCB_MESH_INDEXED, + gradient normals per vertex).  The float4 soup variant is
+    # timed as well and reported next to it.
+    def make_e2e(mode):
+        ctx.set_mesh_mode(mode)
+        cc0 = ctx.polygonise()
+        capT = int(cc0.triangles) + 1024
+        if mode == mcb.MESH_INDEXED:
+            capV = int(cc0.vertices) + 1024
+            bufs = [torch.empty((capV, 3), dtype=torch.float32).pin_memory(), torch.empty((capT, 3), dtype=torch.int32).pin_memory(),
+                    torch.empty((capV, 3), dtype=torch.float32).pin_memory()]
+        else:
+            bufs = [torch.empty((capT, 3, 4), dtype=torch.float32).pin_memory(), torch.empty((capT, 3, 4), dtype=torch.float32).pin_memory()]
 
-    def e2e_step():
-        assert ctx.set_equation(eq) == 0          # tokenise + lower + upload bytecode (H2D) + fold constants
-        ctx.set_grid_step(step)                   # host coordinate loop + upload (H2D)
-        ctx.set_slab(k0, k1)
-        cc = step_fn()
-        ctx.get_mesh_into(pos_h.data_ptr(), nrm_h.data_ptr(), cap)  # D2H of positions + normals
-        return cc
+        def one():
+            assert ctx.set_equation(eq) == 0          # tokenise + lower + upload bytecode (H2D) + fold constants
+            ctx.set_grid_step(step)                   # host coordinate loop + upload (H2D)
+            ctx.set_slab(k0, k1)
+            cc = step_fn()
+            if mode == mcb.MESH_INDEXED:
+                ctx.get_indexed_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), capV, capT)  # D2H
+            else:
+                ctx.get_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), capT)  # D2H of positions + normals
+            return cc
+        return one
 
-    for _ in range(2):
-        e2e_step()
-    sync_all()
-    e2e_steps = max(1, min(args.steps, 10))
-    w0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        cc = e2e_step()
-    e1.record(stream)
-    sync_all()
-    wall_ms = (time.perf_counter() - w0) * 1e3
-    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), wall_ms) / e2e_steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = cubes / (float(e2e_ms.item()) * 1e-3) / 1e9
+    def time_e2e(mode):
+        one = make_e2e(mode)
+        for _ in range(2):
+            one()
+        sync_all()
+        nst = max(1, min(args.steps, 10))
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(nst):
+            cc = one()
+        e1.record(stream)
+        sync_all()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        t_ms = torch.tensor([max(e0.elapsed_time(e1), wall_ms) / nst], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return float(t_ms.item()), cc, nst
+
+    soup_ms, cc_s, e2e_steps = time_e2e(mcb.MESH_SOUP)
+    idx_ms, cc, e2e_steps = time_e2e(mcb.MESH_INDEXED)
+    ctx.set_mesh_mode(mcb.MESH_SOUP)
+    e2e_value = cubes / (idx_ms * 1e-3) / 1e9
     h2d = 4 * (mcb.lib.mcb_grid_axis(step, None, 0) + 3 + 64) + 2052 * 2 + 512
-    d2h = int(cc.triangles) * 96 + 48
+    d2h = int(cc.vertices) * 24 + int(cc.triangles) * 12 + 48
+    d2h_soup = int(cc_s.triangles) * 96 + 48
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -293,7 +315,10 @@ def run_ours(args):
                                                                 "GBps": survey_bytes / (pipe_ms * 1e-3) / 1e9,
                                                                 "frac": survey_bytes / (pipe_ms * 1e-3) / 1e9 / hbm}},
             "e2e": {"value": e2e_value, "unit": "Gvoxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(e2e_ms.item()), "steps": e2e_steps},
+                    "ms_per_step": idx_ms, "steps": e2e_steps,
+                    "what": "equation text in -> Poly_Data on the host (welded vertex_list + tri_list + per-vertex normals), MCB_MESH_INDEXED",
+                    "soup": {"value": cubes / (soup_ms * 1e-3) / 1e9, "ms_per_step": soup_ms, "d2h_bytes_per_step": d2h_soup,
+                             "what": "same, float4 triangle soup + float4 normals out (MCB_MESH_SOUP)"}},
             "gpu_launches": int(launches_all), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

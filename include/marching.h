@@ -6,10 +6,11 @@
  * GPU: field + sign planes -> classify/scan/compact -> emit; the triangle soup comes back in the reference's emission
  * order and fills Poly_Data.
  *
- * Poly_Data::vertex_list / tri_list: by default the soup is welded on the host exactly like add_point
- * (marching.cpp:627-643; std::set with the tolerance comparator of marching.h:38-54, first-inserted coordinates win),
- * because that is what the GL drawer and normal.h expect.  This weld is a host-side consumer of the GPU output, not
- * a CPU implementation of the path; set_weld(false) skips it and hands out the soup with a trivial index list.
+ * Poly_Data::vertex_list / tri_list: by default the GPU produces them directly in the reference's layout — vertices
+ * welded and numbered the way add_step_to_poly_data / add_point do it (marching.cpp:599-654; tolerance comparator of
+ * marching.h:38-54, first-inserted coordinates win) — because that is what the GL drawer and normal.h expect; see
+ * the weld kernels in csrc/mcb_kernels.cuh and DESIGN.md for the one documented deviation.  set_weld(false) hands
+ * out the unwelded float4 soup with a trivial index list instead.
  *
  * Not carried over (GUI teaching aids): seed mode, step-by-step mode and the unused
  * repeating-surface mode.  Their setters exist and keep their return values, but recalculate() always polygonises
@@ -96,12 +97,26 @@ public:
         mcb_set_normals(ctx_, normals_ ? 1 : 0);
         for (int i = 0; i < 3; i++)
             mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
+        /* welded: the GPU builds Poly_Data's own layout (vertex_list + tri_list, numbered and welded like
+         * add_step_to_poly_data, marching.cpp:599-654); unwelded: the float4 triangle soup */
+        mcb_set_mesh_mode(ctx_, weld_ ? MCB_MESH_INDEXED : MCB_MESH_SOUP);
         if (mcb_polygonise(ctx_, &counts_) != MCB_OK) return false;
         const size_t T = (size_t)counts_.triangles;
-        soup_.resize(T * 12);
-        if (normals_) normals_soup_.resize(T * 12); else normals_soup_.clear();
-        if (T && mcb_get_mesh(ctx_, soup_.data(), normals_ ? normals_soup_.data() : nullptr, T) != MCB_OK) return false;
-        fill_poly_data();
+        if (weld_) {
+            const size_t nv = (size_t)counts_.vertices;
+            poly_data.vertex_list.resize(nv * 3);
+            poly_data.tri_list.resize(T * 3);
+            if (normals_) vertex_normals_.resize(nv * 3); else vertex_normals_.clear();
+            soup_.clear(); normals_soup_.clear();
+            if (T && mcb_get_indexed_mesh(ctx_, poly_data.vertex_list.data(), poly_data.tri_list.data(),
+                                          normals_ ? vertex_normals_.data() : nullptr, nv, T) != MCB_OK) return false;
+        } else {
+            soup_.resize(T * 12);
+            if (normals_) normals_soup_.resize(T * 12); else normals_soup_.clear();
+            vertex_normals_.clear();
+            if (T && mcb_get_mesh(ctx_, soup_.data(), normals_ ? normals_soup_.data() : nullptr, T) != MCB_OK) return false;
+            fill_poly_data_from_soup();
+        }
         poly_data.step_data.step_i = -1;
         return true;
     }
@@ -206,9 +221,11 @@ public:
     void set_normals(bool b) { normals_ = b; }
     bool set_slab(int k_begin, int k_end) { slab_[0] = k_begin; slab_[1] = k_end; have_slab_ = true; return true; }
     const mcb_counts& last_counts() const { return counts_; }
-    /* triangle soup of the last recalculate(): 3 float4 per triangle, (x,y,z,1) and (nx,ny,nz,0) */
+    /* set_weld(false): triangle soup of the last recalculate(), 3 float4 per triangle, (x,y,z,1) and (nx,ny,nz,0) */
     const std::vector<float>& get_soup() const { return soup_; }
     const std::vector<float>& get_normals() const { return normals_soup_; }
+    /* set_weld(true), set_normals(true): gradient normal (x,y,z) of every vertex of Poly_Data::vertex_list */
+    const std::vector<float>& get_vertex_normals() const { return vertex_normals_; }
 
 private:
     bool ensure_ctx() {
@@ -220,53 +237,15 @@ private:
         if (have_slab_ && mcb_set_slab(ctx_, slab_[0], slab_[1]) != MCB_OK) return false;
         return true;
     }
-    void fill_poly_data() {
+    void fill_poly_data_from_soup() { /* set_weld(false): every triangle corner is its own vertex */
         const size_t nv = soup_.size() / 4;
-        if (!weld_) {
-            poly_data.vertex_list.resize(nv * 3);
-            poly_data.tri_list.resize(nv);
-            for (size_t v = 0; v < nv; v++) {
-                for (int a = 0; a < 3; a++) poly_data.vertex_list[3 * v + a] = soup_[4 * v + a];
-                poly_data.tri_list[v] = (unsigned)v;
-            }
-            return;
-        }
-        /* add_step_to_poly_data / add_point (marching.cpp:599-643).  The reference adds a cube's vertices in
-         * ascending-edge order before its triangles; a vertex that first appears later in the triangle list would
-         * get a different index, so the per-cube edge order is recovered from the soup: the triangles of one cube
-         * are consecutive and its distinct corners are inserted in edge order via the records' triangle rows. */
-        std::set<xyz> vertex_set;
-        std::vector<uint64_t> rec((size_t)counts_.active);
-        std::vector<uint32_t> off((size_t)counts_.active);
-        if (!rec.empty() && mcb_get_active(ctx_, rec.data(), off.data(), rec.size()) != MCB_OK) return;
-        for (size_t c = 0; c < rec.size(); c++) {
-            const uint32_t t0 = off[c], t1 = (c + 1 < rec.size()) ? off[c + 1] : (uint32_t)counts_.triangles;
-            /* distinct edge -> first soup slot holding it, visited in ascending edge order */
-            int slot_of_edge[12];
-            for (int e = 0; e < 12; e++) slot_of_edge[e] = -1;
-            const uint64_t row = tri_row((int)((rec[c] >> 44) & 0xFF));
-            for (uint32_t t = t0; t < t1; t++)
-                for (int v = 0; v < 3; v++) {
-                    const int e = (int)((row >> (4 * (3 * (t - t0) + v))) & 0xF);
-                    if (slot_of_edge[e] < 0) slot_of_edge[e] = (int)(3 * t + v);
-                }
-            int vid[12];
-            for (int e = 0; e < 12; e++) {
-                vid[e] = -1;
-                if (slot_of_edge[e] < 0) continue;
-                const float* p = &soup_[4 * (size_t)slot_of_edge[e]];
-                if (std::isnan(p[0])) continue;
-                const int new_i = (int)(poly_data.vertex_list.size() / 3);
-                const int found = vertex_set.insert(xyz(p[0], p[1], p[2], new_i)).first->idx;
-                if (found == new_i) { poly_data.vertex_list.push_back(p[0]); poly_data.vertex_list.push_back(p[1]); poly_data.vertex_list.push_back(p[2]); }
-                vid[e] = found;
-            }
-            for (uint32_t t = t0; t < t1; t++)
-                for (int v = 0; v < 3; v++)
-                    poly_data.tri_list.push_back((unsigned)vid[(row >> (4 * (3 * (t - t0) + v))) & 0xF]);
+        poly_data.vertex_list.resize(nv * 3);
+        poly_data.tri_list.resize(nv);
+        for (size_t v = 0; v < nv; v++) {
+            for (int a = 0; a < 3; a++) poly_data.vertex_list[3 * v + a] = soup_[4 * v + a];
+            poly_data.tri_list[v] = (unsigned)v;
         }
     }
-    static uint64_t tri_row(int idx); /* packed triangle table row (defined in libmcb200.so: mcb_tri_row) */
     static const char* mesh_file() { const char* f = std::getenv("MCB_MESH_FILE"); return f ? f : "mesh.ply"; }
 
     mcb_ctx* ctx_;
@@ -282,9 +261,8 @@ private:
     bool have_slab_ = false;
     Poly_Data poly_data;
     std::deque<xyz> seed_queue_;
-    std::vector<float> soup_, normals_soup_;
+    std::vector<float> soup_, normals_soup_, vertex_normals_;
     mcb_counts counts_;
 };
 
-extern "C" uint64_t mcb_tri_row(int table_idx);
-inline uint64_t Marching::tri_row(int idx) { return mcb_tri_row(idx); }
+

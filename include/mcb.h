@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MCB_ABI_VERSION 1
+#define MCB_ABI_VERSION 2
 
 typedef enum {
     MCB_OK = 0,
@@ -57,7 +57,14 @@ typedef struct {
     float ms_total;
     uint32_t launches;    /* kernels launched by this call */
     uint32_t reruns;      /* passes repeated because an output buffer had to grow (0 in steady state) */
+    float ms_weld;        /* device time of the indexed-mesh stage (0 unless MCB_MESH_INDEXED) */
+    uint32_t mesh_mode;   /* MCB_MESH_* bits this result was produced with */
+    uint64_t vertices;    /* welded vertices of the indexed mesh (0 unless MCB_MESH_INDEXED) */
 } mcb_counts;
+
+/* What mcb_polygonise leaves in device memory (mcb_set_mesh_mode; default MCB_MESH_SOUP). */
+#define MCB_MESH_SOUP 1     /* triangle soup: 3 float4 positions (+ 3 float4 normals) per triangle, emission order */
+#define MCB_MESH_INDEXED 2  /* Poly_Data layout: welded vertex_list (xyz floats) + tri_list (3 indices per triangle) */
 
 /* ---- library / host-only helpers (no GPU needed) ---------------------------------------------------------- */
 
@@ -130,6 +137,16 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out);
 int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles);
 /* Device pointers to the same buffers (valid until the next mcb_polygonise / mcb_destroy). */
 int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4);
+
+/* MCB_MESH_SOUP, MCB_MESH_INDEXED or both (3).  The indexed mesh is what Marching::recalculate() leaves in
+ * Poly_Data (marching.h:26-30): vertices welded and numbered as add_step_to_poly_data / add_point do it
+ * (marching.cpp:599-654, tolerance comparator marching.h:38-54), triangles in emission order. */
+int mcb_set_mesh_mode(mcb_ctx* ctx, int mode);
+/* Copy the indexed mesh to host memory: vertex_list = 3*vertices floats (x,y,z), tri_list = 3*triangles indices,
+ * normals = 3*vertices floats (gradient normals per welded vertex; needs mcb_set_normals(1)).  Any may be NULL. */
+int mcb_get_indexed_mesh(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices,
+                         uint64_t cap_triangles);
+int mcb_get_indexed_mesh_device(mcb_ctx* ctx, const float** vertex_list, const uint32_t** tri_list, const float** normals);
 
 /* Parity hooks.  Dense per-cube arrays of the slab in loop order, host memory, `cubes` bytes each (NULL = skip):
  * cube_code = raw 8-bit sign code (marching.cpp:497-505); table_idx = tri_table row actually used (code or

@@ -22,6 +22,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcb200.so")
 
+MESH_SOUP, MESH_INDEXED = 1, 2
 MCB_OK, MCB_E_PARSE, MCB_E_ARG, MCB_E_CUDA, MCB_E_NOMEM, MCB_E_STATE, MCB_E_CAPACITY, MCB_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
 
 
@@ -35,7 +36,8 @@ class Counts(C.Structure):
     _fields_ = [("cubes", C.c_uint64), ("active", C.c_uint64), ("triangles", C.c_uint64), ("ambiguous", C.c_uint64),
                 ("redirected", C.c_uint64), ("M", C.c_int32), ("k_begin", C.c_int32), ("k_end", C.c_int32),
                 ("ms_tables", C.c_float), ("ms_eval", C.c_float), ("ms_classify", C.c_float), ("ms_emit", C.c_float),
-                ("ms_total", C.c_float), ("launches", C.c_uint32), ("reruns", C.c_uint32)]
+                ("ms_total", C.c_float), ("launches", C.c_uint32), ("reruns", C.c_uint32), ("ms_weld", C.c_float),
+                ("mesh_mode", C.c_uint32), ("vertices", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -72,6 +74,9 @@ def _load():
         "mcb_polygonise": ([vp, C.POINTER(Counts)], i),
         "mcb_get_mesh": ([vp, vp, vp, u64], i),
         "mcb_get_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp)], i),
+        "mcb_set_mesh_mode": ([vp, i], i),
+        "mcb_get_indexed_mesh": ([vp, vp, vp, vp, u64, u64], i),
+        "mcb_get_indexed_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i),
         "mcb_get_cases": ([vp, vp, vp], i),
         "mcb_get_field": ([vp, vp], i),
         "mcb_get_active": ([vp, vp, vp, u64], i),
@@ -192,6 +197,25 @@ class Context:
     def set_normals(self, mode):
         self._ck(lib.mcb_set_normals(self.h, int(mode)))
 
+    def set_mesh_mode(self, mode):
+        """MESH_SOUP (float4 triangle soup), MESH_INDEXED (welded Poly_Data layout) or both (3)."""
+        self._ck(lib.mcb_set_mesh_mode(self.h, int(mode)))
+
+    def get_indexed_mesh(self, normals=False):
+        """(vertex_list[V,3] f32, tri_list[T,3] u32[, normals[V,3] f32]) as Marching::recalculate leaves them in Poly_Data."""
+        V, T = int(self.counts.vertices), int(self.counts.triangles)
+        vl = np.empty((V, 3), np.float32)
+        tl = np.empty((T, 3), np.uint32)
+        vn = np.empty((V, 3), np.float32) if normals else None
+        self._ck(lib.mcb_get_indexed_mesh(self.h, vl.ctypes.data_as(C.c_void_p), tl.ctypes.data_as(C.c_void_p),
+                                          vn.ctypes.data_as(C.c_void_p) if normals else None, V, T))
+        return (vl, tl, vn) if normals else (vl, tl)
+
+    def get_indexed_mesh_into(self, v_ptr, t_ptr, n_ptr, cap_v, cap_t):
+        """Raw-pointer variant (pinned host buffers owned by the caller)."""
+        self._ck(lib.mcb_get_indexed_mesh(self.h, C.c_void_p(v_ptr) if v_ptr else None, C.c_void_p(t_ptr) if t_ptr else None,
+                                          C.c_void_p(n_ptr) if n_ptr else None, cap_v, cap_t))
+
     def polygonise(self):
         c = Counts()
         self._ck(lib.mcb_polygonise(self.h, C.byref(c)))
@@ -253,21 +277,20 @@ class Evaluator:
 
 
 class PolyData:
-    """Poly_Data (marching.h:26-30) as the GPU path produces it: the triangle soup in the reference's emission order.
-    vertex_list / tri_list give the same mesh in indexed form WITHOUT welding (every triangle corner is its own
-    vertex); the reference's tolerance weld (marching.cpp:627-643) is a host-side consumer step, see DESIGN.md."""
+    """Poly_Data (marching.h:26-30): vertex_list (xyz per welded vertex) and tri_list (3 indices per triangle), as
+    Marching::recalculate() leaves them — welded and numbered on the GPU like add_step_to_poly_data (marching.cpp:599-654).
+    vertex_normals = gradient normal per welded vertex (None when normals are off)."""
 
-    def __init__(self, pos, nrm):
-        self.positions = pos
-        self.normals = nrm
+    def __init__(self, vertex_list, tri_list, vertex_normals=None):
+        self._v, self._t, self.vertex_normals = vertex_list, tri_list, vertex_normals
 
     @property
     def vertex_list(self):
-        return np.ascontiguousarray(self.positions[:, :, :3]).reshape(-1)
+        return self._v.reshape(-1)
 
     @property
     def tri_list(self):
-        return np.arange(self.positions.shape[0] * 3, dtype=np.uint32)
+        return self._t.reshape(-1)
 
 
 class Marching:
@@ -277,7 +300,9 @@ class Marching:
         self._ctx = Context(device)
         self._step = 0.25
         self._eval = None
-        self._poly = PolyData(np.zeros((0, 3, 4), np.float32), None)
+        self._poly = PolyData(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+        self._normals = True
+        self._ctx.set_mesh_mode(MESH_INDEXED)
         self.counts = None
 
     def set_evaluator(self, e):
@@ -332,6 +357,7 @@ class Marching:
         self._ctx.set_slab(k0, k1)
 
     def set_normals(self, mode):
+        self._normals = bool(mode)
         self._ctx.set_normals(mode)
 
     def recalculate(self, fetch=True):
@@ -341,8 +367,7 @@ class Marching:
             return False
         self.counts = self._ctx.polygonise()
         if fetch:
-            pos, nrm = self._ctx.get_mesh(normals=True)
-            self._poly = PolyData(pos, nrm)
+            self._poly = PolyData(*self._ctx.get_indexed_mesh(normals=self._normals))
         return True
 
     def get_poly_data(self):

@@ -81,7 +81,20 @@ struct mcb_ctx {
     float4* d_nrm = nullptr;
     unsigned long long cap_tris = 0;
     bool nrm_allocated = false;
-    cudaEvent_t ev[6] = {};
+    int mesh_mode = MCB_MESH_SOUP;
+    /* welded, indexed mesh (Poly_Data layout) */
+    float* d_vlist = nullptr;      /* [3 * cap_verts] */
+    float* d_vnrm = nullptr;       /* [3 * cap_verts] */
+    uint32_t* d_tlist = nullptr;   /* [3 * cap_itris] */
+    unsigned long long cap_verts = 0, cap_itris = 0;
+    bool vnrm_allocated = false;
+    uint32_t* d_rowstart = nullptr;
+    size_t cap_rows = 0;
+    uint16_t* d_wmask = nullptr;
+    uint32_t* d_vbase = nullptr;
+    uint32_t* d_chunk_new = nullptr;
+    unsigned long long cap_weld = 0; /* cubes the three arrays above are sized for */
+    cudaEvent_t ev[7] = {};
     mcb_counts last{};
     bool have_result = false;
 };
@@ -270,6 +283,44 @@ int ensure_soup(mcb_ctx* ctx, unsigned long long need, bool normals) {
     return MCB_OK;
 }
 
+int ensure_weld_scratch(mcb_ctx* ctx, const Grid& g) {
+    const size_t rows = (size_t)(g.ke - g.kb) * g.M;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_rowstart, &ctx->cap_rows, rows)) != MCB_OK) return rc;
+    if (ctx->cap_weld >= ctx->cap_active && ctx->d_wmask) return MCB_OK;
+    if (ctx->d_wmask) cudaFree(ctx->d_wmask);
+    if (ctx->d_vbase) cudaFree(ctx->d_vbase);
+    if (ctx->d_chunk_new) cudaFree(ctx->d_chunk_new);
+    ctx->d_wmask = nullptr; ctx->d_vbase = nullptr; ctx->d_chunk_new = nullptr; ctx->cap_weld = 0;
+    MCB_CK(cudaMalloc((void**)&ctx->d_wmask, ctx->cap_active * 2));
+    MCB_CK(cudaMalloc((void**)&ctx->d_vbase, ctx->cap_active * 4));
+    MCB_CK(cudaMalloc((void**)&ctx->d_chunk_new, (ctx->cap_active / kWeldCubes + 2) * 4));
+    ctx->cap_weld = ctx->cap_active;
+    return MCB_OK;
+}
+
+int ensure_indexed(mcb_ctx* ctx, unsigned long long verts, unsigned long long tris, bool normals) {
+    if (ctx->cap_verts < verts || !ctx->d_vlist || (normals && !ctx->vnrm_allocated)) {
+        verts = std::max(verts, ctx->cap_verts);
+        if (ctx->d_vlist) cudaFree(ctx->d_vlist);
+        if (ctx->d_vnrm) cudaFree(ctx->d_vnrm);
+        ctx->d_vlist = nullptr; ctx->d_vnrm = nullptr; ctx->cap_verts = 0; ctx->vnrm_allocated = false;
+        MCB_CK(cudaMalloc((void**)&ctx->d_vlist, verts * 3 * sizeof(float)));
+        if (normals) {
+            MCB_CK(cudaMalloc((void**)&ctx->d_vnrm, verts * 3 * sizeof(float)));
+            ctx->vnrm_allocated = true;
+        }
+        ctx->cap_verts = verts;
+    }
+    if (ctx->cap_itris < tris || !ctx->d_tlist) {
+        if (ctx->d_tlist) cudaFree(ctx->d_tlist);
+        ctx->d_tlist = nullptr; ctx->cap_itris = 0;
+        MCB_CK(cudaMalloc((void**)&ctx->d_tlist, tris * 3 * sizeof(uint32_t)));
+        ctx->cap_itris = tris;
+    }
+    return MCB_OK;
+}
+
 int enter(mcb_ctx* ctx) {
     if (!ctx) return MCB_E_ARG;
     cudaError_t e = cudaSetDevice(ctx->device);
@@ -411,6 +462,8 @@ void mcb_destroy(mcb_ctx* ctx) {
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     cudaFree(ctx->d_status); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_tile_nz);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_trioff); cudaFree(ctx->d_pos); cudaFree(ctx->d_nrm);
+    cudaFree(ctx->d_vlist); cudaFree(ctx->d_vnrm); cudaFree(ctx->d_tlist); cudaFree(ctx->d_rowstart); cudaFree(ctx->d_wmask);
+    cudaFree(ctx->d_vbase); cudaFree(ctx->d_chunk_new);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -535,8 +588,13 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
         guess = std::min<unsigned long long>(guess, (unsigned long long)(g.ke - g.kb) * g.M * g.M);
         if ((rc = ensure_records(ctx, std::max<unsigned long long>(guess, 1024))) != MCB_OK) return rc;
     }
-    if (ctx->cap_tris == 0 || (ctx->normals && !ctx->nrm_allocated)) {
+    const bool want_soup = (ctx->mesh_mode & MCB_MESH_SOUP) != 0, want_indexed = (ctx->mesh_mode & MCB_MESH_INDEXED) != 0;
+    if (want_soup && (ctx->cap_tris == 0 || (ctx->normals && !ctx->nrm_allocated))) {
         if ((rc = ensure_soup(ctx, std::max<unsigned long long>(2 * ctx->cap_active, 1024), ctx->normals != 0)) != MCB_OK) return rc;
+    }
+    if (want_indexed) {
+        if ((rc = ensure_indexed(ctx, std::max<unsigned long long>(ctx->cap_verts, std::max<unsigned long long>(ctx->cap_active + ctx->cap_active / 4, 1024)),
+                                 std::max<unsigned long long>(ctx->cap_itris, std::max<unsigned long long>(2 * ctx->cap_active, 1024)), ctx->normals != 0)) != MCB_OK) return rc;
     }
 
     MCB_CK(cudaEventRecord(ctx->ev[0], s));
@@ -600,34 +658,60 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             launches += 2;
             MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
-        /* K3: interpolation + coalesced float4 emission */
+        /* K3: interpolation + coalesced float4 emission of the triangle soup */
         const unsigned eblocks = (unsigned)ctx->sm_count * 4;
-        if (ctx->normals)
-            emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
-        else
-            emit_kernel<false><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, nullptr);
-        launches++;
+        if (want_soup) {
+            if (ctx->normals)
+                emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
+            else
+                emit_kernel<false><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, nullptr);
+            launches++;
+        }
         MCB_CK(cudaEventRecord(ctx->ev[4], s));
+        /* K4: the reference's welded, indexed mesh (Poly_Data::vertex_list / tri_list) */
+        if (want_indexed) {
+            if ((rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
+            const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr};
+            const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_rowstart, ctx->d_wmask, ctx->d_vbase, ctx->d_chunk_new};
+            MCB_CK(cudaMemsetAsync(ctx->d_rowstart, 0xFF, (size_t)(g.ke - g.kb) * g.M * 4, s));
+            weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
+            weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
+            weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);
+            if (ctx->normals)
+                weld_emit_kernel<true><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
+                                                                           ctx->d_vlist, ctx->d_vnrm, ctx->d_tlist);
+            else
+                weld_emit_kernel<false><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
+                                                                            ctx->d_vlist, nullptr, ctx->d_tlist);
+            launches += 4;
+        }
+        MCB_CK(cudaEventRecord(ctx->ev[5], s));
         MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         MCB_CK(cudaStreamSynchronize(s));
         MCB_CK(cudaGetLastError());
         if (ctx->h_ctr->error == 2 || ctx->h_ctr->triangles >= (1ull << 31))
             return fail(ctx, MCB_E_CAPACITY, "2^31 or more triangles in one slab: split the grid into more z-slabs");
-        if (ctx->h_ctr->active > ctx->cap_active) {
-            if ((rc = ensure_records(ctx, ctx->h_ctr->active + ctx->h_ctr->active / 8 + 1024)) != MCB_OK) return rc;
+        const unsigned long long needA = ctx->h_ctr->active, needT = ctx->h_ctr->triangles, needV = ctx->h_ctr->vertices;
+        bool again = false;
+        need_classify = false;
+        if (needA > ctx->cap_active) {
+            if ((rc = ensure_records(ctx, needA + needA / 8 + 1024)) != MCB_OK) return rc;
             need_classify = true;
-            reruns++;
-            if (ctx->h_ctr->triangles > ctx->cap_tris)
-                if ((rc = ensure_soup(ctx, ctx->h_ctr->triangles + ctx->h_ctr->triangles / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
-            continue;
+            again = true;
         }
-        if (ctx->h_ctr->triangles > ctx->cap_tris) {
-            if ((rc = ensure_soup(ctx, ctx->h_ctr->triangles + ctx->h_ctr->triangles / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
-            need_classify = false;
-            reruns++;
-            continue;
+        if (want_soup && needT > ctx->cap_tris) {
+            if ((rc = ensure_soup(ctx, needT + needT / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
+            again = true;
         }
-        break;
+        if (want_indexed && (needT > ctx->cap_itris || needV > ctx->cap_verts || need_classify)) {
+            /* with truncated records the vertex count is a lower bound: size generously, the re-run settles it */
+            const unsigned long long v = std::max(needV + needV / 8 + 1024, need_classify ? needA + needA / 4 : 0ull);
+            if ((rc = ensure_indexed(ctx, v, needT + needT / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
+            again = true;
+        }
+        if (!again) break;
+        reruns++;
+        if (reruns > 6) return fail(ctx, MCB_E_CAPACITY, "output buffers did not settle");
     }
 
     mcb_counts& c = ctx->last;
@@ -642,7 +726,10 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     cudaEventElapsedTime(&c.ms_eval, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&c.ms_classify, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[4]);
+    cudaEventElapsedTime(&c.ms_weld, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[5]);
+    c.vertices = want_indexed ? ctx->h_ctr->vertices : 0;
+    c.mesh_mode = (uint32_t)ctx->mesh_mode;
     c.launches = launches;
     c.reruns = reruns;
     ctx->have_result = true;
@@ -654,6 +741,7 @@ int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles)
     int rc = enter(ctx);
     if (rc != MCB_OK) return rc;
     if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    if (!(ctx->last.mesh_mode & MCB_MESH_SOUP)) return fail(ctx, MCB_E_STATE, "the triangle soup was not requested (mcb_set_mesh_mode)");
     const uint64_t T = ctx->last.triangles;
     if (T > cap_triangles) return fail(ctx, MCB_E_CAPACITY, "mesh buffer too small");
     if (nrm4 && !ctx->normals) return fail(ctx, MCB_E_STATE, "normals are switched off");
@@ -661,6 +749,40 @@ int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles)
     if (pos4) MCB_CK(cudaMemcpyAsync(pos4, ctx->d_pos, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     if (nrm4) MCB_CK(cudaMemcpyAsync(nrm4, ctx->d_nrm, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_set_mesh_mode(mcb_ctx* ctx, int mode) {
+    if (!ctx || mode < 1 || mode > 3) return MCB_E_ARG;
+    ctx->mesh_mode = mode;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_get_indexed_mesh(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices,
+                         uint64_t cap_triangles) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    if (!(ctx->last.mesh_mode & MCB_MESH_INDEXED)) return fail(ctx, MCB_E_STATE, "the indexed mesh was not requested (mcb_set_mesh_mode)");
+    const uint64_t Vn = ctx->last.vertices, T = ctx->last.triangles;
+    if ((vertex_list || normals) && Vn > cap_vertices) return fail(ctx, MCB_E_CAPACITY, "vertex buffer too small");
+    if (tri_list && T > cap_triangles) return fail(ctx, MCB_E_CAPACITY, "triangle buffer too small");
+    if (normals && !ctx->normals) return fail(ctx, MCB_E_STATE, "normals are switched off");
+    if (vertex_list && Vn) MCB_CK(cudaMemcpyAsync(vertex_list, ctx->d_vlist, Vn * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (normals && Vn) MCB_CK(cudaMemcpyAsync(normals, ctx->d_vnrm, Vn * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (tri_list && T) MCB_CK(cudaMemcpyAsync(tri_list, ctx->d_tlist, T * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_get_indexed_mesh_device(mcb_ctx* ctx, const float** vertex_list, const uint32_t** tri_list, const float** normals) {
+    if (!ctx) return MCB_E_ARG;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    if (!(ctx->last.mesh_mode & MCB_MESH_INDEXED)) return fail(ctx, MCB_E_STATE, "the indexed mesh was not requested (mcb_set_mesh_mode)");
+    if (vertex_list) *vertex_list = ctx->d_vlist;
+    if (tri_list) *tri_list = ctx->d_tlist;
+    if (normals) *normals = ctx->normals ? ctx->d_vnrm : nullptr;
     return MCB_OK;
 }
 

@@ -44,6 +44,7 @@ struct Counters {
     unsigned long long triangles;
     unsigned long long ambiguous;
     unsigned long long redirected;
+    unsigned long long vertices; /* welded vertices (weld_scan_kernel) */
     unsigned int tile_ticket;
     unsigned int error; /* 2 = 2^31 or more triangles in the slab */
 };
@@ -798,6 +799,373 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
                     __stcs(nrm + ov, make_float4(en[0], en[1], en[2], 0.0f));
                 }
             }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K4  weld: the reference's indexed mesh — Poly_Data::vertex_list / tri_list as add_step_to_poly_data / add_point
+ *     build them (marching.cpp:599-654) — produced on the GPU without a std::set.
+ *
+ *     What the reference's tolerance set amounts to (marching.h:38-54: per-axis |d| < 1e-6 counts as equal; first
+ *     inserted coordinates win; vertices are numbered by first insertion):
+ *       - the up to four cubes sharing a grid edge compute the same crossing point to within an ulp, so they share
+ *         one vertex, numbered and positioned by the FIRST of those cubes in loop order — the edge's owner;
+ *       - two different grid edges can only yield points within 1e-6 of each other around a grid vertex they share,
+ *         i.e. when both crossing points lie within the tolerance of that vertex (the surface passes through a grid
+ *         corner: `x+y` on a dyadic grid does it everywhere).  All such points around one grid vertex form one
+ *         cluster whose representative is the member inserted first.
+ *     So (cube, edge) -> welded vertex is a pure function of the grid: owner of the edge; if the owner's point is
+ *     within the tolerance of an end point G, the earliest-inserted member among the six grid edges at G.
+ *     weld_count marks, per active cube, the edges for which the cube inserts a NEW vertex; an exclusive scan of
+ *     those counts in loop order is the reference's vertex numbering; weld_emit writes vertex_list (owner's
+ *     coordinates), tri_list and, optionally, gradient normals per welded vertex.
+ *     Deviation (documented in DESIGN.md): a point that is within the tolerance for one sharing cube and outside it
+ *     for another (an ulp-wide band), and chains that are not transitive, are resolved by the rule above rather
+ *     than by the red-black tree's descent order.
+ * ------------------------------------------------------------------------------------------------------------- */
+struct WeldView {
+    Grid g;
+    const float* __restrict__ cs;
+    const float* __restrict__ F;
+    const uint32_t* __restrict__ V; /* constraint validity planes or nullptr */
+};
+struct CubeEdge { /* an edge of a cube: who inserts a vertex, and as which of its edges */
+    int i, j, k, e;
+};
+struct GridEdge { /* axis 0..2 and the lower end point in cube-vertex coordinates (0..M per axis) */
+    int axis, vx, vy, vz;
+};
+
+__device__ __forceinline__ GridEdge grid_edge_of(int i, int j, int k, int e) {
+    const int oa = mcb_corner_ofs(mcb_edge_a(e)), ob = mcb_corner_ofs(mcb_edge_b(e));
+    const int lo = oa & ob, d = oa ^ ob; /* the end points differ in exactly one axis */
+    GridEdge E;
+    E.axis = d == 1 ? 0 : d == 2 ? 1 : 2;
+    E.vx = i + (lo & 1); E.vy = j + ((lo >> 1) & 1); E.vz = k + ((lo >> 2) & 1);
+    return E;
+}
+__device__ __forceinline__ bool weld_cube_ok(const WeldView& W, int i, int j, int k) {
+    const Grid& g = W.g;
+    if (i < 0 || j < 0 || i >= g.M || j >= g.M || k < g.kb || k >= g.ke) return false;
+    if (W.V == nullptr) return true;
+    bool ok = true; /* all 8 corners must satisfy the constraints (marching.cpp:475-477) */
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+        const int x = i + 1 + (v & 1), y = j + 1 + ((v >> 1) & 1), z = k - g.kb + 1 + (v >> 2);
+        ok = ok && ((W.V[((size_t)z * g.NV + y) * g.WP + (x >> 5)] >> (x & 31)) & 1u);
+    }
+    return ok;
+}
+/* first cube in loop order (z slowest, then y, then x) that contains the grid edge and is visited by the loop */
+__device__ __forceinline__ bool weld_owner(const WeldView& W, const GridEdge& E, CubeEdge& o) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int hi = 1 - (q >> 1), lo = 1 - (q & 1); /* offsets in the slower / faster of the two other axes */
+        if (E.axis == 0) { o.i = E.vx; o.j = E.vy - lo; o.k = E.vz - hi; o.e = 2 * lo + 4 * hi; }
+        else if (E.axis == 1) { o.i = E.vx - lo; o.j = E.vy; o.k = E.vz - hi; o.e = (lo ? 1 : 3) + 4 * hi; }
+        else { o.i = E.vx - lo; o.j = E.vy - hi; o.k = E.vz; o.e = 8 + (hi ? (lo ? 2 : 3) : (lo ? 1 : 0)); }
+        if (weld_cube_ok(W, o.i, o.j, o.k)) return true;
+    }
+    return false;
+}
+/* crossing point of edge e of cube (i,j,k) along the edge's axis, interpolated in that cube's edge direction
+ * (marching.cpp:557-583); crossing = the end points lie on different sides of iso */
+__device__ __forceinline__ float weld_edge_point(const WeldView& W, const CubeEdge& c, int axis, bool& crossing) {
+    const Grid& g = W.g;
+    const int oa = mcb_corner_ofs(mcb_edge_a(c.e)), ob = mcb_corner_ofs(mcb_edge_b(c.e));
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+    const float* f0 = W.F + (size_t)(c.k - g.kb + 1) * planep + (size_t)(c.j + 1) * rowp + (c.i + 1);
+    const float f1 = __ldg(f0 + (oa >> 2) * planep + ((oa >> 1) & 1) * rowp + (oa & 1));
+    const float f2 = __ldg(f0 + (ob >> 2) * planep + ((ob >> 1) & 1) * rowp + (ob & 1));
+    crossing = (f1 > g.iso) != (f2 > g.iso);
+    const int base = (axis == 0 ? c.i : axis == 1 ? c.j : c.k) + 1;
+    const float ca = W.cs[base + ((oa >> axis) & 1)], cb = W.cs[base + ((ob >> axis) & 1)];
+    return interp_ref(ca, cb, (g.iso - f1) / (f2 - f1));
+}
+__device__ __forceinline__ bool weld_close(float a, float b) { return (double)fabsf(a - b) < 0.000001; } /* marching.h:41 */
+__device__ __forceinline__ unsigned long long weld_key(const Grid& g, const CubeEdge& c) {
+    return ((((unsigned long long)c.k * g.M + c.j) * g.M + c.i) << 4) | (unsigned)c.e;
+}
+
+/* (cube, crossing edge) -> the (cube, edge) whose insertion created the welded vertex the reference would use */
+__device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j, int k, int e) {
+    const Grid& g = W.g;
+    const GridEdge E = grid_edge_of(i, j, k, e);
+    CubeEdge own{i, j, k, e};
+    weld_owner(W, E, own); /* (i,j,k) itself is a candidate, so this always succeeds */
+    bool cr;
+    const float p = weld_edge_point(W, own, E.axis, cr);
+    int G[3] = {E.vx, E.vy, E.vz};
+    const int base = G[E.axis] + 1;
+    const bool near_lo = weld_close(p, W.cs[base]), near_hi = weld_close(p, W.cs[base + 1]);
+    if (!near_lo && !near_hi) return own;
+    if (!near_lo) G[E.axis] += 1; /* the shared grid vertex */
+    CubeEdge best = own;
+    unsigned long long best_key = weld_key(g, own);
+    for (int ax = 0; ax < 3; ax++)
+        for (int side = 0; side < 2; side++) { /* side 0: G is the edge's upper end point, 1: its lower end point */
+            GridEdge E2{ax, G[0], G[1], G[2]};
+            if (ax == 0) E2.vx -= 1 - side; else if (ax == 1) E2.vy -= 1 - side; else E2.vz -= 1 - side;
+            if (ax == E.axis && E2.vx == E.vx && E2.vy == E.vy && E2.vz == E.vz) continue;
+            CubeEdge o2;
+            if (!weld_owner(W, E2, o2)) continue;
+            bool cr2;
+            const float p2 = weld_edge_point(W, o2, ax, cr2);
+            if (!cr2 || !weld_close(p2, W.cs[G[ax] + 1])) continue;
+            const unsigned long long key2 = weld_key(g, o2);
+            if (key2 < best_key) { best_key = key2; best = o2; }
+        }
+    return best;
+}
+
+constexpr int kWeldCubes = 128;   /* active cubes per chunk */
+constexpr int kWeldThreads = 256;
+
+struct WeldBuffers {
+    const unsigned long long* __restrict__ rec; /* [A] loop-ordered active cubes (compact_kernel) */
+    const uint32_t* __restrict__ trioff;        /* [A] */
+    uint32_t* rowstart;                         /* [(ke-kb)*M] index of the first active cube of each cube row */
+    uint16_t* wmask;                            /* [A] edges for which the cube inserts a new vertex */
+    uint32_t* vbase;                            /* [A] index of the cube's first new vertex */
+    uint32_t* chunk_new;                        /* [chunks] new vertices per chunk, then their exclusive scan */
+};
+
+/* chunk prologue shared by weld_count and weld_emit: records -> shared memory, crossing-edge work list */
+struct WeldChunk {
+    uint32_t ijk[kWeldCubes];       /* i | j << 12 */
+    uint16_t k[kWeldCubes];
+    uint16_t mask[kWeldCubes];      /* new-vertex edges */
+    uint16_t work[kWeldCubes * 12]; /* local cube << 4 | edge */
+    uint32_t warp[kWeldThreads / 32];
+    uint32_t total;
+};
+__device__ __forceinline__ uint32_t weld_load_chunk(WeldChunk& sh, const unsigned long long* __restrict__ rec,
+                                                    unsigned long long c0, int n, unsigned long long* rec_out) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    uint32_t emask = 0;
+    unsigned long long r = 0;
+    if (t < n) {
+        r = rec[c0 + t];
+        const int code = (int)((r >> 36) & 0xFF);
+        sh.ijk[t] = (uint32_t)(r & 0xFFFFFF);
+        sh.k[t] = (uint16_t)((r >> 24) & 0xFFF);
+#pragma unroll
+        for (int e = 0; e < 12; e++)
+            emask |= (uint32_t)(((code >> mcb_edge_a(e)) ^ (code >> mcb_edge_b(e))) & 1) << e;
+    }
+    if (rec_out) *rec_out = r;
+    const uint32_t nv = __popc(emask);
+    uint32_t inc = nv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    if (lane == 31) sh.warp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = inc - nv, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kWeldThreads / 32; w2++) { if (w2 < warp) wbase += sh.warp[w2]; total += sh.warp[w2]; }
+    while (emask) {
+        const int e = __ffs(emask) - 1;
+        emask &= emask - 1;
+        sh.work[wbase++] = (uint16_t)((t << 4) | e);
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(kWeldThreads)
+weld_count_kernel(const WeldView W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active) {
+    __shared__ WeldChunk sh;
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    const unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    const int t = threadIdx.x;
+    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();
+        const unsigned long long c0 = chunk * kWeldCubes;
+        const int n = (int)((A - c0) < (unsigned long long)kWeldCubes ? (A - c0) : kWeldCubes);
+        if (t < kWeldCubes) sh.mask[t] = 0;
+        unsigned long long r;
+        const uint32_t total_v = weld_load_chunk(sh, B.rec, c0, n, &r);
+        if (t < n) { /* first active cube of every cube row, for the cube -> record look-up in weld_emit */
+            const uint32_t row = (uint32_t)(((r >> 24) & 0xFFF) - W.g.kb) * (uint32_t)W.g.M + (uint32_t)((r >> 12) & 0xFFF);
+            atomicMin(B.rowstart + row, (uint32_t)(c0 + t));
+        }
+        __syncthreads();
+        for (uint32_t q = t; q < total_v; q += kWeldThreads) {
+            const uint32_t wk = sh.work[q];
+            const int lc = (int)(wk >> 4), e = (int)(wk & 15u);
+            const int i = (int)(sh.ijk[lc] & 0xFFF), j = (int)(sh.ijk[lc] >> 12), k = (int)sh.k[lc];
+            const CubeEdge v = weld_resolve(W, i, j, k, e);
+            if (v.i == i && v.j == j && v.k == k && v.e == e)
+                atomicOr(reinterpret_cast<unsigned int*>(sh.mask) + (lc >> 1), (1u << e) << (16 * (lc & 1)));
+        }
+        __syncthreads();
+        uint32_t mine = 0;
+        if (t < n) { B.wmask[c0 + t] = sh.mask[t]; mine = __popc((uint32_t)sh.mask[t]); }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+        if ((t & 31) == 0) sh.warp[t >> 5] = mine;
+        __syncthreads();
+        if (t == 0) {
+            uint32_t s = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < kWeldThreads / 32; w2++) s += sh.warp[w2];
+            B.chunk_new[chunk] = s;
+        }
+    }
+}
+
+/* exclusive scan of the per-chunk new-vertex counts (one block: a few thousand to a few hundred thousand chunks) */
+__global__ void __launch_bounds__(1024)
+weld_scan_kernel(uint32_t* __restrict__ chunk_new, Counters* __restrict__ ctr, unsigned long long cap_active) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry_s;
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    const unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (unsigned long long b0 = 0; b0 < nchunks; b0 += 1024) {
+        const unsigned long long c = b0 + t;
+        const unsigned long long v = c < nchunks ? chunk_new[c] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        unsigned long long base = carry_s;
+        for (int w2 = 0; w2 < warp; w2++) base += warp_tot[w2];
+        if (c < nchunks) chunk_new[c] = (uint32_t)(base + inc - v);
+        __syncthreads();
+        if (t == 1023) carry_s = base + inc;
+        __syncthreads();
+    }
+    if (t == 0) ctr->vertices = carry_s;
+}
+
+__device__ __forceinline__ uint32_t weld_find_cube(const WeldBuffers& B, const Grid& g, unsigned long long A, int i, int j, int k) {
+    uint32_t lo = B.rowstart[(uint32_t)(k - g.kb) * (uint32_t)g.M + (uint32_t)j];
+    uint32_t hi = (uint32_t)((unsigned long long)lo + g.M < A ? lo + g.M : A) - 1u;
+    const uint32_t key = (uint32_t)i | ((uint32_t)j << 12); /* (k, j) are fixed inside a row: compare j:i */
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const unsigned long long r = B.rec[mid];
+        /* records are sorted by k:j:i; entries past the row have a larger k:j */
+        const bool less = ((r >> 24) & 0xFFF) == (unsigned)k ? (uint32_t)(r & 0xFFFFFF) < key : ((r >> 24) & 0xFFF) < (unsigned)k;
+        if (less) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* per-cube first vertex index: chunk base + exclusive scan of the new-vertex counts inside the chunk */
+__global__ void __launch_bounds__(kWeldCubes)
+weld_base_kernel(const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active) {
+    __shared__ uint32_t warp_s[kWeldCubes / 32];
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    const unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();
+        const unsigned long long c = chunk * kWeldCubes + t;
+        const uint32_t nv = c < A ? (uint32_t)__popc((uint32_t)B.wmask[c]) : 0u;
+        uint32_t inc = nv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_s[warp] = inc;
+        __syncthreads();
+        uint32_t base = B.chunk_new[chunk] + inc - nv;
+        for (int w2 = 0; w2 < warp; w2++) base += warp_s[w2];
+        if (c < A) B.vbase[c] = base;
+    }
+}
+
+template <bool NORMALS>
+__global__ void __launch_bounds__(kWeldThreads)
+weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active,
+                 unsigned long long cap_verts, unsigned long long cap_tris, float* __restrict__ vertex_list,
+                 float* __restrict__ vertex_nrm, uint32_t* __restrict__ tri_list) {
+    __shared__ WeldChunk sh;
+    __shared__ uint32_t eidx[kWeldCubes * 12]; /* welded vertex index of [cube][edge] */
+    __shared__ uint32_t off_s[kWeldCubes + 1];
+    __shared__ uint64_t triw_s[kWeldCubes];
+    __shared__ uint32_t vb_s[kWeldCubes];
+    const Grid& g = W.g;
+    unsigned long long A = ctr->active, T = ctr->triangles;
+    if (A > cap_active) A = cap_active;
+    const unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    const int t = threadIdx.x;
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();
+        const unsigned long long c0 = chunk * kWeldCubes;
+        const int n = (int)((A - c0) < (unsigned long long)kWeldCubes ? (A - c0) : kWeldCubes);
+        unsigned long long r;
+        const uint32_t total_v = weld_load_chunk(sh, B.rec, c0, n, &r);
+        if (t < n) {
+            off_s[t] = B.trioff[c0 + t];
+            triw_s[t] = mcb_tri_word((int)((r >> 44) & 0xFF));
+            sh.mask[t] = B.wmask[c0 + t];
+            vb_s[t] = B.vbase[c0 + t];
+        }
+        if (t == 0) off_s[n] = (c0 + n < A) ? B.trioff[c0 + n] : (A == ctr->active ? (uint32_t)T : off_s[n - 1]);
+        __syncthreads();
+        for (uint32_t q = t; q < total_v; q += kWeldThreads) {
+            const uint32_t wk = sh.work[q];
+            const int lc = (int)(wk >> 4), e = (int)(wk & 15u);
+            const int i = (int)(sh.ijk[lc] & 0xFFF), j = (int)(sh.ijk[lc] >> 12), k = (int)sh.k[lc];
+            const CubeEdge v = weld_resolve(W, i, j, k, e);
+            uint32_t idx;
+            if (v.i == i && v.j == j && v.k == k) { /* inserted by this cube (possibly as another of its edges) */
+                idx = vb_s[lc] + (uint32_t)__popc((uint32_t)sh.mask[lc] & ((1u << v.e) - 1u));
+                if (v.e == e && idx < cap_verts) { /* this thread's edge IS the new vertex: write it (add_point) */
+                    const int oa = mcb_corner_ofs(mcb_edge_a(e)), ob = mcb_corner_ofs(mcb_edge_b(e));
+                    const int xa = i + 1 + (oa & 1), ya = j + 1 + ((oa >> 1) & 1), za = k + 1 + ((oa >> 2) & 1);
+                    const int xb = i + 1 + (ob & 1), yb = j + 1 + ((ob >> 1) & 1), zb = k + 1 + ((ob >> 2) & 1);
+                    const float* pa = W.F + (size_t)(za - g.kb) * planep + (size_t)ya * rowp + xa;
+                    const float* pb = W.F + (size_t)(zb - g.kb) * planep + (size_t)yb * rowp + xb;
+                    const float f1 = __ldg(pa), f2 = __ldg(pb);
+                    const float tq = (g.iso - f1) / (f2 - f1);
+                    float* out = vertex_list + 3ull * idx;
+                    out[0] = interp_ref(W.cs[xa], W.cs[xb], tq);
+                    out[1] = interp_ref(W.cs[ya], W.cs[yb], tq);
+                    out[2] = interp_ref(W.cs[za], W.cs[zb], tq);
+                    if (NORMALS) { /* same definition as emit_kernel */
+                        const float* cs = W.cs;
+                        const float gxa = (__ldg(pa + 1) - __ldg(pa - 1)) / (cs[xa + 1] - cs[xa - 1]);
+                        const float gya = (__ldg(pa + rowp) - __ldg(pa - rowp)) / (cs[ya + 1] - cs[ya - 1]);
+                        const float gza = (__ldg(pa + planep) - __ldg(pa - planep)) / (cs[za + 1] - cs[za - 1]);
+                        const float gxb = (__ldg(pb + 1) - __ldg(pb - 1)) / (cs[xb + 1] - cs[xb - 1]);
+                        const float gyb = (__ldg(pb + rowp) - __ldg(pb - rowp)) / (cs[yb + 1] - cs[yb - 1]);
+                        const float gzb = (__ldg(pb + planep) - __ldg(pb - planep)) / (cs[zb + 1] - cs[zb - 1]);
+                        float tt = tq;
+                        if (isinf(tt) || isnan(tt)) tt = 0.5f;
+                        const float nx = gxa + tt * (gxb - gxa), ny = gya + tt * (gyb - gya), nz = gza + tt * (gzb - gza);
+                        const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+                        float* on = vertex_nrm + 3ull * idx;
+                        on[0] = nx * inv; on[1] = ny * inv; on[2] = nz * inv;
+                    }
+                }
+            } else {
+                const uint32_t oc = weld_find_cube(B, g, A, v.i, v.j, v.k);
+                idx = B.vbase[oc] + (uint32_t)__popc((uint32_t)B.wmask[oc] & ((1u << v.e) - 1u));
+            }
+            eidx[lc * 12 + e] = idx;
+        }
+        __syncthreads();
+        const unsigned long long v_begin = 3ull * off_s[0], v_end = 3ull * off_s[n];
+        for (unsigned long long ov = v_begin + t; ov < v_end; ov += kWeldThreads) {
+            const uint32_t tri = (uint32_t)(ov / 3);
+            const int corner = (int)(ov - 3ull * tri);
+            int lo = 0, hi = n - 1; /* last local cube whose first triangle is <= tri */
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (off_s[mid] <= tri) lo = mid; else hi = mid - 1;
+            }
+            const int lt = (int)(tri - off_s[lo]);
+            const int e = (int)((triw_s[lo] >> (4 * (3 * lt + corner))) & 0xF);
+            if (tri < cap_tris) tri_list[ov] = eidx[lo * 12 + e];
         }
     }
 }

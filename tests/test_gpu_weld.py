@@ -1,0 +1,104 @@
+"""-m gpu: the indexed, welded mesh (MCB_MESH_INDEXED) against Poly_Data of the UNMODIFIED reference.
+
+Golden vectors: vertex_list / tri_list exactly as Marching::recalculate() left them (add_step_to_poly_data / add_point,
+marching.cpp:599-654, std::set with the tolerance comparator of marching.h:38-54).  Bar: byte for byte — same vertex
+numbering (first insertion), same coordinates (first inserted wins), same index list — including the degenerate
+`x+y` cases where the surface runs through grid corners and many crossing points coincide.
+"""
+import numpy as np
+import pytest
+
+from .helpers import configure, load_meta, rel_close, same_bits
+from .test_gpu_parity import CASE_NAMES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(mcb):
+    c = mcb.Context(0)
+    c.set_mesh_mode(mcb.MESH_SOUP | mcb.MESH_INDEXED)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_indexed_mesh_equals_reference_poly_data(mcb, ctx, golden, name):
+    case = load_meta(golden)[name]
+    configure(ctx, case)
+    ctx.set_normals(1)
+    cnt = ctx.polygonise()
+    vref = golden[name + "/vertex_list"].reshape(-1, 3)
+    tref = golden[name + "/tri_list"].reshape(-1, 3)
+    assert cnt.triangles == len(tref)
+    assert cnt.vertices == len(vref), "welded vertex count"
+    vl, tl, vn = ctx.get_indexed_mesh(normals=True)
+    assert same_bits(vl, vref), "vertex_list"
+    assert np.array_equal(tl, tref.astype(np.uint32)), "tri_list"
+    # the soup of the same run expands to the same triangles (first-inserted twin within the weld tolerance)
+    pos, nrm = ctx.get_mesh(normals=True)
+    if len(tl):
+        assert rel_close(vl[tl.astype(np.int64)], pos[:, :, :3], 1e-5)
+        # welded normals are the soup normals of the inserting cube's edge: same definition, so compare loosely
+        ok = ~np.isnan(nrm[:, :, :3]).any(axis=2) & ~np.isnan(vn[tl.astype(np.int64)]).any(axis=2)
+        d = np.abs(vn[tl.astype(np.int64)][ok] - nrm[:, :, :3][ok]).max() if ok.any() else 0.0
+        # (quirk_div has poles: the blend of two huge gradients is ill-conditioned there, so it is exempt)
+        assert d < 1e-3 or name.startswith("quirk"), d
+
+
+def test_indexed_only_mode_and_slabs(mcb, golden):
+    """MESH_INDEXED alone (no soup buffers); per-slab welds expand to the same triangles as the full grid."""
+    c = mcb.Context(0)
+    c.set_mesh_mode(mcb.MESH_INDEXED)
+    case = load_meta(golden)["gyr78_17"]
+    configure(c, case)
+    cnt = c.polygonise()
+    vl, tl = c.get_indexed_mesh()
+    assert same_bits(vl, golden["gyr78_17/vertex_list"].reshape(-1, 3))
+    assert np.array_equal(tl, golden["gyr78_17/tri_list"].reshape(-1, 3).astype(np.uint32))
+    with pytest.raises(mcb.McbError):
+        c.get_mesh()
+    full = vl[tl.astype(np.int64)]
+    parts = []
+    M = cnt.M
+    for r in range(3):
+        k0, k1 = mcb.slab_range(M, r, 3)
+        c.set_slab(k0, k1)
+        c.polygonise()
+        v, t = c.get_indexed_mesh()
+        parts.append(v[t.astype(np.int64)])
+    got = np.concatenate(parts)
+    assert got.shape == full.shape and rel_close(got, full, 1e-5)
+    c.close()
+
+
+def test_indexed_mesh_large_sphere_properties(mcb):
+    """257^3 sphere: counts of the unmodified reference (151 398 welded vertices, 302 792
+    triangles), closed-surface Euler characteristic, every vertex referenced."""
+    c = mcb.Context(0)
+    c.set_mesh_mode(mcb.MESH_INDEXED)
+    assert c.set_equation("x^2+y^2+z^2-0.49") == 0
+    assert c.set_grid_step(2.0 / 256) == 257
+    cnt = c.polygonise()
+    assert (cnt.vertices, cnt.triangles) == (151398, 302792)
+    vl, tl = c.get_indexed_mesh()
+    assert np.array_equal(np.unique(tl), np.arange(cnt.vertices, dtype=np.uint32))
+    e = np.sort(np.concatenate([tl[:, [0, 1]], tl[:, [1, 2]], tl[:, [2, 0]]]).astype(np.int64), axis=1)
+    n_edges = len(np.unique(e[:, 0] * (1 << 32) + e[:, 1]))
+    assert cnt.vertices - n_edges + cnt.triangles == 2
+    c.close()
+
+
+def test_python_mirror_reads_like_the_reference(mcb, golden):
+    """Evaluator + Marching used as main.cpp:11-20 / drawer.cpp:785-831 use them; Poly_Data equals the reference's."""
+    case = load_meta(golden)["eq8_gui"]
+    evaluator = mcb.Evaluator()
+    march_maker = mcb.Marching()
+    assert march_maker.set_evaluator(evaluator)
+    assert not evaluator.set_equation("(x(y)") and evaluator.set_equation(case["eq"])
+    assert not march_maker.set_grid_step_size(0.6) and march_maker.set_grid_step_size(case["step"])
+    march_maker.set_scaling_x(1.1); march_maker.set_scaling_y(1.1); march_maker.set_scaling_z(1.1)
+    assert march_maker.recalculate()
+    p = march_maker.get_poly_data()
+    assert same_bits(p.vertex_list, golden["eq8_gui/vertex_list"].reshape(-1))
+    assert np.array_equal(p.tri_list, golden["eq8_gui/tri_list"].reshape(-1))
