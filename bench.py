@@ -31,6 +31,11 @@ WORKLOADS = {
     "sphere": "x^2+y^2+z^2-0.49",
     "torus": "(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)",
     "eq8": "(x^2+y^2-(1/16))^2+(y^2+z^2-(1/16))^2+(z^2+x^2-(1/16))^2-8*(x^2+y^2+z^2-(1/4))^2",
+    # BASELINE.json configs[3]: a true gyroid is not expressible in the reference grammar (no sin/cos); this is the
+    # polynomial gyroid of SURVEY.md Appendix B (Chebyshev T7/T8 in Horner form), the high-triangle-density stress field
+    "gyr78": ("((x*(-7+x^2*(56+x^2*(-112+64*x^2))))*(1+y^2*(-32+y^2*(160+y^2*(-256+128*y^2)))))"
+              "+((y*(-7+y^2*(56+y^2*(-112+64*y^2))))*(1+z^2*(-32+z^2*(160+z^2*(-256+128*z^2)))))"
+              "+((z*(-7+z^2*(56+z^2*(-112+64*z^2))))*(1+x^2*(-32+x^2*(160+x^2*(-256+128*x^2)))))"),
 }
 
 

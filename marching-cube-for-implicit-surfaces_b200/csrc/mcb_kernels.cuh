@@ -815,14 +815,14 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
  *         i.e. when both crossing points lie within the tolerance of that vertex (the surface passes through a grid
  *         corner: `x+y` on a dyadic grid does it everywhere).  All such points around one grid vertex form one
  *         cluster whose representative is the member inserted first.
- *     So (cube, edge) -> welded vertex is a pure function of the grid: owner of the edge; if the owner's point is
- *     within the tolerance of an end point G, the earliest-inserted member among the six grid edges at G.
+ *         corner: `x+y` on a dyadic grid does it everywhere).  There the comparator is not even transitive, so the
+ *         outcome of an insert depends on the insertion history: weld_replay re-enacts the (at most 24) insertions
+ *         around that grid vertex with libstdc++'s unique-insert rule.
+ *     So (cube, edge) -> welded vertex is a pure, local function of the grid: the edge's owner, or the replay's
+ *     answer when the owner's point sits on a grid vertex.
  *     weld_count marks, per active cube, the edges for which the cube inserts a NEW vertex; an exclusive scan of
- *     those counts in loop order is the reference's vertex numbering; weld_emit writes vertex_list (owner's
- *     coordinates), tri_list and, optionally, gradient normals per welded vertex.
- *     Deviation (documented in DESIGN.md): a point that is within the tolerance for one sharing cube and outside it
- *     for another (an ulp-wide band), and chains that are not transitive, are resolved by the rule above rather
- *     than by the red-black tree's descent order.
+ *     those counts in loop order is the reference's vertex numbering; weld_emit writes vertex_list (the inserting
+ *     cube's own interpolation), tri_list and, optionally, gradient normals per welded vertex.
  * ------------------------------------------------------------------------------------------------------------- */
 struct WeldView {
     Grid g;
@@ -888,9 +888,100 @@ __device__ __forceinline__ unsigned long long weld_key(const Grid& g, const Cube
     return ((((unsigned long long)c.k * g.M + c.j) * g.M + c.i) << 4) | (unsigned)c.e;
 }
 
-/* (cube, crossing edge) -> the (cube, edge) whose insertion created the welded vertex the reference would use */
-__device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j, int k, int e) {
+/* the reference's comparator, marching.h:38-54 */
+__device__ __forceinline__ bool weld_less(const float a[3], const float b[3]) {
+    if (!weld_close(a[0], b[0])) return a[0] < b[0];
+    if (!weld_close(a[1], b[1])) return a[1] < b[1];
+    if (!weld_close(a[2], b[2])) return a[2] < b[2];
+    return false;
+}
+__device__ __forceinline__ CubeEdge weld_unkey(const Grid& g, unsigned long long key) {
+    CubeEdge c;
+    c.e = (int)(key & 15u);
+    unsigned long long q = key >> 4;
+    c.i = (int)(q % (unsigned)g.M); q /= (unsigned)g.M;
+    c.j = (int)(q % (unsigned)g.M);
+    c.k = (int)(q / (unsigned)g.M);
+    return c;
+}
+
+/* Around a grid vertex G the tolerance comparator is not an equivalence relation (two collinear crossing points on
+ * opposite sides of G can each be within 1e-6 of G yet 1e-6 apart, while a point on another axis is "equal" to
+ * both), so what std::set::insert returns depends on what was inserted before.  This replays exactly that: every
+ * insertion of a point near G — each cube sharing one of the six grid edges at G inserts its own interpolation of
+ * the crossing point, in loop order — against the elements inserted so far, with libstdc++'s unique-insert rule:
+ * the element found is the last one in order that is not greater than the new point; the new point is dropped when
+ * that element is not less than it either.  At most 24 insertions, a handful of elements; only taken when the
+ * owner's point lies within 1.5e-6 of an end point (the extra half tolerance covers the ulp-level differences
+ * between the sharing cubes' interpolations). */
+__device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], unsigned long long target) {
     const Grid& g = W.g;
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+    unsigned long long ekey[24];
+    float ept[24]; /* coordinate along the edge's own axis; the other two are G's */
+    int n = 0;
+    for (int ax = 0; ax < 3; ax++)
+        for (int side = 0; side < 2; side++) { /* side 0: G is the edge's upper end point, 1: its lower end point */
+            GridEdge E2{ax, G[0], G[1], G[2]};
+            if (ax == 0) E2.vx -= 1 - side; else if (ax == 1) E2.vy -= 1 - side; else E2.vz -= 1 - side;
+            if (E2.vx < 0 || E2.vy < 0 || E2.vz < g.kb) continue; /* the upper bounds fall out of weld_cube_ok */
+            const int lo_idx = (ax == 0 ? E2.vx : ax == 1 ? E2.vy : E2.vz) + 1;
+            if (lo_idx + 1 > g.M + 1) continue;
+            const float* fp = W.F + (size_t)(E2.vz - g.kb + 1) * planep + (size_t)(E2.vy + 1) * rowp + (E2.vx + 1);
+            const float fl = __ldg(fp), fu = __ldg(fp + (ax == 0 ? (size_t)1 : ax == 1 ? rowp : planep));
+            if ((fl > g.iso) == (fu > g.iso)) continue;
+            const float cl = W.cs[lo_idx], cu = W.cs[lo_idx + 1];
+            const float pf = interp_ref(cl, cu, (g.iso - fl) / (fu - fl)); /* cube edge running lower -> upper */
+            const float pb = interp_ref(cu, cl, (g.iso - fu) / (fl - fu)); /* cube edge running upper -> lower */
+            for (int q = 0; q < 4; q++) {
+                const int hi = 1 - (q >> 1), lo = 1 - (q & 1);
+                CubeEdge o;
+                if (ax == 0) { o.i = E2.vx; o.j = E2.vy - lo; o.k = E2.vz - hi; o.e = 2 * lo + 4 * hi; }
+                else if (ax == 1) { o.i = E2.vx - lo; o.j = E2.vy; o.k = E2.vz - hi; o.e = (lo ? 1 : 3) + 4 * hi; }
+                else { o.i = E2.vx - lo; o.j = E2.vy - hi; o.k = E2.vz; o.e = 8 + (hi ? (lo ? 2 : 3) : (lo ? 1 : 0)); }
+                if (!weld_cube_ok(W, o.i, o.j, o.k)) continue;
+                const unsigned long long key = weld_key(g, o);
+                if (key > target) continue; /* inserted after the point we are resolving */
+                const bool forward = ((mcb_corner_ofs(mcb_edge_a(o.e)) >> ax) & 1) == 0;
+                const float pt = forward ? pf : pb;
+                if (!((double)fabsf(pt - W.cs[G[ax] + 1]) < 0.000002)) continue; /* cannot interact with anything at G */
+                ekey[n] = key; ept[n] = pt; n++;
+            }
+        }
+    /* insertion order */
+    for (int a2 = 1; a2 < n; a2++) {
+        const unsigned long long kk = ekey[a2];
+        const float pp = ept[a2];
+        int b2 = a2 - 1;
+        while (b2 >= 0 && ekey[b2] > kk) { ekey[b2 + 1] = ekey[b2]; ept[b2 + 1] = ept[b2]; b2--; }
+        ekey[b2 + 1] = kk; ept[b2 + 1] = pp;
+    }
+    const float gc[3] = {W.cs[G[0] + 1], W.cs[G[1] + 1], W.cs[G[2] + 1]};
+    float sp[8][3];
+    unsigned long long stok[8];
+    int ns = 0;
+    unsigned long long result = target;
+    for (int ev = 0; ev < n; ev++) {
+        const CubeEdge ce = weld_unkey(g, ekey[ev]);
+        const int ax = ce.e >= 8 ? 2 : (ce.e & 1);
+        float kpt[3] = {gc[0], gc[1], gc[2]};
+        kpt[ax] = ept[ev];
+        int j = -1;
+        for (int q = 0; q < ns; q++)
+            if (!weld_less(kpt, sp[q]) && (j < 0 || weld_less(sp[j], sp[q]))) j = q;
+        unsigned long long tok;
+        if (j >= 0 && !weld_less(sp[j], kpt)) tok = stok[j];
+        else {
+            tok = ekey[ev];
+            if (ns < 8) { sp[ns][0] = kpt[0]; sp[ns][1] = kpt[1]; sp[ns][2] = kpt[2]; stok[ns] = tok; ns++; }
+        }
+        if (ekey[ev] == target) result = tok;
+    }
+    return weld_unkey(g, result);
+}
+
+/* (cube, crossing edge) -> the (cube, edge) whose insertion created the welded vertex the reference uses there */
+__device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j, int k, int e) {
     const GridEdge E = grid_edge_of(i, j, k, e);
     CubeEdge own{i, j, k, e};
     weld_owner(W, E, own); /* (i,j,k) itself is a candidate, so this always succeeds */
@@ -898,25 +989,11 @@ __device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j
     const float p = weld_edge_point(W, own, E.axis, cr);
     int G[3] = {E.vx, E.vy, E.vz};
     const int base = G[E.axis] + 1;
-    const bool near_lo = weld_close(p, W.cs[base]), near_hi = weld_close(p, W.cs[base + 1]);
-    if (!near_lo && !near_hi) return own;
-    if (!near_lo) G[E.axis] += 1; /* the shared grid vertex */
-    CubeEdge best = own;
-    unsigned long long best_key = weld_key(g, own);
-    for (int ax = 0; ax < 3; ax++)
-        for (int side = 0; side < 2; side++) { /* side 0: G is the edge's upper end point, 1: its lower end point */
-            GridEdge E2{ax, G[0], G[1], G[2]};
-            if (ax == 0) E2.vx -= 1 - side; else if (ax == 1) E2.vy -= 1 - side; else E2.vz -= 1 - side;
-            if (ax == E.axis && E2.vx == E.vx && E2.vy == E.vy && E2.vz == E.vz) continue;
-            CubeEdge o2;
-            if (!weld_owner(W, E2, o2)) continue;
-            bool cr2;
-            const float p2 = weld_edge_point(W, o2, ax, cr2);
-            if (!cr2 || !weld_close(p2, W.cs[G[ax] + 1])) continue;
-            const unsigned long long key2 = weld_key(g, o2);
-            if (key2 < best_key) { best_key = key2; best = o2; }
-        }
-    return best;
+    const bool near_lo = (double)fabsf(p - W.cs[base]) < 0.0000015, near_hi = (double)fabsf(p - W.cs[base + 1]) < 0.0000015;
+    if (!near_lo && !near_hi) return own; /* the up-to-four sharing cubes agree to within an ulp: first inserter wins */
+    if (!near_lo) G[E.axis] += 1;         /* the grid vertex the point sits on */
+    const CubeEdge me{i, j, k, e};
+    return weld_replay(W, G, weld_key(W.g, me));
 }
 
 constexpr int kWeldCubes = 128;   /* active cubes per chunk */

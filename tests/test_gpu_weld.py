@@ -102,3 +102,21 @@ def test_python_mirror_reads_like_the_reference(mcb, golden):
     p = march_maker.get_poly_data()
     assert same_bits(p.vertex_list, golden["eq8_gui/vertex_list"].reshape(-1))
     assert np.array_equal(p.tri_list, golden["eq8_gui/tri_list"].reshape(-1))
+
+
+@pytest.mark.parametrize("name", ["eq6", "gyr78"])
+def test_deviating_fields_weld_within_tolerance(mcb, name):
+    """The fields on which the reference keeps a few unwelded duplicates (see tests/test_cpp_dropin.py): the GPU mesh has
+    the same triangles, and every indexed corner lies within the weld tolerance (1e-6 per axis) of the soup corner."""
+    from oracle.refbind import EXAMPLE_EQUATIONS, GYR78
+    c = mcb.Context(0)
+    c.set_mesh_mode(mcb.MESH_SOUP | mcb.MESH_INDEXED)
+    assert c.set_equation(GYR78 if name == "gyr78" else EXAMPLE_EQUATIONS[6]) == 0
+    assert c.set_grid_step(2.0 / 256) == 257
+    cnt = c.polygonise()
+    vl, tl = c.get_indexed_mesh()
+    pos, _ = c.get_mesh(normals=False)
+    assert cnt.triangles == {"eq6": 186060, "gyr78": 2396052}[name]
+    d = np.abs(vl[tl.astype(np.int64)].astype(np.float64) - pos[:, :, :3].astype(np.float64)).max()
+    assert d < 1e-6, d
+    c.close()

@@ -3,13 +3,17 @@ import importlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 m = importlib.import_module("marching-cube-for-implicit-surfaces_b200")
-eq = sys.argv[1] if len(sys.argv) > 1 else "x^2+y^2+z^2-0.49"
+import bench
+eq = sys.argv[1] if len(sys.argv) > 1 else "sphere"
+eq = bench.WORKLOADS.get(eq, eq)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 ctx = m.Context(0)
 assert ctx.set_equation(eq) == 0
 ctx.set_grid_step(2.0 / n)
 ctx.set_normals(1)
+ctx.set_mesh_mode(mode)
 for it in range(reps):
     c = ctx.polygonise()
     print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in c.as_dict().items()}))
