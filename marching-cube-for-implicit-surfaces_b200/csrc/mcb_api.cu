@@ -441,7 +441,9 @@ int mcb_create(int device, mcb_ctx** out) {
     }
     if (cudaMalloc((void**)&ctx->d_cls, sizeof(ClsTables)) != cudaSuccess) return bail(MCB_E_NOMEM);
     if (cudaMemcpy(ctx->d_cls, &tb, sizeof tb, cudaMemcpyHostToDevice) != cudaSuccess) return bail(MCB_E_CUDA);
-    if (cudaFuncSetAttribute(eval_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(eval_field_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float)) != cudaSuccess ||
+        cudaFuncSetAttribute(eval_field_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float)) != cudaSuccess)
         return bail(MCB_E_CUDA);
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
@@ -621,7 +623,13 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             if (off >= (1u << 24)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
             launch.code[pc] = MCB_FINSN(MCB_FINSN_OP(wd), src, (uint32_t)off);
         }
-        eval_field_kernel<<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        bool has_pow = false;
+        for (int pc = 0; pc < launch.n; pc++) {
+            const uint32_t fop = MCB_FINSN_OP(launch.code[pc]);
+            has_pow |= fop == MCB_F_POW || fop == MCB_F_RPOW;
+        }
+        if (has_pow) eval_field_kernel<true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        else eval_field_kernel<false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
         launches++;
         if (any_constraint) {
             const long long words = (long long)g.NZ * g.NV * g.WP;

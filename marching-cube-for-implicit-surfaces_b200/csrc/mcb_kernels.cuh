@@ -106,8 +106,16 @@ __device__ __forceinline__ float fused_op(float acc, float v) {
         case MCB_F_MUL: return acc * v;
         case MCB_F_DIV: return acc / v;
         case MCB_F_RDIV: return v / acc;
-        case MCB_F_POW: return powf_call(acc, v);
-        case MCB_F_RPOW: return powf_call(v, acc);
+        case MCB_F_POW: { /* x^2 first: exact fp32 fast path (mcb_pow.h), the fp64 algorithm only for the rare remainder */
+            float r;
+            if (__float_as_uint(v) == 0x40000000u && mcb_pow2_try(acc, &r)) return r;
+            return powf_call(acc, v);
+        }
+        case MCB_F_RPOW: {
+            float r;
+            if (__float_as_uint(acc) == 0x40000000u && mcb_pow2_try(v, &r)) return r;
+            return powf_call(v, acc);
+        }
         default: return v; /* MCB_F_LOAD, MCB_F_PUSH */
     }
 }
@@ -158,6 +166,7 @@ __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, c
 #define MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_K) MCB_STEP(FOP, MCB_SRC_TX) MCB_STEP(FOP, MCB_SRC_TY) MCB_STEP(FOP, MCB_SRC_TZ)
 #define MCB_STEP_ALL(FOP) MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_POP)
 
+template <bool HAS_POW> /* programs without `^` (after hoisting) get a kernel without the powf paths: fewer registers */
 __global__ void __launch_bounds__(kEvalThreads)
 eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
                   float* __restrict__ F, uint32_t* __restrict__ S, int row_groups) {
@@ -191,8 +200,13 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
             MCB_STEP_ALL(MCB_F_MUL)
             MCB_STEP_ALL(MCB_F_DIV)
             MCB_STEP_ALL(MCB_F_RDIV)
-            MCB_STEP_ALL(MCB_F_POW)
-            MCB_STEP_ALL(MCB_F_RPOW)
+#define MCB_STEP_POW(FOP, SRC) \
+    case MCB_FINSN(FOP, SRC, 0): if (HAS_POW) eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
+            MCB_STEP_POW(MCB_F_POW, MCB_SRC_K) MCB_STEP_POW(MCB_F_POW, MCB_SRC_TX) MCB_STEP_POW(MCB_F_POW, MCB_SRC_TY)
+            MCB_STEP_POW(MCB_F_POW, MCB_SRC_TZ) MCB_STEP_POW(MCB_F_POW, MCB_SRC_POP)
+            MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_K) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TX) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TY)
+            MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TZ) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_POP)
+#undef MCB_STEP_POW
             default: /* MCB_F_NEG */
 #pragma unroll
                 for (int e = 0; e < kEvalRows; e++) acc[e] = -acc[e];

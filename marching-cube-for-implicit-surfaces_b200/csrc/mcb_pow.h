@@ -113,7 +113,7 @@ MCB_POW_FN int mcb_pow_checkint(uint32_t iy) {
 MCB_POW_FN int mcb_pow_zeroinfnan(uint32_t ix) { return 2 * ix - 1 >= 2u * 0x7f800000u - 1; }
 MCB_POW_FN int mcb_pow_issignaling(uint32_t ix) { return ((ix ^ 0x00400000u) & 0x7fffffffu) > 0x7fc00000u; }
 
-MCB_POW_FN float mcb_powf(float x, float y) {
+MCB_POW_FN float mcb_powf_full(float x, float y) {
     uint32_t sign_bias = 0;
     uint32_t ix = mcb_f2u(x), iy = mcb_f2u(y);
     if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u || mcb_pow_zeroinfnan(iy)) {
@@ -189,6 +189,37 @@ MCB_POW_FN float mcb_powf(float x, float y) {
     out = fma(zz, rr2, out);
     out = out * s;
     return (float)out;
+}
+
+/* x^2, the exponent every example equation uses, without the fp64 log2/exp2 round trip — and still bit-identical
+ * to the algorithm above (hence to glibc's powf(x, 2)).
+ *
+ * powf(x,2) is the correctly rounded square EXCEPT when x*x lies so close to the midpoint of two floats that the
+ * ~2^-33 relative error of the fp64 evaluation pushes it across.  An exhaustive run over all 2^32 inputs
+ * (oracle/pow2_exhaustive.c) shows that every such input has x*x within 0.00166 ulp of a midpoint (results in
+ * [2^-100, 2^100]).  So: r = RN(x*x), err = fma(x, x, -r) is the exact rounding residual, and whenever
+ * |err| <= (1/2 - 2^-9) ulp(r) the result is r; the rare remainder (0.4 % of inputs) takes the full algorithm.
+ * All of it is fp32: one multiply, one fused multiply-add, a few integer operations. */
+MCB_POW_FN int mcb_pow2_try(float x, float* out) {
+#if defined(__CUDA_ARCH__)
+    const float r = __fmul_rn(x, x);
+    const float err = __fmaf_rn(x, x, -r);
+#else
+    const float r = x * x;
+    const float err = fmaf(x, x, -r);
+#endif
+    const uint32_t ex = mcb_f2u(r) >> 23; /* r >= 0 or NaN: no sign bit to strip for finite values */
+    if (ex < 27u || ex > 227u) return 0;   /* result outside [2^-100, 2^100] (or NaN/inf): full algorithm */
+    const float lim = 0.498046875f * mcb_u2f((ex - 23u) << 23); /* (1/2 - 2^-9) * ulp(r), exact */
+    if (!(mcb_u2f(mcb_f2u(err) & 0x7fffffffu) <= lim)) return 0;
+    *out = r;
+    return 1;
+}
+
+MCB_POW_FN float mcb_powf(float x, float y) {
+    float r;
+    if (mcb_f2u(y) == 0x40000000u && mcb_pow2_try(x, &r)) return r;
+    return mcb_powf_full(x, y);
 }
 
 #endif /* MCB_POW_H */
