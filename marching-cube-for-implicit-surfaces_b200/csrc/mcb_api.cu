@@ -88,12 +88,11 @@ struct mcb_ctx {
     uint32_t* d_tlist = nullptr;   /* [3 * cap_itris] */
     unsigned long long cap_verts = 0, cap_itris = 0;
     bool vnrm_allocated = false;
-    uint32_t* d_rowstart = nullptr;
-    size_t cap_rows = 0;
-    uint16_t* d_wmask = nullptr;
-    uint32_t* d_vbase = nullptr;
+    unsigned long long* d_item = nullptr;  /* per 32-cube word: first record | active mask << 32 (compact -> weld) */
+    size_t cap_items = 0;
+    unsigned long long* d_vinfo = nullptr; /* per active cube: first new vertex | new-edge mask | on-vertex mask */
     uint32_t* d_chunk_new = nullptr;
-    unsigned long long cap_weld = 0; /* cubes the three arrays above are sized for */
+    unsigned long long cap_weld = 0;       /* cubes the two arrays above are sized for */
     cudaEvent_t ev[7] = {};
     mcb_counts last{};
     bool have_result = false;
@@ -284,16 +283,14 @@ int ensure_soup(mcb_ctx* ctx, unsigned long long need, bool normals) {
 }
 
 int ensure_weld_scratch(mcb_ctx* ctx, const Grid& g) {
-    const size_t rows = (size_t)(g.ke - g.kb) * g.M;
+    const size_t items = (size_t)(g.ke - g.kb) * g.M * ((g.M + 31) / 32);
     int rc;
-    if ((rc = ensure(ctx, &ctx->d_rowstart, &ctx->cap_rows, rows)) != MCB_OK) return rc;
-    if (ctx->cap_weld >= ctx->cap_active && ctx->d_wmask) return MCB_OK;
-    if (ctx->d_wmask) cudaFree(ctx->d_wmask);
-    if (ctx->d_vbase) cudaFree(ctx->d_vbase);
+    if ((rc = ensure(ctx, &ctx->d_item, &ctx->cap_items, items)) != MCB_OK) return rc;
+    if (ctx->cap_weld >= ctx->cap_active && ctx->d_vinfo) return MCB_OK;
+    if (ctx->d_vinfo) cudaFree(ctx->d_vinfo);
     if (ctx->d_chunk_new) cudaFree(ctx->d_chunk_new);
-    ctx->d_wmask = nullptr; ctx->d_vbase = nullptr; ctx->d_chunk_new = nullptr; ctx->cap_weld = 0;
-    MCB_CK(cudaMalloc((void**)&ctx->d_wmask, ctx->cap_active * 2));
-    MCB_CK(cudaMalloc((void**)&ctx->d_vbase, ctx->cap_active * 4));
+    ctx->d_vinfo = nullptr; ctx->d_chunk_new = nullptr; ctx->cap_weld = 0;
+    MCB_CK(cudaMalloc((void**)&ctx->d_vinfo, ctx->cap_active * 8));
     MCB_CK(cudaMalloc((void**)&ctx->d_chunk_new, (ctx->cap_active / kWeldCubes + 2) * 4));
     ctx->cap_weld = ctx->cap_active;
     return MCB_OK;
@@ -464,8 +461,8 @@ void mcb_destroy(mcb_ctx* ctx) {
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     cudaFree(ctx->d_status); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_tile_nz);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_trioff); cudaFree(ctx->d_pos); cudaFree(ctx->d_nrm);
-    cudaFree(ctx->d_vlist); cudaFree(ctx->d_vnrm); cudaFree(ctx->d_tlist); cudaFree(ctx->d_rowstart); cudaFree(ctx->d_wmask);
-    cudaFree(ctx->d_vbase); cudaFree(ctx->d_chunk_new);
+    cudaFree(ctx->d_vlist); cudaFree(ctx->d_vnrm); cudaFree(ctx->d_tlist); cudaFree(ctx->d_item); cudaFree(ctx->d_vinfo);
+    cudaFree(ctx->d_chunk_new);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -661,8 +658,10 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             else
                 classify_kernel<false><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
                                                                                  ctx->d_status, ctx->d_ctr);
+            if (want_indexed && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
             compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,
-                                                         ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active);
+                                                         ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active,
+                                                         want_indexed ? ctx->d_item : nullptr);
             launches += 2;
             MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
@@ -680,8 +679,7 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
         if (want_indexed) {
             if ((rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
             const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr};
-            const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_rowstart, ctx->d_wmask, ctx->d_vbase, ctx->d_chunk_new};
-            MCB_CK(cudaMemsetAsync(ctx->d_rowstart, 0xFF, (size_t)(g.ke - g.kb) * g.M * 4, s));
+            const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_item, ctx->d_vinfo, ctx->d_chunk_new, cg.WC};
             weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
             weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
             weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);

@@ -549,7 +549,7 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
                const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
                const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status,
                Counters* __restrict__ ctr, unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
-               unsigned long long cap_active) {
+               unsigned long long cap_active, unsigned long long* __restrict__ item_info /* nullptr unless the weld needs it */) {
     __shared__ uint32_t chunk_a[kClsChunkCap], chunk_t[kClsChunkCap]; /* per 32 list entries */
     __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];
     __shared__ unsigned long long base_a_s, base_t_s;
@@ -655,8 +655,11 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
         unsigned long long oa = tile_a + chunk_a[kb >> 5] + ((inc - mine) & 0xffffu);
         unsigned long long ot = tile_t + chunk_t[kb >> 5] + ((inc - mine) >> 16);
         ItemView it;
-        view_item(it, glist[k], j0, kz0, q, g, S, V, plane);
+        const uint32_t item_local = glist[k];
+        view_item(it, item_local, j0, kz0, q, g, S, V, plane);
         uint32_t m = it.m;
+        if (item_info != nullptr) /* cube -> record look-up of the weld: first record of the word | its active mask */
+            item_info[(size_t)tile * sc.tile_items + item_local] = (oa & 0xFFFFFFFFull) | ((unsigned long long)m << 32);
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
@@ -710,6 +713,7 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
     __shared__ uint32_t ijk_s[kEmitCubes];   /* i | j << 12 (k kept apart: 3 x 12 bits do not fit with the code) */
     __shared__ uint16_t kc_s[kEmitCubes * 2]; /* k, raw cube code */
     __shared__ uint16_t work_s[kEmitCubes * 12]; /* local cube << 4 | edge, one per crossing edge */
+    __shared__ uint8_t tri2cube[kEmitCubes * 5]; /* chunk-local triangle -> local cube (a cube has at most 5) */
     __shared__ uint32_t warp_s[kEmitThreads / 32];
 
     unsigned long long A = ctr->active, T = ctr->triangles;
@@ -794,15 +798,16 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
         __syncthreads();
 
         /* ---- 3: coalesced float4 emission ---- */
+        if (t < n) { /* off_s is complete here (barrier after phase 1) */
+            const uint32_t first = off_s[t] - off_s[0], cnt = off_s[t + 1] - off_s[t];
+            for (uint32_t q2 = 0; q2 < cnt && q2 < 5u; q2++) tri2cube[first + q2] = (uint8_t)t;
+        }
+        __syncthreads();
         const unsigned long long v_begin = 3ull * off_s[0], v_end = 3ull * off_s[n];
         for (unsigned long long ov = v_begin + t; ov < v_end; ov += kEmitThreads) {
             const uint32_t tri = (uint32_t)(ov / 3);
             const int corner = (int)(ov - 3ull * tri);
-            int lo = 0, hi = n - 1; /* last local cube whose first triangle is <= tri */
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (off_s[mid] <= tri) lo = mid; else hi = mid - 1;
-            }
+            const int lo = (int)tri2cube[tri - off_s[0]]; /* local cube this triangle belongs to */
             const int lt = (int)(tri - off_s[lo]);
             const int e = (int)((triw_s[lo] >> (4 * (3 * lt + corner))) & 0xF);
             if (tri < cap_tris) {
@@ -994,18 +999,48 @@ __device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], 
     return weld_unkey(g, result);
 }
 
-/* (cube, crossing edge) -> the (cube, edge) whose insertion created the welded vertex the reference uses there */
-__device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j, int k, int e) {
+/* Owner of a grid edge, closed form for the unconstrained grid: the first cube in loop order is the one furthest
+ * back in the two other axes that still exists ((i,j) >= 0, k >= kb); with constraints, the candidate loop. */
+__device__ __forceinline__ void weld_owner_fast(const WeldView& W, const GridEdge& E, CubeEdge& o) {
+    if (W.V != nullptr) { weld_owner(W, E, o); return; }
+    const int kb = W.g.kb;
+    if (E.axis == 0) {
+        const int lo = E.vy >= 1, hi = E.vz >= kb + 1;
+        o.i = E.vx; o.j = E.vy - lo; o.k = E.vz - hi; o.e = 2 * lo + 4 * hi;
+    } else if (E.axis == 1) {
+        const int lo = E.vx >= 1, hi = E.vz >= kb + 1;
+        o.i = E.vx - lo; o.j = E.vy; o.k = E.vz - hi; o.e = (lo ? 1 : 3) + 4 * hi;
+    } else {
+        const int lo = E.vx >= 1, hi = E.vy >= 1;
+        o.i = E.vx - lo; o.j = E.vy - hi; o.k = E.vz; o.e = 8 + (hi ? (lo ? 2 : 3) : (lo ? 1 : 0));
+    }
+}
+
+/* Does the crossing point of (cube, edge), as this cube interpolates it, sit on a grid vertex?  The sharing cubes'
+ * interpolations differ by an ulp or two (< 2.5e-7), so 1.5e-6 catches every edge any of whose versions is within
+ * the reference's 1e-6.  Returns 0 (no), 1 (lower end point) or 2 (upper end point). */
+__device__ __forceinline__ int weld_on_vertex(const WeldView& W, int i, int j, int k, int e) {
     const GridEdge E = grid_edge_of(i, j, k, e);
-    CubeEdge own{i, j, k, e};
-    weld_owner(W, E, own); /* (i,j,k) itself is a candidate, so this always succeeds */
     bool cr;
-    const float p = weld_edge_point(W, own, E.axis, cr);
+    const CubeEdge me{i, j, k, e};
+    const float p = weld_edge_point(W, me, E.axis, cr);
+    const int base = (E.axis == 0 ? E.vx : E.axis == 1 ? E.vy : E.vz) + 1;
+    if ((double)fabsf(p - W.cs[base]) < 0.0000015) return 1;
+    if ((double)fabsf(p - W.cs[base + 1]) < 0.0000015) return 2;
+    return 0;
+}
+
+/* (cube, crossing edge) -> the (cube, edge) whose insertion created the welded vertex the reference uses there.
+ * on_vertex = weld_on_vertex() of this pair (computed once, in weld_count, and handed on in the vinfo words). */
+__device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j, int k, int e, int on_vertex) {
+    const GridEdge E = grid_edge_of(i, j, k, e);
+    if (on_vertex == 0) { /* the up-to-four sharing cubes agree to within an ulp: the first inserter wins */
+        CubeEdge own{i, j, k, e};
+        weld_owner_fast(W, E, own);
+        return own;
+    }
     int G[3] = {E.vx, E.vy, E.vz};
-    const int base = G[E.axis] + 1;
-    const bool near_lo = (double)fabsf(p - W.cs[base]) < 0.0000015, near_hi = (double)fabsf(p - W.cs[base + 1]) < 0.0000015;
-    if (!near_lo && !near_hi) return own; /* the up-to-four sharing cubes agree to within an ulp: first inserter wins */
-    if (!near_lo) G[E.axis] += 1;         /* the grid vertex the point sits on */
+    if (on_vertex == 2) G[E.axis] += 1; /* the grid vertex the point sits on */
     const CubeEdge me{i, j, k, e};
     return weld_replay(W, G, weld_key(W.g, me));
 }
@@ -1013,23 +1048,34 @@ __device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j
 constexpr int kWeldCubes = 128;   /* active cubes per chunk */
 constexpr int kWeldThreads = 256;
 
+/* vinfo word per active cube: [31:0] index of its first new vertex, [43:32] edges for which the cube inserts a new
+ * vertex, [55:44] edges whose crossing point sits on a grid vertex (which end point is recomputed on that rare path) */
 struct WeldBuffers {
-    const unsigned long long* __restrict__ rec; /* [A] loop-ordered active cubes (compact_kernel) */
-    const uint32_t* __restrict__ trioff;        /* [A] */
-    uint32_t* rowstart;                         /* [(ke-kb)*M] index of the first active cube of each cube row */
-    uint16_t* wmask;                            /* [A] edges for which the cube inserts a new vertex */
-    uint32_t* vbase;                            /* [A] index of the cube's first new vertex */
-    uint32_t* chunk_new;                        /* [chunks] new vertices per chunk, then their exclusive scan */
+    const unsigned long long* __restrict__ rec;  /* [A] loop-ordered active cubes (compact_kernel) */
+    const uint32_t* __restrict__ trioff;         /* [A] */
+    const unsigned long long* __restrict__ item; /* [items] per 32-cube word: first record | active mask << 32 (compact_kernel) */
+    unsigned long long* vinfo;                   /* [A] see above */
+    uint32_t* chunk_new;                         /* [chunks] new vertices per chunk, then their exclusive scan */
+    uint32_t WC;                                 /* 32-cube words per cube row */
 };
+#define MCB_VINFO_BASE(v) ((uint32_t)(v))
+#define MCB_VINFO_NEW(v) ((uint32_t)((v) >> 32) & 0xFFFu)
+#define MCB_VINFO_ONV(v) ((uint32_t)((v) >> 44) & 0xFFFu)
+
+/* record index of an ACTIVE cube: first record of its 32-cube word + rank of the cube among the word's active cubes */
+__device__ __forceinline__ uint32_t weld_find_cube(const WeldBuffers& B, const Grid& g, int i, int j, int k) {
+    const size_t item = ((size_t)(k - g.kb) * g.M + j) * B.WC + (i >> 5);
+    const unsigned long long w = B.item[item];
+    return (uint32_t)w + (uint32_t)__popc((uint32_t)(w >> 32) & ((1u << (i & 31)) - 1u));
+}
 
 /* chunk prologue shared by weld_count and weld_emit: records -> shared memory, crossing-edge work list */
 struct WeldChunk {
     uint32_t ijk[kWeldCubes];       /* i | j << 12 */
     uint16_t k[kWeldCubes];
-    uint16_t mask[kWeldCubes];      /* new-vertex edges */
+    uint32_t mask[kWeldCubes];      /* new-vertex edges | on-vertex edges << 12 */
     uint16_t work[kWeldCubes * 12]; /* local cube << 4 | edge */
     uint32_t warp[kWeldThreads / 32];
-    uint32_t total;
 };
 __device__ __forceinline__ uint32_t weld_load_chunk(WeldChunk& sh, const unsigned long long* __restrict__ rec,
                                                     unsigned long long c0, int n, unsigned long long* rec_out) {
@@ -1063,6 +1109,7 @@ __device__ __forceinline__ uint32_t weld_load_chunk(WeldChunk& sh, const unsigne
     return total;
 }
 
+/* marks, per active cube, the edges for which it inserts a new vertex and those whose point sits on a grid vertex */
 __global__ void __launch_bounds__(kWeldThreads)
 weld_count_kernel(const WeldView W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active) {
     __shared__ WeldChunk sh;
@@ -1075,33 +1122,30 @@ weld_count_kernel(const WeldView W, const WeldBuffers B, const Counters* __restr
         const unsigned long long c0 = chunk * kWeldCubes;
         const int n = (int)((A - c0) < (unsigned long long)kWeldCubes ? (A - c0) : kWeldCubes);
         if (t < kWeldCubes) sh.mask[t] = 0;
-        unsigned long long r;
-        const uint32_t total_v = weld_load_chunk(sh, B.rec, c0, n, &r);
-        if (t < n) { /* first active cube of every cube row, for the cube -> record look-up in weld_emit */
-            const uint32_t row = (uint32_t)(((r >> 24) & 0xFFF) - W.g.kb) * (uint32_t)W.g.M + (uint32_t)((r >> 12) & 0xFFF);
-            atomicMin(B.rowstart + row, (uint32_t)(c0 + t));
-        }
+        const uint32_t total_v = weld_load_chunk(sh, B.rec, c0, n, nullptr);
         __syncthreads();
         for (uint32_t q = t; q < total_v; q += kWeldThreads) {
             const uint32_t wk = sh.work[q];
             const int lc = (int)(wk >> 4), e = (int)(wk & 15u);
             const int i = (int)(sh.ijk[lc] & 0xFFF), j = (int)(sh.ijk[lc] >> 12), k = (int)sh.k[lc];
-            const CubeEdge v = weld_resolve(W, i, j, k, e);
-            if (v.i == i && v.j == j && v.k == k && v.e == e)
-                atomicOr(reinterpret_cast<unsigned int*>(sh.mask) + (lc >> 1), (1u << e) << (16 * (lc & 1)));
+            const int onv = weld_on_vertex(W, i, j, k, e);
+            const CubeEdge v = weld_resolve(W, i, j, k, e, onv);
+            uint32_t bits = onv ? (1u << (12 + e)) : 0u;
+            if (v.i == i && v.j == j && v.k == k && v.e == e) bits |= 1u << e;
+            if (bits) atomicOr(&sh.mask[lc], bits);
         }
         __syncthreads();
         uint32_t mine = 0;
-        if (t < n) { B.wmask[c0 + t] = sh.mask[t]; mine = __popc((uint32_t)sh.mask[t]); }
+        if (t < n) { B.vinfo[c0 + t] = (unsigned long long)sh.mask[t] << 32; mine = __popc(sh.mask[t] & 0xFFFu); }
 #pragma unroll
         for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
         if ((t & 31) == 0) sh.warp[t >> 5] = mine;
         __syncthreads();
         if (t == 0) {
-            uint32_t s = 0;
+            uint32_t s2 = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < kWeldThreads / 32; w2++) s += sh.warp[w2];
-            B.chunk_new[chunk] = s;
+            for (int w2 = 0; w2 < kWeldThreads / 32; w2++) s2 += sh.warp[w2];
+            B.chunk_new[chunk] = s2;
         }
     }
 }
@@ -1135,20 +1179,6 @@ weld_scan_kernel(uint32_t* __restrict__ chunk_new, Counters* __restrict__ ctr, u
     if (t == 0) ctr->vertices = carry_s;
 }
 
-__device__ __forceinline__ uint32_t weld_find_cube(const WeldBuffers& B, const Grid& g, unsigned long long A, int i, int j, int k) {
-    uint32_t lo = B.rowstart[(uint32_t)(k - g.kb) * (uint32_t)g.M + (uint32_t)j];
-    uint32_t hi = (uint32_t)((unsigned long long)lo + g.M < A ? lo + g.M : A) - 1u;
-    const uint32_t key = (uint32_t)i | ((uint32_t)j << 12); /* (k, j) are fixed inside a row: compare j:i */
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const unsigned long long r = B.rec[mid];
-        /* records are sorted by k:j:i; entries past the row have a larger k:j */
-        const bool less = ((r >> 24) & 0xFFF) == (unsigned)k ? (uint32_t)(r & 0xFFFFFF) < key : ((r >> 24) & 0xFFF) < (unsigned)k;
-        if (less) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
 /* per-cube first vertex index: chunk base + exclusive scan of the new-vertex counts inside the chunk */
 __global__ void __launch_bounds__(kWeldCubes)
 weld_base_kernel(const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active) {
@@ -1160,7 +1190,8 @@ weld_base_kernel(const WeldBuffers B, const Counters* __restrict__ ctr, unsigned
     for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         __syncthreads();
         const unsigned long long c = chunk * kWeldCubes + t;
-        const uint32_t nv = c < A ? (uint32_t)__popc((uint32_t)B.wmask[c]) : 0u;
+        const unsigned long long vi = c < A ? B.vinfo[c] : 0ull;
+        const uint32_t nv = (uint32_t)__popc(MCB_VINFO_NEW(vi));
         uint32_t inc = nv;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
@@ -1168,7 +1199,7 @@ weld_base_kernel(const WeldBuffers B, const Counters* __restrict__ ctr, unsigned
         __syncthreads();
         uint32_t base = B.chunk_new[chunk] + inc - nv;
         for (int w2 = 0; w2 < warp; w2++) base += warp_s[w2];
-        if (c < A) B.vbase[c] = base;
+        if (c < A) B.vinfo[c] = (vi & 0xFFFFFFFF00000000ull) | base;
     }
 }
 
@@ -1179,6 +1210,7 @@ weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restri
                  float* __restrict__ vertex_nrm, uint32_t* __restrict__ tri_list) {
     __shared__ WeldChunk sh;
     __shared__ uint32_t eidx[kWeldCubes * 12]; /* welded vertex index of [cube][edge] */
+    __shared__ uint8_t tri2cube[kWeldCubes * 5]; /* chunk-local triangle -> local cube (a cube has at most 5) */
     __shared__ uint32_t off_s[kWeldCubes + 1];
     __shared__ uint64_t triw_s[kWeldCubes];
     __shared__ uint32_t vb_s[kWeldCubes];
@@ -1195,10 +1227,11 @@ weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restri
         unsigned long long r;
         const uint32_t total_v = weld_load_chunk(sh, B.rec, c0, n, &r);
         if (t < n) {
+            const unsigned long long vi = B.vinfo[c0 + t];
             off_s[t] = B.trioff[c0 + t];
             triw_s[t] = mcb_tri_word((int)((r >> 44) & 0xFF));
-            sh.mask[t] = B.wmask[c0 + t];
-            vb_s[t] = B.vbase[c0 + t];
+            sh.mask[t] = (uint32_t)(vi >> 32);
+            vb_s[t] = MCB_VINFO_BASE(vi);
         }
         if (t == 0) off_s[n] = (c0 + n < A) ? B.trioff[c0 + n] : (A == ctr->active ? (uint32_t)T : off_s[n - 1]);
         __syncthreads();
@@ -1206,11 +1239,11 @@ weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restri
             const uint32_t wk = sh.work[q];
             const int lc = (int)(wk >> 4), e = (int)(wk & 15u);
             const int i = (int)(sh.ijk[lc] & 0xFFF), j = (int)(sh.ijk[lc] >> 12), k = (int)sh.k[lc];
-            const CubeEdge v = weld_resolve(W, i, j, k, e);
+            const uint32_t m = sh.mask[lc];
             uint32_t idx;
-            if (v.i == i && v.j == j && v.k == k) { /* inserted by this cube (possibly as another of its edges) */
-                idx = vb_s[lc] + (uint32_t)__popc((uint32_t)sh.mask[lc] & ((1u << v.e) - 1u));
-                if (v.e == e && idx < cap_verts) { /* this thread's edge IS the new vertex: write it (add_point) */
+            if ((m >> e) & 1u) { /* this cube inserts the vertex of this edge: write it (add_point, marching.cpp:627-643) */
+                idx = vb_s[lc] + (uint32_t)__popc(m & ((1u << e) - 1u));
+                if (idx < cap_verts) {
                     const int oa = mcb_corner_ofs(mcb_edge_a(e)), ob = mcb_corner_ofs(mcb_edge_b(e));
                     const int xa = i + 1 + (oa & 1), ya = j + 1 + ((oa >> 1) & 1), za = k + 1 + ((oa >> 2) & 1);
                     const int xb = i + 1 + (ob & 1), yb = j + 1 + ((ob >> 1) & 1), zb = k + 1 + ((ob >> 2) & 1);
@@ -1238,22 +1271,26 @@ weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restri
                         on[0] = nx * inv; on[1] = ny * inv; on[2] = nz * inv;
                     }
                 }
-            } else {
-                const uint32_t oc = weld_find_cube(B, g, A, v.i, v.j, v.k);
-                idx = B.vbase[oc] + (uint32_t)__popc((uint32_t)B.wmask[oc] & ((1u << v.e) - 1u));
+            } else { /* somebody else inserted it: the edge's owner, or the replay's answer on a grid vertex */
+                const int onv = ((m >> (12 + e)) & 1u) ? weld_on_vertex(W, i, j, k, e) : 0;
+                const CubeEdge v = weld_resolve(W, i, j, k, e, onv);
+                unsigned long long vi;
+                if (v.i == i && v.j == j && v.k == k) vi = ((unsigned long long)m << 32) | vb_s[lc];
+                else vi = B.vinfo[weld_find_cube(B, g, v.i, v.j, v.k)];
+                idx = MCB_VINFO_BASE(vi) + (uint32_t)__popc(MCB_VINFO_NEW(vi) & ((1u << v.e) - 1u));
             }
             eidx[lc * 12 + e] = idx;
+        }
+        if (t < n) {
+            const uint32_t first = off_s[t] - off_s[0], cnt = off_s[t + 1] - off_s[t];
+            for (uint32_t q2 = 0; q2 < cnt && q2 < 5u; q2++) tri2cube[first + q2] = (uint8_t)t;
         }
         __syncthreads();
         const unsigned long long v_begin = 3ull * off_s[0], v_end = 3ull * off_s[n];
         for (unsigned long long ov = v_begin + t; ov < v_end; ov += kWeldThreads) {
             const uint32_t tri = (uint32_t)(ov / 3);
             const int corner = (int)(ov - 3ull * tri);
-            int lo = 0, hi = n - 1; /* last local cube whose first triangle is <= tri */
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (off_s[mid] <= tri) lo = mid; else hi = mid - 1;
-            }
+            const int lo = (int)tri2cube[tri - off_s[0]]; /* local cube this triangle belongs to */
             const int lt = (int)(tri - off_s[lo]);
             const int e = (int)((triw_s[lo] >> (4 * (3 * lt + corner))) & 0xF);
             if (tri < cap_tris) tri_list[ov] = eidx[lo * 12 + e];
