@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcb200.so")
 SOURCES = ["mcb_api.cu", "mcb_lower.cpp"]
-HEADERS = ["mcb_kernels.cuh", "mcb_bytecode.h", "mcb_pow.h", "mcb_tables.h", "mcb_tri_words.inc", "mcb_lower.h",
+HEADERS = [os.path.join("..", "..", "tools", "headless_main.cpp"), os.path.join("..", "..", "include", "marching.h"),
+           os.path.join("..", "..", "include", "evaluator.h"), "mcb_kernels.cuh", "mcb_bytecode.h", "mcb_pow.h", "mcb_tables.h", "mcb_tri_words.inc", "mcb_lower.h",
            os.path.join("..", "..", "include", "mcb.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
@@ -23,7 +24,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-li
 
 
 def stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(os.path.join(HERE, "mcb_headless")):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS) or os.path.getmtime(__file__) > t
@@ -38,7 +39,21 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libmcb200.so")
+    build_headless()
     return LIB
+
+
+def build_headless():
+    """mcb_headless: the reference's main.cpp wiring without the GUI (tools/headless_main.cpp), on the C++ drop-in headers."""
+    root = os.path.dirname(HERE)
+    exe = os.path.join(HERE, "mcb_headless")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++14", "-O2", "-Wall", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tools", "headless_main.cpp"), "-o", exe, "-L", HERE, "-lmcb200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building mcb_headless")
+    return exe
 
 
 if __name__ == "__main__":

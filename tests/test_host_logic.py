@@ -189,3 +189,11 @@ def test_no_device_is_a_loud_failure(mcb):
         with pytest.raises(mcb.McbError) as ei:
             mcb.Context(0)
         assert ei.value.status == mcb.MCB_E_NODEVICE
+
+
+def test_grid_limits(mcb):
+    """M is capped at 4094 (12-bit cube indices in the active-cube records); steps outside (0, 1] are rejected."""
+    assert mcb.lib.mcb_grid_axis(2.0 / 4093, None, 0) in (4093, 4094)
+    assert mcb.lib.mcb_grid_axis(2.0 / 5000, None, 0) < 0
+    for bad in (0.0, -0.1, 1.5, float("nan"), float("inf")):
+        assert mcb.lib.mcb_grid_axis(bad, None, 0) < 0
