@@ -94,7 +94,7 @@ public:
         if (mcb_set_equation(ctx_, 0, evaluator_->equation().c_str()) != MCB_OK) return false;
         mcb_set_surface_constant(ctx_, iso_);
         mcb_set_scaling(ctx_, sx_, sy_, sz_);
-        mcb_set_normals(ctx_, normals_ ? 1 : 0);
+        mcb_set_normals(ctx_, normals_ ? (weld_ && reference_normals_ ? 2 : 1) : 0);
         for (int i = 0; i < 3; i++)
             mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
         /* welded: the GPU builds Poly_Data's own layout (vertex_list + tri_list, numbered and welded like
@@ -219,6 +219,9 @@ public:
     /* ---- extensions ---- */
     void set_weld(bool b) { weld_ = b; }
     void set_normals(bool b) { normals_ = b; }
+    /* true: get_vertex_normals() returns what CalculateNormal(get_poly_data()) would (normal.h:3-42), computed on the GPU,
+     * bit for bit; false (default): central-difference gradient normals */
+    void set_reference_normals(bool b) { reference_normals_ = b; }
     bool set_slab(int k_begin, int k_end) { slab_[0] = k_begin; slab_[1] = k_end; have_slab_ = true; return true; }
     const mcb_counts& last_counts() const { return counts_; }
     /* set_weld(false): triangle soup of the last recalculate(), 3 float4 per triangle, (x,y,z,1) and (nx,ny,nz,0) */
@@ -252,6 +255,7 @@ private:
     Evaluator* evaluator_;
     float step_, iso_, sx_, sy_, sz_;
     bool weld_, normals_, seed_mode_, step_mode_, repeat_;
+    bool reference_normals_ = false;
     float repeat_step_;
     float seed_[3];
     bool cons_valid_[3], cons_use_[3];

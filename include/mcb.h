@@ -124,7 +124,9 @@ int mcb_set_scaling(mcb_ctx* ctx, float sx, float sy, float sz); /* marching.cpp
  * in_use as Marching::use_constraint (marching.cpp:202-207).  The lhs is slot i+1 of mcb_set_equation.  A cube is
  * skipped unless all 8 corners satisfy every constraint in use (marching.cpp:255-280, 475-477). */
 int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use);
-/* 0 = positions only; 1 = also per-vertex normals from central-difference field gradients. */
+/* 0 = positions only; 1 = also normals from central-difference field gradients (per soup vertex and per welded
+ * vertex; DESIGN.md, normals); 2 = CalculateNormal of the reference (normal.h:3-42: area-weighted face normals summed
+ * per welded vertex in triangle order, glm::normalize), bit-exact, per welded vertex — needs MCB_MESH_INDEXED. */
 int mcb_set_normals(mcb_ctx* ctx, int mode);
 
 /* The hot path: Marching::recalculate() (marching.cpp:368-384) for this context's slab, entirely on the GPU.

@@ -88,6 +88,14 @@ struct mcb_ctx {
     uint32_t* d_tlist = nullptr;   /* [3 * cap_itris] */
     unsigned long long cap_verts = 0, cap_itris = 0;
     bool vnrm_allocated = false;
+    /* normal.h normals (mcb_set_normals 2): face normals, vertex -> corner CSR */
+    float* d_fn = nullptr;
+    uint32_t* d_nh_count = nullptr;
+    uint32_t* d_nh_start = nullptr;
+    uint32_t* d_nh_cursor = nullptr;
+    uint32_t* d_nh_sums = nullptr;
+    uint32_t* d_nh_adj = nullptr;
+    unsigned long long cap_nh_verts = 0, cap_nh_tris = 0;
     unsigned long long* d_item = nullptr;  /* per 32-cube word: first record | active mask << 32 (compact -> weld) */
     size_t cap_items = 0;
     unsigned long long* d_vinfo = nullptr; /* per active cube: first new vertex | new-edge mask | on-vertex mask */
@@ -296,6 +304,26 @@ int ensure_weld_scratch(mcb_ctx* ctx, const Grid& g) {
     return MCB_OK;
 }
 
+int ensure_normal_h_scratch(mcb_ctx* ctx) {
+    if (ctx->cap_nh_verts < ctx->cap_verts || !ctx->d_nh_count) {
+        cudaFree(ctx->d_nh_count); cudaFree(ctx->d_nh_start); cudaFree(ctx->d_nh_cursor); cudaFree(ctx->d_nh_sums);
+        ctx->d_nh_count = ctx->d_nh_start = ctx->d_nh_cursor = ctx->d_nh_sums = nullptr; ctx->cap_nh_verts = 0;
+        MCB_CK(cudaMalloc((void**)&ctx->d_nh_count, ctx->cap_verts * 4));
+        MCB_CK(cudaMalloc((void**)&ctx->d_nh_start, ctx->cap_verts * 4));
+        MCB_CK(cudaMalloc((void**)&ctx->d_nh_cursor, ctx->cap_verts * 4));
+        MCB_CK(cudaMalloc((void**)&ctx->d_nh_sums, (ctx->cap_verts / kScanBlock + 2) * 4));
+        ctx->cap_nh_verts = ctx->cap_verts;
+    }
+    if (ctx->cap_nh_tris < ctx->cap_itris || !ctx->d_fn) {
+        cudaFree(ctx->d_fn); cudaFree(ctx->d_nh_adj);
+        ctx->d_fn = nullptr; ctx->d_nh_adj = nullptr; ctx->cap_nh_tris = 0;
+        MCB_CK(cudaMalloc((void**)&ctx->d_fn, ctx->cap_itris * 3 * sizeof(float)));
+        MCB_CK(cudaMalloc((void**)&ctx->d_nh_adj, ctx->cap_itris * 3 * sizeof(uint32_t)));
+        ctx->cap_nh_tris = ctx->cap_itris;
+    }
+    return MCB_OK;
+}
+
 int ensure_indexed(mcb_ctx* ctx, unsigned long long verts, unsigned long long tris, bool normals) {
     if (ctx->cap_verts < verts || !ctx->d_vlist || (normals && !ctx->vnrm_allocated)) {
         verts = std::max(verts, ctx->cap_verts);
@@ -462,7 +490,8 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaFree(ctx->d_status); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_tile_nz);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_trioff); cudaFree(ctx->d_pos); cudaFree(ctx->d_nrm);
     cudaFree(ctx->d_vlist); cudaFree(ctx->d_vnrm); cudaFree(ctx->d_tlist); cudaFree(ctx->d_item); cudaFree(ctx->d_vinfo);
-    cudaFree(ctx->d_chunk_new);
+    cudaFree(ctx->d_chunk_new); cudaFree(ctx->d_fn); cudaFree(ctx->d_nh_count); cudaFree(ctx->d_nh_start); cudaFree(ctx->d_nh_cursor);
+    cudaFree(ctx->d_nh_sums); cudaFree(ctx->d_nh_adj);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -555,7 +584,7 @@ int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use) {
 }
 
 int mcb_set_normals(mcb_ctx* ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 1) return MCB_E_ARG;
+    if (!ctx || mode < 0 || mode > 2) return MCB_E_ARG;
     ctx->normals = mode;
     ctx->have_result = false;
     return MCB_OK;
@@ -575,6 +604,8 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
 
     bool any_constraint = false;
     for (int i = 0; i < 3; i++) any_constraint |= ctx->cons[i].in_use && ctx->eq[i + 1].valid;
+    if (ctx->normals == 2 && !(ctx->mesh_mode & MCB_MESH_INDEXED))
+        return fail(ctx, MCB_E_STATE, "normal.h normals (mode 2) are defined on the welded mesh: request MCB_MESH_INDEXED");
 
     const size_t ntab = (size_t)3 * eq.max_per_axis * g.P + 64;
     if ((rc = ensure(ctx, &ctx->d_tables, &ctx->cap_tables, ntab)) != MCB_OK) return rc;
@@ -668,7 +699,7 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
         /* K3: interpolation + coalesced float4 emission of the triangle soup */
         const unsigned eblocks = (unsigned)ctx->sm_count * 4;
         if (want_soup) {
-            if (ctx->normals)
+            if (ctx->normals == 1)
                 emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
             else
                 emit_kernel<false><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, nullptr);
@@ -683,13 +714,26 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
             weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
             weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);
-            if (ctx->normals)
+            if (ctx->normals == 1)
                 weld_emit_kernel<true><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
                                                                            ctx->d_vlist, ctx->d_vnrm, ctx->d_tlist);
             else
                 weld_emit_kernel<false><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
                                                                             ctx->d_vlist, nullptr, ctx->d_tlist);
             launches += 4;
+            if (ctx->normals == 2) { /* K5: CalculateNormal (normal.h:3-42) on the welded mesh, bit-exact */
+                if ((rc = ensure_normal_h_scratch(ctx)) != MCB_OK) return rc;
+                const unsigned long long* nv = &ctx->d_ctr->vertices;
+                MCB_CK(cudaMemsetAsync(ctx->d_nh_count, 0, ctx->cap_verts * 4, s));
+                MCB_CK(cudaMemsetAsync(ctx->d_nh_cursor, 0, ctx->cap_verts * 4, s));
+                nh_face_normals_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_vlist, ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_fn, ctx->d_nh_count);
+                scan_block_sums_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, nv, ctx->d_nh_sums);
+                scan_sums_kernel<<<1, kScanBlock, 0, s>>>(ctx->d_nh_sums, nv);
+                scan_apply_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, ctx->d_nh_sums, nv, ctx->d_nh_start);
+                nh_fill_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_nh_start, ctx->d_nh_cursor, ctx->d_nh_adj);
+                nh_accumulate_kernel<<<eblocks * 4, 128, 0, s>>>(ctx->d_fn, ctx->d_nh_start, ctx->d_nh_count, ctx->d_nh_adj, ctx->d_ctr, ctx->cap_verts, ctx->d_vnrm);
+                launches += 6;
+            }
         }
         MCB_CK(cudaEventRecord(ctx->ev[5], s));
         MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -750,7 +794,7 @@ int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles)
     if (!(ctx->last.mesh_mode & MCB_MESH_SOUP)) return fail(ctx, MCB_E_STATE, "the triangle soup was not requested (mcb_set_mesh_mode)");
     const uint64_t T = ctx->last.triangles;
     if (T > cap_triangles) return fail(ctx, MCB_E_CAPACITY, "mesh buffer too small");
-    if (nrm4 && !ctx->normals) return fail(ctx, MCB_E_STATE, "normals are switched off");
+    if (nrm4 && ctx->normals != 1) return fail(ctx, MCB_E_STATE, "soup normals need mcb_set_normals(ctx, 1)");
     if (T == 0) return MCB_OK;
     if (pos4) MCB_CK(cudaMemcpyAsync(pos4, ctx->d_pos, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     if (nrm4) MCB_CK(cudaMemcpyAsync(nrm4, ctx->d_nrm, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -796,7 +840,7 @@ int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4) {
     if (!ctx) return MCB_E_ARG;
     if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
     if (pos4) *pos4 = (const float*)ctx->d_pos;
-    if (nrm4) *nrm4 = ctx->normals ? (const float*)ctx->d_nrm : nullptr;
+    if (nrm4) *nrm4 = ctx->normals == 1 ? (const float*)ctx->d_nrm : nullptr;
     return MCB_OK;
 }
 

@@ -1299,6 +1299,135 @@ weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restri
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * K5  normal.h normals (mcb_set_normals(ctx, 2)): CalculateNormal, normal.h:3-42, on the indexed mesh — bit-exact.
+ *     The reference walks the triangles in order and does vNormal[i] = faceNormal + vNormal[i] for the three corners
+ *     of each, then glm::normalize.  fp32 addition is not associative, so the result depends on that order: per
+ *     vertex the additions happen in ascending (triangle, corner) order, a repeated index accumulating twice.
+ *     Here: face normals once per triangle (glm::cross of B-A and C-A, no FMA contraction); a CSR list of the
+ *     corners referencing each vertex (count, scan, fill by atomic cursor), sorted per vertex so that the sum runs in
+ *     the reference's order; x * (1.0f / sqrt(dot)) like glm 0.9.5.3 (func_geometric.inl:257-267,
+ *     func_exponential.inl:226-229).
+ * ------------------------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256)
+nh_face_normals_kernel(const float* __restrict__ vl, const uint32_t* __restrict__ tl, const Counters* __restrict__ ctr,
+                       unsigned long long cap_tris, float* __restrict__ fn, uint32_t* __restrict__ count) {
+    unsigned long long T = ctr->triangles;
+    if (T > cap_tris) T = cap_tris;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t i1 = tl[3 * t], i2 = tl[3 * t + 1], i3 = tl[3 * t + 2];
+        const float ax = vl[3ull * i1], ay = vl[3ull * i1 + 1], az = vl[3ull * i1 + 2];
+        const float bx = vl[3ull * i2] - ax, by = vl[3ull * i2 + 1] - ay, bz = vl[3ull * i2 + 2] - az;
+        const float cx = vl[3ull * i3] - ax, cy = vl[3ull * i3 + 1] - ay, cz = vl[3ull * i3 + 2] - az;
+        fn[3 * t] = by * cz - cy * bz;
+        fn[3 * t + 1] = bz * cx - cz * bx;
+        fn[3 * t + 2] = bx * cy - cx * by;
+        atomicAdd(count + i1, 1u); atomicAdd(count + i2, 1u); atomicAdd(count + i3, 1u);
+    }
+}
+
+/* exclusive scan of n counters in three steps (n read from the device): block sums, one-block scan, local scan */
+constexpr int kScanBlock = 1024;
+__global__ void __launch_bounds__(kScanBlock)
+scan_block_sums_kernel(const uint32_t* __restrict__ in, const unsigned long long* __restrict__ n_ptr, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t warp_s[32];
+    const unsigned long long n = *n_ptr;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (unsigned long long b0 = (unsigned long long)blockIdx.x * kScanBlock; b0 < n; b0 += (unsigned long long)gridDim.x * kScanBlock) {
+        uint32_t v = b0 + t < n ? in[b0 + t] : 0u;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) warp_s[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = warp_s[lane];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == 0) sums[b0 / kScanBlock] = s;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kScanBlock)
+scan_sums_kernel(uint32_t* __restrict__ sums, const unsigned long long* __restrict__ n_ptr) {
+    __shared__ uint32_t warp_s[32];
+    __shared__ uint32_t carry_s;
+    const unsigned long long nb = (*n_ptr + kScanBlock - 1) / kScanBlock;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (unsigned long long b0 = 0; b0 < nb; b0 += kScanBlock) {
+        const uint32_t v = b0 + t < nb ? sums[b0 + t] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_s[warp] = inc;
+        __syncthreads();
+        uint32_t base = carry_s;
+        for (int w2 = 0; w2 < warp; w2++) base += warp_s[w2];
+        if (b0 + t < nb) sums[b0 + t] = base + inc - v;
+        __syncthreads();
+        if (t == kScanBlock - 1) carry_s = base + inc;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kScanBlock)
+scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ sums, const unsigned long long* __restrict__ n_ptr,
+                  uint32_t* __restrict__ out) {
+    __shared__ uint32_t warp_s[32];
+    const unsigned long long n = *n_ptr;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (unsigned long long b0 = (unsigned long long)blockIdx.x * kScanBlock; b0 < n; b0 += (unsigned long long)gridDim.x * kScanBlock) {
+        const uint32_t v = b0 + t < n ? in[b0 + t] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_s[warp] = inc;
+        __syncthreads();
+        uint32_t base = sums[b0 / kScanBlock];
+        for (int w2 = 0; w2 < warp; w2++) base += warp_s[w2];
+        if (b0 + t < n) out[b0 + t] = base + inc - v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nh_fill_kernel(const uint32_t* __restrict__ tl, const Counters* __restrict__ ctr, unsigned long long cap_tris,
+               const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor, uint32_t* __restrict__ adj) {
+    unsigned long long T = ctr->triangles;
+    if (T > cap_tris) T = cap_tris;
+    const unsigned long long n = 3 * T;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t v = tl[c];
+        adj[start[v] + atomicAdd(cursor + v, 1u)] = (uint32_t)c;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+nh_accumulate_kernel(const float* __restrict__ fn, const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
+                     uint32_t* __restrict__ adj, const Counters* __restrict__ ctr, unsigned long long cap_verts,
+                     float* __restrict__ vnrm) {
+    unsigned long long Vn = ctr->vertices;
+    if (Vn > cap_verts) Vn = cap_verts;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t* a = adj + start[v];
+        const uint32_t n = count[v];
+        for (uint32_t i = 1; i < n; i++) { /* ascending corner order = the order of the reference's triangle loop */
+            const uint32_t key = a[i];
+            uint32_t j = i;
+            while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; j--; }
+            a[j] = key;
+        }
+        float ox = 0.f, oy = 0.f, oz = 0.f; /* vNormal.resize(): zero-initialised glm::vec3 */
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t t = a[i] / 3u;
+            ox = fn[3ull * t] + ox; oy = fn[3ull * t + 1] + oy; oz = fn[3ull * t + 2] + oz;
+        }
+        const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
+        vnrm[3 * v] = ox * inv; vnrm[3 * v + 1] = oy * inv; vnrm[3 * v + 2] = oz * inv;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Parity hooks (not on the hot path).
  * ------------------------------------------------------------------------------------------------------------- */
 __global__ void dense_codes_kernel(const Grid g, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,

@@ -120,3 +120,27 @@ def test_deviating_fields_weld_within_tolerance(mcb, name):
     d = np.abs(vl[tl.astype(np.int64)].astype(np.float64) - pos[:, :, :3].astype(np.float64)).max()
     assert d < 1e-6, d
     c.close()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_normal_h_normals_bit_exact(mcb, golden, name):
+    """mcb_set_normals(2): CalculateNormal (normal.h:3-42) on the GPU — the sum per welded vertex runs in the reference's
+    triangle order, so the fp32 result is the reference's bit for bit (isolated / degenerate vertices: NaN in both)."""
+    case = load_meta(golden)[name]
+    c = mcb.Context(0)
+    c.set_mesh_mode(mcb.MESH_INDEXED)
+    configure(c, case)
+    c.set_normals(2)
+    c.polygonise()
+    vl, tl, vn = c.get_indexed_mesh(normals=True)
+    ref = golden[name + "/normals"].reshape(-1, 3)
+    assert vn.shape == ref.shape and same_bits(vn, ref)
+    c.close()
+
+
+def test_normal_h_normals_need_the_indexed_mesh(mcb):
+    c = mcb.Context(0)
+    c.set_normals(2)
+    with pytest.raises(mcb.McbError):
+        c.polygonise()
+    c.close()
