@@ -179,12 +179,12 @@ def run_ours(args):
     ctx.set_slab(k0, k1)
     ctx.set_normals(1)
     slabs = importlib.import_module(PKG + ".slabs")
-    placement = {}
+    placement = slabs.DeviceCounts(ctx, torch.device("cuda", local)) if world > 1 else None
 
     def step_fn():
         c = ctx.polygonise()
-        if world > 1:  # the path's only exchange: per-slab triangle counts -> global output offsets (NCCL all-gather)
-            placement["offset"], placement["total"], _ = slabs.exchange_counts(c.triangles, device=torch.device("cuda", local))
+        if world > 1:  # the path's only exchange: per-slab triangle counts -> global output offsets (NCCL all-gather,
+            placement.exchange()  # straight from the device counters; offset/total stay on the device)
         return c
 
     def sync_all():
@@ -275,6 +275,12 @@ def run_ours(args):
     h2d = 4 * (mcb.lib.mcb_grid_axis(step, None, 0) + 3 + 64) + 2052 * 2 + 512
     d2h = int(cc.vertices) * 24 + int(cc.triangles) * 12 + 48
     d2h_soup = int(cc_s.triangles) * 96 + 48
+    if world > 1:  # bytes of all ranks, and a consistency check of the device-side placement
+        bt = torch.tensor([float(d2h), float(d2h_soup)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(bt, op=dist.ReduceOp.SUM)
+        d2h, d2h_soup = int(bt[0].item()), int(bt[1].item())
+        off, total, per_rank = placement.result()
+        assert total == sum(per_rank) and off == sum(per_rank[:rank]) and per_rank[rank] == int(cc.triangles), (off, total, per_rank)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

@@ -140,6 +140,11 @@ int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles)
 /* Device pointers to the same buffers (valid until the next mcb_polygonise / mcb_destroy). */
 int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4);
 
+/* Device address of the live counters of the last mcb_polygonise, five uint64: active cubes, triangles, ambiguous,
+ * redirected, welded vertices (stable for the lifetime of the context).  For multi-GPU placement the per-slab
+ * triangle count can be all-gathered straight from here (NCCL) without a host round trip. */
+int mcb_counts_device(mcb_ctx* ctx, const uint64_t** counts);
+
 /* MCB_MESH_SOUP, MCB_MESH_INDEXED or both (3).  The indexed mesh is what Marching::recalculate() leaves in
  * Poly_Data (marching.h:26-30): vertices welded and numbered as add_step_to_poly_data / add_point do it
  * (marching.cpp:599-654, tolerance comparator marching.h:38-54), triangles in emission order. */

@@ -74,6 +74,7 @@ def _load():
         "mcb_polygonise": ([vp, C.POINTER(Counts)], i),
         "mcb_get_mesh": ([vp, vp, vp, u64], i),
         "mcb_get_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp)], i),
+        "mcb_counts_device": ([vp, C.POINTER(vp)], i),
         "mcb_set_mesh_mode": ([vp, i], i),
         "mcb_get_indexed_mesh": ([vp, vp, vp, vp, u64, u64], i),
         "mcb_get_indexed_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i),
@@ -196,6 +197,12 @@ class Context:
 
     def set_normals(self, mode):
         self._ck(lib.mcb_set_normals(self.h, int(mode)))
+
+    def counts_device_ptr(self):
+        """Device address of the live counters (5 x uint64: active, triangles, ambiguous, redirected, vertices)."""
+        p = C.c_void_p()
+        self._ck(lib.mcb_counts_device(self.h, C.byref(p)))
+        return p.value
 
     def set_mesh_mode(self, mode):
         """MESH_SOUP (float4 triangle soup), MESH_INDEXED (welded Poly_Data layout) or both (3)."""

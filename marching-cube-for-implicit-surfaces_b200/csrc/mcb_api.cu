@@ -836,6 +836,12 @@ int mcb_get_indexed_mesh_device(mcb_ctx* ctx, const float** vertex_list, const u
     return MCB_OK;
 }
 
+int mcb_counts_device(mcb_ctx* ctx, const uint64_t** counts) {
+    if (!ctx || !counts) return MCB_E_ARG;
+    *counts = reinterpret_cast<const uint64_t*>(ctx->d_ctr);
+    return MCB_OK;
+}
+
 int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4) {
     if (!ctx) return MCB_E_ARG;
     if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");

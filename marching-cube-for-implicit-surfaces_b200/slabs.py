@@ -31,6 +31,37 @@ def exchange_counts(local_triangles, device=None, group=None):
     return sum(counts[:rank]), sum(counts), counts
 
 
+class DeviceCounts:
+    """The same exchange without a host round trip (NCCL only): the slab's triangle count is all-gathered straight from
+    the context's device counters, and the placement (offset of this slab, total) stays on the device as int64
+    tensors.  Nothing here synchronises the host; `result()` does, when the caller finally wants Python ints."""
+
+    def __init__(self, ctx, device):
+        import ctypes
+        self.device = device
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        ptr = ctx.counts_device_ptr()
+        n = 5  # uint64 active, triangles, ambiguous, redirected, vertices (mcb_counts_device)
+
+        class _Holder:  # minimal __cuda_array_interface__ view of the context's counters (no copy, no ownership)
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        self._holder = _Holder()
+        self.counters = torch.as_tensor(self._holder, device=device)
+        self.all = torch.empty(self.world, dtype=torch.int64, device=device)
+        self.offset = torch.zeros(1, dtype=torch.int64, device=device)
+        self.total = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def exchange(self):
+        dist.all_gather_into_tensor(self.all, self.counters[1:2].contiguous())
+        torch.sum(self.all[:self.rank], dim=0, keepdim=True, out=self.offset)
+        torch.sum(self.all, dim=0, keepdim=True, out=self.total)
+
+    def result(self):
+        counts = [int(x) for x in self.all.tolist()]
+        return sum(counts[:self.rank]), sum(counts), counts
+
+
 def gather_soup_to_rank0(local_soup, offset, total, group=None):
     """Optional (NOT part of the timed path): place every slab's soup at its global offset on rank 0.
     local_soup: [T_r, 3, C] tensor.  Returns the [total, 3, C] tensor on rank 0, None elsewhere."""
