@@ -607,7 +607,7 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     if (ctx->normals == 2 && !(ctx->mesh_mode & MCB_MESH_INDEXED))
         return fail(ctx, MCB_E_STATE, "normal.h normals (mode 2) are defined on the welded mesh: request MCB_MESH_INDEXED");
 
-    const size_t ntab = (size_t)3 * eq.max_per_axis * g.P + 64;
+    const size_t ntab = (size_t)3 * eq.max_per_axis * g.P + 256; /* the last 128-column tile reads past the pitch */
     if ((rc = ensure(ctx, &ctx->d_tables, &ctx->cap_tables, ntab)) != MCB_OK) return rc;
     if (any_constraint) {
         const size_t nS = (size_t)g.NZ * g.NV * g.WP + 64;
@@ -638,23 +638,25 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     MCB_CK(cudaEventRecord(ctx->ev[1], s));
     /* K1: field + sign bit-plane */
     {
-        const int rgpp = (g.NV + kEvalRows - 1) / kEvalRows; /* row groups per plane */
-        const dim3 blocks((unsigned)g.WP, (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)), (unsigned)g.NZ);
+        const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY; /* 4-row groups per plane */
+        const dim3 blocks((unsigned)((g.P + kEvalTileX - 1) / kEvalTileX), (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)),
+                          (unsigned)g.NZ);
         const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
         /* resolve the table operands for this grid: argument = float offset of the table row inside d_tables */
         mcb_program launch = eq.grid;
-        for (int pc = 0; pc < launch.n; pc++) {
-            const uint32_t wd = launch.code[pc], src = MCB_FINSN_SRC(wd);
-            if (MCB_FINSN_OP(wd) == MCB_F_NEG || src == MCB_SRC_K || src == MCB_SRC_POP) continue;
-            if (src < MCB_SRC_TX) return fail(ctx, MCB_E_STATE, "internal: raw coordinate operand in a grid program");
-            const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + MCB_FINSN_ARG(wd)) * g.P;
-            if (off >= (1u << 24)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
-            launch.code[pc] = MCB_FINSN(MCB_FINSN_OP(wd), src, (uint32_t)off);
-        }
         bool has_pow = false;
         for (int pc = 0; pc < launch.n; pc++) {
-            const uint32_t fop = MCB_FINSN_OP(launch.code[pc]);
+            const uint32_t wd = launch.code[pc], fop = MCB_FINSN_OP(wd), src = MCB_FINSN_SRC(wd);
             has_pow |= fop == MCB_F_POW || fop == MCB_F_RPOW;
+            if (fop == MCB_F_NEG) { launch.code[pc] = MCB_HANDLER_NEG; continue; }
+            uint32_t arg = MCB_FINSN_ARG(wd);
+            if (src < MCB_SRC_K || src > MCB_SRC_POP) return fail(ctx, MCB_E_STATE, "internal: raw coordinate operand in a grid program");
+            if (src >= MCB_SRC_TX && src <= MCB_SRC_TZ) {
+                const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + arg) * g.P;
+                if (off >= (1u << 24)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
+                arg = (uint32_t)off;
+            }
+            launch.code[pc] = (uint32_t)MCB_HANDLER(fop, src) | (arg << 8); /* dense handler number | operand */
         }
         if (has_pow) eval_field_kernel<true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
         else eval_field_kernel<false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);

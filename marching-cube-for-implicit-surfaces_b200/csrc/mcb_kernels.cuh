@@ -84,16 +84,18 @@ __global__ void axis_tables_kernel(const uint32_t* __restrict__ slot_code, const
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K1  eval_field: the bytecode interpreter over the grid.
- *     A warp owns 32 consecutive x-columns x kEvalRows consecutive y-rows of one z-plane.  Every lane executes the
- *     same fused instruction word (mcb_bytecode.h), fetched from the kernel-parameter block (constant bank), so
- *     there is no divergence; the cost of fetching/decoding a word is shared by the kEvalRows vertices a lane
- *     carries.  The accumulator (top of the operand stack) lives in kEvalRows registers; an operator's other
- *     operand comes straight from its source — a coordinate, a constant-bank constant, an axis table (L1-resident)
- *     or, only for products of two compound subtrees, the shared-memory stack ([level][row][thread], conflict
- *     free).  Operands that are the same for all rows of a lane (x, z, constants, x/z tables) are applied from one
- *     register.  Outputs: F (evict-first 128 B per warp row store: the field is far larger than L2 and is only
- *     revisited around the surface) and the sign bit-plane S (one ballot per row) — the comparison against iso is
- *     fused here so that classification never reads the 4 B/vertex field.
+ *     A warp owns a tile of 128 consecutive x-columns x 4 consecutive y-rows of one z-plane; a lane owns 4
+ *     consecutive x of each of the 4 rows (16 vertices, accumulator acc[row][x] in 16 registers).  Every lane
+ *     executes the same fused instruction word (mcb_bytecode.h), fetched from the kernel-parameter block (constant
+ *     bank), so there is no divergence and the cost of fetching/decoding a word is shared by 16 vertices per lane.
+ *     An operator's other operand comes straight from its source: a constant-bank constant or a z-table entry (one
+ *     register for all 16), an x-table (one LDG.128: 4 values shared by the rows), a y-table (one broadcast
+ *     LDG.128: 4 values shared by the columns) or, only for products of two compound subtrees, the shared-memory
+ *     stack ([level][16][thread], conflict free).
+ *     Outputs: F — four evict-first STG.128 per lane, 512 contiguous bytes per warp and row (the field is far
+ *     larger than L2 and is only revisited around the surface) — and the sign bit-plane S: each lane builds a
+ *     nibble per row, three xor-shuffles OR the nibbles of 8 lanes into a 32-bit word.  The comparison against iso
+ *     is fused here so that classification never reads the 4 B/vertex field.
  * ------------------------------------------------------------------------------------------------------------- */
 __device__ __noinline__ float powf_call(float a, float b) { return mcb_powf(a, b); } /* one copy, register args */
 
@@ -122,11 +124,12 @@ __device__ __forceinline__ float fused_op(float acc, float v) {
 
 struct EvalLane { /* what an operand fetch needs besides the instruction argument */
     const float* __restrict__ tables;
-    int x, y0, zi;
+    int x0, y0, zi; /* first of the lane's 4 columns, first of the warp's 4 rows, index into the z tables */
 };
-constexpr int kEvalLevel = kEvalRows * kEvalThreads; /* floats per memory-stack level */
+constexpr int kEvalLevel = kEvalRows * kEvalThreads; /* floats per memory-stack level (kEvalRows = 16 values per lane) */
 
-/* One fused instruction, fully specialised on (operation, operand source): straight-line code, no inner dispatch. */
+/* One fused instruction, fully specialised on (operation, operand source): straight-line code, no inner dispatch.
+ * acc[4 * r + q] = row r, column q of the lane. */
 template <int FOP, int SRC>
 __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, const uint32_t arg, const mcb_program& prog,
                                           const EvalLane& L) {
@@ -139,48 +142,58 @@ __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, c
         sp -= kEvalLevel;
 #pragma unroll
         for (int e = 0; e < kEvalRows; e++) acc[e] = fused_op<FOP>(acc[e], sp[e * kEvalThreads]);
-    } else if (SRC == MCB_SRC_TY) { /* rows y0..y0+kEvalRows-1 of a table: 16-byte aligned, same address in every lane */
-        const float4* ty = reinterpret_cast<const float4*>(L.tables + arg + L.y0);
+    } else if (SRC == MCB_SRC_TY) { /* 4 rows of a y-table: 16-byte aligned, same address in every lane */
+        const float4 t = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.y0));
+        const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int e = 0; e < kEvalRows; e += 4) {
-            const float4 t = __ldg(ty + (e >> 2));
-            acc[e] = fused_op<FOP>(acc[e], t.x);
-            acc[e + 1] = fused_op<FOP>(acc[e + 1], t.y);
-            acc[e + 2] = fused_op<FOP>(acc[e + 2], t.z);
-            acc[e + 3] = fused_op<FOP>(acc[e + 3], t.w);
-        }
-    } else { /* one value for all rows of the lane */
-        const float u = SRC == MCB_SRC_K ? prog.k[arg] : __ldg(L.tables + arg + (SRC == MCB_SRC_TX ? L.x : L.zi));
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[4 * r + q] = fused_op<FOP>(acc[4 * r + q], tv[r]);
+    } else if (SRC == MCB_SRC_TX) { /* the lane's 4 columns of an x-table (the tables are padded past the last tile) */
+        const float4 t = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.x0));
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[4 * r + q] = fused_op<FOP>(acc[4 * r + q], tv[q]);
+    } else { /* one value for all 16 vertices of the lane */
+        const float u = SRC == MCB_SRC_K ? prog.k[arg] : __ldg(L.tables + arg + L.zi);
 #pragma unroll
         for (int e = 0; e < kEvalRows; e++) acc[e] = fused_op<FOP>(acc[e], u);
     }
 }
 
 /* `prog` is the fused grid program with its table operands already resolved by the host for this launch:
- * for src TX/TY/TZ the argument is the float offset of the table row inside `tables` ((axis*slots + slot) * P),
+ * for src TX/TY/TZ the argument is the float offset of the table row inside `tables` ((axis*slots + slot) * PT),
  * so an operand fetch is one address add and one load.  Grid programs contain no raw X/Y/Z operands: bare
- * variables are axis tables too (mcb_lower.cpp).  The low byte of an instruction word (operation | source << 4)
- * indexes one jump table whose targets are the straight-line bodies above. */
+ * variables are axis tables too (mcb_lower.cpp).  The host also replaces the low byte of each word by a dense
+ * handler number (operation * 5 + operand class), so that the dispatch is one jump table, not a compare tree. */
+#define MCB_HANDLER(FOP, SRC) ((FOP) * 5 + ((SRC) == MCB_SRC_K ? 0 : (SRC) == MCB_SRC_TX ? 1 : (SRC) == MCB_SRC_TY ? 2 : (SRC) == MCB_SRC_TZ ? 3 : 4))
+#define MCB_HANDLER_NEG (MCB_F_NEG * 5)
 #define MCB_STEP(FOP, SRC) \
-    case MCB_FINSN(FOP, SRC, 0): eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
+    case MCB_HANDLER(FOP, SRC): eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
 #define MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_K) MCB_STEP(FOP, MCB_SRC_TX) MCB_STEP(FOP, MCB_SRC_TY) MCB_STEP(FOP, MCB_SRC_TZ)
 #define MCB_STEP_ALL(FOP) MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_POP)
+
+constexpr int kEvalTileX = 128; /* columns per warp tile */
+constexpr int kEvalTileY = 4;   /* rows per warp tile */
+static_assert(kEvalRows == 16, "a lane carries a 4 x 4 patch");
 
 template <bool HAS_POW> /* programs without `^` (after hoisting) get a kernel without the powf paths: fewer registers */
 __global__ void __launch_bounds__(kEvalThreads)
 eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
                   float* __restrict__ F, uint32_t* __restrict__ S, int row_groups) {
-    extern __shared__ float stack_smem[]; /* [level][kEvalRows][kEvalThreads] */
+    extern __shared__ float stack_smem[]; /* [level][16][kEvalThreads] */
     const int lane = threadIdx.x & 31;
-    const int w = (int)blockIdx.x;                                             /* 32-vertex word of the row */
-    const int yq = (int)blockIdx.y * (kEvalThreads / 32) + (threadIdx.x >> 5); /* row group */
+    const int cx = (int)blockIdx.x;                                            /* 128-column tile of the row */
+    const int yq = (int)blockIdx.y * (kEvalThreads / 32) + (threadIdx.x >> 5); /* 4-row group */
     const int pz = (int)blockIdx.z;                                            /* plane: vertex kb-1+pz */
     if (yq >= row_groups) return; /* whole warp exits together; the kernel has no block-wide barrier */
     EvalLane L;
     L.tables = tables;
-    L.x = w * 32 + lane;
-    L.y0 = yq * kEvalRows;
-    L.zi = pz + g.kb; /* index into the z tables */
+    L.x0 = cx * kEvalTileX + 4 * lane;
+    L.y0 = yq * kEvalTileY;
+    L.zi = pz + g.kb;
 
     float acc[kEvalRows];
 #pragma unroll
@@ -201,7 +214,7 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
             MCB_STEP_ALL(MCB_F_DIV)
             MCB_STEP_ALL(MCB_F_RDIV)
 #define MCB_STEP_POW(FOP, SRC) \
-    case MCB_FINSN(FOP, SRC, 0): if (HAS_POW) eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
+    case MCB_HANDLER(FOP, SRC): if (HAS_POW) eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
             MCB_STEP_POW(MCB_F_POW, MCB_SRC_K) MCB_STEP_POW(MCB_F_POW, MCB_SRC_TX) MCB_STEP_POW(MCB_F_POW, MCB_SRC_TY)
             MCB_STEP_POW(MCB_F_POW, MCB_SRC_TZ) MCB_STEP_POW(MCB_F_POW, MCB_SRC_POP)
             MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_K) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TX) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TY)
@@ -214,36 +227,43 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
         }
     }
 
-    const int x = L.x, y0 = L.y0;
+    /* ---- outputs ---- */
+    const int x0 = L.x0, y0 = L.y0;
     const unsigned row0 = (unsigned)pz * (unsigned)g.NV + (unsigned)y0;
-    float* fp = F + (size_t)row0 * g.P + x; /* x < P always: P is the padded pitch */
-    const bool xin = x < g.NV;
-    uint32_t mine = 0;
-    if (y0 + kEvalRows <= g.NV) { /* uniform per warp; false only for the last row group of a plane */
+    const bool xin = x0 < g.P; /* P is a multiple of 32: a lane's 4 columns are inside the pitch together or not at all */
+    /* columns that are real vertices (x < NV): only they may set sign bits */
+    const uint32_t xmask = x0 + 3 < g.NV ? 0xFu : x0 >= g.NV ? 0u : (0xFu >> (x0 + 4 - g.NV));
+    float4* fp = reinterpret_cast<float4*>(F + (size_t)row0 * g.P + x0);
+    uint32_t word[kEvalTileY];
 #pragma unroll
-        for (int e = 0; e < kEvalRows; e++) {
-            __stcs(fp, acc[e]);
-            fp += g.P;
-        }
-#pragma unroll
-        for (int e = 0; e < kEvalRows; e++) {
-            const unsigned bits = __ballot_sync(0xffffffffu, xin && acc[e] > g.iso);
-            if (lane == e) mine = bits;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < kEvalRows; e++) {
-            const bool in = (y0 + e < g.NV);
-            if (in) __stcs(fp + (unsigned)(e * g.P), acc[e]);
-            const unsigned bits = __ballot_sync(0xffffffffu, in && xin && acc[e] > g.iso);
-            if (lane == e) mine = bits;
-        }
+    for (int r = 0; r < kEvalTileY; r++) {
+        const bool rin = y0 + r < g.NV; /* uniform per warp */
+        if (rin && xin) __stcs(fp + (size_t)r * (g.P >> 2), make_float4(acc[4 * r], acc[4 * r + 1], acc[4 * r + 2], acc[4 * r + 3]));
+        /* acc > iso  <=>  the sign bit of (iso - acc) is set: NaN differences are the canonical positive NaN, an exact
+         * zero difference is +0, and with gradual underflow a non-zero difference never rounds to zero.  The four
+         * sign bytes are gathered with byte permutes and squeezed into a nibble by one multiply: far fewer ALU-pipe
+         * instructions than four compare/select pairs (the kernel is ALU-pipe bound, not FMA-pipe bound). */
+        const uint32_t d0 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r])), d1 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r + 1]));
+        const uint32_t d2 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r + 2])), d3 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r + 3]));
+        const uint32_t tops = __byte_perm(__byte_perm(d0, d1, 0x0073), __byte_perm(d2, d3, 0x7300), 0x7610);
+        const uint32_t nib = ((tops & 0x80808080u) * 0x00204081u) >> 28;
+        uint32_t v = (nib & xmask) << (4 * (lane & 7));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1); /* OR over the 8 lanes of a word (a partial-mask redux.sync is emulated) */
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        word[r] = v;
     }
-    if (lane < kEvalRows && y0 + lane < g.NV) S[(size_t)(row0 + lane) * g.WP + w] = mine;
+    /* lane (8 j + r), r < 4, stores word j of row r */
+    const int r = lane & 7, wj = cx * (kEvalTileX / 32) + (lane >> 3);
+    if (r < kEvalTileY && y0 + r < g.NV && wj < g.WP) {
+        const uint32_t mine = r == 0 ? word[0] : r == 1 ? word[1] : r == 2 ? word[2] : word[3];
+        S[(size_t)(row0 + r) * g.WP + wj] = mine;
+    }
 }
 #undef MCB_STEP
 #undef MCB_STEP_LEAF
 #undef MCB_STEP_ALL
+/* MCB_HANDLER / MCB_HANDLER_NEG stay defined: mcb_api.cu encodes the launch program with them */
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
 __global__ void __launch_bounds__(256)
