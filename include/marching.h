@@ -12,9 +12,11 @@
  * the weld kernels in csrc/mcb_kernels.cuh and DESIGN.md for the one documented deviation.  set_weld(false) hands
  * out the unwelded float4 soup with a trivial index list instead.
  *
- * Not carried over (GUI teaching aids): seed mode, step-by-step mode and the unused
- * repeating-surface mode.  Their setters exist and keep their return values, but recalculate() always polygonises
- * the full grid.  load/save of .ply use plain files ("mesh.ply" or $MCB_MESH_FILE) instead of Win32 dialogs.
+ * Seed mode (seed_mode / set_seed, marching.cpp:42-137, 310-331) runs on the GPU too: the same cubes and triangles as
+ * the reference's BFS from the seed cube, emitted in the full-grid loop order instead of BFS order (get_seed_queue()
+ * stays empty).  Not carried over (GUI teaching aids): step-by-step mode and the unused
+ * repeating-surface mode; their setters exist and keep their return values, but recalculate() never steps cube by
+ * cube.  load/save of .ply use plain files ("mesh.ply" or $MCB_MESH_FILE) instead of Win32 dialogs.
  *
  * Extensions: set_grid_resolution(n) (step 2/n without the 0.001 floor), set_slab(k0,k1) for z-slab
  * sharding, set_normals(bool), get_normals() (central-difference gradient normals per soup vertex), last_counts().
@@ -99,6 +101,7 @@ public:
             mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
         /* welded: the GPU builds Poly_Data's own layout (vertex_list + tri_list, numbered and welded like
          * add_step_to_poly_data, marching.cpp:599-654); unwelded: the float4 triangle soup */
+        mcb_set_seed(ctx_, seed_mode_ ? 1 : 0, seed_[0], seed_[1], seed_[2]); /* marching.cpp:310-331, as a set (loop order) */
         mcb_set_mesh_mode(ctx_, weld_ ? MCB_MESH_INDEXED : MCB_MESH_SOUP);
         if (mcb_polygonise(ctx_, &counts_) != MCB_OK) return false;
         const size_t T = (size_t)counts_.triangles;

@@ -124,6 +124,11 @@ int mcb_set_scaling(mcb_ctx* ctx, float sx, float sy, float sz); /* marching.cpp
  * in_use as Marching::use_constraint (marching.cpp:202-207).  The lhs is slot i+1 of mcb_set_equation.  A cube is
  * skipped unless all 8 corners satisfy every constraint in use (marching.cpp:255-280, 475-477). */
 int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use);
+/* Seed mode (Marching::seed_mode + set_seed, marching.cpp:42-137, 310-331): polygonise only the cubes connected to
+ * the cube containing (x,y,z) — a point of [-1,1]^3, else MCB_E_ARG — through cube faces that carry a crossing edge.
+ * Same set of cubes and triangles as the reference's BFS, emitted in the full-grid loop order instead of BFS order.
+ * With z-slabs the walk stays inside the context's slab.  enabled = 0 switches back to the full grid. */
+int mcb_set_seed(mcb_ctx* ctx, int enabled, float x, float y, float z);
 /* 0 = positions only; 1 = also normals from central-difference field gradients (per soup vertex and per welded
  * vertex; DESIGN.md, normals); 2 = CalculateNormal of the reference (normal.h:3-42: area-weighted face normals summed
  * per welded vertex in triangle order, glm::normalize), bit-exact, per welded vertex — needs MCB_MESH_INDEXED. */

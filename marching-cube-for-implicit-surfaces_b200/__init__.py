@@ -71,6 +71,7 @@ def _load():
         "mcb_set_scaling": ([vp, f, f, f], i),
         "mcb_set_constraint": ([vp, i, i, f, i], i),
         "mcb_set_normals": ([vp, i], i),
+        "mcb_set_seed": ([vp, i, f, f, f], i),
         "mcb_polygonise": ([vp, C.POINTER(Counts)], i),
         "mcb_get_mesh": ([vp, vp, vp, u64], i),
         "mcb_get_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp)], i),
@@ -197,6 +198,10 @@ class Context:
 
     def set_normals(self, mode):
         self._ck(lib.mcb_set_normals(self.h, int(mode)))
+
+    def set_seed(self, enabled, x=0.0, y=0.0, z=0.0):
+        """Seed mode: keep only the component of the cube containing (x,y,z). Returns the status (MCB_E_ARG outside [-1,1]^3)."""
+        return lib.mcb_set_seed(self.h, int(bool(enabled)), x, y, z)
 
     def counts_device_ptr(self):
         """Device address of the live counters (5 x uint64: active, triangles, ambiguous, redirected, vertices)."""
@@ -362,6 +367,18 @@ class Marching:
 
     def set_slab(self, k0, k1):
         self._ctx.set_slab(k0, k1)
+
+    def seed_mode(self, b):
+        self._seed_on = bool(b)
+        s = getattr(self, "_seed", (0.0, 0.0, 0.0))
+        self._ctx.set_seed(self._seed_on, *s)
+
+    def set_seed(self, x, y, z):
+        if not (-1 <= x <= 1 and -1 <= y <= 1 and -1 <= z <= 1):  # marching.cpp:128-137
+            return False
+        self._seed = (x, y, z)
+        self._ctx.set_seed(getattr(self, "_seed_on", False), x, y, z)
+        return True
 
     def set_normals(self, mode):
         self._normals = bool(mode)

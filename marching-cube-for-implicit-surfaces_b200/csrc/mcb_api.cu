@@ -88,6 +88,15 @@ struct mcb_ctx {
     uint32_t* d_tlist = nullptr;   /* [3 * cap_itris] */
     unsigned long long cap_verts = 0, cap_itris = 0;
     bool vnrm_allocated = false;
+    /* seed mode (mcb_set_seed) */
+    bool seed_on = false;
+    float seed[3] = {0.f, 0.f, 0.f};
+    uint8_t* d_mark = nullptr;
+    uint32_t* d_changed = nullptr;
+    uint32_t* d_seed_u32 = nullptr; /* keep | ktri | pa | pt, cap_seed entries each, then the block sums */
+    unsigned long long* d_rec2 = nullptr;
+    uint32_t* d_trioff2 = nullptr;
+    unsigned long long cap_seed = 0;
     /* normal.h normals (mcb_set_normals 2): face normals, vertex -> corner CSR */
     float* d_fn = nullptr;
     uint32_t* d_nh_count = nullptr;
@@ -304,6 +313,28 @@ int ensure_weld_scratch(mcb_ctx* ctx, const Grid& g) {
     return MCB_OK;
 }
 
+int ensure_seed_scratch(mcb_ctx* ctx) {
+    if (ctx->cap_seed >= ctx->cap_active && ctx->d_mark) return MCB_OK;
+    cudaFree(ctx->d_mark); cudaFree(ctx->d_seed_u32); cudaFree(ctx->d_rec2); cudaFree(ctx->d_trioff2);
+    ctx->d_mark = nullptr; ctx->d_seed_u32 = nullptr; ctx->d_rec2 = nullptr; ctx->d_trioff2 = nullptr; ctx->cap_seed = 0;
+    const unsigned long long n = ctx->cap_active;
+    MCB_CK(cudaMalloc((void**)&ctx->d_mark, n));
+    MCB_CK(cudaMalloc((void**)&ctx->d_seed_u32, (4 * n + n / kScanBlock + 2) * 4));
+    MCB_CK(cudaMalloc((void**)&ctx->d_rec2, n * 8));
+    MCB_CK(cudaMalloc((void**)&ctx->d_trioff2, n * 4));
+    if (!ctx->d_changed) MCB_CK(cudaMalloc((void**)&ctx->d_changed, 4));
+    ctx->cap_seed = n;
+    return MCB_OK;
+}
+
+/* Marching::get_starting_seed_grid (marching.cpp:104-113), as cube indices: floor(((seed/scale) - (-1)) / step), fp32 */
+void seed_cube(const mcb_ctx* ctx, int out[3]) {
+    for (int a = 0; a < 3; a++) {
+        const float d = ((ctx->seed[a] / ctx->scale[a] - (-1.0f)) / ctx->step);
+        out[a] = (int)std::floor(d);
+    }
+}
+
 int ensure_normal_h_scratch(mcb_ctx* ctx) {
     if (ctx->cap_nh_verts < ctx->cap_verts || !ctx->d_nh_count) {
         cudaFree(ctx->d_nh_count); cudaFree(ctx->d_nh_start); cudaFree(ctx->d_nh_cursor); cudaFree(ctx->d_nh_sums);
@@ -492,6 +523,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaFree(ctx->d_vlist); cudaFree(ctx->d_vnrm); cudaFree(ctx->d_tlist); cudaFree(ctx->d_item); cudaFree(ctx->d_vinfo);
     cudaFree(ctx->d_chunk_new); cudaFree(ctx->d_fn); cudaFree(ctx->d_nh_count); cudaFree(ctx->d_nh_start); cudaFree(ctx->d_nh_cursor);
     cudaFree(ctx->d_nh_sums); cudaFree(ctx->d_nh_adj);
+    cudaFree(ctx->d_mark); cudaFree(ctx->d_changed); cudaFree(ctx->d_seed_u32); cudaFree(ctx->d_rec2); cudaFree(ctx->d_trioff2);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -579,6 +611,16 @@ int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use) {
     if (i < 0 || i > 2 || op < 0 || op > 3) return fail(ctx, MCB_E_ARG, "constraint index 0..2, op 0..3");
     if (in_use && !ctx->eq[i + 1].valid) return fail(ctx, MCB_E_STATE, "constraint has no left-hand side (mcb_set_equation slot i+1)");
     ctx->cons[i].op = op; ctx->cons[i].rhs = rhs; ctx->cons[i].in_use = in_use != 0;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_set_seed(mcb_ctx* ctx, int enabled, float x, float y, float z) {
+    if (!ctx) return MCB_E_ARG;
+    if (enabled && !((x <= 1 && x >= -1) && (y >= -1 && y <= 1) && (z >= -1 && z <= 1))) /* marching.cpp:128-137 */
+        return fail(ctx, MCB_E_ARG, "seed outside [-1,1]^3");
+    ctx->seed_on = enabled != 0;
+    if (enabled) { ctx->seed[0] = x; ctx->seed[1] = y; ctx->seed[2] = z; }
     ctx->have_result = false;
     return MCB_OK;
 }
@@ -691,11 +733,60 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             else
                 classify_kernel<false><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
                                                                                  ctx->d_status, ctx->d_ctr);
-            if (want_indexed && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
+            if ((want_indexed || ctx->seed_on) && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
             compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,
                                                          ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active,
-                                                         want_indexed ? ctx->d_item : nullptr);
+                                                         (want_indexed || ctx->seed_on) ? ctx->d_item : nullptr);
             launches += 2;
+            if (ctx->seed_on) { /* K6: keep the component of the seed cube (marching.cpp:42-137, 310-331) */
+                MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+                MCB_CK(cudaStreamSynchronize(s));
+                if (ctx->h_ctr->active <= ctx->cap_active) { /* otherwise the records are truncated: the re-run comes first */
+                    if ((rc = ensure_seed_scratch(ctx)) != MCB_OK) return rc;
+                    const unsigned long long n = ctx->cap_seed;
+                    uint32_t *keep = ctx->d_seed_u32, *ktri = keep + n, *pa = ktri + n, *pt = pa + n, *sums = pt + n;
+                    const SeedBuffers SB{ctx->d_rec, ctx->d_item, cg.WC, ctx->d_mark, ctx->d_changed};
+                    const WeldView W{g, ctx->d_cs, ctx->d_F, dV, nullptr, cg.WC};
+                    const unsigned sblocks = (unsigned)ctx->sm_count * 8;
+                    int sc3[3];
+                    seed_cube(ctx, sc3);
+                    MCB_CK(cudaMemsetAsync(ctx->d_mark, 0, std::max<unsigned long long>(ctx->h_ctr->active, 1), s));
+                    MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
+                    if (sc3[0] >= 0 && sc3[1] >= 0 && sc3[2] >= g.kb && sc3[0] < g.M && sc3[1] < g.M && sc3[2] < g.ke) {
+                        seed_init_kernel<<<1, 1, 0, s>>>(SB, g, ctx->d_ctr, ctx->cap_active, sc3[0], sc3[1], sc3[2]);
+                        launches++;
+                    }
+                    for (int round = 0; round < 100000; round++) { /* monotone marking until nothing changes */
+                        uint32_t changed = 0;
+                        MCB_CK(cudaMemcpyAsync(&changed, ctx->d_changed, 4, cudaMemcpyDeviceToHost, s));
+                        MCB_CK(cudaStreamSynchronize(s));
+                        if (!changed) break;
+                        MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
+                        for (int q = 0; q < 8; q++) {
+                            seed_sweep_kernel<<<sblocks, 256, 0, s>>>(SB, W, ctx->d_ctr, ctx->cap_active, 0.5 * (double)ctx->step);
+                            launches++;
+                        }
+                    }
+                    const unsigned long long* na = &ctx->d_ctr->active;
+                    seed_flags_kernel<<<sblocks, 256, 0, s>>>(SB, ctx->d_cls, ctx->d_ctr, ctx->cap_active, keep, ktri);
+                    scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, na, sums);
+                    scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
+                    scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, sums, na, pa);
+                    scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, na, sums);
+                    scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
+                    scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, sums, na, pt);
+                    seed_scatter_kernel<<<sblocks, 256, 0, s>>>(SB, keep, ktri, pa, pt, ctx->d_ctr, ctx->cap_active, ctx->d_rec2, ctx->d_trioff2);
+                    seed_commit_kernel<<<1, 1, 0, s>>>(ctx->d_ctr);
+                    std::swap(ctx->d_rec, ctx->d_rec2);
+                    std::swap(ctx->d_trioff, ctx->d_trioff2);
+                    launches += 9;
+                    if (want_indexed) { /* the weld must only see the kept cubes: rebuild the per-word look-up from scratch */
+                        MCB_CK(cudaMemsetAsync(ctx->d_item, 0, (size_t)(g.ke - g.kb) * g.M * cg.WC * 8, s));
+                        seed_items_kernel<<<sblocks, 256, 0, s>>>(ctx->d_rec, g, cg.WC, ctx->d_ctr, ctx->d_item);
+                        launches++;
+                    }
+                }
+            }
             MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
         /* K3: interpolation + coalesced float4 emission of the triangle soup */
@@ -711,7 +802,7 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
         /* K4: the reference's welded, indexed mesh (Poly_Data::vertex_list / tri_list) */
         if (want_indexed) {
             if ((rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
-            const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr};
+            const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr, ctx->seed_on ? ctx->d_item : nullptr, cg.WC};
             const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_item, ctx->d_vinfo, ctx->d_chunk_new, cg.WC};
             weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
             weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);

@@ -45,6 +45,7 @@ struct Counters {
     unsigned long long ambiguous;
     unsigned long long redirected;
     unsigned long long vertices; /* welded vertices (weld_scan_kernel) */
+    unsigned long long seed_active, seed_triangles; /* seed mode: counts of the kept component */
     unsigned int tile_ticket;
     unsigned int error; /* 2 = 2^31 or more triangles in the slab */
 };
@@ -868,6 +869,10 @@ struct WeldView {
     const float* __restrict__ cs;
     const float* __restrict__ F;
     const uint32_t* __restrict__ V; /* constraint validity planes or nullptr */
+    /* seed mode: only the kept cubes insert vertices.  Per 32-cube word `first record | kept mask << 32` (zero for
+     * words without a kept cube), or nullptr when every active cube is present. */
+    const unsigned long long* __restrict__ present;
+    uint32_t WC;
 };
 struct CubeEdge { /* an edge of a cube: who inserts a vertex, and as which of its edges */
     int i, j, k, e;
@@ -887,6 +892,8 @@ __device__ __forceinline__ GridEdge grid_edge_of(int i, int j, int k, int e) {
 __device__ __forceinline__ bool weld_cube_ok(const WeldView& W, int i, int j, int k) {
     const Grid& g = W.g;
     if (i < 0 || j < 0 || i >= g.M || j >= g.M || k < g.kb || k >= g.ke) return false;
+    if (W.present != nullptr &&
+        !(((uint32_t)(W.present[((size_t)(k - g.kb) * g.M + j) * W.WC + (i >> 5)] >> 32) >> (i & 31)) & 1u)) return false;
     if (W.V == nullptr) return true;
     bool ok = true; /* all 8 corners must satisfy the constraints (marching.cpp:475-477) */
 #pragma unroll
@@ -1022,7 +1029,7 @@ __device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], 
 /* Owner of a grid edge, closed form for the unconstrained grid: the first cube in loop order is the one furthest
  * back in the two other axes that still exists ((i,j) >= 0, k >= kb); with constraints, the candidate loop. */
 __device__ __forceinline__ void weld_owner_fast(const WeldView& W, const GridEdge& E, CubeEdge& o) {
-    if (W.V != nullptr) { weld_owner(W, E, o); return; }
+    if (W.V != nullptr || W.present != nullptr) { weld_owner(W, E, o); return; }
     const int kb = W.g.kb;
     if (E.axis == 0) {
         const int lo = E.vy >= 1, hi = E.vz >= kb + 1;
@@ -1444,6 +1451,116 @@ nh_accumulate_kernel(const float* __restrict__ fn, const uint32_t* __restrict__ 
         }
         const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
         vnrm[3 * v] = ox * inv; vnrm[3 * v + 1] = oy * inv; vnrm[3 * v + 2] = oz * inv;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K6  seed mode (Marching::seed_mode / set_seed, marching.cpp:42-137, 310-331): keep only the cubes reachable from
+ *     the cube containing the seed point by stepping across cube faces that carry a crossing edge
+ *     (find_cubes_for_seeding: a face is crossed when its four corner signs are not all equal; the neighbour must lie
+ *     inside the reference's bound check and, with constraints, be a cube the loop would not skip).  The reference
+ *     does this as a BFS and emits in BFS order; here it is a monotone marking over the compacted active-cube list
+ *     (0 = untouched, 1 = reached, 2 = reached and expanded) repeated until nothing changes, followed by a scan that
+ *     compacts the reached cubes — so the same SET of cubes and triangles comes out, in the full-grid loop order.
+ * ------------------------------------------------------------------------------------------------------------- */
+struct SeedBuffers {
+    const unsigned long long* __restrict__ rec;
+    const unsigned long long* __restrict__ item; /* per 32-cube word: first record | active mask << 32 */
+    uint32_t WC;
+    uint8_t* mark;      /* [A] */
+    uint32_t* changed;  /* [1] */
+};
+__device__ __forceinline__ bool seed_lookup(const SeedBuffers& B, const Grid& g, int i, int j, int k, uint32_t* idx) {
+    const size_t item = ((size_t)(k - g.kb) * g.M + j) * B.WC + (i >> 5);
+    const unsigned long long w = B.item[item];
+    const uint32_t mask = (uint32_t)(w >> 32);
+    if (!((mask >> (i & 31)) & 1u)) return false; /* note: words without any active cube are never read (see caller) */
+    *idx = (uint32_t)w + (uint32_t)__popc(mask & ((1u << (i & 31)) - 1u));
+    return true;
+}
+/* the seed cube: Marching::get_starting_seed_grid (marching.cpp:104-113) gives its index per axis on the host */
+__global__ void seed_init_kernel(const SeedBuffers B, const Grid g, const Counters* __restrict__ ctr, unsigned long long cap_active,
+                                 int si, int sj, int sk) {
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    /* the seed cube's word may hold no active cube at all, in which case its item word was never written: find the
+     * record by bisection over the loop-ordered list instead */
+    const unsigned long long key = (unsigned long long)si | ((unsigned long long)sj << 12) | ((unsigned long long)sk << 24);
+    unsigned long long lo = 0, hi = A;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if ((B.rec[mid] & 0xFFFFFFFFFull) < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo < A && (B.rec[lo] & 0xFFFFFFFFFull) == key) { B.mark[lo] = 1; *B.changed = 1u; }
+}
+__global__ void __launch_bounds__(256)
+seed_sweep_kernel(const SeedBuffers B, const WeldView W, const Counters* __restrict__ ctr, unsigned long long cap_active, double half_step) {
+    const Grid& g = W.g;
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < A; c += (unsigned long long)gridDim.x * blockDim.x) {
+        if (*(volatile uint8_t*)(B.mark + c) != 1) continue;
+        B.mark[c] = 2;
+        const unsigned long long r = B.rec[c];
+        const int i = (int)(r & 0xFFF), j = (int)((r >> 12) & 0xFFF), k = (int)((r >> 24) & 0xFFF), code = (int)((r >> 36) & 0xFF);
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            const int b0 = (code >> mcb_face_corner(f, 0)) & 1, b1 = (code >> mcb_face_corner(f, 1)) & 1;
+            const int b2 = (code >> mcb_face_corner(f, 2)) & 1, b3 = (code >> mcb_face_corner(f, 3)) & 1;
+            if (b0 == b1 && b1 == b2 && b2 == b3) continue; /* no edge of this face is crossed */
+            /* cube_face_normal, marching_lookup.h:43-50 */
+            const int ni = i + (f == 1 ? 1 : f == 3 ? -1 : 0), nj = j + (f == 4 ? 1 : f == 5 ? -1 : 0), nk = k + (f == 2 ? 1 : f == 0 ? -1 : 0);
+            if (!weld_cube_ok(W, ni, nj, nk)) continue;
+            /* marching.cpp:81-84: origin >= -1 - h/2 and origin + h/2 <= 1 on every axis, evaluated in double */
+            const double ox = (double)W.cs[ni + 1], oy = (double)W.cs[nj + 1], oz = (double)W.cs[nk + 1];
+            if (!(ox >= -1.0 - half_step && ox + half_step <= 1.0 && oy >= -1.0 - half_step && oy + half_step <= 1.0 &&
+                  oz >= -1.0 - half_step && oz + half_step <= 1.0)) continue;
+            uint32_t n;
+            if (!seed_lookup(B, g, ni, nj, nk, &n)) continue; /* the neighbour shares the crossed face, so it is active */
+            if (*(volatile uint8_t*)(B.mark + n) == 0) { B.mark[n] = 1; *B.changed = 1u; }
+        }
+    }
+}
+/* keep[c], kept triangle count -> two u32 arrays for the scans */
+__global__ void __launch_bounds__(256)
+seed_flags_kernel(const SeedBuffers B, const ClsTables* __restrict__ gtb, const Counters* __restrict__ ctr, unsigned long long cap_active,
+                  uint32_t* __restrict__ keep, uint32_t* __restrict__ ktri) {
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < A; c += (unsigned long long)gridDim.x * blockDim.x) {
+        const bool k = B.mark[c] != 0;
+        keep[c] = k ? 1u : 0u;
+        ktri[c] = k ? (uint32_t)__ldg(gtb->ntri + (int)((B.rec[c] >> 44) & 0xFF)) : 0u;
+    }
+}
+__global__ void __launch_bounds__(256)
+seed_scatter_kernel(const SeedBuffers B, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ ktri,
+                    const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pt, Counters* __restrict__ ctr,
+                    unsigned long long cap_active, unsigned long long* __restrict__ rec2, uint32_t* __restrict__ trioff2) {
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < A; c += (unsigned long long)gridDim.x * blockDim.x) {
+        if (keep[c]) { rec2[pa[c]] = B.rec[c]; trioff2[pa[c]] = pt[c]; }
+        if (c == A - 1) { ctr->seed_active = (unsigned long long)pa[c] + keep[c]; ctr->seed_triangles = (unsigned long long)pt[c] + ktri[c]; }
+    }
+}
+/* the counters switch over to the kept set once every reader of the old count is done */
+__global__ void seed_commit_kernel(Counters* __restrict__ ctr) {
+    ctr->active = ctr->seed_active;
+    ctr->triangles = ctr->seed_triangles;
+}
+/* rebuild the per-word look-up (first record | mask) for the kept, compacted list */
+__global__ void __launch_bounds__(256)
+seed_items_kernel(const unsigned long long* __restrict__ rec2, const Grid g, uint32_t WC, const Counters* __restrict__ ctr,
+                  unsigned long long* __restrict__ item) {
+    const unsigned long long A = ctr->active;
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < A; c += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long wkey = rec2[c] & 0xFFFFFFFE0ull; /* k : j : i / 32 */
+        if (c > 0 && (rec2[c - 1] & 0xFFFFFFFE0ull) == wkey) continue; /* not the first kept cube of its word */
+        uint32_t mask = 0;
+        for (unsigned long long d = c; d < A && (rec2[d] & 0xFFFFFFFE0ull) == wkey; d++) mask |= 1u << (uint32_t)(rec2[d] & 31u);
+        const int i = (int)(rec2[c] & 0xFFF), j = (int)((rec2[c] >> 12) & 0xFFF), k = (int)((rec2[c] >> 24) & 0xFFF);
+        item[((size_t)(k - g.kb) * g.M + j) * WC + (i >> 5)] = (c & 0xFFFFFFFFull) | ((unsigned long long)mask << 32);
     }
 }
 

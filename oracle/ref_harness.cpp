@@ -105,6 +105,15 @@ int mcref_set_constraint(mcref* h, int i, const char* lhs, int op, float rhs, in
 }
 
 int mcref_recalculate(mcref* h) { return h->march.recalculate() ? 1 : 0; }
+/* Seed mode (marching.cpp:42-137, 310-331): Marching::set_seed + seed_mode(true) + recalculate(), then back to the
+ * full-grid mode.  Returns 0 when set_seed rejects the point. */
+int mcref_seed_recalculate(mcref* h, float sx, float sy, float sz) {
+    if (!h->march.set_seed(sx, sy, sz)) return 0;
+    h->march.seed_mode(true);
+    const bool ok = h->march.recalculate();
+    h->march.seed_mode(false);
+    return ok ? 1 : 0;
+}
 long mcref_num_vertices(mcref* h) { return (long)h->march.poly_data.vertex_list.size() / 3; }
 long mcref_num_triangles(mcref* h) { return (long)h->march.poly_data.tri_list.size() / 3; }
 void mcref_copy_mesh(mcref* h, float* verts, unsigned* tris) {

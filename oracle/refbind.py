@@ -59,6 +59,7 @@ def lib():
         L.mcref_set_iso.argtypes = [C.c_void_p, C.c_float]
         L.mcref_set_constraint.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_float, C.c_int]
         L.mcref_recalculate.argtypes = [C.c_void_p]
+        L.mcref_seed_recalculate.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
         L.mcref_num_vertices.argtypes = [C.c_void_p]
         L.mcref_num_vertices.restype = C.c_long
         L.mcref_num_triangles.argtypes = [C.c_void_p]
@@ -140,6 +141,13 @@ class Ref:
     def recalculate(self):
         """Unmodified Marching::recalculate(); returns (vertex_list[n,3], tri_list[t,3])."""
         self.L.mcref_recalculate(self.h)
+        return self.mesh()
+
+    def seed_recalculate(self, sx, sy, sz):
+        """Seed mode: only the cubes face-connected (through crossing faces) to the cube containing the seed, in BFS
+        order (marching.cpp:310-331).  Returns (vertex_list, tri_list) or None when the seed is rejected."""
+        if not self.L.mcref_seed_recalculate(self.h, sx, sy, sz):
+            return None
         return self.mesh()
 
     def mesh(self):
