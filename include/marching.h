@@ -14,9 +14,10 @@
  *
  * Seed mode (seed_mode / set_seed, marching.cpp:42-137, 310-331) runs on the GPU too: the same cubes and triangles as
  * the reference's BFS from the seed cube, emitted in the full-grid loop order instead of BFS order (get_seed_queue()
- * stays empty).  Not carried over (GUI teaching aids): step-by-step mode and the unused
- * repeating-surface mode; their setters exist and keep their return values, but recalculate() never steps cube by
- * cube.  load/save of .ply use plain files ("mesh.ply" or $MCB_MESH_FILE) instead of Win32 dialogs.
+ * stays empty).  Step-by-step mode (marching.cpp:386-428) advances one cube per recalculate() like the reference: the
+ * cube is computed on the GPU (mcb_inspect_cube = calculate_step) and appended on the host.  Not carried over: the
+ * unused repeating-surface mode (its setters exist) and step-by-step inside seed mode.
+ * load/save of .ply use plain files ("mesh.ply" or $MCB_MESH_FILE) instead of Win32 dialogs.
  *
  * Extensions: set_grid_resolution(n) (step 2/n without the 0.001 floor), set_slab(k0,k1) for z-slab
  * sharding, set_normals(bool), get_normals() (central-difference gradient normals per soup vertex), last_counts().
@@ -91,14 +92,10 @@ public:
 
     bool recalculate() {
         if (!ensure_ctx()) return false;
+        if (step_mode_ && !seed_mode_) return step_once(); /* marching.cpp:386-428 */
         reset_all_data();
         if (!evaluator_) return true; /* Marching::evaluate returns 0 without an evaluator: nothing is above iso */
-        if (mcb_set_equation(ctx_, 0, evaluator_->equation().c_str()) != MCB_OK) return false;
-        mcb_set_surface_constant(ctx_, iso_);
-        mcb_set_scaling(ctx_, sx_, sy_, sz_);
-        mcb_set_normals(ctx_, normals_ ? (weld_ && reference_normals_ ? 2 : 1) : 0);
-        for (int i = 0; i < 3; i++)
-            mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
+        if (!push_parameters()) return false;
         /* welded: the GPU builds Poly_Data's own layout (vertex_list + tri_list, numbered and welded like
          * add_step_to_poly_data, marching.cpp:599-654); unwelded: the float4 triangle soup */
         mcb_set_seed(ctx_, seed_mode_ ? 1 : 0, seed_[0], seed_[1], seed_[2]); /* marching.cpp:310-331, as a set (loop order) */
@@ -128,6 +125,7 @@ public:
         poly_data.tri_list.clear(); poly_data.vertex_list.clear();
         poly_data.step_data.intersect_coord.clear(); poly_data.step_data.tri_vlist.clear(); poly_data.step_data.edge_list.clear();
         seed_queue_.clear();
+        vertex_set_.clear();
         reset_step();
     }
 
@@ -243,6 +241,70 @@ private:
         if (have_slab_ && mcb_set_slab(ctx_, slab_[0], slab_[1]) != MCB_OK) return false;
         return true;
     }
+    bool push_parameters() {
+        if (mcb_set_equation(ctx_, 0, evaluator_->equation().c_str()) != MCB_OK) return false;
+        mcb_set_surface_constant(ctx_, iso_);
+        mcb_set_scaling(ctx_, sx_, sy_, sz_);
+        mcb_set_normals(ctx_, normals_ ? (weld_ && reference_normals_ ? 2 : 1) : 0);
+        for (int i = 0; i < 3; i++)
+            mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
+        return true;
+    }
+
+    /* Step-by-step mode (marching.cpp:386-428): one cube per recalculate() call, in the reference's own traversal
+     * (x fastest, coordinates carried over from the previous cube's corners, `< 1.0` bounds).  The cube itself is
+     * computed on the GPU (mcb_inspect_cube = calculate_step); appending it to Poly_Data is the reference's
+     * add_step_to_poly_data / add_point with its std::set — a handful of points per call, host side like the GUI. */
+    bool step_once() {
+        Step_Data& sd = poly_data.step_data;
+        if (sd.step_i == 0) { add_step_to_poly_data(); sd.step_i = -1; return true; } /* last step */
+        if (sd.step_i == -1) return false;                                                /* finished already */
+        float x_0, y_0, z_0;
+        if (sd.step_i == -2) { /* first step */
+            reset_all_data();
+            x_0 = y_0 = z_0 = -1;
+            sd.step_i = 0;
+            for (float x0 = -1.0; x0 < 1.0; x0 += step_) sd.step_i++;
+            sd.step_i *= sd.step_i * sd.step_i;
+            sd.step_i--;
+        } else {
+            x_0 = sd.corner_coords[3]; y_0 = sd.corner_coords[4]; z_0 = sd.corner_coords[5];
+            if (x_0 >= 1.0) { x_0 = -1; y_0 += step_; }
+            if (y_0 >= 1.0) { y_0 = -1; z_0 += step_; }
+            sd.step_i--;
+        }
+        add_step_to_poly_data();
+        return calculate_step(x_0, y_0, z_0);
+    }
+    bool calculate_step(float x_0, float y_0, float z_0) { /* marching.cpp:456-595, on the GPU */
+        Step_Data& sd = poly_data.step_data;
+        sd.intersect_coord.clear(); sd.tri_vlist.clear(); sd.edge_list.clear();
+        if (!evaluator_ || !push_parameters()) return false;
+        mcb_step_data o;
+        if (mcb_inspect_cube(ctx_, x_0, y_0, z_0, &o) != MCB_OK) return false;
+        sd.corner_coords.assign(o.corner_coords, o.corner_coords + 24);
+        sd.corner_values.assign(o.corner_values, o.corner_values + 8);
+        sd.edge_list.assign(o.edge_list, o.edge_list + o.n_edges);
+        sd.intersect_coord.assign(o.intersect_coord, o.intersect_coord + 3 * o.n_edges);
+        sd.tri_vlist.assign(o.tri_vlist, o.tri_vlist + o.n_tri_idx);
+        return true;
+    }
+    void add_step_to_poly_data() { /* marching.cpp:599-654 */
+        const Step_Data& sd = poly_data.step_data;
+        int v_i_list[12];
+        for (int i = 0; i < 12; i++) v_i_list[i] = -1;
+        for (size_t i = 0; i < sd.intersect_coord.size(); i += 3) {
+            const float x = sd.intersect_coord[i], y = sd.intersect_coord[i + 1], z = sd.intersect_coord[i + 2];
+            if (std::isnan(x)) continue;
+            const int new_i = (int)(poly_data.vertex_list.size() / 3);
+            const int found = vertex_set_.insert(xyz(x, y, z, new_i)).first->idx;
+            if (found == new_i) { poly_data.vertex_list.push_back(x); poly_data.vertex_list.push_back(y); poly_data.vertex_list.push_back(z); }
+            v_i_list[i / 3] = found;
+        }
+        for (size_t i = 0; i + 2 < sd.tri_vlist.size(); i += 3)
+            for (int q = 0; q < 3; q++) poly_data.tri_list.push_back((unsigned)v_i_list[sd.tri_vlist[i + q]]);
+    }
+
     void fill_poly_data_from_soup() { /* set_weld(false): every triangle corner is its own vertex */
         const size_t nv = soup_.size() / 4;
         poly_data.vertex_list.resize(nv * 3);
@@ -268,6 +330,7 @@ private:
     bool have_slab_ = false;
     Poly_Data poly_data;
     std::deque<xyz> seed_queue_;
+    std::set<xyz> vertex_set_; /* step-by-step mode only (marching.h:149) */
     std::vector<float> soup_, normals_soup_, vertex_normals_;
     mcb_counts counts_;
 };

@@ -160,6 +160,19 @@ int mcb_get_indexed_mesh(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, f
                          uint64_t cap_triangles);
 int mcb_get_indexed_mesh_device(mcb_ctx* ctx, const float** vertex_list, const uint32_t** tri_list, const float** normals);
 
+/* Marching::calculate_step(x_0, y_0, z_0) (marching.cpp:456-595) for ONE cube with origin (x0,y0,z0) and the context's
+ * step, scale, iso, equation and constraints: the Step_Data (marching.h:15-23) the GUI's step-by-step / movie mode
+ * displays.  skipped = 1 when a constraint rejects a corner (the reference returns before filling anything else). */
+typedef struct {
+    float corner_coords[24];
+    float corner_values[8];
+    float intersect_coord[36]; /* 3 per crossing edge, ascending edge order */
+    int32_t edge_list[12];
+    int32_t tri_vlist[15];     /* indices into intersect_coord / 3, three per triangle */
+    int32_t n_edges, n_tri_idx, cube_code, table_idx, skipped;
+} mcb_step_data;
+int mcb_inspect_cube(mcb_ctx* ctx, float x0, float y0, float z0, mcb_step_data* out);
+
 /* Parity hooks.  Dense per-cube arrays of the slab in loop order, host memory, `cubes` bytes each (NULL = skip):
  * cube_code = raw 8-bit sign code (marching.cpp:497-505); table_idx = tri_table row actually used (code or
  * 255-code); a cube skipped by a constraint reports 0 in both. */

@@ -43,6 +43,13 @@ class Counts(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class StepData(C.Structure):
+    """mcb_step_data: Step_Data (marching.h:15-23) of one cube, as Marching::calculate_step fills it."""
+    _fields_ = [("corner_coords", C.c_float * 24), ("corner_values", C.c_float * 8), ("intersect_coord", C.c_float * 36),
+                ("edge_list", C.c_int32 * 12), ("tri_vlist", C.c_int32 * 15), ("n_edges", C.c_int32), ("n_tri_idx", C.c_int32),
+                ("cube_code", C.c_int32), ("table_idx", C.c_int32), ("skipped", C.c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError("libmcb200.so is not built: run `python __graft_entry__.py` (or build.py) first — "
@@ -72,6 +79,7 @@ def _load():
         "mcb_set_constraint": ([vp, i, i, f, i], i),
         "mcb_set_normals": ([vp, i], i),
         "mcb_set_seed": ([vp, i, f, f, f], i),
+        "mcb_inspect_cube": ([vp, f, f, f, C.POINTER(StepData)], i),
         "mcb_polygonise": ([vp, C.POINTER(Counts)], i),
         "mcb_get_mesh": ([vp, vp, vp, u64], i),
         "mcb_get_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp)], i),
@@ -198,6 +206,12 @@ class Context:
 
     def set_normals(self, mode):
         self._ck(lib.mcb_set_normals(self.h, int(mode)))
+
+    def inspect_cube(self, x0, y0, z0):
+        """Marching::calculate_step(x0, y0, z0) for one cube, on the GPU."""
+        sd = StepData()
+        self._ck(lib.mcb_inspect_cube(self.h, x0, y0, z0, C.byref(sd)))
+        return sd
 
     def set_seed(self, enabled, x=0.0, y=0.0, z=0.0):
         """Seed mode: keep only the component of the cube containing (x,y,z). Returns the status (MCB_E_ARG outside [-1,1]^3)."""

@@ -615,6 +615,34 @@ int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use) {
     return MCB_OK;
 }
 
+int mcb_inspect_cube(mcb_ctx* ctx, float x0, float y0, float z0, mcb_step_data* out) {
+    static_assert(sizeof(StepOut) == sizeof(mcb_step_data), "StepOut mirrors mcb_step_data");
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!out) return fail(ctx, MCB_E_ARG, "null output");
+    if (!ctx->eq[0].valid) return fail(ctx, MCB_E_STATE, "no surface equation");
+    mcb_program* d_progs = nullptr;
+    StepOut* d_out = nullptr;
+    MCB_CK(cudaMalloc((void**)&d_progs, 4 * sizeof(mcb_program)));
+    if (cudaMalloc((void**)&d_out, sizeof(StepOut)) != cudaSuccess) { cudaFree(d_progs); return fail(ctx, MCB_E_NOMEM, "cudaMalloc"); }
+    InspectCons cons{};
+    int slots[3] = {0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+        if (!(ctx->cons[i].in_use && ctx->eq[i + 1].valid)) continue;
+        cons.op[cons.n] = ctx->cons[i].op; cons.rhs[cons.n] = ctx->cons[i].rhs; slots[cons.n] = i + 1; cons.n++;
+    }
+    for (int sl = 0; sl < 4; sl++)
+        if (ctx->eq[sl].valid) cudaMemcpyAsync(d_progs + sl, &ctx->eq[sl].point, sizeof(mcb_program), cudaMemcpyHostToDevice, ctx->stream);
+    inspect_cube_kernel<<<1, 1, 0, ctx->stream>>>(d_progs, cons, slots[0], slots[1], slots[2], x0, y0, z0, ctx->step, ctx->scale[0],
+                                                  ctx->scale[1], ctx->scale[2], ctx->iso, ctx->d_cls, d_out);
+    cudaMemcpyAsync(out, d_out, sizeof(StepOut), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e2 = cudaGetLastError();
+    cudaFree(d_progs); cudaFree(d_out);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, MCB_E_CUDA, std::string("inspect_cube: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return MCB_OK;
+}
+
 int mcb_set_seed(mcb_ctx* ctx, int enabled, float x, float y, float z) {
     if (!ctx) return MCB_E_ARG;
     if (enabled && !((x <= 1 && x >= -1) && (y >= -1 && y <= 1) && (z >= -1 && z <= 1))) /* marching.cpp:128-137 */

@@ -1565,6 +1565,89 @@ seed_items_kernel(const unsigned long long* __restrict__ rec2, const Grid g, uin
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * K7  inspect: Marching::calculate_step(x_0, y_0, z_0) (marching.cpp:456-595) for ONE cube at an arbitrary origin —
+ *     what the GUI's step-by-step / movie mode shows per cube (Step_Data, marching.h:15-23).  One thread; the point
+ *     programs of the surface and of the constraints in use.
+ * ------------------------------------------------------------------------------------------------------------- */
+struct StepOut { /* mirrors mcb_step_data (include/mcb.h) */
+    float corner_coords[24];
+    float corner_values[8];
+    float intersect_coord[36];
+    int32_t edge_list[12];
+    int32_t tri_vlist[15];
+    int32_t n_edges, n_tri_idx, cube_code, table_idx, skipped;
+};
+struct InspectCons {
+    int n;            /* constraints in use */
+    int op[3];        /* 0 '>', 1 '<', 2 '>=', 3 '<=' */
+    float rhs[3];
+};
+__global__ void inspect_cube_kernel(const mcb_program* __restrict__ progs /* [0] surface, [1..3] constraint lhs */, const InspectCons cons,
+                                    const int cons_slot0, const int cons_slot1, const int cons_slot2,
+                                    float x0, float y0, float z0, float step, float sx, float sy, float sz, float iso,
+                                    const ClsTables* __restrict__ gtb, StepOut* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    StepOut o;
+    const float x1 = x0 + step, y1 = y0 + step, z1 = z0 + step; /* marching.cpp:458-460 */
+    const float cc[24] = {x0, y0, z0, x1, y0, z0, x1, y1, z0, x0, y1, z0, x0, y0, z1, x1, y0, z1, x1, y1, z1, x0, y1, z1};
+    for (int q = 0; q < 24; q++) o.corner_coords[q] = cc[q];
+    for (int q = 0; q < 8; q++) o.corner_values[q] = 0.f;
+    o.n_edges = 0; o.n_tri_idx = 0; o.cube_code = 0; o.table_idx = 0; o.skipped = 0;
+    const int slots[3] = {cons_slot0, cons_slot1, cons_slot2};
+    for (int v = 0; v < 8 && !o.skipped; v++) {
+        const float X = sx * cc[3 * v], Y = sy * cc[3 * v + 1], Z = sz * cc[3 * v + 2]; /* Marching::evaluate, marching.cpp:211 */
+        for (int c = 0; c < cons.n; c++) { /* check_constraints, marching.cpp:255-280 */
+            const mcb_program& p = progs[slots[c]];
+            const float lhs = mcb_interp_scalar(p.code, p.n, p.k, X, Y, Z, nullptr, nullptr, nullptr);
+            const int op = cons.op[c];
+            const bool ok = op == 0 ? lhs > cons.rhs[c] : op == 1 ? lhs < cons.rhs[c] : op == 2 ? lhs >= cons.rhs[c] : lhs <= cons.rhs[c];
+            if (!ok) o.skipped = 1;
+        }
+        if (o.skipped) break;
+        o.corner_values[v] = mcb_interp_scalar(progs[0].code, progs[0].n, progs[0].k, X, Y, Z, nullptr, nullptr, nullptr);
+    }
+    if (!o.skipped) {
+        int code = 0;
+        for (int v = 0; v < 8; v++) code |= (o.corner_values[v] > iso ? 1 : 0) << v;
+        o.cube_code = code;
+        o.table_idx = code;
+        if (code != 0 && code != 255) {
+            const int face = (int)gtb->face[code];
+            if (face >= 0) { /* marching.cpp:521-549 */
+                float mx = 0.f, my = 0.f, mz = 0.f;
+                for (int q = 0; q < 4; q++) {
+                    const int cv = mcb_face_corner(face, q);
+                    mx += cc[3 * cv]; my += cc[3 * cv + 1]; mz += cc[3 * cv + 2];
+                }
+                mx /= 4.0f; my /= 4.0f; mz /= 4.0f;
+                const float mid = mcb_interp_scalar(progs[0].code, progs[0].n, progs[0].k, sx * mx, sy * my, sz * mz, nullptr, nullptr, nullptr);
+                if (mid > iso) o.table_idx = 255 - code;
+            }
+            int mapper[12];
+            for (int e = 0; e < 12; e++) {
+                mapper[e] = 12;
+                const int a = mcb_edge_a(e), b = mcb_edge_b(e);
+                if ((((code >> a) ^ (code >> b)) & 1) == 0) continue;
+                const float t = (iso - o.corner_values[a]) / (o.corner_values[b] - o.corner_values[a]);
+                mapper[e] = o.n_edges;
+                o.edge_list[o.n_edges] = e;
+                o.intersect_coord[3 * o.n_edges] = interp_ref(cc[3 * a], cc[3 * b], t);
+                o.intersect_coord[3 * o.n_edges + 1] = interp_ref(cc[3 * a + 1], cc[3 * b + 1], t);
+                o.intersect_coord[3 * o.n_edges + 2] = interp_ref(cc[3 * a + 2], cc[3 * b + 2], t);
+                o.n_edges++;
+            }
+            const uint64_t row = gtb->tri[o.table_idx];
+            for (int f = 0; f < 15; f++) {
+                const int e = (int)((row >> (4 * f)) & 0xF);
+                if (e == 0xF) break;
+                o.tri_vlist[o.n_tri_idx++] = mapper[e];
+            }
+        }
+    }
+    *out = o;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Parity hooks (not on the hot path).
  * ------------------------------------------------------------------------------------------------------------- */
 __global__ void dense_codes_kernel(const Grid g, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,

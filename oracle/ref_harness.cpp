@@ -105,6 +105,15 @@ int mcref_set_constraint(mcref* h, int i, const char* lhs, int op, float rhs, in
 }
 
 int mcref_recalculate(mcref* h) { return h->march.recalculate() ? 1 : 0; }
+/* Step-by-step mode (marching.cpp:386-428): recalculate() once per cube until it reports that it has finished, then
+ * back to the full-grid mode.  Returns the number of calls that returned true. */
+long mcref_step_all(mcref* h, long max_calls) {
+    h->march.step_by_step_mode(true);
+    long n = 0;
+    while (n < max_calls && h->march.recalculate()) n++;
+    h->march.step_by_step_mode(false);
+    return n;
+}
 /* Seed mode (marching.cpp:42-137, 310-331): Marching::set_seed + seed_mode(true) + recalculate(), then back to the
  * full-grid mode.  Returns 0 when set_seed rejects the point. */
 int mcref_seed_recalculate(mcref* h, float sx, float sy, float sz) {

@@ -60,6 +60,8 @@ def lib():
         L.mcref_set_constraint.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_float, C.c_int]
         L.mcref_recalculate.argtypes = [C.c_void_p]
         L.mcref_seed_recalculate.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+        L.mcref_step_all.argtypes = [C.c_void_p, C.c_long]
+        L.mcref_step_all.restype = C.c_long
         L.mcref_num_vertices.argtypes = [C.c_void_p]
         L.mcref_num_vertices.restype = C.c_long
         L.mcref_num_triangles.argtypes = [C.c_void_p]
@@ -142,6 +144,13 @@ class Ref:
         """Unmodified Marching::recalculate(); returns (vertex_list[n,3], tri_list[t,3])."""
         self.L.mcref_recalculate(self.h)
         return self.mesh()
+
+    def step_all(self, max_calls=10 ** 7):
+        """Step-by-step mode run to completion (one cube per recalculate(), marching.cpp:386-428).
+        Returns (calls, vertex_list, tri_list)."""
+        n = self.L.mcref_step_all(self.h, max_calls)
+        v, t = self.mesh()
+        return n, v, t
 
     def seed_recalculate(self, sx, sy, sz):
         """Seed mode: only the cubes face-connected (through crossing faces) to the cube containing the seed, in BFS

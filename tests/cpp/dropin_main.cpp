@@ -31,7 +31,14 @@ int main(int argc, char** argv) {
         march_maker.set_scaling_y((float)atof(argv[a + 4]));
         march_maker.set_scaling_z((float)atof(argv[a + 5]));
         march_maker.set_surface_constant((float)atof(argv[a + 6]));
-        if (!march_maker.recalculate()) { std::printf("%s RECALCULATE_FAILED\n", argv[a]); continue; }
+        const bool stepping = std::strncmp(argv[a], "step_", 5) == 0; /* step-by-step mode, one cube per call */
+        long calls = 0;
+        if (stepping) {
+            march_maker.step_by_step_mode(true);
+            while (calls < 10000000 && march_maker.recalculate()) calls++;
+            march_maker.step_by_step_mode(false);
+            std::printf("%s_calls %ld\n", argv[a], calls);
+        } else if (!march_maker.recalculate()) { std::printf("%s RECALCULATE_FAILED\n", argv[a]); continue; }
         std::printf("%s %zu %zu %016llx %016llx\n", argv[a], pData->vertex_list.size() / 3, pData->tri_list.size() / 3,
                     (unsigned long long)fnv(pData->vertex_list.data(), pData->vertex_list.size() * 4),
                     (unsigned long long)fnv(pData->tri_list.data(), pData->tri_list.size() * 4));

@@ -37,5 +37,18 @@ for name, c in CASES.items():
     meta[name] = dict(eq=c["eq"], step=c["step"], scale=[c["scale"]] * 3, seed=list(c["seed"]), T=int(len(t)), V=int(len(v)),
                       T_full=int(len(full_t)))
     print(name, meta[name]["T"], "of", meta[name]["T_full"])
+# step-by-step mode run to completion: the reference's own traversal (`< 1.0` bounds, carried coordinates)
+STEP_CASES = {
+    "step_eq1_ctor": dict(eq=R.EXAMPLE_EQUATIONS[1], step=0.25, scale=1.0),
+    "step_sphere": dict(eq=R.SPHERE, step=0.25, scale=1.0),
+    "step_eq8_gui": dict(eq=R.EXAMPLE_EQUATIONS[8], step=0.2, scale=1.1),
+}
+for name, c in STEP_CASES.items():
+    r = R.Ref(c["eq"], c["step"], scale=(c["scale"],) * 3)
+    n, v, t = r.step_all()
+    out[name + "/vertex_list"] = v
+    out[name + "/tri_list"] = t
+    meta[name] = dict(eq=c["eq"], step=c["step"], scale=[c["scale"]] * 3, calls=int(n), V=int(len(v)), T=int(len(t)))
+    print(name, n, "calls", len(v), "vertices", len(t), "triangles")
 out["meta_json"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "seed_cases.npz"), **out)
