@@ -713,20 +713,47 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
                           (unsigned)g.NZ);
         const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
         /* resolve the table operands for this grid: argument = float offset of the table row inside d_tables */
+        /* device form of the fused program: dense handler numbers, table operands as absolute float offsets, and
+         * LOAD/PUSH a ; op b  pairs folded into one two-word instruction (eval_pair) */
         mcb_program launch = eq.grid;
         bool has_pow = false;
-        for (int pc = 0; pc < launch.n; pc++) {
-            const uint32_t wd = launch.code[pc], fop = MCB_FINSN_OP(wd), src = MCB_FINSN_SRC(wd);
-            has_pow |= fop == MCB_F_POW || fop == MCB_F_RPOW;
-            if (fop == MCB_F_NEG) { launch.code[pc] = MCB_HANDLER_NEG; continue; }
-            uint32_t arg = MCB_FINSN_ARG(wd);
-            if (src < MCB_SRC_K || src > MCB_SRC_POP) return fail(ctx, MCB_E_STATE, "internal: raw coordinate operand in a grid program");
-            if (src >= MCB_SRC_TX && src <= MCB_SRC_TZ) {
-                const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + arg) * g.P;
-                if (off >= (1u << 24)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
-                arg = (uint32_t)off;
+        {
+            auto leaf_class = [](uint32_t src) { return src == MCB_SRC_K ? 0 : src == MCB_SRC_TX ? 1 : src == MCB_SRC_TY ? 2 : src == MCB_SRC_TZ ? 3 : -1; };
+            auto resolve = [&](uint32_t src, uint32_t arg, uint32_t* out) {
+                if (src >= MCB_SRC_TX && src <= MCB_SRC_TZ) {
+                    const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + arg) * g.P;
+                    if (off >= (1u << 24)) return false;
+                    arg = (uint32_t)off;
+                }
+                *out = arg;
+                return true;
+            };
+            int n = 0;
+            for (int pc = 0; pc < eq.grid.n; pc++) {
+                const uint32_t wd = eq.grid.code[pc], fop = MCB_FINSN_OP(wd), src = MCB_FINSN_SRC(wd);
+                has_pow |= fop == MCB_F_POW || fop == MCB_F_RPOW;
+                if (fop == MCB_F_NEG) { launch.code[n++] = MCB_HANDLER_NEG; continue; }
+                if (src < MCB_SRC_K || src > MCB_SRC_POP) return fail(ctx, MCB_E_STATE, "internal: raw coordinate operand in a grid program");
+                uint32_t arg;
+                if (!resolve(src, MCB_FINSN_ARG(wd), &arg)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
+                if ((fop == MCB_F_LOAD || fop == MCB_F_PUSH) && pc + 1 < eq.grid.n) {
+                    const uint32_t nx = eq.grid.code[pc + 1], nop = MCB_FINSN_OP(nx), nsrc = MCB_FINSN_SRC(nx);
+                    if (nop >= MCB_F_ADD && nop <= MCB_F_RPOW && leaf_class(nsrc) >= 0) {
+                        uint32_t arg_b;
+                        if (!resolve(nsrc, MCB_FINSN_ARG(nx), &arg_b)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
+                        has_pow |= nop == MCB_F_POW || nop == MCB_F_RPOW;
+                        if (fop == MCB_F_PUSH) launch.code[n++] = MCB_HANDLER_SPILL;
+                        if (n + 2 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
+                        launch.code[n++] = (uint32_t)MCB_HANDLER_PAIR(nop, leaf_class(src), leaf_class(nsrc)) | (arg << 8);
+                        launch.code[n++] = arg_b;
+                        pc++;
+                        continue;
+                    }
+                }
+                if (n + 1 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
+                launch.code[n++] = (uint32_t)MCB_HANDLER(fop, src) | (arg << 8); /* dense handler number | operand */
             }
-            launch.code[pc] = (uint32_t)MCB_HANDLER(fop, src) | (arg << 8); /* dense handler number | operand */
+            launch.n = n;
         }
         if (has_pow) eval_field_kernel<true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
         else eval_field_kernel<false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);

@@ -164,6 +164,36 @@ __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, c
     }
 }
 
+/* A leaf operand as the 4 x 4 patch of a lane sees it: class 0 constant, 1 x-table, 2 y-table, 3 z-table */
+template <int CLS>
+struct LeafOperand {
+    float4 v;
+    __device__ __forceinline__ LeafOperand(uint32_t arg, const mcb_program& prog, const EvalLane& L) {
+        if (CLS == 0) v = make_float4(prog.k[arg], 0.f, 0.f, 0.f);
+        else if (CLS == 1) v = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.x0));
+        else if (CLS == 2) v = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.y0));
+        else v = make_float4(__ldg(L.tables + arg + L.zi), 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ float at(int r, int q) const {
+        const int c = CLS == 1 ? q : CLS == 2 ? r : 0;
+        return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+    }
+};
+/* LOAD a ; op b  in one step: acc = a (op) b without first copying a into the 16 accumulator registers.  The host
+ * pairs them up when it encodes the launch program (two words: handler | arg(a) << 8, then arg(b)). */
+template <int FOP, int CA, int CB>
+__device__ __forceinline__ void eval_pair(float (&acc)[kEvalRows], uint32_t arg_a, uint32_t arg_b, const mcb_program& prog,
+                                          const EvalLane& L) {
+    const LeafOperand<CA> a(arg_a, prog, L);
+    const LeafOperand<CB> b(arg_b, prog, L);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[4 * r + q] = fused_op<FOP>(a.at(r, q), b.at(r, q));
+}
+#define MCB_HANDLER_SPILL 55 /* push the accumulator on the memory stack; the new value comes from the next (pair) word */
+#define MCB_HANDLER_PAIR(FOP, CA, CB) (64 + ((FOP) - MCB_F_ADD) * 16 + (CA) * 4 + (CB))
+
 /* `prog` is the fused grid program with its table operands already resolved by the host for this launch:
  * for src TX/TY/TZ the argument is the float offset of the table row inside `tables` ((axis*slots + slot) * PT),
  * so an operand fetch is one address add and one load.  Grid programs contain no raw X/Y/Z operands: bare
@@ -181,7 +211,7 @@ constexpr int kEvalTileY = 4;   /* rows per warp tile */
 static_assert(kEvalRows == 16, "a lane carries a 4 x 4 patch");
 
 template <bool HAS_POW> /* programs without `^` (after hoisting) get a kernel without the powf paths: fewer registers */
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
 eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
                   float* __restrict__ F, uint32_t* __restrict__ S, int row_groups) {
     extern __shared__ float stack_smem[]; /* [level][16][kEvalThreads] */
@@ -221,6 +251,20 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
             MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_K) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TX) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TY)
             MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TZ) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_POP)
 #undef MCB_STEP_POW
+#define MCB_PAIR(FOP, CA, CB) \
+    case MCB_HANDLER_PAIR(FOP, CA, CB): if (HAS_POW || ((FOP) != MCB_F_POW && (FOP) != MCB_F_RPOW)) eval_pair<FOP, CA, CB>(acc, arg, prog.code[++pc], prog, L); break;
+#define MCB_PAIR_B(FOP, CA) MCB_PAIR(FOP, CA, 0) MCB_PAIR(FOP, CA, 1) MCB_PAIR(FOP, CA, 2) MCB_PAIR(FOP, CA, 3)
+#define MCB_PAIR_AB(FOP) MCB_PAIR_B(FOP, 0) MCB_PAIR_B(FOP, 1) MCB_PAIR_B(FOP, 2) MCB_PAIR_B(FOP, 3)
+            MCB_PAIR_AB(MCB_F_ADD) MCB_PAIR_AB(MCB_F_SUB) MCB_PAIR_AB(MCB_F_RSUB) MCB_PAIR_AB(MCB_F_MUL)
+            MCB_PAIR_AB(MCB_F_DIV) MCB_PAIR_AB(MCB_F_RDIV) MCB_PAIR_AB(MCB_F_POW) MCB_PAIR_AB(MCB_F_RPOW)
+#undef MCB_PAIR
+#undef MCB_PAIR_B
+#undef MCB_PAIR_AB
+            case MCB_HANDLER_SPILL:
+#pragma unroll
+                for (int e = 0; e < kEvalRows; e++) sp[e * kEvalThreads] = acc[e];
+                sp += kEvalLevel;
+                break;
             default: /* MCB_F_NEG */
 #pragma unroll
                 for (int e = 0; e < kEvalRows; e++) acc[e] = -acc[e];
@@ -264,7 +308,7 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
 #undef MCB_STEP
 #undef MCB_STEP_LEAF
 #undef MCB_STEP_ALL
-/* MCB_HANDLER / MCB_HANDLER_NEG stay defined: mcb_api.cu encodes the launch program with them */
+/* MCB_HANDLER* stay defined: mcb_api.cu encodes the launch program with them */
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
 __global__ void __launch_bounds__(256)
