@@ -238,13 +238,19 @@ def run_ours(args):
         else:
             bufs = [torch.empty((capT, 3, 4), dtype=torch.float32).pin_memory(), torch.empty((capT, 3, 4), dtype=torch.float32).pin_memory()]
 
+        if mode == mcb.MESH_INDEXED:  # registered once: polygonise() streams the mesh into these pinned buffers
+            ctx.set_host_output(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), capV, capT)
+        else:
+            ctx.set_host_output(0, 0, 0, 0, 0)
+
         def one():
             assert ctx.set_equation(eq) == 0          # tokenise + lower + upload bytecode (H2D) + fold constants
             ctx.set_grid_step(step)                   # host coordinate loop + upload (H2D)
             ctx.set_slab(k0, k1)
-            cc = step_fn()
+            cc = step_fn()                            # MESH_INDEXED: returns when Poly_Data is in the host buffers (D2H inside)
             if mode == mcb.MESH_INDEXED:
-                ctx.get_indexed_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), capV, capT)  # D2H
+                if not ctx.host_output_filled():      # first call after a buffer had to grow: plain copy
+                    ctx.get_indexed_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), capV, capT)
             else:
                 ctx.get_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), capT)  # D2H of positions + normals
             return cc
@@ -270,6 +276,7 @@ def run_ours(args):
 
     soup_ms, cc_s, e2e_steps = time_e2e(mcb.MESH_SOUP)
     idx_ms, cc, e2e_steps = time_e2e(mcb.MESH_INDEXED)
+    ctx.set_host_output(0, 0, 0, 0, 0)
     ctx.set_mesh_mode(mcb.MESH_SOUP)
     e2e_value = cubes / (idx_ms * 1e-3) / 1e9
     h2d = 4 * (mcb.lib.mcb_grid_axis(step, None, 0) + 3 + 64) + 2052 * 2 + 512

@@ -159,6 +159,15 @@ int mcb_set_mesh_mode(mcb_ctx* ctx, int mode);
 int mcb_get_indexed_mesh(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices,
                          uint64_t cap_triangles);
 int mcb_get_indexed_mesh_device(mcb_ctx* ctx, const float** vertex_list, const uint32_t** tri_list, const float** normals);
+/* Register host buffers (pinned memory for real overlap) as the destination of the indexed mesh.  While they are
+ * registered, mcb_polygonise in MCB_MESH_INDEXED mode streams vertex_list / normals / tri_list out range by range
+ * while the later ranges are still being produced, and returns when the mesh is on the host — one call, like
+ * Marching::recalculate() filling Poly_Data.  normals may be NULL when normals are off.  When a device buffer has to
+ * grow first, the mesh does not fit the registered capacities, or normal.h normals (mode 2) are on, nothing is
+ * streamed: mcb_host_output_filled() returns 0 and mcb_get_indexed_mesh delivers the mesh.  NULL pointers unregister. */
+int mcb_set_host_output(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices,
+                        uint64_t cap_triangles);
+int mcb_host_output_filled(const mcb_ctx* ctx);
 
 /* Marching::calculate_step(x_0, y_0, z_0) (marching.cpp:456-595) for ONE cube with origin (x0,y0,z0) and the context's
  * step, scale, iso, equation and constraints: the Step_Data (marching.h:15-23) the GUI's step-by-step / movie mode

@@ -87,6 +87,8 @@ def _load():
         "mcb_set_mesh_mode": ([vp, i], i),
         "mcb_get_indexed_mesh": ([vp, vp, vp, vp, u64, u64], i),
         "mcb_get_indexed_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i),
+        "mcb_set_host_output": ([vp, vp, vp, vp, u64, u64], i),
+        "mcb_host_output_filled": ([vp], i),
         "mcb_get_cases": ([vp, vp, vp], i),
         "mcb_get_field": ([vp, vp], i),
         "mcb_get_active": ([vp, vp, vp, u64], i),
@@ -236,6 +238,14 @@ class Context:
         self._ck(lib.mcb_get_indexed_mesh(self.h, vl.ctypes.data_as(C.c_void_p), tl.ctypes.data_as(C.c_void_p),
                                           vn.ctypes.data_as(C.c_void_p) if normals else None, V, T))
         return (vl, tl, vn) if normals else (vl, tl)
+
+    def set_host_output(self, v_ptr, t_ptr, n_ptr, cap_v, cap_t):
+        """Register (pinned) host buffers: polygonise() in MESH_INDEXED mode then streams the mesh into them."""
+        self._ck(lib.mcb_set_host_output(self.h, C.c_void_p(v_ptr) if v_ptr else None, C.c_void_p(t_ptr) if t_ptr else None,
+                                         C.c_void_p(n_ptr) if n_ptr else None, cap_v, cap_t))
+
+    def host_output_filled(self):
+        return bool(lib.mcb_host_output_filled(self.h))
 
     def get_indexed_mesh_into(self, v_ptr, t_ptr, n_ptr, cap_v, cap_t):
         """Raw-pointer variant (pinned host buffers owned by the caller)."""

@@ -88,6 +88,16 @@ struct mcb_ctx {
     uint32_t* d_tlist = nullptr;   /* [3 * cap_itris] */
     unsigned long long cap_verts = 0, cap_itris = 0;
     bool vnrm_allocated = false;
+    /* host output registered with mcb_set_host_output: the indexed mesh is streamed out while it is produced */
+    float* h_out_v = nullptr;
+    uint32_t* h_out_t = nullptr;
+    float* h_out_n = nullptr;
+    unsigned long long h_cap_v = 0, h_cap_t = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t seg_ev[9] = {};
+    unsigned long long* d_bounds = nullptr;
+    unsigned long long* h_bounds = nullptr; /* pinned */
+    bool streamed = false;                  /* the last polygonise delivered the mesh to the registered buffers */
     /* seed mode (mcb_set_seed) */
     bool seed_on = false;
     float seed[3] = {0.f, 0.f, 0.f};
@@ -485,6 +495,11 @@ int mcb_create(int device, mcb_ctx** out) {
     ctx->stream = ctx->own_stream;
     for (auto& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return bail(MCB_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MCB_E_CUDA);
+    for (auto& e : ctx->seg_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(MCB_E_CUDA);
+    if (cudaMalloc((void**)&ctx->d_bounds, 3 * 9 * 8) != cudaSuccess) return bail(MCB_E_NOMEM);
+    if (cudaMallocHost((void**)&ctx->h_bounds, 3 * 9 * 8) != cudaSuccess) return bail(MCB_E_NOMEM);
     if (cudaMalloc((void**)&ctx->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(MCB_E_NOMEM);
     if (cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(MCB_E_NOMEM);
     ClsTables tb;
@@ -525,6 +540,10 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaFree(ctx->d_nh_sums); cudaFree(ctx->d_nh_adj);
     cudaFree(ctx->d_mark); cudaFree(ctx->d_changed); cudaFree(ctx->d_seed_u32); cudaFree(ctx->d_rec2); cudaFree(ctx->d_trioff2);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->seg_ev) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    cudaFree(ctx->d_bounds);
+    if (ctx->h_bounds) cudaFreeHost(ctx->h_bounds);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -862,13 +881,50 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
             weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
             weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);
-            if (ctx->normals == 1)
-                weld_emit_kernel<true><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
-                                                                           ctx->d_vlist, ctx->d_vnrm, ctx->d_tlist);
-            else
-                weld_emit_kernel<false><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
-                                                                            ctx->d_vlist, nullptr, ctx->d_tlist);
-            launches += 4;
+            /* streaming: with a registered host destination and everything fitting, weld_emit runs range by range and
+             * each finished range of vertices / normals / triangles leaves over PCIe on the copy stream meanwhile */
+            constexpr int K = 8;
+            bool stream_out = ctx->h_out_v && ctx->h_out_t && ctx->normals != 2 && (ctx->normals == 0 || ctx->h_out_n);
+            ctx->streamed = false;
+            if (stream_out) {
+                weld_bounds_kernel<<<1, 32, 0, s>>>(B, ctx->d_ctr, ctx->cap_active, K, ctx->d_bounds);
+                MCB_CK(cudaMemcpyAsync(ctx->h_bounds, ctx->d_bounds, 3 * (K + 1) * 8, cudaMemcpyDeviceToHost, s));
+                MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+                MCB_CK(cudaStreamSynchronize(s));
+                launches++;
+                const Counters& hc = *ctx->h_ctr;
+                if (hc.active > ctx->cap_active || hc.vertices > ctx->cap_verts || hc.triangles > ctx->cap_itris ||
+                    hc.vertices > ctx->h_cap_v || hc.triangles > ctx->h_cap_t)
+                    stream_out = false; /* a device buffer has to grow first, or the host buffers are too small */
+            }
+            for (int j = 0; j < (stream_out ? K : 1); j++) {
+                const unsigned long long cb = stream_out ? ctx->h_bounds[3 * j] : 0ull, ce = stream_out ? ctx->h_bounds[3 * j + 3] : ~0ull;
+                if (stream_out && cb == ce) continue;
+                if (ctx->normals == 1)
+                    weld_emit_kernel<true><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
+                                                                               ctx->d_vlist, ctx->d_vnrm, ctx->d_tlist, cb, ce);
+                else
+                    weld_emit_kernel<false><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
+                                                                                ctx->d_vlist, nullptr, ctx->d_tlist, cb, ce);
+                launches++;
+                if (!stream_out) break;
+                const unsigned long long v0 = ctx->h_bounds[3 * j + 1], v1 = ctx->h_bounds[3 * j + 4];
+                const unsigned long long t0 = ctx->h_bounds[3 * j + 2], t1 = ctx->h_bounds[3 * j + 5];
+                MCB_CK(cudaEventRecord(ctx->seg_ev[j], s));
+                MCB_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->seg_ev[j], 0));
+                if (v1 > v0) {
+                    MCB_CK(cudaMemcpyAsync(ctx->h_out_v + 3 * v0, ctx->d_vlist + 3 * v0, (v1 - v0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    if (ctx->normals == 1)
+                        MCB_CK(cudaMemcpyAsync(ctx->h_out_n + 3 * v0, ctx->d_vnrm + 3 * v0, (v1 - v0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                }
+                if (t1 > t0)
+                    MCB_CK(cudaMemcpyAsync(ctx->h_out_t + 3 * t0, ctx->d_tlist + 3 * t0, (t1 - t0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
+            if (stream_out) {
+                MCB_CK(cudaEventRecord(ctx->seg_ev[K], ctx->copy_stream));
+                ctx->streamed = true;
+            }
+            launches += 3;
             if (ctx->normals == 2) { /* K5: CalculateNormal (normal.h:3-42) on the welded mesh, bit-exact */
                 if ((rc = ensure_normal_h_scratch(ctx)) != MCB_OK) return rc;
                 const unsigned long long* nv = &ctx->d_ctr->vertices;
@@ -884,6 +940,7 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             }
         }
         MCB_CK(cudaEventRecord(ctx->ev[5], s));
+        if (want_indexed && ctx->streamed) MCB_CK(cudaStreamWaitEvent(s, ctx->seg_ev[8], 0)); /* return when the mesh is on the host */
         MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         MCB_CK(cudaStreamSynchronize(s));
         MCB_CK(cudaGetLastError());
@@ -956,6 +1013,16 @@ int mcb_set_mesh_mode(mcb_ctx* ctx, int mode) {
     ctx->have_result = false;
     return MCB_OK;
 }
+
+int mcb_set_host_output(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices, uint64_t cap_triangles) {
+    if (!ctx) return MCB_E_ARG;
+    ctx->h_out_v = vertex_list; ctx->h_out_t = tri_list; ctx->h_out_n = normals;
+    ctx->h_cap_v = vertex_list ? cap_vertices : 0; ctx->h_cap_t = tri_list ? cap_triangles : 0;
+    ctx->streamed = false;
+    return MCB_OK;
+}
+
+int mcb_host_output_filled(const mcb_ctx* ctx) { return ctx && ctx->streamed ? 1 : 0; }
 
 int mcb_get_indexed_mesh(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices,
                          uint64_t cap_triangles) {

@@ -1274,11 +1274,27 @@ weld_base_kernel(const WeldBuffers B, const Counters* __restrict__ ctr, unsigned
     }
 }
 
+/* first vertex and first triangle of K+1 chunk boundaries (boundary j = chunk j * nchunks / K): what the host needs
+ * to stream the mesh out in K ranges while weld_emit is still producing the later ones */
+__global__ void weld_bounds_kernel(const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active, int K,
+                                   unsigned long long* __restrict__ out /* [3 * (K + 1)]: chunk, vertex, triangle */) {
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    const unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    const int j = threadIdx.x;
+    if (j > K) return;
+    const unsigned long long c = j == K ? nchunks : nchunks * (unsigned long long)j / (unsigned long long)K;
+    out[3 * j] = c;
+    out[3 * j + 1] = c < nchunks ? (unsigned long long)B.chunk_new[c] : ctr->vertices;
+    out[3 * j + 2] = c < nchunks ? (unsigned long long)B.trioff[c * kWeldCubes] : ctr->triangles;
+}
+
 template <bool NORMALS>
 __global__ void __launch_bounds__(kWeldThreads)
 weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active,
                  unsigned long long cap_verts, unsigned long long cap_tris, float* __restrict__ vertex_list,
-                 float* __restrict__ vertex_nrm, uint32_t* __restrict__ tri_list) {
+                 float* __restrict__ vertex_nrm, uint32_t* __restrict__ tri_list, unsigned long long chunk_begin,
+                 unsigned long long chunk_end /* chunks [begin,end) of kWeldCubes cubes: the host streams the mesh out range by range */) {
     __shared__ WeldChunk sh;
     __shared__ uint32_t eidx[kWeldCubes * 12]; /* welded vertex index of [cube][edge] */
     __shared__ uint8_t tri2cube[kWeldCubes * 5]; /* chunk-local triangle -> local cube (a cube has at most 5) */
@@ -1288,10 +1304,11 @@ weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restri
     const Grid& g = W.g;
     unsigned long long A = ctr->active, T = ctr->triangles;
     if (A > cap_active) A = cap_active;
-    const unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    if (nchunks > chunk_end) nchunks = chunk_end;
     const int t = threadIdx.x;
     const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
-    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (unsigned long long chunk = chunk_begin + blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         __syncthreads();
         const unsigned long long c0 = chunk * kWeldCubes;
         const int n = (int)((A - c0) < (unsigned long long)kWeldCubes ? (A - c0) : kWeldCubes);

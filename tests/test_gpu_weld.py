@@ -144,3 +144,34 @@ def test_normal_h_normals_need_the_indexed_mesh(mcb):
     with pytest.raises(mcb.McbError):
         c.polygonise()
     c.close()
+
+
+def test_streamed_host_output_equals_the_plain_copy(mcb):
+    """mcb_set_host_output: the mesh streamed into registered (pinned) buffers while weld_emit is still running equals
+    what mcb_get_indexed_mesh copies afterwards; too-small buffers and the first (buffer-growing) call fall back."""
+    import torch
+    c = mcb.Context(0)
+    c.set_mesh_mode(mcb.MESH_INDEXED)
+    c.set_normals(1)
+    assert c.set_equation("x^2+y^2+z^2-0.49") == 0 and c.set_grid_step(2.0 / 256) == 257
+    cnt = c.polygonise()
+    v0, t0, n0 = c.get_indexed_mesh(normals=True)
+    capV, capT = int(cnt.vertices) + 100, int(cnt.triangles) + 100
+    bv = torch.full((capV, 3), -7.0, dtype=torch.float32).pin_memory()
+    bt = torch.full((capT, 3), -7, dtype=torch.int32).pin_memory()
+    bn = torch.full((capV, 3), -7.0, dtype=torch.float32).pin_memory()
+    c.set_host_output(bv.data_ptr(), bt.data_ptr(), bn.data_ptr(), capV, capT)
+    cnt2 = c.polygonise()
+    assert c.host_output_filled() and (cnt2.vertices, cnt2.triangles) == (cnt.vertices, cnt.triangles)
+    V, T = int(cnt.vertices), int(cnt.triangles)
+    assert same_bits(bv.numpy()[:V], v0) and same_bits(bn.numpy()[:V], n0)
+    assert np.array_equal(bt.numpy()[:T].view(np.uint32), t0)
+    assert float(bv[V:].min()) == -7.0 and int(bt[T:].min()) == -7  # nothing written past the mesh
+    # host buffers too small: nothing is streamed, the plain getter still works
+    c.set_host_output(bv.data_ptr(), bt.data_ptr(), bn.data_ptr(), 10, 10)
+    c.polygonise()
+    assert not c.host_output_filled()
+    v1, t1 = c.get_indexed_mesh()
+    assert same_bits(v1, v0) and np.array_equal(t1, t0)
+    c.set_host_output(0, 0, 0, 0, 0)
+    c.close()
