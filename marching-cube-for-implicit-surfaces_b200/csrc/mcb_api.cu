@@ -679,23 +679,36 @@ int mcb_set_normals(mcb_ctx* ctx, int mode) {
     return MCB_OK;
 }
 
-int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
-    int rc = enter(ctx);
-    if (rc != MCB_OK) return rc;
-    EqSlot& eq = ctx->eq[0];
-    if (!eq.valid) return fail(ctx, MCB_E_STATE, "no surface equation");
-    if ((rc = setup_grid(ctx)) != MCB_OK) return rc;
-    Grid& g = ctx->g;
-    g.sx = ctx->scale[0]; g.sy = ctx->scale[1]; g.sz = ctx->scale[2];
-    g.iso = ctx->iso;
-    cudaStream_t s = ctx->stream;
-    uint32_t launches = 0, reruns = 0;
+} /* extern "C" */
 
-    bool any_constraint = false;
-    for (int i = 0; i < 3; i++) any_constraint |= ctx->cons[i].in_use && ctx->eq[i + 1].valid;
-    if (ctx->normals == 2 && !(ctx->mesh_mode & MCB_MESH_INDEXED))
-        return fail(ctx, MCB_E_STATE, "normal.h normals (mode 2) are defined on the welded mesh: request MCB_MESH_INDEXED");
+namespace {
 
+/* One mcb_polygonise call, stage by stage.  Every stage only enqueues work on the context's stream; the host reads
+ * the counters once at the end (seed mode and streamed output need them earlier and synchronise there). */
+struct Run {
+    mcb_ctx* ctx;
+    Grid& g;
+    EqSlot& eq;
+    cudaStream_t s;
+    bool any_constraint, want_soup, want_indexed;
+    const uint32_t* dV; /* constraint validity planes or nullptr */
+    ClsGeom cg;
+    unsigned tiles, eblocks;
+    uint32_t launches;
+
+    int prepare_buffers();
+    int encode_program(mcb_program& launch, bool& has_pow);
+    int stage_tables();
+    int stage_eval();
+    int stage_classify();
+    int stage_seed();
+    int stage_soup();
+    int stage_weld();
+    int stage_normal_h();
+};
+
+int Run::prepare_buffers() {
+    int rc;
     const size_t ntab = (size_t)3 * eq.max_per_axis * g.P + 256; /* the last 128-column tile reads past the pitch */
     if ((rc = ensure(ctx, &ctx->d_tables, &ctx->cap_tables, ntab)) != MCB_OK) return rc;
     if (any_constraint) {
@@ -707,7 +720,6 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
         guess = std::min<unsigned long long>(guess, (unsigned long long)(g.ke - g.kb) * g.M * g.M);
         if ((rc = ensure_records(ctx, std::max<unsigned long long>(guess, 1024))) != MCB_OK) return rc;
     }
-    const bool want_soup = (ctx->mesh_mode & MCB_MESH_SOUP) != 0, want_indexed = (ctx->mesh_mode & MCB_MESH_INDEXED) != 0;
     if (want_soup && (ctx->cap_tris == 0 || (ctx->normals && !ctx->nrm_allocated))) {
         if ((rc = ensure_soup(ctx, std::max<unsigned long long>(2 * ctx->cap_active, 1024), ctx->normals != 0)) != MCB_OK) return rc;
     }
@@ -715,232 +727,296 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
         if ((rc = ensure_indexed(ctx, std::max<unsigned long long>(ctx->cap_verts, std::max<unsigned long long>(ctx->cap_active + ctx->cap_active / 4, 1024)),
                                  std::max<unsigned long long>(ctx->cap_itris, std::max<unsigned long long>(2 * ctx->cap_active, 1024)), ctx->normals != 0)) != MCB_OK) return rc;
     }
+    return MCB_OK;
+}
 
-    MCB_CK(cudaEventRecord(ctx->ev[0], s));
-    /* K0b: per-axis tables of the hoisted single-variable subtrees */
+/* Device form of the fused grid program: dense handler numbers, table operands as absolute float offsets into
+ * d_tables, and  LOAD/PUSH a ; op b  pairs folded into one two-word instruction (eval_pair). */
+int Run::encode_program(mcb_program& launch, bool& has_pow) {
+    launch = eq.grid;
+    has_pow = false;
+    {
+        auto leaf_class = [](uint32_t src) { return src == MCB_SRC_K ? 0 : src == MCB_SRC_TX ? 1 : src == MCB_SRC_TY ? 2 : src == MCB_SRC_TZ ? 3 : -1; };
+        auto resolve = [&](uint32_t src, uint32_t arg, uint32_t* out) {
+            if (src >= MCB_SRC_TX && src <= MCB_SRC_TZ) {
+                const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + arg) * g.P;
+                if (off >= (1u << 24)) return false;
+                arg = (uint32_t)off;
+            }
+            *out = arg;
+            return true;
+        };
+        int n = 0;
+        for (int pc = 0; pc < eq.grid.n; pc++) {
+            const uint32_t wd = eq.grid.code[pc], fop = MCB_FINSN_OP(wd), src = MCB_FINSN_SRC(wd);
+            has_pow |= fop == MCB_F_POW || fop == MCB_F_RPOW;
+            if (fop == MCB_F_NEG) { launch.code[n++] = MCB_HANDLER_NEG; continue; }
+            if (src < MCB_SRC_K || src > MCB_SRC_POP) return fail(ctx, MCB_E_STATE, "internal: raw coordinate operand in a grid program");
+            uint32_t arg;
+            if (!resolve(src, MCB_FINSN_ARG(wd), &arg)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
+            if ((fop == MCB_F_LOAD || fop == MCB_F_PUSH) && pc + 1 < eq.grid.n) {
+                const uint32_t nx = eq.grid.code[pc + 1], nop = MCB_FINSN_OP(nx), nsrc = MCB_FINSN_SRC(nx);
+                if (nop >= MCB_F_ADD && nop <= MCB_F_RPOW && leaf_class(nsrc) >= 0) {
+                    uint32_t arg_b;
+                    if (!resolve(nsrc, MCB_FINSN_ARG(nx), &arg_b)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
+                    has_pow |= nop == MCB_F_POW || nop == MCB_F_RPOW;
+                    if (fop == MCB_F_PUSH) launch.code[n++] = MCB_HANDLER_SPILL;
+                    if (n + 2 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
+                    launch.code[n++] = (uint32_t)MCB_HANDLER_PAIR(nop, leaf_class(src), leaf_class(nsrc)) | (arg << 8);
+                    launch.code[n++] = arg_b;
+                    pc++;
+                    continue;
+                }
+            }
+            if (n + 1 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
+            launch.code[n++] = (uint32_t)MCB_HANDLER(fop, src) | (arg << 8); /* dense handler number | operand */
+        }
+        launch.n = n;
+    }
+    return MCB_OK;
+}
+
+/* K0b: per-axis tables of the hoisted single-variable subtrees */
+int Run::stage_tables() {
     if (eq.n_axis > 0) {
         dim3 grid((g.P + 127) / 128, eq.n_axis);
         axis_tables_kernel<<<grid, 128, 0, s>>>(eq.d_slot_code, eq.d_slots, eq.n_const, eq.d_kpool, ctx->d_cs, g.NV, g.P,
                                                 eq.max_per_axis, g.sx, g.sy, g.sz, ctx->d_tables);
         launches++;
     }
-    MCB_CK(cudaEventRecord(ctx->ev[1], s));
-    /* K1: field + sign bit-plane */
-    {
-        const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY; /* 4-row groups per plane */
-        const dim3 blocks((unsigned)((g.P + kEvalTileX - 1) / kEvalTileX), (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)),
-                          (unsigned)g.NZ);
-        const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
-        /* resolve the table operands for this grid: argument = float offset of the table row inside d_tables */
-        /* device form of the fused program: dense handler numbers, table operands as absolute float offsets, and
-         * LOAD/PUSH a ; op b  pairs folded into one two-word instruction (eval_pair) */
-        mcb_program launch = eq.grid;
-        bool has_pow = false;
-        {
-            auto leaf_class = [](uint32_t src) { return src == MCB_SRC_K ? 0 : src == MCB_SRC_TX ? 1 : src == MCB_SRC_TY ? 2 : src == MCB_SRC_TZ ? 3 : -1; };
-            auto resolve = [&](uint32_t src, uint32_t arg, uint32_t* out) {
-                if (src >= MCB_SRC_TX && src <= MCB_SRC_TZ) {
-                    const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + arg) * g.P;
-                    if (off >= (1u << 24)) return false;
-                    arg = (uint32_t)off;
-                }
-                *out = arg;
-                return true;
-            };
-            int n = 0;
-            for (int pc = 0; pc < eq.grid.n; pc++) {
-                const uint32_t wd = eq.grid.code[pc], fop = MCB_FINSN_OP(wd), src = MCB_FINSN_SRC(wd);
-                has_pow |= fop == MCB_F_POW || fop == MCB_F_RPOW;
-                if (fop == MCB_F_NEG) { launch.code[n++] = MCB_HANDLER_NEG; continue; }
-                if (src < MCB_SRC_K || src > MCB_SRC_POP) return fail(ctx, MCB_E_STATE, "internal: raw coordinate operand in a grid program");
-                uint32_t arg;
-                if (!resolve(src, MCB_FINSN_ARG(wd), &arg)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
-                if ((fop == MCB_F_LOAD || fop == MCB_F_PUSH) && pc + 1 < eq.grid.n) {
-                    const uint32_t nx = eq.grid.code[pc + 1], nop = MCB_FINSN_OP(nx), nsrc = MCB_FINSN_SRC(nx);
-                    if (nop >= MCB_F_ADD && nop <= MCB_F_RPOW && leaf_class(nsrc) >= 0) {
-                        uint32_t arg_b;
-                        if (!resolve(nsrc, MCB_FINSN_ARG(nx), &arg_b)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
-                        has_pow |= nop == MCB_F_POW || nop == MCB_F_RPOW;
-                        if (fop == MCB_F_PUSH) launch.code[n++] = MCB_HANDLER_SPILL;
-                        if (n + 2 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
-                        launch.code[n++] = (uint32_t)MCB_HANDLER_PAIR(nop, leaf_class(src), leaf_class(nsrc)) | (arg << 8);
-                        launch.code[n++] = arg_b;
-                        pc++;
-                        continue;
-                    }
-                }
-                if (n + 1 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
-                launch.code[n++] = (uint32_t)MCB_HANDLER(fop, src) | (arg << 8); /* dense handler number | operand */
-            }
-            launch.n = n;
+    return MCB_OK;
+}
+
+/* K1: field + sign bit-planes (+ K1b: constraint validity bit-planes) */
+int Run::stage_eval() {
+    const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY; /* 4-row groups per plane */
+    const dim3 blocks((unsigned)((g.P + kEvalTileX - 1) / kEvalTileX), (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)),
+                      (unsigned)g.NZ);
+    const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
+    mcb_program launch;
+    bool has_pow;
+    int rc = encode_program(launch, has_pow);
+    if (rc != MCB_OK) return rc;
+    if (has_pow) eval_field_kernel<true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+    else eval_field_kernel<false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+    launches++;
+    if (any_constraint) {
+        const long long words = (long long)g.NZ * g.NV * g.WP;
+        int first = 1;
+        for (int i = 0; i < 3; i++) {
+            if (!(ctx->cons[i].in_use && ctx->eq[i + 1].valid)) continue;
+            eval_constraint_kernel<<<(unsigned)((words + 7) / 8), 256, 0, s>>>(ctx->eq[i + 1].point, g, ctx->d_cs, ctx->cons[i].op,
+                                                                                 ctx->cons[i].rhs, first, ctx->d_V, words);
+            first = 0;
+            launches++;
         }
-        if (has_pow) eval_field_kernel<true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
-        else eval_field_kernel<false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
-        launches++;
-        if (any_constraint) {
-            const long long words = (long long)g.NZ * g.NV * g.WP;
-            int first = 1;
-            for (int i = 0; i < 3; i++) {
-                if (!(ctx->cons[i].in_use && ctx->eq[i + 1].valid)) continue;
-                eval_constraint_kernel<<<(unsigned)((words + 7) / 8), 256, 0, s>>>(ctx->eq[i + 1].point, g, ctx->d_cs, ctx->cons[i].op,
-                                                                                     ctx->cons[i].rhs, first, ctx->d_V, words);
-                first = 0;
+    }
+    return MCB_OK;
+}
+
+/* K2: classification + ambiguity (per tile, independent) -> look-back scan + compaction */
+int Run::stage_classify() {
+    int rc;
+    MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
+    const ClsScratch sc{ctx->d_tile_list, ctx->d_tile_cnt, ctx->d_tile_nz, cg.tile_rows * cg.WC};
+    if (dV)
+        classify_kernel<true><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
+                                                                        ctx->d_status, ctx->d_ctr);
+    else
+        classify_kernel<false><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
+                                                                         ctx->d_status, ctx->d_ctr);
+    const bool need_items = want_indexed || ctx->seed_on; /* per-word record index for the weld / the seed walk */
+    if (need_items && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
+    compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status, ctx->d_ctr,
+                                                 ctx->d_rec, ctx->d_trioff, ctx->cap_active, need_items ? ctx->d_item : nullptr);
+    launches += 2;
+    return MCB_OK;
+}
+
+/* K6: keep the component of the seed cube (marching.cpp:42-137, 310-331) */
+int Run::stage_seed() {
+    int rc;
+    MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    MCB_CK(cudaStreamSynchronize(s));
+    if (ctx->h_ctr->active <= ctx->cap_active) { /* otherwise the records are truncated: the re-run comes first */
+        if ((rc = ensure_seed_scratch(ctx)) != MCB_OK) return rc;
+        const unsigned long long n = ctx->cap_seed;
+        uint32_t *keep = ctx->d_seed_u32, *ktri = keep + n, *pa = ktri + n, *pt = pa + n, *sums = pt + n;
+        const SeedBuffers SB{ctx->d_rec, ctx->d_item, cg.WC, ctx->d_mark, ctx->d_changed};
+        const WeldView W{g, ctx->d_cs, ctx->d_F, dV, nullptr, cg.WC};
+        const unsigned sblocks = (unsigned)ctx->sm_count * 8;
+        int sc3[3];
+        seed_cube(ctx, sc3);
+        MCB_CK(cudaMemsetAsync(ctx->d_mark, 0, std::max<unsigned long long>(ctx->h_ctr->active, 1), s));
+        MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
+        if (sc3[0] >= 0 && sc3[1] >= 0 && sc3[2] >= g.kb && sc3[0] < g.M && sc3[1] < g.M && sc3[2] < g.ke) {
+            seed_init_kernel<<<1, 1, 0, s>>>(SB, g, ctx->d_ctr, ctx->cap_active, sc3[0], sc3[1], sc3[2]);
+            launches++;
+        }
+        for (int round = 0; round < 100000; round++) { /* monotone marking until nothing changes */
+            uint32_t changed = 0;
+            MCB_CK(cudaMemcpyAsync(&changed, ctx->d_changed, 4, cudaMemcpyDeviceToHost, s));
+            MCB_CK(cudaStreamSynchronize(s));
+            if (!changed) break;
+            MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
+            for (int q = 0; q < 8; q++) {
+                seed_sweep_kernel<<<sblocks, 256, 0, s>>>(SB, W, ctx->d_ctr, ctx->cap_active, 0.5 * (double)ctx->step);
                 launches++;
             }
         }
+        const unsigned long long* na = &ctx->d_ctr->active;
+        seed_flags_kernel<<<sblocks, 256, 0, s>>>(SB, ctx->d_cls, ctx->d_ctr, ctx->cap_active, keep, ktri);
+        scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, na, sums);
+        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
+        scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, sums, na, pa);
+        scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, na, sums);
+        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
+        scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, sums, na, pt);
+        seed_scatter_kernel<<<sblocks, 256, 0, s>>>(SB, keep, ktri, pa, pt, ctx->d_ctr, ctx->cap_active, ctx->d_rec2, ctx->d_trioff2);
+        seed_commit_kernel<<<1, 1, 0, s>>>(ctx->d_ctr);
+        std::swap(ctx->d_rec, ctx->d_rec2);
+        std::swap(ctx->d_trioff, ctx->d_trioff2);
+        launches += 9;
+        if (want_indexed) { /* the weld must only see the kept cubes: rebuild the per-word look-up from scratch */
+            MCB_CK(cudaMemsetAsync(ctx->d_item, 0, (size_t)(g.ke - g.kb) * g.M * cg.WC * 8, s));
+            seed_items_kernel<<<sblocks, 256, 0, s>>>(ctx->d_rec, g, cg.WC, ctx->d_ctr, ctx->d_item);
+            launches++;
+        }
     }
+    return MCB_OK;
+}
+
+/* K3: interpolation + coalesced float4 emission of the triangle soup */
+int Run::stage_soup() {
+    if (ctx->normals == 1)
+        emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
+                                                           ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
+    else
+        emit_kernel<false><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
+                                                            ctx->cap_tris, ctx->d_pos, nullptr);
+    launches++;
+    return MCB_OK;
+}
+
+/* K4: the reference's welded, indexed mesh (Poly_Data::vertex_list / tri_list) */
+int Run::stage_weld() {
+    int rc;
+    if ((rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
+    const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr, ctx->seed_on ? ctx->d_item : nullptr, cg.WC};
+    const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_item, ctx->d_vinfo, ctx->d_chunk_new, cg.WC};
+    weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
+    weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
+    weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);
+    /* streaming: with a registered host destination and everything fitting, weld_emit runs range by range and
+     * each finished range of vertices / normals / triangles leaves over PCIe on the copy stream meanwhile */
+    constexpr int K = 8;
+    bool stream_out = ctx->h_out_v && ctx->h_out_t && ctx->normals != 2 && (ctx->normals == 0 || ctx->h_out_n);
+    ctx->streamed = false;
+    if (stream_out) {
+        weld_bounds_kernel<<<1, 32, 0, s>>>(B, ctx->d_ctr, ctx->cap_active, K, ctx->d_bounds);
+        MCB_CK(cudaMemcpyAsync(ctx->h_bounds, ctx->d_bounds, 3 * (K + 1) * 8, cudaMemcpyDeviceToHost, s));
+        MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        MCB_CK(cudaStreamSynchronize(s));
+        launches++;
+        const Counters& hc = *ctx->h_ctr;
+        if (hc.active > ctx->cap_active || hc.vertices > ctx->cap_verts || hc.triangles > ctx->cap_itris ||
+            hc.vertices > ctx->h_cap_v || hc.triangles > ctx->h_cap_t)
+            stream_out = false; /* a device buffer has to grow first, or the host buffers are too small */
+    }
+    for (int j = 0; j < (stream_out ? K : 1); j++) {
+        const unsigned long long cb = stream_out ? ctx->h_bounds[3 * j] : 0ull, ce = stream_out ? ctx->h_bounds[3 * j + 3] : ~0ull;
+        if (stream_out && cb == ce) continue;
+        if (ctx->normals == 1)
+            weld_emit_kernel<true><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
+                                                                       ctx->d_vlist, ctx->d_vnrm, ctx->d_tlist, cb, ce);
+        else
+            weld_emit_kernel<false><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
+                                                                        ctx->d_vlist, nullptr, ctx->d_tlist, cb, ce);
+        launches++;
+        if (!stream_out) break;
+        const unsigned long long v0 = ctx->h_bounds[3 * j + 1], v1 = ctx->h_bounds[3 * j + 4];
+        const unsigned long long t0 = ctx->h_bounds[3 * j + 2], t1 = ctx->h_bounds[3 * j + 5];
+        MCB_CK(cudaEventRecord(ctx->seg_ev[j], s));
+        MCB_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->seg_ev[j], 0));
+        if (v1 > v0) {
+            MCB_CK(cudaMemcpyAsync(ctx->h_out_v + 3 * v0, ctx->d_vlist + 3 * v0, (v1 - v0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (ctx->normals == 1)
+                MCB_CK(cudaMemcpyAsync(ctx->h_out_n + 3 * v0, ctx->d_vnrm + 3 * v0, (v1 - v0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        if (t1 > t0)
+            MCB_CK(cudaMemcpyAsync(ctx->h_out_t + 3 * t0, ctx->d_tlist + 3 * t0, (t1 - t0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    if (stream_out) {
+        MCB_CK(cudaEventRecord(ctx->seg_ev[K], ctx->copy_stream));
+        ctx->streamed = true;
+    }
+    launches += 3;
+    return MCB_OK;
+}
+
+/* K5: CalculateNormal (normal.h:3-42) on the welded mesh, bit-exact */
+int Run::stage_normal_h() {
+    int rc;
+    if ((rc = ensure_normal_h_scratch(ctx)) != MCB_OK) return rc;
+    const unsigned long long* nv = &ctx->d_ctr->vertices;
+    MCB_CK(cudaMemsetAsync(ctx->d_nh_count, 0, ctx->cap_verts * 4, s));
+    MCB_CK(cudaMemsetAsync(ctx->d_nh_cursor, 0, ctx->cap_verts * 4, s));
+    nh_face_normals_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_vlist, ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_fn, ctx->d_nh_count);
+    scan_block_sums_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, nv, ctx->d_nh_sums);
+    scan_sums_kernel<<<1, kScanBlock, 0, s>>>(ctx->d_nh_sums, nv);
+    scan_apply_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, ctx->d_nh_sums, nv, ctx->d_nh_start);
+    nh_fill_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_nh_start, ctx->d_nh_cursor, ctx->d_nh_adj);
+    nh_accumulate_kernel<<<eblocks * 4, 128, 0, s>>>(ctx->d_fn, ctx->d_nh_start, ctx->d_nh_count, ctx->d_nh_adj, ctx->d_ctr, ctx->cap_verts, ctx->d_vnrm);
+    launches += 6;
+    return MCB_OK;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->eq[0].valid) return fail(ctx, MCB_E_STATE, "no surface equation");
+    if ((rc = setup_grid(ctx)) != MCB_OK) return rc;
+    Grid& g = ctx->g;
+    g.sx = ctx->scale[0]; g.sy = ctx->scale[1]; g.sz = ctx->scale[2];
+    g.iso = ctx->iso;
+    if (ctx->normals == 2 && !(ctx->mesh_mode & MCB_MESH_INDEXED))
+        return fail(ctx, MCB_E_STATE, "normal.h normals (mode 2) are defined on the welded mesh: request MCB_MESH_INDEXED");
+
+    Run run{ctx, g, ctx->eq[0], ctx->stream, false, (ctx->mesh_mode & MCB_MESH_SOUP) != 0, (ctx->mesh_mode & MCB_MESH_INDEXED) != 0,
+            nullptr, ClsGeom{}, 0u, (unsigned)ctx->sm_count * 4, 0u};
+    for (int i = 0; i < 3; i++) run.any_constraint |= ctx->cons[i].in_use && ctx->eq[i + 1].valid;
+    if ((rc = run.prepare_buffers()) != MCB_OK) return rc;
+    run.dV = run.any_constraint ? ctx->d_V : nullptr;
+    run.cg = classify_geometry(ctx, g, &run.tiles);
+    cudaStream_t s = ctx->stream;
+    uint32_t reruns = 0;
+
+    MCB_CK(cudaEventRecord(ctx->ev[0], s));
+    if ((rc = run.stage_tables()) != MCB_OK) return rc;
+    MCB_CK(cudaEventRecord(ctx->ev[1], s));
+    if ((rc = run.stage_eval()) != MCB_OK) return rc;
     MCB_CK(cudaEventRecord(ctx->ev[2], s));
     MCB_CK(cudaGetLastError());
 
-    unsigned tiles = 0;
-    const ClsGeom cg = classify_geometry(ctx, g, &tiles);
     bool need_classify = true;
-    for (;;) {
+    for (;;) { /* repeated only when an output buffer had to grow (mcb_counts::reruns) */
         if (need_classify) {
-            /* K2: classification + ambiguity (per tile, independent) -> look-back scan + compaction */
-            MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
-            const ClsScratch sc{ctx->d_tile_list, ctx->d_tile_cnt, ctx->d_tile_nz, cg.tile_rows * cg.WC};
-            const uint32_t* dV = any_constraint ? ctx->d_V : nullptr;
-            if (dV)
-                classify_kernel<true><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
-                                                                                ctx->d_status, ctx->d_ctr);
-            else
-                classify_kernel<false><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
-                                                                                 ctx->d_status, ctx->d_ctr);
-            if ((want_indexed || ctx->seed_on) && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
-            compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,
-                                                         ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active,
-                                                         (want_indexed || ctx->seed_on) ? ctx->d_item : nullptr);
-            launches += 2;
-            if (ctx->seed_on) { /* K6: keep the component of the seed cube (marching.cpp:42-137, 310-331) */
-                MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-                MCB_CK(cudaStreamSynchronize(s));
-                if (ctx->h_ctr->active <= ctx->cap_active) { /* otherwise the records are truncated: the re-run comes first */
-                    if ((rc = ensure_seed_scratch(ctx)) != MCB_OK) return rc;
-                    const unsigned long long n = ctx->cap_seed;
-                    uint32_t *keep = ctx->d_seed_u32, *ktri = keep + n, *pa = ktri + n, *pt = pa + n, *sums = pt + n;
-                    const SeedBuffers SB{ctx->d_rec, ctx->d_item, cg.WC, ctx->d_mark, ctx->d_changed};
-                    const WeldView W{g, ctx->d_cs, ctx->d_F, dV, nullptr, cg.WC};
-                    const unsigned sblocks = (unsigned)ctx->sm_count * 8;
-                    int sc3[3];
-                    seed_cube(ctx, sc3);
-                    MCB_CK(cudaMemsetAsync(ctx->d_mark, 0, std::max<unsigned long long>(ctx->h_ctr->active, 1), s));
-                    MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
-                    if (sc3[0] >= 0 && sc3[1] >= 0 && sc3[2] >= g.kb && sc3[0] < g.M && sc3[1] < g.M && sc3[2] < g.ke) {
-                        seed_init_kernel<<<1, 1, 0, s>>>(SB, g, ctx->d_ctr, ctx->cap_active, sc3[0], sc3[1], sc3[2]);
-                        launches++;
-                    }
-                    for (int round = 0; round < 100000; round++) { /* monotone marking until nothing changes */
-                        uint32_t changed = 0;
-                        MCB_CK(cudaMemcpyAsync(&changed, ctx->d_changed, 4, cudaMemcpyDeviceToHost, s));
-                        MCB_CK(cudaStreamSynchronize(s));
-                        if (!changed) break;
-                        MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
-                        for (int q = 0; q < 8; q++) {
-                            seed_sweep_kernel<<<sblocks, 256, 0, s>>>(SB, W, ctx->d_ctr, ctx->cap_active, 0.5 * (double)ctx->step);
-                            launches++;
-                        }
-                    }
-                    const unsigned long long* na = &ctx->d_ctr->active;
-                    seed_flags_kernel<<<sblocks, 256, 0, s>>>(SB, ctx->d_cls, ctx->d_ctr, ctx->cap_active, keep, ktri);
-                    scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, na, sums);
-                    scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
-                    scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, sums, na, pa);
-                    scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, na, sums);
-                    scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
-                    scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, sums, na, pt);
-                    seed_scatter_kernel<<<sblocks, 256, 0, s>>>(SB, keep, ktri, pa, pt, ctx->d_ctr, ctx->cap_active, ctx->d_rec2, ctx->d_trioff2);
-                    seed_commit_kernel<<<1, 1, 0, s>>>(ctx->d_ctr);
-                    std::swap(ctx->d_rec, ctx->d_rec2);
-                    std::swap(ctx->d_trioff, ctx->d_trioff2);
-                    launches += 9;
-                    if (want_indexed) { /* the weld must only see the kept cubes: rebuild the per-word look-up from scratch */
-                        MCB_CK(cudaMemsetAsync(ctx->d_item, 0, (size_t)(g.ke - g.kb) * g.M * cg.WC * 8, s));
-                        seed_items_kernel<<<sblocks, 256, 0, s>>>(ctx->d_rec, g, cg.WC, ctx->d_ctr, ctx->d_item);
-                        launches++;
-                    }
-                }
-            }
+            if ((rc = run.stage_classify()) != MCB_OK) return rc;
+            if (ctx->seed_on && (rc = run.stage_seed()) != MCB_OK) return rc;
             MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
-        /* K3: interpolation + coalesced float4 emission of the triangle soup */
-        const unsigned eblocks = (unsigned)ctx->sm_count * 4;
-        if (want_soup) {
-            if (ctx->normals == 1)
-                emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
-            else
-                emit_kernel<false><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, nullptr);
-            launches++;
-        }
+        if (run.want_soup && (rc = run.stage_soup()) != MCB_OK) return rc;
         MCB_CK(cudaEventRecord(ctx->ev[4], s));
-        /* K4: the reference's welded, indexed mesh (Poly_Data::vertex_list / tri_list) */
-        if (want_indexed) {
-            if ((rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
-            const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr, ctx->seed_on ? ctx->d_item : nullptr, cg.WC};
-            const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_item, ctx->d_vinfo, ctx->d_chunk_new, cg.WC};
-            weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
-            weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
-            weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);
-            /* streaming: with a registered host destination and everything fitting, weld_emit runs range by range and
-             * each finished range of vertices / normals / triangles leaves over PCIe on the copy stream meanwhile */
-            constexpr int K = 8;
-            bool stream_out = ctx->h_out_v && ctx->h_out_t && ctx->normals != 2 && (ctx->normals == 0 || ctx->h_out_n);
-            ctx->streamed = false;
-            if (stream_out) {
-                weld_bounds_kernel<<<1, 32, 0, s>>>(B, ctx->d_ctr, ctx->cap_active, K, ctx->d_bounds);
-                MCB_CK(cudaMemcpyAsync(ctx->h_bounds, ctx->d_bounds, 3 * (K + 1) * 8, cudaMemcpyDeviceToHost, s));
-                MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-                MCB_CK(cudaStreamSynchronize(s));
-                launches++;
-                const Counters& hc = *ctx->h_ctr;
-                if (hc.active > ctx->cap_active || hc.vertices > ctx->cap_verts || hc.triangles > ctx->cap_itris ||
-                    hc.vertices > ctx->h_cap_v || hc.triangles > ctx->h_cap_t)
-                    stream_out = false; /* a device buffer has to grow first, or the host buffers are too small */
-            }
-            for (int j = 0; j < (stream_out ? K : 1); j++) {
-                const unsigned long long cb = stream_out ? ctx->h_bounds[3 * j] : 0ull, ce = stream_out ? ctx->h_bounds[3 * j + 3] : ~0ull;
-                if (stream_out && cb == ce) continue;
-                if (ctx->normals == 1)
-                    weld_emit_kernel<true><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
-                                                                               ctx->d_vlist, ctx->d_vnrm, ctx->d_tlist, cb, ce);
-                else
-                    weld_emit_kernel<false><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
-                                                                                ctx->d_vlist, nullptr, ctx->d_tlist, cb, ce);
-                launches++;
-                if (!stream_out) break;
-                const unsigned long long v0 = ctx->h_bounds[3 * j + 1], v1 = ctx->h_bounds[3 * j + 4];
-                const unsigned long long t0 = ctx->h_bounds[3 * j + 2], t1 = ctx->h_bounds[3 * j + 5];
-                MCB_CK(cudaEventRecord(ctx->seg_ev[j], s));
-                MCB_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->seg_ev[j], 0));
-                if (v1 > v0) {
-                    MCB_CK(cudaMemcpyAsync(ctx->h_out_v + 3 * v0, ctx->d_vlist + 3 * v0, (v1 - v0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                    if (ctx->normals == 1)
-                        MCB_CK(cudaMemcpyAsync(ctx->h_out_n + 3 * v0, ctx->d_vnrm + 3 * v0, (v1 - v0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                }
-                if (t1 > t0)
-                    MCB_CK(cudaMemcpyAsync(ctx->h_out_t + 3 * t0, ctx->d_tlist + 3 * t0, (t1 - t0) * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            }
-            if (stream_out) {
-                MCB_CK(cudaEventRecord(ctx->seg_ev[K], ctx->copy_stream));
-                ctx->streamed = true;
-            }
-            launches += 3;
-            if (ctx->normals == 2) { /* K5: CalculateNormal (normal.h:3-42) on the welded mesh, bit-exact */
-                if ((rc = ensure_normal_h_scratch(ctx)) != MCB_OK) return rc;
-                const unsigned long long* nv = &ctx->d_ctr->vertices;
-                MCB_CK(cudaMemsetAsync(ctx->d_nh_count, 0, ctx->cap_verts * 4, s));
-                MCB_CK(cudaMemsetAsync(ctx->d_nh_cursor, 0, ctx->cap_verts * 4, s));
-                nh_face_normals_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_vlist, ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_fn, ctx->d_nh_count);
-                scan_block_sums_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, nv, ctx->d_nh_sums);
-                scan_sums_kernel<<<1, kScanBlock, 0, s>>>(ctx->d_nh_sums, nv);
-                scan_apply_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, ctx->d_nh_sums, nv, ctx->d_nh_start);
-                nh_fill_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_nh_start, ctx->d_nh_cursor, ctx->d_nh_adj);
-                nh_accumulate_kernel<<<eblocks * 4, 128, 0, s>>>(ctx->d_fn, ctx->d_nh_start, ctx->d_nh_count, ctx->d_nh_adj, ctx->d_ctr, ctx->cap_verts, ctx->d_vnrm);
-                launches += 6;
-            }
+        if (run.want_indexed) {
+            if ((rc = run.stage_weld()) != MCB_OK) return rc;
+            if (ctx->normals == 2 && (rc = run.stage_normal_h()) != MCB_OK) return rc;
         }
         MCB_CK(cudaEventRecord(ctx->ev[5], s));
-        if (want_indexed && ctx->streamed) MCB_CK(cudaStreamWaitEvent(s, ctx->seg_ev[8], 0)); /* return when the mesh is on the host */
+        if (run.want_indexed && ctx->streamed) MCB_CK(cudaStreamWaitEvent(s, ctx->seg_ev[8], 0)); /* return when the mesh is on the host */
         MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         MCB_CK(cudaStreamSynchronize(s));
         MCB_CK(cudaGetLastError());
@@ -954,11 +1030,11 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             need_classify = true;
             again = true;
         }
-        if (want_soup && needT > ctx->cap_tris) {
+        if (run.want_soup && needT > ctx->cap_tris) {
             if ((rc = ensure_soup(ctx, needT + needT / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
             again = true;
         }
-        if (want_indexed && (needT > ctx->cap_itris || needV > ctx->cap_verts || need_classify)) {
+        if (run.want_indexed && (needT > ctx->cap_itris || needV > ctx->cap_verts || need_classify)) {
             /* with truncated records the vertex count is a lower bound: size generously, the re-run settles it */
             const unsigned long long v = std::max(needV + needV / 8 + 1024, need_classify ? needA + needA / 4 : 0ull);
             if ((rc = ensure_indexed(ctx, v, needT + needT / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
@@ -983,9 +1059,9 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&c.ms_weld, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[5]);
-    c.vertices = want_indexed ? ctx->h_ctr->vertices : 0;
+    c.vertices = run.want_indexed ? ctx->h_ctr->vertices : 0;
     c.mesh_mode = (uint32_t)ctx->mesh_mode;
-    c.launches = launches;
+    c.launches = run.launches;
     c.reruns = reruns;
     ctx->have_result = true;
     if (out) *out = c;

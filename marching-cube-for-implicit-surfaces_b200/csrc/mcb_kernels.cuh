@@ -11,6 +11,20 @@
  *   records  R[capA] (u64)      i | j<<12 | k<<24 | code<<36 | table_idx<<44, in cube loop order
  *   trioff   O[capA] (u32)      index of the cube's first triangle
  *   pos,nrm  float4[3*capT]     triangle soup in the reference's emission order
+ *   item     I[NZ-3][M][WC] u64 per 32-cube word: first record | active mask << 32 (compact -> weld, seed walk)
+ *   vinfo    [capA] (u64)       per active cube: first new welded vertex | new-edge mask << 32 | on-vertex mask << 44
+ *   vlist    float[3*capV], tlist u32[3*capT], vnrm float[3*capV]   the welded Poly_Data (marching.h:26-30)
+ *
+ * Kernels, in launch order of one mcb_polygonise (DESIGN.md §kernels has the roofline of each):
+ *   K0  fold_constants, axis_tables      constant subtrees once; single-variable subtrees per grid coordinate
+ *   K1  eval_field<HAS_POW>              field + sign bit-plane; warp tile 128 x 4, a lane holds a 4 x 4 patch
+ *   K1b eval_constraint                  validity bit-plane of the constraints in use
+ *   K2  classify<HAS_V>, compact         case codes + ambiguity redirect per tile; look-back scan + records
+ *   K6  seed_*                           seed mode: component of the seed cube by monotone marking
+ *   K3  emit<NORMALS>                    triangle soup, one thread per crossing edge, coalesced float4 stores
+ *   K4  weld_count/scan/base/emit        the reference's welded, indexed mesh
+ *   K5  nh_*                             normal.h normals on the welded mesh
+ *   K7  inspect_cube                     calculate_step for one cube (step-by-step mode)
  */
 #pragma once
 
@@ -22,8 +36,8 @@
 
 namespace mcbk {
 
-constexpr int kEvalThreads = 128;   /* 4 warps; each warp: 32 x-columns x kEvalRows y-rows of one z-plane */
-constexpr int kEvalRows = 16;
+constexpr int kEvalThreads = 128;   /* 4 warps; each warp: one 128-column x 4-row tile of one z-plane */
+constexpr int kEvalRows = 16;       /* field values per lane: a 4 x 4 patch */
 constexpr int kClsThreads = 256;
 constexpr int kEmitCubes = 128;     /* active cubes per emit chunk */
 constexpr int kEmitThreads = 256;   /* threads working on one chunk */
