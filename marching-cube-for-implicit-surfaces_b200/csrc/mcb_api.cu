@@ -239,7 +239,7 @@ int setup_grid(mcb_ctx* ctx) {
     g.M = ctx->M;
     g.NV = ctx->M + 3;
     g.P = (g.NV + 31) / 32 * 32;
-    g.WP = g.P / 32;
+    g.WP = (g.P / 32 + 3) / 4 * 4; /* whole 128-column eval tiles: a tile row's 4 sign words are one aligned 16-byte store */
     g.kb = ctx->kb;
     g.ke = ctx->ke;
     g.NZ = (g.ke - g.kb) + 3;

@@ -5,7 +5,7 @@
  *   halo):  NV = M+3 vertex columns per axis, vertex v in [-1, M+1] stored at index v+1;
  *   coords   cs[P]              cs[v+1] = coordinate of vertex v (host-accumulated exactly like marching.cpp:375-377)
  *   field    F[NZ][NV][P]       fp32, x fastest, row pitch P = NV rounded up to 32, NZ = (ke-kb)+3 planes
- *   signs    S[NZ][NV][WP]      1 bit per vertex: F > iso (strict, NaN -> 0; marching.cpp:497-505), WP = P/32
+ *   signs    S[NZ][NV][WP]      1 bit per vertex: F > iso (strict, NaN -> 0; marching.cpp:497-505), WP = P/32 rounded up to 4
  *   valid    V[NZ][NV][WP]      1 bit per vertex: all constraints in use hold (marching.cpp:255-280); optional
  *   tables   T[axis][slot][P]   hoisted single-variable subtrees per grid coordinate
  *   records  R[capA] (u64)      i | j<<12 | k<<24 | code<<36 | table_idx<<44, in cube loop order
@@ -139,7 +139,7 @@ __device__ __forceinline__ float fused_op(float acc, float v) {
 
 struct EvalLane { /* what an operand fetch needs besides the instruction argument */
     const float* __restrict__ tables;
-    int x0, y0, zi; /* first of the lane's 4 columns, first of the warp's 4 rows, index into the z tables */
+    int x0, y0, zi; /* the lane's first column (its others: x0 + 32 q), first of the warp's 4 rows, index into the z tables */
 };
 constexpr int kEvalLevel = kEvalRows * kEvalThreads; /* floats per memory-stack level (kEvalRows = 16 values per lane) */
 
@@ -165,8 +165,8 @@ __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, c
 #pragma unroll
             for (int q = 0; q < 4; q++) acc[4 * r + q] = fused_op<FOP>(acc[4 * r + q], tv[r]);
     } else if (SRC == MCB_SRC_TX) { /* the lane's 4 columns of an x-table (the tables are padded past the last tile) */
-        const float4 t = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.x0));
-        const float tv[4] = {t.x, t.y, t.z, t.w};
+        const float* t = L.tables + arg + L.x0;
+        const float tv[4] = {__ldg(t), __ldg(t + 32), __ldg(t + 64), __ldg(t + 96)};
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -184,7 +184,10 @@ struct LeafOperand {
     float4 v;
     __device__ __forceinline__ LeafOperand(uint32_t arg, const mcb_program& prog, const EvalLane& L) {
         if (CLS == 0) v = make_float4(prog.k[arg], 0.f, 0.f, 0.f);
-        else if (CLS == 1) v = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.x0));
+        else if (CLS == 1) {
+            const float* t = L.tables + arg + L.x0;
+            v = make_float4(__ldg(t), __ldg(t + 32), __ldg(t + 64), __ldg(t + 96));
+        }
         else if (CLS == 2) v = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.y0));
         else v = make_float4(__ldg(L.tables + arg + L.zi), 0.f, 0.f, 0.f);
     }
@@ -236,7 +239,7 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
     if (yq >= row_groups) return; /* whole warp exits together; the kernel has no block-wide barrier */
     EvalLane L;
     L.tables = tables;
-    L.x0 = cx * kEvalTileX + 4 * lane;
+    L.x0 = cx * kEvalTileX + lane;
     L.y0 = yq * kEvalTileY;
     L.zi = pz + g.kb;
 
@@ -286,37 +289,27 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
         }
     }
 
-    /* ---- outputs ---- */
+    /* ---- outputs ----
+     * A lane's columns are x0 + 32 q: every field store is one fully coalesced 128-byte line per warp, and the warp
+     * ballot of (acc > iso) for column group q IS sign word q of the tile row — no bit gathering at all (the kernel
+     * was issue-bound in its epilogue).  Strict >, NaN -> 0 (marching.cpp:497-505).  Bits of the padding columns
+     * (x >= NV) are unspecified: every reader masks by cube column (column_mask) or addresses a real vertex. */
     const int x0 = L.x0, y0 = L.y0;
     const unsigned row0 = (unsigned)pz * (unsigned)g.NV + (unsigned)y0;
-    const bool xin = x0 < g.P; /* P is a multiple of 32: a lane's 4 columns are inside the pitch together or not at all */
-    /* columns that are real vertices (x < NV): only they may set sign bits */
-    const uint32_t xmask = x0 + 3 < g.NV ? 0xFu : x0 >= g.NV ? 0u : (0xFu >> (x0 + 4 - g.NV));
-    float4* fp = reinterpret_cast<float4*>(F + (size_t)row0 * g.P + x0);
-    uint32_t word[kEvalTileY];
+    float* fp = F + (size_t)row0 * g.P + x0;
+    /* lane r < 4 stores the four sign words of tile row r; WP is a multiple of 4, so that is one aligned uint4 */
+    uint4* sw = reinterpret_cast<uint4*>(S + ((size_t)row0 + (lane & 3)) * g.WP + cx * (kEvalTileX / 32));
 #pragma unroll
     for (int r = 0; r < kEvalTileY; r++) {
-        const bool rin = y0 + r < g.NV; /* uniform per warp */
-        if (rin && xin) __stcs(fp + (size_t)r * (g.P >> 2), make_float4(acc[4 * r], acc[4 * r + 1], acc[4 * r + 2], acc[4 * r + 3]));
-        /* acc > iso  <=>  the sign bit of (iso - acc) is set: NaN differences are the canonical positive NaN, an exact
-         * zero difference is +0, and with gradual underflow a non-zero difference never rounds to zero.  The four
-         * sign bytes are gathered with byte permutes and squeezed into a nibble by one multiply: far fewer ALU-pipe
-         * instructions than four compare/select pairs (the kernel is ALU-pipe bound, not FMA-pipe bound). */
-        const uint32_t d0 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r])), d1 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r + 1]));
-        const uint32_t d2 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r + 2])), d3 = __float_as_uint(__fsub_rn(g.iso, acc[4 * r + 3]));
-        const uint32_t tops = __byte_perm(__byte_perm(d0, d1, 0x0073), __byte_perm(d2, d3, 0x7300), 0x7610);
-        const uint32_t nib = ((tops & 0x80808080u) * 0x00204081u) >> 28;
-        uint32_t v = (nib & xmask) << (4 * (lane & 7));
-        v |= __shfl_xor_sync(0xffffffffu, v, 1); /* OR over the 8 lanes of a word (a partial-mask redux.sync is emulated) */
-        v |= __shfl_xor_sync(0xffffffffu, v, 2);
-        v |= __shfl_xor_sync(0xffffffffu, v, 4);
-        word[r] = v;
-    }
-    /* lane (8 j + r), r < 4, stores word j of row r */
-    const int r = lane & 7, wj = cx * (kEvalTileX / 32) + (lane >> 3);
-    if (r < kEvalTileY && y0 + r < g.NV && wj < g.WP) {
-        const uint32_t mine = r == 0 ? word[0] : r == 1 ? word[1] : r == 2 ? word[2] : word[3];
-        S[(size_t)(row0 + r) * g.WP + wj] = mine;
+        if (y0 + r >= g.NV) break; /* uniform per warp */
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int x = x0 + 32 * q;
+            if (x < g.P) __stcs(fp + (size_t)r * g.P + 32 * q, acc[4 * r + q]); /* P is a multiple of 32: uniform per warp */
+            w[q] = __ballot_sync(0xffffffffu, acc[4 * r + q] > g.iso);
+        }
+        if (lane == r) *sw = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 #undef MCB_STEP
