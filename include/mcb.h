@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MCB_ABI_VERSION 2
+#define MCB_ABI_VERSION 3
 
 typedef enum {
     MCB_OK = 0,
@@ -60,7 +60,16 @@ typedef struct {
     float ms_weld;        /* device time of the indexed-mesh stage (0 unless MCB_MESH_INDEXED) */
     uint32_t mesh_mode;   /* MCB_MESH_* bits this result was produced with */
     uint64_t vertices;    /* welded vertices of the indexed mesh (0 unless MCB_MESH_INDEXED) */
+    float ms_fill;        /* sparse-field mode: device time of the block refill (flag, list, evaluate); else 0 */
+    uint32_t field_mode;  /* MCB_FIELD_* this result was produced with */
+    uint64_t field_blocks; /* sparse-field mode: 32 x 4 x 4 vertex blocks the field was written in */
 } mcb_counts;
+
+/* Where the scalar field lives (mcb_set_field_mode; default MCB_FIELD_DENSE). */
+#define MCB_FIELD_DENSE 0   /* every grid vertex's value is written to device memory (4 B per vertex) */
+#define MCB_FIELD_SPARSE 1  /* every vertex is still evaluated, but only its sign is kept; the values are written again,
+                               by the same arithmetic, in 32 x 4 x 4 vertex blocks around the active cubes.  Meshes,
+                               normals and counts are bit-identical to MCB_FIELD_DENSE; mcb_get_field is unavailable */
 
 /* What mcb_polygonise leaves in device memory (mcb_set_mesh_mode; default MCB_MESH_SOUP). */
 #define MCB_MESH_SOUP 1     /* triangle soup: 3 float4 positions (+ 3 float4 normals) per triangle, emission order */
@@ -149,6 +158,10 @@ int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4);
  * redirected, welded vertices (stable for the lifetime of the context).  For multi-GPU placement the per-slab
  * triangle count can be all-gathered straight from here (NCCL) without a host round trip. */
 int mcb_counts_device(mcb_ctx* ctx, const uint64_t** counts);
+
+/* MCB_FIELD_DENSE (default) or MCB_FIELD_SPARSE: whether mcb_polygonise writes the whole scalar field to device
+ * memory or only the blocks of it that the mesh stages read.  Results are bit-identical. */
+int mcb_set_field_mode(mcb_ctx* ctx, int mode);
 
 /* MCB_MESH_SOUP, MCB_MESH_INDEXED or both (3).  The indexed mesh is what Marching::recalculate() leaves in
  * Poly_Data (marching.h:26-30): vertices welded and numbered as add_step_to_poly_data / add_point do it

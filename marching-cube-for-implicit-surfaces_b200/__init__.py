@@ -23,6 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcb200.so")
 
 MESH_SOUP, MESH_INDEXED = 1, 2
+FIELD_DENSE, FIELD_SPARSE = 0, 1
 MCB_OK, MCB_E_PARSE, MCB_E_ARG, MCB_E_CUDA, MCB_E_NOMEM, MCB_E_STATE, MCB_E_CAPACITY, MCB_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
 
 
@@ -37,7 +38,8 @@ class Counts(C.Structure):
                 ("redirected", C.c_uint64), ("M", C.c_int32), ("k_begin", C.c_int32), ("k_end", C.c_int32),
                 ("ms_tables", C.c_float), ("ms_eval", C.c_float), ("ms_classify", C.c_float), ("ms_emit", C.c_float),
                 ("ms_total", C.c_float), ("launches", C.c_uint32), ("reruns", C.c_uint32), ("ms_weld", C.c_float),
-                ("mesh_mode", C.c_uint32), ("vertices", C.c_uint64)]
+                ("mesh_mode", C.c_uint32), ("vertices", C.c_uint64), ("ms_fill", C.c_float), ("field_mode", C.c_uint32),
+                ("field_blocks", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -85,6 +87,7 @@ def _load():
         "mcb_get_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp)], i),
         "mcb_counts_device": ([vp, C.POINTER(vp)], i),
         "mcb_set_mesh_mode": ([vp, i], i),
+        "mcb_set_field_mode": ([vp, i], i),
         "mcb_get_indexed_mesh": ([vp, vp, vp, vp, u64, u64], i),
         "mcb_get_indexed_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i),
         "mcb_set_host_output": ([vp, vp, vp, vp, u64, u64], i),
@@ -224,6 +227,10 @@ class Context:
         p = C.c_void_p()
         self._ck(lib.mcb_counts_device(self.h, C.byref(p)))
         return p.value
+
+    def set_field_mode(self, mode):
+        """FIELD_DENSE (whole field in device memory) or FIELD_SPARSE (signs everywhere, values only around the surface)."""
+        self._ck(lib.mcb_set_field_mode(self.h, int(mode)))
 
     def set_mesh_mode(self, mode):
         """MESH_SOUP (float4 triangle soup), MESH_INDEXED (welded Poly_Data layout) or both (3)."""

@@ -120,7 +120,14 @@ struct mcb_ctx {
     unsigned long long* d_vinfo = nullptr; /* per active cube: first new vertex | new-edge mask | on-vertex mask */
     uint32_t* d_chunk_new = nullptr;
     unsigned long long cap_weld = 0;       /* cubes the two arrays above are sized for */
-    cudaEvent_t ev[7] = {};
+    cudaEvent_t ev[9] = {};
+    /* sparse-field mode (mcb_set_field_mode): the field is only written in 32 x 4 x 4 vertex blocks around the surface */
+    int field_mode = MCB_FIELD_DENSE;
+    bool field_is_sparse = false;  /* what the last polygonisation left in d_F */
+    bool poison_field = false;     /* $MCB_POISON_FIELD: NaN-fill d_F first, so a read outside the blocks shows (tests) */
+    uint8_t* d_fflags = nullptr;   /* [cap_fblocks] */
+    uint32_t* d_flist = nullptr;   /* [cap_fblocks] */
+    size_t cap_fblocks = 0;
     mcb_counts last{};
     bool have_result = false;
 };
@@ -512,11 +519,16 @@ int mcb_create(int device, mcb_ctx** out) {
     }
     if (cudaMalloc((void**)&ctx->d_cls, sizeof(ClsTables)) != cudaSuccess) return bail(MCB_E_NOMEM);
     if (cudaMemcpy(ctx->d_cls, &tb, sizeof tb, cudaMemcpyHostToDevice) != cudaSuccess) return bail(MCB_E_CUDA);
-    if (cudaFuncSetAttribute(eval_field_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float)) != cudaSuccess ||
-        cudaFuncSetAttribute(eval_field_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float)) != cudaSuccess)
-        return bail(MCB_E_CUDA);
+    {
+        const int stack_bytes = MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float);
+        const void* evals[] = {(const void*)eval_field_kernel<true, true>,  (const void*)eval_field_kernel<false, true>,
+                               (const void*)eval_field_kernel<true, false>, (const void*)eval_field_kernel<false, false>,
+                               (const void*)eval_blocks_kernel<true>,       (const void*)eval_blocks_kernel<false>};
+        for (const void* k : evals)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, stack_bytes) != cudaSuccess) return bail(MCB_E_CUDA);
+        const char* poison = std::getenv("MCB_POISON_FIELD");
+        ctx->poison_field = poison && poison[0] == '1';
+    }
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
     rc = mcb_set_grid_step(ctx, 0.25f); /* Marching::Marching(), marching.cpp:24 */
@@ -530,6 +542,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->eq) free_slot(s);
+    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist);
     cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -697,7 +710,8 @@ struct Run {
     uint32_t launches;
 
     int prepare_buffers();
-    int encode_program(mcb_program& launch, bool& has_pow);
+    int encode_program(mcb_program& launch, bool& has_pow, bool blocks);
+    int stage_fill();
     int stage_tables();
     int stage_eval();
     int stage_classify();
@@ -732,11 +746,14 @@ int Run::prepare_buffers() {
 
 /* Device form of the fused grid program: dense handler numbers, table operands as absolute float offsets into
  * d_tables, and  LOAD/PUSH a ; op b  pairs folded into one two-word instruction (eval_pair). */
-int Run::encode_program(mcb_program& launch, bool& has_pow) {
+int Run::encode_program(mcb_program& launch, bool& has_pow, bool blocks) {
     launch = eq.grid;
     has_pow = false;
     {
-        auto leaf_class = [](uint32_t src) { return src == MCB_SRC_K ? 0 : src == MCB_SRC_TX ? 1 : src == MCB_SRC_TY ? 2 : src == MCB_SRC_TZ ? 3 : -1; };
+        /* operand class of a source as the kernel's lane patch sees it; eval_blocks_kernel's patch is (y, z) per x
+         * column, so there the x and z tables trade places */
+        auto role = [blocks](uint32_t src) { return !blocks ? src : src == MCB_SRC_TX ? (uint32_t)MCB_SRC_TZ : src == MCB_SRC_TZ ? (uint32_t)MCB_SRC_TX : src; };
+        auto leaf_class = [&](uint32_t src0) { const uint32_t src = role(src0); return src == MCB_SRC_K ? 0 : src == MCB_SRC_TX ? 1 : src == MCB_SRC_TY ? 2 : src == MCB_SRC_TZ ? 3 : -1; };
         auto resolve = [&](uint32_t src, uint32_t arg, uint32_t* out) {
             if (src >= MCB_SRC_TX && src <= MCB_SRC_TZ) {
                 const size_t off = ((size_t)(src - MCB_SRC_TX) * eq.max_per_axis + arg) * g.P;
@@ -769,7 +786,7 @@ int Run::encode_program(mcb_program& launch, bool& has_pow) {
                 }
             }
             if (n + 1 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
-            launch.code[n++] = (uint32_t)MCB_HANDLER(fop, src) | (arg << 8); /* dense handler number | operand */
+            launch.code[n++] = (uint32_t)MCB_HANDLER(fop, role(src)) | (arg << 8); /* dense handler number | operand */
         }
         launch.n = n;
     }
@@ -795,10 +812,18 @@ int Run::stage_eval() {
     const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
     mcb_program launch;
     bool has_pow;
-    int rc = encode_program(launch, has_pow);
+    int rc = encode_program(launch, has_pow, false);
     if (rc != MCB_OK) return rc;
-    if (has_pow) eval_field_kernel<true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
-    else eval_field_kernel<false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+    const bool sparse = ctx->field_mode == MCB_FIELD_SPARSE;
+    if (sparse && ctx->poison_field) MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
+    if (sparse) {
+        if (has_pow) eval_field_kernel<true, false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        else eval_field_kernel<false, false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+    } else {
+        if (has_pow) eval_field_kernel<true, true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        else eval_field_kernel<false, true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+    }
+    ctx->field_is_sparse = sparse;
     launches++;
     if (any_constraint) {
         const long long words = (long long)g.NZ * g.NV * g.WP;
@@ -830,6 +855,36 @@ int Run::stage_classify() {
     compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status, ctx->d_ctr,
                                                  ctx->d_rec, ctx->d_trioff, ctx->cap_active, need_items ? ctx->d_item : nullptr);
     launches += 2;
+    return MCB_OK;
+}
+
+/* Sparse-field mode: the field values the later stages read — the corners of the active cubes and their +-1
+ * neighbours — are written now, block by block, by the same interpreter (the field is not materialised) */
+int Run::stage_fill() {
+    int rc;
+    const FieldBlocks shape{g.P / kFieldBlockX, (g.NV + kFieldBlockY - 1) / kFieldBlockY, (g.NZ + kFieldBlockZ - 1) / kFieldBlockZ, nullptr, nullptr};
+    const size_t nb = (size_t)shape.nbx * shape.nby * shape.nbz;
+    if (nb >= (1ull << 32)) return fail(ctx, MCB_E_CAPACITY, "too many field blocks: split the grid into more z-slabs");
+    if (ctx->cap_fblocks < nb) {
+        if (ctx->d_fflags) cudaFree(ctx->d_fflags);
+        if (ctx->d_flist) cudaFree(ctx->d_flist);
+        ctx->d_fflags = nullptr; ctx->d_flist = nullptr; ctx->cap_fblocks = 0;
+        if (cudaMalloc((void**)&ctx->d_fflags, nb) != cudaSuccess || cudaMalloc((void**)&ctx->d_flist, nb * sizeof(uint32_t)) != cudaSuccess)
+            return fail(ctx, MCB_E_NOMEM, "cudaMalloc of the field-block list failed");
+        ctx->cap_fblocks = nb;
+    }
+    const FieldBlocks fb{shape.nbx, shape.nby, shape.nbz, ctx->d_fflags, ctx->d_flist};
+    mcb_program launch;
+    bool has_pow;
+    if ((rc = encode_program(launch, has_pow, true)) != MCB_OK) return rc;
+    const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
+    const unsigned fill_ctas = (unsigned)ctx->sm_count * 16;
+    MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb, s));
+    field_flag_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(ctx->d_rec, g, ctx->d_ctr, ctx->cap_active, fb);
+    field_list_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(fb, (unsigned)nb, ctx->d_ctr);
+    if (has_pow) eval_blocks_kernel<true><<<fill_ctas, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
+    else eval_blocks_kernel<false><<<fill_ctas, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
+    launches += 3;
     return MCB_OK;
 }
 
@@ -1006,6 +1061,9 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     for (;;) { /* repeated only when an output buffer had to grow (mcb_counts::reruns) */
         if (need_classify) {
             if ((rc = run.stage_classify()) != MCB_OK) return rc;
+            MCB_CK(cudaEventRecord(ctx->ev[6], s));
+            if (ctx->field_is_sparse && (rc = run.stage_fill()) != MCB_OK) return rc;
+            MCB_CK(cudaEventRecord(ctx->ev[7], s));
             if (ctx->seed_on && (rc = run.stage_seed()) != MCB_OK) return rc;
             MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
@@ -1056,6 +1114,10 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     cudaEventElapsedTime(&c.ms_tables, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&c.ms_eval, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&c.ms_classify, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&c.ms_fill, ctx->ev[6], ctx->ev[7]);
+    c.ms_classify -= c.ms_fill;
+    c.field_mode = ctx->field_is_sparse ? MCB_FIELD_SPARSE : MCB_FIELD_DENSE;
+    c.field_blocks = ctx->field_is_sparse ? ctx->h_ctr->field_blocks : 0;
     cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&c.ms_weld, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[5]);
@@ -1080,6 +1142,13 @@ int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles)
     if (pos4) MCB_CK(cudaMemcpyAsync(pos4, ctx->d_pos, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     if (nrm4) MCB_CK(cudaMemcpyAsync(nrm4, ctx->d_nrm, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_set_field_mode(mcb_ctx* ctx, int mode) {
+    if (!ctx || (mode != MCB_FIELD_DENSE && mode != MCB_FIELD_SPARSE)) return MCB_E_ARG;
+    ctx->field_mode = mode;
+    ctx->have_result = false;
     return MCB_OK;
 }
 
@@ -1169,6 +1238,7 @@ int mcb_get_field(mcb_ctx* ctx, float* out) {
     if (rc != MCB_OK) return rc;
     if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
     if (!out) return fail(ctx, MCB_E_ARG, "null buffer");
+    if (ctx->field_is_sparse) return fail(ctx, MCB_E_STATE, "the field is not materialised in sparse-field mode (mcb_set_field_mode)");
     const Grid& g = ctx->g;
     const size_t n1 = (size_t)g.M + 1;
     cudaMemcpy3DParms p = {};

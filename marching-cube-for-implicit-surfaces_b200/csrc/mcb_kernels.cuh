@@ -62,6 +62,7 @@ struct Counters {
     unsigned long long seed_active, seed_triangles; /* seed mode: counts of the kept component */
     unsigned int tile_ticket;
     unsigned int error; /* 2 = 2^31 or more triangles in the slab */
+    unsigned int field_blocks, pad_; /* sparse-field mode: 32 x 4 x 4 vertex blocks the field was written in */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -100,17 +101,18 @@ __global__ void axis_tables_kernel(const uint32_t* __restrict__ slot_code, const
 /* ---------------------------------------------------------------------------------------------------------------
  * K1  eval_field: the bytecode interpreter over the grid.
  *     A warp owns a tile of 128 consecutive x-columns x 4 consecutive y-rows of one z-plane; a lane owns 4
- *     consecutive x of each of the 4 rows (16 vertices, accumulator acc[row][x] in 16 registers).  Every lane
+ *     columns, 32 apart, of each of the 4 rows (16 vertices, accumulator acc[row][x] in 16 registers).  Every lane
  *     executes the same fused instruction word (mcb_bytecode.h), fetched from the kernel-parameter block (constant
  *     bank), so there is no divergence and the cost of fetching/decoding a word is shared by 16 vertices per lane.
  *     An operator's other operand comes straight from its source: a constant-bank constant or a z-table entry (one
- *     register for all 16), an x-table (one LDG.128: 4 values shared by the rows), a y-table (one broadcast
+ *     register for all 16), an x-table (four coalesced loads: 4 values shared by the rows), a y-table (one broadcast
  *     LDG.128: 4 values shared by the columns) or, only for products of two compound subtrees, the shared-memory
  *     stack ([level][16][thread], conflict free).
- *     Outputs: F — four evict-first STG.128 per lane, 512 contiguous bytes per warp and row (the field is far
- *     larger than L2 and is only revisited around the surface) — and the sign bit-plane S: each lane builds a
- *     nibble per row, three xor-shuffles OR the nibbles of 8 lanes into a 32-bit word.  The comparison against iso
- *     is fused here so that classification never reads the 4 B/vertex field.
+ *     Outputs: a lane's four columns are x0 + 32 q, so a field store is one evict-first, fully coalesced 128-byte
+ *     line per warp (the field is far larger than L2 and is only revisited around the surface), and the warp ballot
+ *     of (value > iso) for column group q is sign word q of the tile row: the sign bit-plane S costs one compare
+ *     and one vote per vertex and one 16-byte store per tile row.  The comparison against iso is fused here so that
+ *     classification never reads the 4 B/vertex field.
  * ------------------------------------------------------------------------------------------------------------- */
 __device__ __noinline__ float powf_call(float a, float b) { return mcb_powf(a, b); } /* one copy, register args */
 
@@ -145,7 +147,7 @@ constexpr int kEvalLevel = kEvalRows * kEvalThreads; /* floats per memory-stack 
 
 /* One fused instruction, fully specialised on (operation, operand source): straight-line code, no inner dispatch.
  * acc[4 * r + q] = row r, column q of the lane. */
-template <int FOP, int SRC>
+template <int FOP, int SRC, int QS>
 __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, const uint32_t arg, const mcb_program& prog,
                                           const EvalLane& L) {
     if (FOP == MCB_F_PUSH) {
@@ -166,7 +168,7 @@ __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, c
             for (int q = 0; q < 4; q++) acc[4 * r + q] = fused_op<FOP>(acc[4 * r + q], tv[r]);
     } else if (SRC == MCB_SRC_TX) { /* the lane's 4 columns of an x-table (the tables are padded past the last tile) */
         const float* t = L.tables + arg + L.x0;
-        const float tv[4] = {__ldg(t), __ldg(t + 32), __ldg(t + 64), __ldg(t + 96)};
+        const float tv[4] = {__ldg(t), __ldg(t + QS), __ldg(t + 2 * QS), __ldg(t + 3 * QS)};
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -179,14 +181,14 @@ __device__ __forceinline__ void eval_step(float (&acc)[kEvalRows], float*& sp, c
 }
 
 /* A leaf operand as the 4 x 4 patch of a lane sees it: class 0 constant, 1 x-table, 2 y-table, 3 z-table */
-template <int CLS>
+template <int CLS, int QS>
 struct LeafOperand {
     float4 v;
     __device__ __forceinline__ LeafOperand(uint32_t arg, const mcb_program& prog, const EvalLane& L) {
         if (CLS == 0) v = make_float4(prog.k[arg], 0.f, 0.f, 0.f);
         else if (CLS == 1) {
             const float* t = L.tables + arg + L.x0;
-            v = make_float4(__ldg(t), __ldg(t + 32), __ldg(t + 64), __ldg(t + 96));
+            v = make_float4(__ldg(t), __ldg(t + QS), __ldg(t + 2 * QS), __ldg(t + 3 * QS));
         }
         else if (CLS == 2) v = __ldg(reinterpret_cast<const float4*>(L.tables + arg + L.y0));
         else v = make_float4(__ldg(L.tables + arg + L.zi), 0.f, 0.f, 0.f);
@@ -198,11 +200,11 @@ struct LeafOperand {
 };
 /* LOAD a ; op b  in one step: acc = a (op) b without first copying a into the 16 accumulator registers.  The host
  * pairs them up when it encodes the launch program (two words: handler | arg(a) << 8, then arg(b)). */
-template <int FOP, int CA, int CB>
+template <int FOP, int CA, int CB, int QS>
 __device__ __forceinline__ void eval_pair(float (&acc)[kEvalRows], uint32_t arg_a, uint32_t arg_b, const mcb_program& prog,
                                           const EvalLane& L) {
-    const LeafOperand<CA> a(arg_a, prog, L);
-    const LeafOperand<CB> b(arg_b, prog, L);
+    const LeafOperand<CA, QS> a(arg_a, prog, L);
+    const LeafOperand<CB, QS> b(arg_b, prog, L);
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -219,7 +221,7 @@ __device__ __forceinline__ void eval_pair(float (&acc)[kEvalRows], uint32_t arg_
 #define MCB_HANDLER(FOP, SRC) ((FOP) * 5 + ((SRC) == MCB_SRC_K ? 0 : (SRC) == MCB_SRC_TX ? 1 : (SRC) == MCB_SRC_TY ? 2 : (SRC) == MCB_SRC_TZ ? 3 : 4))
 #define MCB_HANDLER_NEG (MCB_F_NEG * 5)
 #define MCB_STEP(FOP, SRC) \
-    case MCB_HANDLER(FOP, SRC): eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
+    case MCB_HANDLER(FOP, SRC): eval_step<FOP, SRC, QS>(acc, sp, arg, prog, L); break;
 #define MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_K) MCB_STEP(FOP, MCB_SRC_TX) MCB_STEP(FOP, MCB_SRC_TY) MCB_STEP(FOP, MCB_SRC_TZ)
 #define MCB_STEP_ALL(FOP) MCB_STEP_LEAF(FOP) MCB_STEP(FOP, MCB_SRC_POP)
 
@@ -227,27 +229,12 @@ constexpr int kEvalTileX = 128; /* columns per warp tile */
 constexpr int kEvalTileY = 4;   /* rows per warp tile */
 static_assert(kEvalRows == 16, "a lane carries a 4 x 4 patch");
 
-template <bool HAS_POW> /* programs without `^` (after hoisting) get a kernel without the powf paths: fewer registers */
-__global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
-eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
-                  float* __restrict__ F, uint32_t* __restrict__ S, int row_groups) {
-    extern __shared__ float stack_smem[]; /* [level][16][kEvalThreads] */
-    const int lane = threadIdx.x & 31;
-    const int cx = (int)blockIdx.x;                                            /* 128-column tile of the row */
-    const int yq = (int)blockIdx.y * (kEvalThreads / 32) + (threadIdx.x >> 5); /* 4-row group */
-    const int pz = (int)blockIdx.z;                                            /* plane: vertex kb-1+pz */
-    if (yq >= row_groups) return; /* whole warp exits together; the kernel has no block-wide barrier */
-    EvalLane L;
-    L.tables = tables;
-    L.x0 = cx * kEvalTileX + lane;
-    L.y0 = yq * kEvalTileY;
-    L.zi = pz + g.kb;
-
-    float acc[kEvalRows];
+/* The interpreter proper: runs the launch program on the lane's 16 accumulators.  QS = distance, in table entries,
+ * between the lane's four class-1 operands (32 in the plane-tile kernel, 1 in the block kernel below). */
+template <bool HAS_POW, int QS>
+__device__ __forceinline__ void eval_run(const mcb_program& prog, const EvalLane& L, float (&acc)[kEvalRows], float* sp) {
 #pragma unroll
     for (int e = 0; e < kEvalRows; e++) acc[e] = 0.f;
-    float* sp = stack_smem + threadIdx.x; /* next free level */
-
 #pragma unroll 1
     for (int pc = 0; pc < prog.n; pc++) {
         const uint32_t insn = prog.code[pc];
@@ -262,14 +249,14 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
             MCB_STEP_ALL(MCB_F_DIV)
             MCB_STEP_ALL(MCB_F_RDIV)
 #define MCB_STEP_POW(FOP, SRC) \
-    case MCB_HANDLER(FOP, SRC): if (HAS_POW) eval_step<FOP, SRC>(acc, sp, arg, prog, L); break;
+    case MCB_HANDLER(FOP, SRC): if (HAS_POW) eval_step<FOP, SRC, QS>(acc, sp, arg, prog, L); break;
             MCB_STEP_POW(MCB_F_POW, MCB_SRC_K) MCB_STEP_POW(MCB_F_POW, MCB_SRC_TX) MCB_STEP_POW(MCB_F_POW, MCB_SRC_TY)
             MCB_STEP_POW(MCB_F_POW, MCB_SRC_TZ) MCB_STEP_POW(MCB_F_POW, MCB_SRC_POP)
             MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_K) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TX) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TY)
             MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_TZ) MCB_STEP_POW(MCB_F_RPOW, MCB_SRC_POP)
 #undef MCB_STEP_POW
 #define MCB_PAIR(FOP, CA, CB) \
-    case MCB_HANDLER_PAIR(FOP, CA, CB): if (HAS_POW || ((FOP) != MCB_F_POW && (FOP) != MCB_F_RPOW)) eval_pair<FOP, CA, CB>(acc, arg, prog.code[++pc], prog, L); break;
+    case MCB_HANDLER_PAIR(FOP, CA, CB): if (HAS_POW || ((FOP) != MCB_F_POW && (FOP) != MCB_F_RPOW)) eval_pair<FOP, CA, CB, QS>(acc, arg, prog.code[++pc], prog, L); break;
 #define MCB_PAIR_B(FOP, CA) MCB_PAIR(FOP, CA, 0) MCB_PAIR(FOP, CA, 1) MCB_PAIR(FOP, CA, 2) MCB_PAIR(FOP, CA, 3)
 #define MCB_PAIR_AB(FOP) MCB_PAIR_B(FOP, 0) MCB_PAIR_B(FOP, 1) MCB_PAIR_B(FOP, 2) MCB_PAIR_B(FOP, 3)
             MCB_PAIR_AB(MCB_F_ADD) MCB_PAIR_AB(MCB_F_SUB) MCB_PAIR_AB(MCB_F_RSUB) MCB_PAIR_AB(MCB_F_MUL)
@@ -288,6 +275,31 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
                 break;
         }
     }
+}
+#undef MCB_STEP
+#undef MCB_STEP_LEAF
+#undef MCB_STEP_ALL
+/* MCB_HANDLER* stay defined: mcb_api.cu encodes the launch program with them */
+
+/* K1.  STORE_F = false is the sparse-field mode (mcb_set_field_mode): only the sign bit-plane leaves the kernel and
+ * eval_blocks_kernel later writes the field where the surface needs it. */
+template <bool HAS_POW, bool STORE_F> /* programs without `^` (after hoisting) get a kernel without the powf paths: fewer registers */
+__global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
+eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
+                  float* __restrict__ F, uint32_t* __restrict__ S, int row_groups) {
+    extern __shared__ float stack_smem[]; /* [level][16][kEvalThreads] */
+    const int lane = threadIdx.x & 31;
+    const int cx = (int)blockIdx.x;                                            /* 128-column tile of the row */
+    const int yq = (int)blockIdx.y * (kEvalThreads / 32) + (threadIdx.x >> 5); /* 4-row group */
+    const int pz = (int)blockIdx.z;                                            /* plane: vertex kb-1+pz */
+    if (yq >= row_groups) return; /* whole warp exits together; the kernel has no block-wide barrier */
+    EvalLane L;
+    L.tables = tables;
+    L.x0 = cx * kEvalTileX + lane;
+    L.y0 = yq * kEvalTileY;
+    L.zi = pz + g.kb;
+    float acc[kEvalRows];
+    eval_run<HAS_POW, 32>(prog, L, acc, stack_smem + threadIdx.x);
 
     /* ---- outputs ----
      * A lane's columns are x0 + 32 q: every field store is one fully coalesced 128-byte line per warp, and the warp
@@ -306,16 +318,82 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int x = x0 + 32 * q;
-            if (x < g.P) __stcs(fp + (size_t)r * g.P + 32 * q, acc[4 * r + q]); /* P is a multiple of 32: uniform per warp */
+            if (STORE_F && x < g.P) __stcs(fp + (size_t)r * g.P + 32 * q, acc[4 * r + q]); /* P is a multiple of 32: uniform per warp */
             w[q] = __ballot_sync(0xffffffffu, acc[4 * r + q] > g.iso);
         }
         if (lane == r) *sw = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
-#undef MCB_STEP
-#undef MCB_STEP_LEAF
-#undef MCB_STEP_ALL
-/* MCB_HANDLER* stay defined: mcb_api.cu encodes the launch program with them */
+
+/* Sparse-field mode, second half: the field inside the listed 32 x 4 x 4 vertex blocks (x, y, plane), i.e. around
+ * the active cubes.  Same interpreter, same arithmetic per vertex as eval_field_kernel, hence the same bits; a lane
+ * is one x column and holds 4 rows x 4 planes, so the host swaps the operand classes of the x and z tables when it
+ * encodes this kernel's launch program (class 1 = z, stride 1; class 2 = y; class 3 = x, per lane). */
+constexpr int kFieldBlockX = 32, kFieldBlockY = 4, kFieldBlockZ = 4;
+struct FieldBlocks {
+    int nbx, nby, nbz;            /* blocks per axis: P/32, ceil(NV/4), ceil(NZ/4) */
+    uint8_t* flags;               /* [nbz][nby][nbx] */
+    uint32_t* list;               /* flagged blocks, any order */
+};
+template <bool HAS_POW>
+__global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
+eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
+                   float* __restrict__ F, const FieldBlocks fb, const Counters* __restrict__ ctr) {
+    extern __shared__ float stack_smem[];
+    const int lane = threadIdx.x & 31;
+    const unsigned nwarps = gridDim.x * (kEvalThreads / 32);
+    const unsigned n = ctr->field_blocks;
+    for (unsigned b = blockIdx.x * (kEvalThreads / 32) + (threadIdx.x >> 5); b < n; b += nwarps) {
+        const uint32_t id = fb.list[b];
+        const int bx = (int)(id % (unsigned)fb.nbx), by = (int)(id / (unsigned)fb.nbx % (unsigned)fb.nby);
+        const int bz = (int)(id / ((unsigned)fb.nbx * (unsigned)fb.nby));
+        EvalLane L;
+        L.tables = tables;
+        L.x0 = bz * kFieldBlockZ + g.kb; /* class 1: the z tables, consecutive planes */
+        L.y0 = by * kFieldBlockY;        /* class 2: the y tables */
+        L.zi = bx * kFieldBlockX + lane; /* class 3: the x tables, this lane's column */
+        float acc[kEvalRows];
+        eval_run<HAS_POW, 1>(prog, L, acc, stack_smem + threadIdx.x);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int y = L.y0 + r;
+            if (y >= g.NV) break;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int pz = bz * kFieldBlockZ + q;
+                if (pz < g.NZ) F[((size_t)pz * g.NV + y) * g.P + L.zi] = acc[4 * r + q];
+            }
+        }
+    }
+}
+
+/* blocks touched by the field reads around an active cube: its corners and their +-1 neighbours along each axis
+ * (gradient normals, the weld's look at the neighbouring grid edges) = stored vertices [i,i+3] x [j,j+3] x [k-kb,k-kb+3] */
+__global__ void __launch_bounds__(256)
+field_flag_kernel(const unsigned long long* __restrict__ rec, const Grid g, const Counters* __restrict__ ctr,
+                  unsigned long long cap_active, const FieldBlocks fb) {
+    const unsigned long long n = min(ctr->active, cap_active);
+    for (unsigned long long a = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long rc = rec[a];
+        const int i = (int)(rc & 0xfffu), j = (int)((rc >> 12) & 0xfffu), pz = (int)((rc >> 24) & 0xfffu) - g.kb;
+        const int bx0 = i >> 5, bx1 = (i + 3) >> 5, by0 = j >> 2, by1 = (j + 3) >> 2, bz0 = pz >> 2, bz1 = (pz + 3) >> 2;
+        for (int bz = bz0; bz <= bz1; bz++)
+            for (int by = by0; by <= by1; by++)
+                for (int bx = bx0; bx <= bx1; bx++) fb.flags[((size_t)bz * fb.nby + by) * fb.nbx + bx] = 1;
+    }
+}
+__global__ void __launch_bounds__(256)
+field_list_kernel(const FieldBlocks fb, unsigned nblocks, Counters* __restrict__ ctr) {
+    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = b < nblocks && fb.flags[b] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->field_blocks, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (on) fb.list[base + __popc(m & ((1u << lane) - 1u))] = b;
+}
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
 __global__ void __launch_bounds__(256)

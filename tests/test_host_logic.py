@@ -38,7 +38,7 @@ def test_abi_exports_every_declared_symbol(mcb):
     for name in sorted(declared):
         assert hasattr(lib, name), "libmcb200.so does not export " + name
     assert set(mcb.EXPORTS) == declared
-    assert mcb.lib.mcb_abi_version() == 2
+    assert mcb.lib.mcb_abi_version() == 3
 
 
 @pytest.mark.parametrize("eq,ok", EVALUATOR_TEST_CASES)
