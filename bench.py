@@ -70,17 +70,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def count_since(self, t0):
+        return sum(1 for (t, _) in self.rows if t >= t0)
+
     def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         for (t, line) in self.rows:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
-            inside = t0 - 0.05 <= t <= t1 + 0.15
+            inside = t0 - 0.05 <= t <= t1 + 0.05
             try:
                 if inside:
                     sm.append(float(parts[0]))
@@ -192,12 +194,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None  # nvidia-smi takes ~0.1 s to start: it runs from the warm-up on
     for _ in range(max(3, args.warmup)):
         c = step_fn()
     sync_all()
 
     # ---- timed region: device-resident inputs ---------------------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {"ms_tables": 0.0, "ms_eval": 0.0, "ms_classify": 0.0, "ms_emit": 0.0}
     launches = 0
@@ -208,11 +210,25 @@ def run_ours(args):
         for k in stage:
             stage[k] += getattr(c, k)
         launches += c.launches
+    if world > 1:
+        placement.wait(stream)  # the last exchange is inside the timed region
     e1.record(stream)
     sync_all()
     t1 = time.time()
     ms = e0.elapsed_time(e1)
+    soak = 0
+    if sampler and sampler.proc and world == 1:
+        # a timed region shorter than the sampling period holds no sample: keep the same load running (untimed) until
+        # one has been taken, so that the clocks reported are clocks under this load
+        t_soak = time.time()
+        while sampler.count_since(t0) < 2 and time.time() - t_soak < 1.0:
+            step_fn()
+            soak += 1
+        torch.cuda.synchronize()
+        t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "timed region" if soak == 0 else "timed region + %d untimed steps of the same load after it" % soak
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(c.cubes), float(c.triangles), float(c.active), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -222,6 +238,27 @@ def run_ours(args):
     cubes, tris, active, launches_all = [float(x) for x in tot.tolist()]
     ms_per_step = ms / args.steps
     value = cubes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- variant: sparse-field mode (signs everywhere, field values only around the surface); informational ----------
+    variants = {}
+    if world == 1:
+        ctx.set_field_mode(mcb.FIELD_SPARSE)
+        for _ in range(3):
+            cs_ = ctx.polygonise()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nv = max(1, min(args.steps, 10))
+        ev0.record(stream)
+        for _ in range(nv):
+            cs_ = ctx.polygonise()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        sp_ms = ev0.elapsed_time(ev1) / nv
+        variants["sparse_field"] = {"value": float(cs_.cubes) / (sp_ms * 1e-3) / 1e9, "ms_per_step": sp_ms, "ms_eval_signs_only": cs_.ms_eval,
+                                    "ms_fill": cs_.ms_fill, "field_blocks": int(cs_.field_blocks), "steps": nv,
+                                    "what": "mcb_set_field_mode(MCB_FIELD_SPARSE): same outputs bit for bit, the 4 B/vertex field is not "
+                                            "written; not the default because it loses on dense surfaces (DESIGN.md)"}
+        ctx.set_field_mode(mcb.FIELD_DENSE)
 
     # ---- e2e: through the reference-facing call with HOST buffers: equation text in, Poly_Data out ----------------
     # Marching::recalculate() leaves a welded, indexed mesh in Poly_Data (vertex_list + tri_list, marching.h:26-30);
@@ -337,6 +374,7 @@ def run_ours(args):
                     "what": "equation text in -> Poly_Data on the host (welded vertex_list + tri_list + per-vertex normals), MCB_MESH_INDEXED",
                     "soup": {"value": cubes / (soup_ms * 1e-3) / 1e9, "ms_per_step": soup_ms, "d2h_bytes_per_step": d2h_soup,
                              "what": "same, float4 triangle soup + float4 normals out (MCB_MESH_SOUP)"}},
+            "variants": variants,
             "gpu_launches": int(launches_all), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -358,7 +396,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sphere", choices=sorted(WORKLOADS))

@@ -34,10 +34,10 @@ def exchange_counts(local_triangles, device=None, group=None):
 class DeviceCounts:
     """The same exchange without a host round trip (NCCL only): the slab's triangle count is all-gathered straight from
     the context's device counters, and the placement (offset of this slab, total) stays on the device as int64
-    tensors.  Nothing here synchronises the host; `result()` does, when the caller finally wants Python ints."""
+    tensors.  The collective runs on a side stream, so the next polygonisation does not wait for the slowest rank's
+    count; a consumer of `offset` / `total` calls `wait()` (stream order) or `result()` (Python ints) first."""
 
     def __init__(self, ctx, device):
-        import ctypes
         self.device = device
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
@@ -51,13 +51,32 @@ class DeviceCounts:
         self.all = torch.empty(self.world, dtype=torch.int64, device=device)
         self.offset = torch.zeros(1, dtype=torch.int64, device=device)
         self.total = torch.zeros(1, dtype=torch.int64, device=device)
+        # the next polygonisation resets the live counters: the count is first copied aside, in stream order
+        self._staged = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(2)]
+        self._flip = 0
+        self._side = torch.cuda.Stream(device=device)
+        self._ready = torch.cuda.Event()
+        self._done = torch.cuda.Event()
 
     def exchange(self):
-        dist.all_gather_into_tensor(self.all, self.counters[1:2].contiguous())
-        torch.sum(self.all[:self.rank], dim=0, keepdim=True, out=self.offset)
-        torch.sum(self.all, dim=0, keepdim=True, out=self.total)
+        cur = torch.cuda.current_stream(self.device)
+        stg = self._staged[self._flip]
+        self._flip ^= 1
+        stg.copy_(self.counters[1:2])
+        self._ready.record(cur)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ready)
+            dist.all_gather_into_tensor(self.all, stg)
+            torch.sum(self.all[:self.rank], dim=0, keepdim=True, out=self.offset)
+            torch.sum(self.all, dim=0, keepdim=True, out=self.total)
+            self._done.record(self._side)
+
+    def wait(self, stream=None):
+        """Make `stream` (default: the current one) wait for the last exchange."""
+        (stream or torch.cuda.current_stream(self.device)).wait_event(self._done)
 
     def result(self):
+        self._done.synchronize()
         counts = [int(x) for x in self.all.tolist()]
         return sum(counts[:self.rank]), sum(counts), counts
 
