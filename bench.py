@@ -264,8 +264,9 @@ def run_ours(args):
     # Marching::recalculate() leaves a welded, indexed mesh in Poly_Data (vertex_list + tri_list, marching.h:26-30);
     # that is what comes back here (MCB_MESH_INDEXED, + gradient normals per vertex).  The float4 soup variant is
     # timed as well and reported next to it.
-    def make_e2e(mode):
+    def make_e2e(mode, normals=1):
         ctx.set_mesh_mode(mode)
+        ctx.set_normals(normals)
         cc0 = ctx.polygonise()
         capT = int(cc0.triangles) + 1024
         if mode == mcb.MESH_INDEXED:
@@ -276,7 +277,7 @@ def run_ours(args):
             bufs = [torch.empty((capT, 3, 4), dtype=torch.float32).pin_memory(), torch.empty((capT, 3, 4), dtype=torch.float32).pin_memory()]
 
         if mode == mcb.MESH_INDEXED:  # registered once: polygonise() streams the mesh into these pinned buffers
-            ctx.set_host_output(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), capV, capT)
+            ctx.set_host_output(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr() if normals else 0, capV, capT)
         else:
             ctx.set_host_output(0, 0, 0, 0, 0)
 
@@ -287,14 +288,14 @@ def run_ours(args):
             cc = step_fn()                            # MESH_INDEXED: returns when Poly_Data is in the host buffers (D2H inside)
             if mode == mcb.MESH_INDEXED:
                 if not ctx.host_output_filled():      # first call after a buffer had to grow: plain copy
-                    ctx.get_indexed_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), capV, capT)
+                    ctx.get_indexed_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr() if normals else 0, capV, capT)
             else:
                 ctx.get_mesh_into(bufs[0].data_ptr(), bufs[1].data_ptr(), capT)  # D2H of positions + normals
             return cc
         return one
 
-    def time_e2e(mode):
-        one = make_e2e(mode)
+    def time_e2e(mode, normals=1):
+        one = make_e2e(mode, normals)
         for _ in range(2):
             one()
         sync_all()
@@ -312,6 +313,7 @@ def run_ours(args):
         return float(t_ms.item()), cc, nst
 
     soup_ms, cc_s, e2e_steps = time_e2e(mcb.MESH_SOUP)
+    pd_ms, cc_pd, _ = time_e2e(mcb.MESH_INDEXED, 0)  # exactly what Marching::recalculate() leaves: vertex_list + tri_list
     idx_ms, cc, e2e_steps = time_e2e(mcb.MESH_INDEXED)
     ctx.set_host_output(0, 0, 0, 0, 0)
     ctx.set_mesh_mode(mcb.MESH_SOUP)
@@ -319,10 +321,11 @@ def run_ours(args):
     h2d = 4 * (mcb.lib.mcb_grid_axis(step, None, 0) + 3 + 64) + 2052 * 2 + 512
     d2h = int(cc.vertices) * 24 + int(cc.triangles) * 12 + 48
     d2h_soup = int(cc_s.triangles) * 96 + 48
+    d2h_pd = int(cc_pd.vertices) * 12 + int(cc_pd.triangles) * 12 + 48
     if world > 1:  # bytes of all ranks, and a consistency check of the device-side placement
-        bt = torch.tensor([float(d2h), float(d2h_soup)], dtype=torch.float64, device="cuda")
+        bt = torch.tensor([float(d2h), float(d2h_soup), float(d2h_pd)], dtype=torch.float64, device="cuda")
         dist.all_reduce(bt, op=dist.ReduceOp.SUM)
-        d2h, d2h_soup = int(bt[0].item()), int(bt[1].item())
+        d2h, d2h_soup, d2h_pd = int(bt[0].item()), int(bt[1].item()), int(bt[2].item())
         off, total, per_rank = placement.result()
         assert total == sum(per_rank) and off == sum(per_rank[:rank]) and per_rank[rank] == int(cc.triangles), (off, total, per_rank)
 
@@ -372,6 +375,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "Gvoxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": idx_ms, "steps": e2e_steps,
                     "what": "equation text in -> Poly_Data on the host (welded vertex_list + tri_list + per-vertex normals), MCB_MESH_INDEXED",
+                    "poly_data_only": {"value": cubes / (pd_ms * 1e-3) / 1e9, "ms_per_step": pd_ms, "d2h_bytes_per_step": d2h_pd,
+                                       "what": "same without the per-vertex normals: exactly the Poly_Data the reference's recalculate() leaves"},
                     "soup": {"value": cubes / (soup_ms * 1e-3) / 1e9, "ms_per_step": soup_ms, "d2h_bytes_per_step": d2h_soup,
                              "what": "same, float4 triangle soup + float4 normals out (MCB_MESH_SOUP)"}},
             "variants": variants,

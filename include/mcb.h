@@ -78,6 +78,8 @@ typedef struct {
 /* ---- library / host-only helpers (no GPU needed) ---------------------------------------------------------- */
 
 int mcb_abi_version(void);
+/* sizeof of the structs that cross the boundary, so a binding can check its mirror: 0 = mcb_counts, 1 = mcb_step_data */
+int mcb_struct_size(int which);
 const char* mcb_status_string(int status);
 
 /* Evaluator::tokenize accept/reject (evaluator.cpp:139-237) + the operand-stack check: MCB_OK or MCB_E_PARSE. */

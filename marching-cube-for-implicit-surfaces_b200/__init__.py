@@ -60,6 +60,7 @@ def _load():
     vp, cp, i, f, u64, sz = C.c_void_p, C.c_char_p, C.c_int, C.c_float, C.c_uint64, C.c_size_t
     sigs = {
         "mcb_abi_version": ([], i),
+        "mcb_struct_size": ([i], i),
         "mcb_status_string": ([i], cp),
         "mcb_parse": ([cp], i),
         "mcb_tokens": ([cp, cp, sz], i),
@@ -104,6 +105,8 @@ def _load():
 
 
 lib, EXPORTS = _load()
+if lib.mcb_struct_size(0) != C.sizeof(Counts) or lib.mcb_struct_size(1) != C.sizeof(StepData):
+    raise ImportError("libmcb200.so and this ctypes mirror disagree on a struct layout: rebuild the library")
 
 
 def status_string(s):

@@ -413,6 +413,8 @@ extern "C" {
 
 int mcb_abi_version(void) { return MCB_ABI_VERSION; }
 
+int mcb_struct_size(int which) { return which == 0 ? (int)sizeof(mcb_counts) : which == 1 ? (int)sizeof(mcb_step_data) : MCB_E_ARG; }
+
 const char* mcb_status_string(int s) {
     switch (s) {
         case MCB_OK: return "ok";

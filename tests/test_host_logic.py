@@ -39,6 +39,9 @@ def test_abi_exports_every_declared_symbol(mcb):
         assert hasattr(lib, name), "libmcb200.so does not export " + name
     assert set(mcb.EXPORTS) == declared
     assert mcb.lib.mcb_abi_version() == 3
+    import ctypes
+    assert mcb.lib.mcb_struct_size(0) == ctypes.sizeof(mcb.Counts) and mcb.lib.mcb_struct_size(1) == ctypes.sizeof(mcb.StepData)
+    assert mcb.lib.mcb_struct_size(7) < 0
 
 
 @pytest.mark.parametrize("eq,ok", EVALUATOR_TEST_CASES)
