@@ -16,7 +16,7 @@
  * the reference's BFS from the seed cube, emitted in the full-grid loop order instead of BFS order (get_seed_queue()
  * stays empty).  Step-by-step mode (marching.cpp:386-428) advances one cube per recalculate() like the reference: the
  * cube is computed on the GPU (mcb_inspect_cube = calculate_step) and appended on the host.  Not carried over: the
- * unused repeating-surface mode (its setters exist) and step-by-step inside seed mode.
+ * step-by-step inside seed mode and the repeating-surface mode combined with seed mode.
  * load/save of .ply use plain files ("mesh.ply" or $MCB_MESH_FILE) instead of Win32 dialogs.
  *
  * Extensions: set_grid_resolution(n) (step 2/n without the 0.001 floor), set_slab(k0,k1) for z-slab
@@ -100,6 +100,12 @@ public:
          * add_step_to_poly_data, marching.cpp:599-654); unwelded: the float4 triangle soup */
         mcb_set_seed(ctx_, seed_mode_ ? 1 : 0, seed_[0], seed_[1], seed_[2]); /* marching.cpp:310-331, as a set (loop order) */
         mcb_set_mesh_mode(ctx_, weld_ ? MCB_MESH_INDEXED : MCB_MESH_SOUP);
+        if (repeat_ && !(repeat_step_ > 0.f)) { /* distance 0: NaN iso levels, no cube is active */
+            poly_data.vertex_list.clear(); poly_data.tri_list.clear();
+            soup_.clear(); normals_soup_.clear(); vertex_normals_.clear();
+            poly_data.step_data.step_i = -1;
+            return true;
+        }
         if (mcb_polygonise(ctx_, &counts_) != MCB_OK) return false;
         const size_t T = (size_t)counts_.triangles;
         if (weld_) {
@@ -151,7 +157,10 @@ public:
     void get_seed(float* x, float* y, float* z) { *x = seed_[0]; *y = seed_[1]; *z = seed_[2]; }
 
     bool set_surface_repeat_step_distance(float l) { if (l <= 0) return false; repeat_step_ = l; reset_step(); return true; }
-    bool repeating_surface_mode(bool b) { repeat_ = b; reset_step(); return true; }
+    bool repeating_surface_mode(bool b) { /* marching.cpp:164-170 */
+        if (repeat_step_ < 0) return repeat_ = false;
+        repeat_ = b; reset_step(); return true;
+    }
 
     bool set_constraint0(std::string lhs, std::string op, float rhs) { return set_constraint(0, lhs, op, rhs); }
     bool set_constraint1(std::string lhs, std::string op, float rhs) { return set_constraint(1, lhs, op, rhs); }
@@ -246,6 +255,9 @@ private:
         mcb_set_surface_constant(ctx_, iso_);
         mcb_set_scaling(ctx_, sx_, sy_, sz_);
         mcb_set_normals(ctx_, normals_ ? (weld_ && reference_normals_ ? 2 : 1) : 0);
+        /* marching.cpp:156-170, 481-494.  The reference accepts the mode with its initial distance 0: every cube's iso is
+         * then NaN and nothing is drawn; recalculate() short-cuts that case, the GPU only sees positive distances */
+        mcb_set_repeat(ctx_, repeat_ && repeat_step_ > 0.f ? 1 : 0, repeat_step_);
         for (int i = 0; i < 3; i++)
             mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
         return true;
@@ -287,6 +299,7 @@ private:
         sd.edge_list.assign(o.edge_list, o.edge_list + o.n_edges);
         sd.intersect_coord.assign(o.intersect_coord, o.intersect_coord + 3 * o.n_edges);
         sd.tri_vlist.assign(o.tri_vlist, o.tri_vlist + o.n_tri_idx);
+        if (repeat_) sd.surf_constant = o.surf_constant; /* marching.cpp:493: only written in repeating-surface mode */
         return true;
     }
     void add_step_to_poly_data() { /* marching.cpp:599-654 */

@@ -161,6 +161,12 @@ int mcb_get_mesh_device(mcb_ctx* ctx, const float** pos4, const float** nrm4);
  * triangle count can be all-gathered straight from here (NCCL) without a host round trip. */
 int mcb_counts_device(mcb_ctx* ctx, const uint64_t** counts);
 
+/* Repeating-surface mode (Marching::repeating_surface_mode / set_surface_repeat_step_distance, marching.cpp:156-170,
+ * 481-494; no GUI control in the reference): every cube is polygonised with the highest level
+ * surface_constant + n * distance that does not exceed its largest corner value, so one call draws the whole family of
+ * level sets.  distance must be > 0.  Forces MCB_FIELD_DENSE; not available together with seed mode. */
+int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance);
+
 /* MCB_FIELD_DENSE (default) or MCB_FIELD_SPARSE: whether mcb_polygonise writes the whole scalar field to device
  * memory or only the blocks of it that the mesh stages read.  Results are bit-identical. */
 int mcb_set_field_mode(mcb_ctx* ctx, int mode);
@@ -194,6 +200,7 @@ typedef struct {
     int32_t edge_list[12];
     int32_t tri_vlist[15];     /* indices into intersect_coord / 3, three per triangle */
     int32_t n_edges, n_tri_idx, cube_code, table_idx, skipped;
+    float surf_constant;       /* the iso value this cube was polygonised with (Step_Data::surf_constant in repeating-surface mode) */
 } mcb_step_data;
 int mcb_inspect_cube(mcb_ctx* ctx, float x0, float y0, float z0, mcb_step_data* out);
 

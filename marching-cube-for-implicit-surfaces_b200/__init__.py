@@ -49,7 +49,7 @@ class StepData(C.Structure):
     """mcb_step_data: Step_Data (marching.h:15-23) of one cube, as Marching::calculate_step fills it."""
     _fields_ = [("corner_coords", C.c_float * 24), ("corner_values", C.c_float * 8), ("intersect_coord", C.c_float * 36),
                 ("edge_list", C.c_int32 * 12), ("tri_vlist", C.c_int32 * 15), ("n_edges", C.c_int32), ("n_tri_idx", C.c_int32),
-                ("cube_code", C.c_int32), ("table_idx", C.c_int32), ("skipped", C.c_int32)]
+                ("cube_code", C.c_int32), ("table_idx", C.c_int32), ("skipped", C.c_int32), ("surf_constant", C.c_float)]
 
 
 def _load():
@@ -82,6 +82,7 @@ def _load():
         "mcb_set_constraint": ([vp, i, i, f, i], i),
         "mcb_set_normals": ([vp, i], i),
         "mcb_set_seed": ([vp, i, f, f, f], i),
+        "mcb_set_repeat": ([vp, i, f], i),
         "mcb_inspect_cube": ([vp, f, f, f, C.POINTER(StepData)], i),
         "mcb_polygonise": ([vp, C.POINTER(Counts)], i),
         "mcb_get_mesh": ([vp, vp, vp, u64], i),
@@ -220,6 +221,10 @@ class Context:
         sd = StepData()
         self._ck(lib.mcb_inspect_cube(self.h, x0, y0, z0, C.byref(sd)))
         return sd
+
+    def set_repeat(self, enabled, distance=0.0):
+        """Repeating-surface mode (marching.cpp:481-494): per-cube iso = highest level iso + n*distance <= the cube's largest corner value."""
+        return lib.mcb_set_repeat(self.h, int(bool(enabled)), float(distance))
 
     def set_seed(self, enabled, x=0.0, y=0.0, z=0.0):
         """Seed mode: keep only the component of the cube containing (x,y,z). Returns the status (MCB_E_ARG outside [-1,1]^3)."""
@@ -401,6 +406,16 @@ class Marching:
 
     def set_slab(self, k0, k1):
         self._ctx.set_slab(k0, k1)
+
+    def set_surface_repeat_step_distance(self, l):  # marching.cpp:156-162
+        if l <= 0:
+            return False
+        self._repeat_step = float(l)
+        return self._ctx.set_repeat(getattr(self, "_repeat_on", False), self._repeat_step) == MCB_OK
+
+    def repeating_surface_mode(self, b):  # marching.cpp:164-170; a positive distance must have been set (the reference's 0 draws nothing)
+        self._repeat_on = bool(b)
+        return self._ctx.set_repeat(self._repeat_on and getattr(self, "_repeat_step", 0.0) > 0, getattr(self, "_repeat_step", 0.0)) == MCB_OK
 
     def seed_mode(self, b):
         self._seed_on = bool(b)

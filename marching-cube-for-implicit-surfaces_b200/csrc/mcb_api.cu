@@ -100,6 +100,10 @@ struct mcb_ctx {
     bool streamed = false;                  /* the last polygonise delivered the mesh to the registered buffers */
     /* seed mode (mcb_set_seed) */
     bool seed_on = false;
+    bool repeat_on = false;        /* repeating-surface mode (mcb_set_repeat) */
+    float repeat_step = 0.f;
+    uint32_t* d_cw = nullptr;      /* [items][8] corner words of every 32-cube item, repeating-surface mode only */
+    size_t cap_cw = 0;
     float seed[3] = {0.f, 0.f, 0.f};
     uint8_t* d_mark = nullptr;
     uint32_t* d_changed = nullptr;
@@ -544,7 +548,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->eq) free_slot(s);
-    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist);
+    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw);
     cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -668,12 +672,21 @@ int mcb_inspect_cube(mcb_ctx* ctx, float x0, float y0, float z0, mcb_step_data* 
     for (int sl = 0; sl < 4; sl++)
         if (ctx->eq[sl].valid) cudaMemcpyAsync(d_progs + sl, &ctx->eq[sl].point, sizeof(mcb_program), cudaMemcpyHostToDevice, ctx->stream);
     inspect_cube_kernel<<<1, 1, 0, ctx->stream>>>(d_progs, cons, slots[0], slots[1], slots[2], x0, y0, z0, ctx->step, ctx->scale[0],
-                                                  ctx->scale[1], ctx->scale[2], ctx->iso, ctx->d_cls, d_out);
+                                                  ctx->scale[1], ctx->scale[2], ctx->iso, ctx->repeat_on ? 1 : 0, ctx->repeat_step, ctx->d_cls, d_out);
     cudaMemcpyAsync(out, d_out, sizeof(StepOut), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaError_t e2 = cudaGetLastError();
     cudaFree(d_progs); cudaFree(d_out);
     if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, MCB_E_CUDA, std::string("inspect_cube: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return MCB_OK;
+}
+
+int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance) {
+    if (!ctx) return MCB_E_ARG;
+    if (enabled && !(distance > 0.f)) return fail(ctx, MCB_E_ARG, "the distance between repeated surfaces must be positive"); /* marching.cpp:156-162 */
+    ctx->repeat_on = enabled != 0;
+    if (enabled) ctx->repeat_step = distance;
+    ctx->have_result = false;
     return MCB_OK;
 }
 
@@ -816,7 +829,7 @@ int Run::stage_eval() {
     bool has_pow;
     int rc = encode_program(launch, has_pow, false);
     if (rc != MCB_OK) return rc;
-    const bool sparse = ctx->field_mode == MCB_FIELD_SPARSE;
+    const bool sparse = ctx->field_mode == MCB_FIELD_SPARSE && !g.repeat; /* per-cube iso levels read the field everywhere */
     if (sparse && ctx->poison_field) MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
     if (sparse) {
         if (has_pow) eval_field_kernel<true, false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
@@ -846,16 +859,24 @@ int Run::stage_classify() {
     int rc;
     MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     const ClsScratch sc{ctx->d_tile_list, ctx->d_tile_cnt, ctx->d_tile_nz, cg.tile_rows * cg.WC};
+    const uint32_t* cw = nullptr;
+    if (g.repeat) { /* per-cube iso levels: the corner signs come from the field, item by item */
+        const unsigned long long items = (unsigned long long)cg.total_rows * cg.WC;
+        if ((rc = ensure(ctx, &ctx->d_cw, &ctx->cap_cw, (size_t)items * 8)) != MCB_OK) return rc;
+        repeat_words_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(g, ctx->d_F, cg.WC, ctx->d_cw, items);
+        launches++;
+        cw = ctx->d_cw;
+    }
     if (dV)
         classify_kernel<true><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
-                                                                        ctx->d_status, ctx->d_ctr);
+                                                                        ctx->d_status, ctx->d_ctr, ctx->d_F, cw);
     else
         classify_kernel<false><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
-                                                                         ctx->d_status, ctx->d_ctr);
+                                                                         ctx->d_status, ctx->d_ctr, ctx->d_F, cw);
     const bool need_items = want_indexed || ctx->seed_on; /* per-word record index for the weld / the seed walk */
     if (need_items && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
     compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status, ctx->d_ctr,
-                                                 ctx->d_rec, ctx->d_trioff, ctx->cap_active, need_items ? ctx->d_item : nullptr);
+                                                 ctx->d_rec, ctx->d_trioff, ctx->cap_active, need_items ? ctx->d_item : nullptr, ctx->d_F, cw);
     launches += 2;
     return MCB_OK;
 }
@@ -1015,7 +1036,8 @@ int Run::stage_weld() {
 int Run::stage_normal_h() {
     int rc;
     if ((rc = ensure_normal_h_scratch(ctx)) != MCB_OK) return rc;
-    const unsigned long long* nv = &ctx->d_ctr->vertices;
+    const unsigned long long* nv = &ctx->d_ctr->nh_vertices;
+    nh_gate_kernel<<<1, 1, 0, s>>>(ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris);
     MCB_CK(cudaMemsetAsync(ctx->d_nh_count, 0, ctx->cap_verts * 4, s));
     MCB_CK(cudaMemsetAsync(ctx->d_nh_cursor, 0, ctx->cap_verts * 4, s));
     nh_face_normals_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_vlist, ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_fn, ctx->d_nh_count);
@@ -1024,7 +1046,7 @@ int Run::stage_normal_h() {
     scan_apply_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, ctx->d_nh_sums, nv, ctx->d_nh_start);
     nh_fill_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_nh_start, ctx->d_nh_cursor, ctx->d_nh_adj);
     nh_accumulate_kernel<<<eblocks * 4, 128, 0, s>>>(ctx->d_fn, ctx->d_nh_start, ctx->d_nh_count, ctx->d_nh_adj, ctx->d_ctr, ctx->cap_verts, ctx->d_vnrm);
-    launches += 6;
+    launches += 7;
     return MCB_OK;
 }
 
@@ -1040,6 +1062,9 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     Grid& g = ctx->g;
     g.sx = ctx->scale[0]; g.sy = ctx->scale[1]; g.sz = ctx->scale[2];
     g.iso = ctx->iso;
+    g.repeat = ctx->repeat_on ? 1 : 0;
+    g.rstep = ctx->repeat_step;
+    if (ctx->repeat_on && ctx->seed_on) return fail(ctx, MCB_E_STATE, "repeating-surface mode and seed mode cannot be combined");
     if (ctx->normals == 2 && !(ctx->mesh_mode & MCB_MESH_INDEXED))
         return fail(ctx, MCB_E_STATE, "normal.h normals (mode 2) are defined on the welded mesh: request MCB_MESH_INDEXED");
 
@@ -1223,7 +1248,8 @@ int mcb_get_cases(mcb_ctx* ctx, uint8_t* cube_code, uint8_t* table_idx) {
     uint8_t *d_code = nullptr, *d_tidx = nullptr;
     MCB_CK(cudaMalloc((void**)&d_code, (size_t)n));
     if (cudaMalloc((void**)&d_tidx, (size_t)n) != cudaSuccess) { cudaFree(d_code); return fail(ctx, MCB_E_NOMEM, "cudaMalloc"); }
-    dense_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_S, any_constraint ? ctx->d_V : nullptr, d_code, d_tidx, n);
+    dense_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_S, any_constraint ? ctx->d_V : nullptr, d_code, d_tidx, n,
+                                                                             g.repeat ? ctx->d_cw : nullptr, (uint32_t)((g.M + 31) / 32));
     if (ctx->last.active)
         scatter_tidx_kernel<<<(unsigned)((ctx->last.active + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_rec, ctx->last.active, d_tidx);
     if (cube_code) cudaMemcpyAsync(cube_code, d_code, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);

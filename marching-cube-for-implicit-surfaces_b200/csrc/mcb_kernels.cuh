@@ -51,7 +51,32 @@ struct Grid {
     int NZ;       /* (ke-kb) + 3 vertex planes */
     float sx, sy, sz;
     float iso;
+    int repeat;   /* repeating-surface mode (marching.cpp:481-494): every cube takes its own iso level, see cube_iso */
+    float rstep;  /* distance between the levels */
 };
+
+/* The iso value one cube is polygonised with.  Plain mode: the surface constant.  Repeating-surface mode
+ * (Marching::calculate_step, marching.cpp:481-494): the highest level  c + n * step  that does not exceed the largest of
+ * the cube's eight corner values — same comparison chain (a NaN corner never raises the maximum), same fp32 division,
+ * floor and multiply-add order.  (i, j, k) = cube indices, k global.  The level decides the cube code and the
+ * ambiguity test only: Marching::interp (marching.cpp:437-446) keeps interpolating towards the surface constant
+ * itself, so in that mode the reference's crossing points are extrapolated along their edges; that is reproduced. */
+__device__ __forceinline__ float cube_iso(const Grid& g, const float* __restrict__ F, int i, int j, int k) {
+    if (!g.repeat) return g.iso;
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+    const float* f0 = F + (size_t)(k - g.kb + 1) * planep + (size_t)(j + 1) * rowp + (i + 1);
+    float mx = __ldg(f0);
+#pragma unroll
+    for (int v = 1; v < 8; v++) {
+        const int o = mcb_corner_ofs(v);
+        const float f = __ldg(f0 + (size_t)(o >> 2) * planep + (size_t)((o >> 1) & 1) * rowp + (o & 1));
+        if (mx < f) mx = f;
+    }
+    float a = (mx - g.iso) / g.rstep;
+    a = floorf(a);
+    return g.iso + g.rstep * a;
+}
+
 
 struct Counters {
     unsigned long long active;
@@ -63,6 +88,7 @@ struct Counters {
     unsigned int tile_ticket;
     unsigned int error; /* 2 = 2^31 or more triangles in the slab */
     unsigned int field_blocks, pad_; /* sparse-field mode: 32 x 4 x 4 vertex blocks the field was written in */
+    unsigned long long nh_vertices, nh_triangles; /* what the normal.h stage works on: the mesh, or nothing when it is truncated */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -499,7 +525,7 @@ __device__ __forceinline__ int code_of(const uint32_t c[8], int b) {
 
 /* Face-centre test of marching.cpp:527-547; returns true when the redirect row 255-code must be used. */
 __device__ __noinline__ bool ambiguity_redirects(const mcb_program& prog, const Grid& g, const float* __restrict__ cs,
-                                                 int face, int i, int j, int k) {
+                                                 int face, int i, int j, int k, float iso) {
     float mx = 0.f, my = 0.f, mz = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -510,7 +536,7 @@ __device__ __noinline__ bool ambiguity_redirects(const mcb_program& prog, const 
     }
     mx /= 4.0f; my /= 4.0f; mz /= 4.0f;
     const float mid = mcb_interp_scalar(prog.code, prog.n, prog.k, g.sx * mx, g.sy * my, g.sz * mz, nullptr, nullptr, nullptr);
-    return mid > g.iso;
+    return mid > iso;
 }
 
 __device__ __forceinline__ uint32_t column_mask(const Grid& g, uint32_t w) { /* cubes of word w inside the row */
@@ -535,19 +561,53 @@ struct ItemView {
     uint32_t w, j, kz, m;
     uint32_t c[8];
 };
+/* Repeating-surface mode: a cube's corner signs are relative to ITS iso level, so they cannot be shared through the
+ * vertex sign planes; repeat_words_kernel stores the eight corner words of every item instead (Cw[item][8]). */
+__device__ __forceinline__ void repeat_item_words(const uint32_t* __restrict__ Cw, size_t item, uint32_t c[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(Cw + item * 8)), b = __ldg(reinterpret_cast<const uint4*>(Cw + item * 8 + 4));
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+}
+__global__ void __launch_bounds__(256)
+repeat_words_kernel(const Grid g, const float* __restrict__ F, uint32_t WC, uint32_t* __restrict__ Cw, unsigned long long items) {
+    const int lane = threadIdx.x & 31;
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+    for (unsigned long long item = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < items;
+         item += (unsigned long long)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t w = (uint32_t)(item % WC);
+        const unsigned long long row = item / WC;
+        const int j = (int)(row % (unsigned)g.M), kz = (int)(row / (unsigned)g.M), i = (int)w * 32 + lane;
+        const bool in = i < g.M;
+        float iso = 0.f;
+        const float* f0 = F + (size_t)(kz + 1) * planep + (size_t)(j + 1) * rowp + (i + 1);
+        if (in) iso = cube_iso(g, F, i, j, kz + g.kb);
+        uint32_t mine = 0;
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            const int o = mcb_corner_ofs(v);
+            const bool up = in && __ldg(f0 + (size_t)(o >> 2) * planep + (size_t)((o >> 1) & 1) * rowp + (o & 1)) > iso; /* marching.cpp:497-505 */
+            const uint32_t word = __ballot_sync(0xffffffffu, up);
+            if (lane == v) mine = word;
+        }
+        if (lane < 8) Cw[item * 8 + lane] = mine;
+    }
+}
+
 __device__ __forceinline__ void view_item(ItemView& it, uint32_t item_local, uint32_t j0, uint32_t kz0, const ClsGeom& q,
                                           const Grid& g, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
-                                          uint32_t plane) {
+                                          uint32_t plane, const uint32_t* __restrict__ Cw = nullptr) {
     const uint32_t r = div_small(item_local, q.inv_wc);
     it.w = item_local - r * q.WC;
     const uint32_t jj = j0 + r, dk = div_small(jj, q.inv_m);
     it.j = jj - dk * (uint32_t)g.M;
     it.kz = kz0 + dk;
     const uint32_t idx = ((it.kz + 1u) * (uint32_t)g.NV + (it.j + 1u)) * (uint32_t)g.WP + it.w;
-    uint32_t lo[4], hi[4];
-    vertex_row_words(S, idx, plane, lo);
-    vertex_row_words(S, idx + (uint32_t)g.WP, plane, hi);
-    corner_words(lo, hi, it.c);
+    if (Cw != nullptr) repeat_item_words(Cw, ((size_t)it.kz * (uint32_t)g.M + it.j) * q.WC + it.w, it.c);
+    else {
+        uint32_t lo[4], hi[4];
+        vertex_row_words(S, idx, plane, lo);
+        vertex_row_words(S, idx + (uint32_t)g.WP, plane, hi);
+        corner_words(lo, hi, it.c);
+    }
     it.m = active_mask(it.c, column_mask(g, it.w));
     if (V != nullptr && it.m) it.m &= valid_mask(V, idx, (uint32_t)g.WP, plane);
 }
@@ -563,7 +623,8 @@ template <bool HAS_V>
 __global__ void __launch_bounds__(kClsThreads, 4)
 classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
                 const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
-                const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status, Counters* __restrict__ ctr) {
+                const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status, Counters* __restrict__ ctr,
+                const float* __restrict__ F, const uint32_t* __restrict__ Cw /* repeating-surface mode: corner words, else nullptr */) {
     extern __shared__ uint32_t cls_smem[];
     uint32_t* bitmap = cls_smem;                                          /* [kClsChunkCap] one bit per item */
     uint16_t* list = reinterpret_cast<uint16_t*>(cls_smem + kClsChunkCap); /* [kClsItemCap] active items, loop order */
@@ -587,6 +648,16 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
             const uint32_t colmask = column_mask(g, w);
             uint32_t kz = kz0 + (j0 + r) / M, j = (j0 + r) - (kz - kz0) * M;
             uint32_t item = r * q.WC + w;
+            while (Cw != nullptr && r < r_end) { /* repeating-surface mode: nothing is shared between cube rows */
+                uint32_t c[8];
+                repeat_item_words(Cw, ((size_t)kz * M + j) * q.WC + w, c);
+                uint32_t m = active_mask(c, colmask);
+                if (HAS_V && m) m &= valid_mask(V, ((kz + 1u) * (uint32_t)g.NV + (j + 1u)) * WP + w, WP, plane);
+                if (m) atomicOr(&bitmap[item >> 5], 1u << (item & 31u));
+                item += q.WC;
+                r++;
+                if (++j == M) { j = 0; kz++; }
+            }
             while (r < r_end) {
                 uint32_t idx = ((kz + 1u) * (uint32_t)g.NV + (j + 1u)) * WP + w;
                 uint32_t lo[4];
@@ -653,7 +724,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
         if (k < nz) {
             const uint32_t item_local = list[k];
             ItemView it;
-            view_item(it, item_local, j0, kz0, q, g, S, V, plane);
+            view_item(it, item_local, j0, kz0, q, g, S, V, plane, Cw);
             const uint32_t na = __popc(it.m);
             uint32_t nt = 0, mm = it.m;
             while (mm) {
@@ -663,7 +734,8 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
                 const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
                 if (face >= 0) {
                     n_amb++;
-                    if (ambiguity_redirects(point_prog, g, cs, face, (int)it.w * 32 + b, (int)it.j, (int)it.kz + g.kb)) {
+                    const int ci = (int)it.w * 32 + b, cj = (int)it.j, ck = (int)it.kz + g.kb;
+                    if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, cube_iso(g, F, ci, cj, ck))) {
                         code = 255 - code;
                         n_red++;
                     }
@@ -699,7 +771,8 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
                const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
                const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status,
                Counters* __restrict__ ctr, unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
-               unsigned long long cap_active, unsigned long long* __restrict__ item_info /* nullptr unless the weld needs it */) {
+               unsigned long long cap_active, unsigned long long* __restrict__ item_info /* nullptr unless the weld needs it */,
+               const float* __restrict__ F, const uint32_t* __restrict__ Cw /* repeating-surface mode, else nullptr */) {
     __shared__ uint32_t chunk_a[kClsChunkCap], chunk_t[kClsChunkCap]; /* per 32 list entries */
     __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];
     __shared__ unsigned long long base_a_s, base_t_s;
@@ -806,7 +879,7 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
         unsigned long long ot = tile_t + chunk_t[kb >> 5] + ((inc - mine) >> 16);
         ItemView it;
         const uint32_t item_local = glist[k];
-        view_item(it, item_local, j0, kz0, q, g, S, V, plane);
+        view_item(it, item_local, j0, kz0, q, g, S, V, plane, Cw);
         uint32_t m = it.m;
         if (item_info != nullptr) /* cube -> record look-up of the weld: first record of the word | its active mask */
             item_info[(size_t)tile * sc.tile_items + item_local] = (oa & 0xFFFFFFFFull) | ((unsigned long long)m << 32);
@@ -816,8 +889,10 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
             const int code = code_of(it.c, b);
             int tidx = code;
             const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
-            if (face >= 0 && ambiguity_redirects(point_prog, g, cs, face, (int)it.w * 32 + b, (int)it.j, (int)it.kz + g.kb))
-                tidx = 255 - code;
+            if (face >= 0) {
+                const int ci = (int)it.w * 32 + b, cj = (int)it.j, ck = (int)it.kz + g.kb;
+                if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, cube_iso(g, F, ci, cj, ck))) tidx = 255 - code;
+            }
             if (oa < cap_active) {
                 rec[oa] = (unsigned long long)(it.w * 32 + b) | ((unsigned long long)it.j << 12) |
                           ((unsigned long long)(it.kz + g.kb) << 24) | ((unsigned long long)code << 36) |
@@ -923,7 +998,7 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
             const float* pa = F + (size_t)(za - g.kb) * planep + (size_t)ya * rowp + xa;
             const float* pb = F + (size_t)(zb - g.kb) * planep + (size_t)yb * rowp + xb;
             const float f1 = __ldg(pa), f2 = __ldg(pb);
-            const float tq = (g.iso - f1) / (f2 - f1);
+            const float tq = (g.iso - f1) / (f2 - f1); /* Marching::interp uses the surface constant itself, also in repeating-surface mode */
             float* ep = epos + lc * kEdgeStride + 3 * e;
             ep[0] = interp_ref(cs[xa], cs[xb], tq);
             ep[1] = interp_ref(cs[ya], cs[yb], tq);
@@ -1018,9 +1093,12 @@ __device__ __forceinline__ GridEdge grid_edge_of(int i, int j, int k, int e) {
     E.vx = i + (lo & 1); E.vy = j + ((lo >> 1) & 1); E.vz = k + ((lo >> 2) & 1);
     return E;
 }
-__device__ __forceinline__ bool weld_cube_ok(const WeldView& W, int i, int j, int k) {
+/* `level`: repeating-surface mode only — the iso level of the cube that asks.  A neighbour polygonised with another level
+ * puts no point on the shared grid edge at this level, so for this edge it does not exist. */
+__device__ __forceinline__ bool weld_cube_ok(const WeldView& W, int i, int j, int k, float level = 0.f) {
     const Grid& g = W.g;
     if (i < 0 || j < 0 || i >= g.M || j >= g.M || k < g.kb || k >= g.ke) return false;
+    if (g.repeat && !(cube_iso(g, W.F, i, j, k) == level)) return false;
     if (W.present != nullptr &&
         !(((uint32_t)(W.present[((size_t)(k - g.kb) * g.M + j) * W.WC + (i >> 5)] >> 32) >> (i & 31)) & 1u)) return false;
     if (W.V == nullptr) return true;
@@ -1033,14 +1111,14 @@ __device__ __forceinline__ bool weld_cube_ok(const WeldView& W, int i, int j, in
     return ok;
 }
 /* first cube in loop order (z slowest, then y, then x) that contains the grid edge and is visited by the loop */
-__device__ __forceinline__ bool weld_owner(const WeldView& W, const GridEdge& E, CubeEdge& o) {
+__device__ __forceinline__ bool weld_owner(const WeldView& W, const GridEdge& E, CubeEdge& o, float level) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int hi = 1 - (q >> 1), lo = 1 - (q & 1); /* offsets in the slower / faster of the two other axes */
         if (E.axis == 0) { o.i = E.vx; o.j = E.vy - lo; o.k = E.vz - hi; o.e = 2 * lo + 4 * hi; }
         else if (E.axis == 1) { o.i = E.vx - lo; o.j = E.vy; o.k = E.vz - hi; o.e = (lo ? 1 : 3) + 4 * hi; }
         else { o.i = E.vx - lo; o.j = E.vy - hi; o.k = E.vz; o.e = 8 + (hi ? (lo ? 2 : 3) : (lo ? 1 : 0)); }
-        if (weld_cube_ok(W, o.i, o.j, o.k)) return true;
+        if (weld_cube_ok(W, o.i, o.j, o.k, level)) return true;
     }
     return false;
 }
@@ -1053,10 +1131,11 @@ __device__ __forceinline__ float weld_edge_point(const WeldView& W, const CubeEd
     const float* f0 = W.F + (size_t)(c.k - g.kb + 1) * planep + (size_t)(c.j + 1) * rowp + (c.i + 1);
     const float f1 = __ldg(f0 + (oa >> 2) * planep + ((oa >> 1) & 1) * rowp + (oa & 1));
     const float f2 = __ldg(f0 + (ob >> 2) * planep + ((ob >> 1) & 1) * rowp + (ob & 1));
-    crossing = (f1 > g.iso) != (f2 > g.iso);
+    const float level = cube_iso(g, W.F, c.i, c.j, c.k);
+    crossing = (f1 > level) != (f2 > level);
     const int base = (axis == 0 ? c.i : axis == 1 ? c.j : c.k) + 1;
     const float ca = W.cs[base + ((oa >> axis) & 1)], cb = W.cs[base + ((ob >> axis) & 1)];
-    return interp_ref(ca, cb, (g.iso - f1) / (f2 - f1));
+    return interp_ref(ca, cb, (g.iso - f1) / (f2 - f1)); /* Marching::interp (marching.cpp:437-446) always uses the surface constant */
 }
 __device__ __forceinline__ bool weld_close(float a, float b) { return (double)fabsf(a - b) < 0.000001; } /* marching.h:41 */
 __device__ __forceinline__ unsigned long long weld_key(const Grid& g, const CubeEdge& c) {
@@ -1095,6 +1174,8 @@ __device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], 
     unsigned long long ekey[24];
     float ept[24]; /* coordinate along the edge's own axis; the other two are G's */
     int n = 0;
+    const CubeEdge asking = weld_unkey(g, target);
+    const float iso = cube_iso(g, W.F, asking.i, asking.j, asking.k); /* repeating-surface mode: only this level's points can meet here */
     for (int ax = 0; ax < 3; ax++)
         for (int side = 0; side < 2; side++) { /* side 0: G is the edge's upper end point, 1: its lower end point */
             GridEdge E2{ax, G[0], G[1], G[2]};
@@ -1104,7 +1185,7 @@ __device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], 
             if (lo_idx + 1 > g.M + 1) continue;
             const float* fp = W.F + (size_t)(E2.vz - g.kb + 1) * planep + (size_t)(E2.vy + 1) * rowp + (E2.vx + 1);
             const float fl = __ldg(fp), fu = __ldg(fp + (ax == 0 ? (size_t)1 : ax == 1 ? rowp : planep));
-            if ((fl > g.iso) == (fu > g.iso)) continue;
+            if ((fl > iso) == (fu > iso)) continue;
             const float cl = W.cs[lo_idx], cu = W.cs[lo_idx + 1];
             const float pf = interp_ref(cl, cu, (g.iso - fl) / (fu - fl)); /* cube edge running lower -> upper */
             const float pb = interp_ref(cu, cl, (g.iso - fu) / (fl - fu)); /* cube edge running upper -> lower */
@@ -1114,7 +1195,7 @@ __device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], 
                 if (ax == 0) { o.i = E2.vx; o.j = E2.vy - lo; o.k = E2.vz - hi; o.e = 2 * lo + 4 * hi; }
                 else if (ax == 1) { o.i = E2.vx - lo; o.j = E2.vy; o.k = E2.vz - hi; o.e = (lo ? 1 : 3) + 4 * hi; }
                 else { o.i = E2.vx - lo; o.j = E2.vy - hi; o.k = E2.vz; o.e = 8 + (hi ? (lo ? 2 : 3) : (lo ? 1 : 0)); }
-                if (!weld_cube_ok(W, o.i, o.j, o.k)) continue;
+                if (!weld_cube_ok(W, o.i, o.j, o.k, iso)) continue;
                 const unsigned long long key = weld_key(g, o);
                 if (key > target) continue; /* inserted after the point we are resolving */
                 const bool forward = ((mcb_corner_ofs(mcb_edge_a(o.e)) >> ax) & 1) == 0;
@@ -1158,7 +1239,10 @@ __device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], 
 /* Owner of a grid edge, closed form for the unconstrained grid: the first cube in loop order is the one furthest
  * back in the two other axes that still exists ((i,j) >= 0, k >= kb); with constraints, the candidate loop. */
 __device__ __forceinline__ void weld_owner_fast(const WeldView& W, const GridEdge& E, CubeEdge& o) {
-    if (W.V != nullptr || W.present != nullptr) { weld_owner(W, E, o); return; }
+    if (W.V != nullptr || W.present != nullptr || W.g.repeat) { /* o comes in as the asking (cube, edge) */
+        weld_owner(W, E, o, cube_iso(W.g, W.F, o.i, o.j, o.k));
+        return;
+    }
     const int kb = W.g.kb;
     if (E.axis == 0) {
         const int lo = E.vy >= 1, hi = E.vz >= kb + 1;
@@ -1481,10 +1565,17 @@ weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restri
  *     the reference's order; x * (1.0f / sqrt(dot)) like glm 0.9.5.3 (func_geometric.inl:257-267,
  *     func_exponential.inl:226-229).
  * ------------------------------------------------------------------------------------------------------------- */
+/* A welded mesh that did not fit its buffers is incomplete (indices point past the vertex list); the host grows the
+ * buffers and repeats the pass, and until then this stage must not touch it. */
+__global__ void nh_gate_kernel(Counters* __restrict__ ctr, unsigned long long cap_active, unsigned long long cap_verts, unsigned long long cap_tris) {
+    const bool fits = ctr->active <= cap_active && ctr->vertices <= cap_verts && ctr->triangles <= cap_tris;
+    ctr->nh_vertices = fits ? ctr->vertices : 0ull;
+    ctr->nh_triangles = fits ? ctr->triangles : 0ull;
+}
 __global__ void __launch_bounds__(256)
 nh_face_normals_kernel(const float* __restrict__ vl, const uint32_t* __restrict__ tl, const Counters* __restrict__ ctr,
                        unsigned long long cap_tris, float* __restrict__ fn, uint32_t* __restrict__ count) {
-    unsigned long long T = ctr->triangles;
+    unsigned long long T = ctr->nh_triangles;
     if (T > cap_tris) T = cap_tris;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t i1 = tl[3 * t], i2 = tl[3 * t + 1], i3 = tl[3 * t + 2];
@@ -1566,7 +1657,7 @@ scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(256)
 nh_fill_kernel(const uint32_t* __restrict__ tl, const Counters* __restrict__ ctr, unsigned long long cap_tris,
                const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor, uint32_t* __restrict__ adj) {
-    unsigned long long T = ctr->triangles;
+    unsigned long long T = ctr->nh_triangles;
     if (T > cap_tris) T = cap_tris;
     const unsigned long long n = 3 * T;
     for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (unsigned long long)gridDim.x * blockDim.x) {
@@ -1579,7 +1670,7 @@ __global__ void __launch_bounds__(128)
 nh_accumulate_kernel(const float* __restrict__ fn, const uint32_t* __restrict__ start, const uint32_t* __restrict__ count,
                      uint32_t* __restrict__ adj, const Counters* __restrict__ ctr, unsigned long long cap_verts,
                      float* __restrict__ vnrm) {
-    unsigned long long Vn = ctr->vertices;
+    unsigned long long Vn = ctr->nh_vertices;
     if (Vn > cap_verts) Vn = cap_verts;
     for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t* a = adj + start[v];
@@ -1722,6 +1813,7 @@ struct StepOut { /* mirrors mcb_step_data (include/mcb.h) */
     int32_t edge_list[12];
     int32_t tri_vlist[15];
     int32_t n_edges, n_tri_idx, cube_code, table_idx, skipped;
+    float surf_constant;
 };
 struct InspectCons {
     int n;            /* constraints in use */
@@ -1730,8 +1822,8 @@ struct InspectCons {
 };
 __global__ void inspect_cube_kernel(const mcb_program* __restrict__ progs /* [0] surface, [1..3] constraint lhs */, const InspectCons cons,
                                     const int cons_slot0, const int cons_slot1, const int cons_slot2,
-                                    float x0, float y0, float z0, float step, float sx, float sy, float sz, float iso,
-                                    const ClsTables* __restrict__ gtb, StepOut* __restrict__ out) {
+                                    float x0, float y0, float z0, float step, float sx, float sy, float sz, float iso_in,
+                                    int repeat, float rstep, const ClsTables* __restrict__ gtb, StepOut* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     StepOut o;
     const float x1 = x0 + step, y1 = y0 + step, z1 = z0 + step; /* marching.cpp:458-460 */
@@ -1752,6 +1844,16 @@ __global__ void inspect_cube_kernel(const mcb_program* __restrict__ progs /* [0]
         if (o.skipped) break;
         o.corner_values[v] = mcb_interp_scalar(progs[0].code, progs[0].n, progs[0].k, X, Y, Z, nullptr, nullptr, nullptr);
     }
+    float iso = iso_in;
+    if (!o.skipped && repeat) { /* marching.cpp:481-494 */
+        float mx = o.corner_values[0];
+        for (int v = 1; v < 8; v++)
+            if (mx < o.corner_values[v]) mx = o.corner_values[v];
+        float a = (mx - iso_in) / rstep;
+        a = floorf(a);
+        iso = iso_in + rstep * a;
+    }
+    o.surf_constant = iso;
     if (!o.skipped) {
         int code = 0;
         for (int v = 0; v < 8; v++) code |= (o.corner_values[v] > iso ? 1 : 0) << v;
@@ -1797,7 +1899,8 @@ __global__ void inspect_cube_kernel(const mcb_program* __restrict__ progs /* [0]
  * Parity hooks (not on the hot path).
  * ------------------------------------------------------------------------------------------------------------- */
 __global__ void dense_codes_kernel(const Grid g, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
-                                   uint8_t* __restrict__ code_out, uint8_t* __restrict__ tidx_out, long long ncubes) {
+                                   uint8_t* __restrict__ code_out, uint8_t* __restrict__ tidx_out, long long ncubes,
+                                   const uint32_t* __restrict__ Cw, uint32_t WC) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= ncubes) return;
     const int i = (int)(idx % g.M);
@@ -1810,7 +1913,8 @@ __global__ void dense_codes_kernel(const Grid g, const uint32_t* __restrict__ S,
         const int o = mcb_corner_ofs(v);
         const int x = i + 1 + (o & 1), y = j + 1 + ((o >> 1) & 1), z = kz + 1 + ((o >> 2) & 1);
         const size_t widx = ((size_t)z * g.NV + y) * g.WP + (x >> 5);
-        code |= (int)((S[widx] >> (x & 31)) & 1u) << v;
+        if (Cw != nullptr) code |= (int)((Cw[(((size_t)kz * g.M + j) * WC + (i >> 5)) * 8 + v] >> (i & 31)) & 1u) << v;
+        else code |= (int)((S[widx] >> (x & 31)) & 1u) << v;
         if (V) ok = ok && ((V[widx] >> (x & 31)) & 1u);
     }
     if (!ok) code = 0;

@@ -104,6 +104,11 @@ int mcref_set_constraint(mcref* h, int i, const char* lhs, int op, float rhs, in
     return 1;
 }
 
+/* Repeating-surface mode (marching.cpp:156-170, 481-494) through the reference's own setters. */
+int mcref_set_repeat(mcref* h, int on, float distance) {
+    if (on && !h->march.set_surface_repeat_step_distance(distance)) return 0;
+    return h->march.repeating_surface_mode(on != 0) ? 1 : 0;
+}
 int mcref_recalculate(mcref* h) { return h->march.recalculate() ? 1 : 0; }
 /* Step-by-step mode (marching.cpp:386-428): recalculate() once per cube until it reports that it has finished, then
  * back to the full-grid mode.  Returns the number of calls that returned true. */

@@ -59,6 +59,7 @@ def lib():
         L.mcref_set_iso.argtypes = [C.c_void_p, C.c_float]
         L.mcref_set_constraint.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_float, C.c_int]
         L.mcref_recalculate.argtypes = [C.c_void_p]
+        L.mcref_set_repeat.argtypes = [C.c_void_p, C.c_int, C.c_float]
         L.mcref_seed_recalculate.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
         L.mcref_step_all.argtypes = [C.c_void_p, C.c_long]
         L.mcref_step_all.restype = C.c_long
@@ -139,6 +140,10 @@ class Ref:
         c = np.empty(M + 1, dtype=np.float32)
         self.L.mcref_grid_coords(self.h, _p(c), M + 1)
         return M, c
+
+    def set_repeat(self, on, distance=0.0):
+        """Repeating-surface mode via set_surface_repeat_step_distance + repeating_surface_mode."""
+        return bool(self.L.mcref_set_repeat(self.h, int(bool(on)), distance))
 
     def recalculate(self):
         """Unmodified Marching::recalculate(); returns (vertex_list[n,3], tri_list[t,3])."""
