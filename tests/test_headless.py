@@ -60,3 +60,22 @@ def test_headless_finer_than_the_reference_allows(mcb, tmp_path):
     out = subprocess.check_output([EXE, "--eq", "x^2+y^2+z^2-0.49", "--res", "256", "--scale", "1", "1", "1"], text=True)
     info = json.loads(out.strip().splitlines()[-1])
     assert (info["M"], info["vertices"], info["triangles"]) == (257, 151398, 302792)
+
+
+@pytest.mark.gpu
+def test_headless_repeating_surface_mode(mcb, tmp_path):
+    """The drop-in class in repeating-surface mode (set_surface_repeat_step_distance + repeating_surface_mode, the setting of
+    the reference's own test drawer, marching_test_drawer.h:238) against the unmodified reference's Poly_Data."""
+    rep = np.load(os.path.join(ROOT, "tests", "golden", "repeat_cases.npz"), allow_pickle=False)
+    case = json.loads(bytes(rep["meta_json"]).decode())["rep_testdrawer"]
+    dump = tmp_path / "m.bin"
+    out = subprocess.check_output([EXE, "--eq", case["eq"], "--step", str(case["step"]), "--scale", "1", "1", "1", "--levels", str(case["dist"]),
+                                   "--dump", str(dump)], text=True)
+    info = json.loads(out.strip().splitlines()[-1])
+    assert (info["M"], info["vertices"], info["triangles"]) == (case["M"], case["V"], case["T"])
+    raw = dump.read_bytes()
+    nv, nt = struct.unpack("<QQ", raw[:16])
+    v = np.frombuffer(raw, np.float32, nv * 3, 16).reshape(-1, 3)
+    t = np.frombuffer(raw, np.uint32, nt * 3, 16 + nv * 12).reshape(-1, 3)
+    assert same_bits(v, rep["rep_testdrawer/vertex_list"]) and np.array_equal(t, rep["rep_testdrawer/tri_list"])
+    assert subprocess.run([EXE, "--levels", "0"], capture_output=True).returncode == 1
