@@ -69,22 +69,29 @@ def test_1024_properties(mcb):
     c.close()
 
 
-def test_layers_against_live_reference_at_1024(mcb, refbind):
-    """BASELINE.json configs[2] at full size: three z-layers of the 1025^3-cube sphere grid (1.05 M cubes each), cube
-    codes, table rows and the triangle soup bit-exact against the reference executed live; plus the welded layer."""
+LIVE_1024 = [
+    ("x^2+y^2+z^2-0.49", (154, 512, 870)),                       # BASELINE.json configs[2]
+    ("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)", (512,)),           # configs[2], torus: `^` of a three-variable sum
+]   # (one layer of the polynomial gyroid takes the reference 100 s: it is covered at 17^3 and 257^3 instead)
+
+
+@pytest.mark.parametrize("eq,layers", LIVE_1024)
+def test_layers_against_live_reference_at_1024(mcb, refbind, eq, layers):
+    """BASELINE.json configs[2] at full size: z-layers of the 1025^3-cube grid (1.05 M cubes each), cube codes,
+    table rows and the triangle soup bit-exact against the reference executed live; plus the welded layer."""
     from .helpers import same_bits
-    eq = "x^2+y^2+z^2-0.49"
     r = refbind.Ref(eq, 2.0 / 1024)
     c = mcb.Context(0)
     c.set_mesh_mode(mcb.MESH_SOUP | mcb.MESH_INDEXED)
     assert c.set_equation(eq) == 0 and c.set_grid_step(2.0 / 1024) == 1025
-    for k0 in (154, 512, 870):
+    for k0 in layers:
         c.set_slab(k0, k0 + 1)
         cnt = c.polygonise()
         sw = r.sweep(k0, k0 + 1, soup=True)
         code, tidx = c.get_cases()
         assert np.array_equal(code, sw["code"]) and np.array_equal(tidx, sw["table_idx"])
         assert cnt.triangles == sw["T"] and cnt.triangles > 0
+        assert (cnt.ambiguous, cnt.redirected) == (sw["ambiguous"], sw["redirected"])
         pos, _ = c.get_mesh()
         assert same_bits(pos[:, :, :3], sw["soup"])
         vl, tl = c.get_indexed_mesh()
