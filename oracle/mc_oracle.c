@@ -48,6 +48,8 @@ struct mco {
     Cons cons[3];
     int pow_mode;
     float step, sx, sy, sz, iso;
+    int repeat;  /* repeating-surface mode, marching.cpp:481-494 */
+    float rstep;
     int M;
     float* c;  /* loop values c[0..M-1], c[M] = c[M-1]+step */
     float* cs; /* with apron: cs[v+1] = c[v], v in [-1, M+1] */
@@ -231,6 +233,8 @@ void mco_eval_points(mco* m, int slot, const float* p, float* out, long n, int a
 int mco_set_step(mco* m, float step) { if (!(step > 0.f) || step > 1.f) return -1; m->step = step; build_axis(m); return m->M; }
 void mco_set_scale(mco* m, float sx, float sy, float sz) { m->sx = sx; m->sy = sy; m->sz = sz; }
 void mco_set_iso(mco* m, float iso) { m->iso = iso; }
+/* Marching::set_surface_repeat_step_distance + repeating_surface_mode, marching.cpp:156-170 */
+int mco_set_repeat(mco* m, int on, float distance) { if (on && !(distance > 0.f)) return 0; m->repeat = on != 0; if (on) m->rstep = distance; return 1; }
 int mco_set_constraint(mco* m, int i, int op, float rhs, int in_use) {
     if (i < 0 || i > 2 || op < 0 || op > 3) return 0;
     m->cons[i].op = op; m->cons[i].rhs = rhs; m->cons[i].in_use = in_use;
@@ -283,8 +287,16 @@ static void calc_cube(const mco* m, int i, int j, int k, Cube* q, int want_grad)
         if (!check_constraints(m, cc[v][0], cc[v][1], cc[v][2])) return;
         val[v] = march_eval(m, 0, cc[v][0], cc[v][1], cc[v][2]);
     }
+    float level = m->iso; /* repeating-surface mode, :481-494: the cube's own level decides the code and the ambiguity test... */
+    if (m->repeat) {
+        float vmax = val[0];
+        for (int v = 1; v < 8; v++) if (vmax < val[v]) vmax = val[v];
+        float a = (vmax - m->iso) / m->rstep;
+        a = floorf(a);
+        level = m->iso + m->rstep * a;
+    }                     /* ...while interp() below keeps using the surface constant itself (:437-446) */
     int code = 0;
-    for (int v = 0; v < 8; v++) if (val[v] > m->iso) code |= 1 << v; /* :497-505 */
+    for (int v = 0; v < 8; v++) if (val[v] > level) code |= 1 << v; /* :497-505 */
     q->code = q->tidx = code;
     if (code == 0 || code == 255) return;                              /* :508-510 */
     int tidx = code;
@@ -298,7 +310,7 @@ static void calc_cube(const mco* m, int i, int j, int k, Cube* q, int want_grad)
         }
         mx /= 4.0; my /= 4.0; mz /= 4.0; /* float /= double constant: exact for a power of two */
         const float mid = march_eval(m, 0, mx, my, mz);
-        if (mid > m->iso) { tidx = 255 - code; q->red = 1; }
+        if (mid > level) { tidx = 255 - code; q->red = 1; }
     }
     q->tidx = tidx;
     int mapper[12];

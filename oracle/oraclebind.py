@@ -30,6 +30,7 @@ def lib():
         L.mco_set_step.argtypes = [vp, f]
         L.mco_set_scale.argtypes = [vp, f, f, f]
         L.mco_set_iso.argtypes = [vp, f]
+        L.mco_set_repeat.argtypes = [vp, i, f]
         L.mco_set_constraint.argtypes = [vp, i, i, f, i]
         L.mco_grid.argtypes = [vp, vp, i]
         L.mco_sweep.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, l, vp, vp, vp]
@@ -53,7 +54,7 @@ def _p(a):
 
 
 class Oracle:
-    def __init__(self, eq=None, step=None, scale=(1.0, 1.0, 1.0), iso=0.0, pow_mode=0, cons=()):
+    def __init__(self, eq=None, step=None, scale=(1.0, 1.0, 1.0), iso=0.0, pow_mode=0, cons=(), repeat=0.0):
         self.L = lib()
         self.h = C.c_void_p(self.L.mco_create())
         self.L.mco_set_pow_mode(self.h, pow_mode)
@@ -63,6 +64,8 @@ class Oracle:
             self.M = self.L.mco_set_step(self.h, step)
         self.L.mco_set_scale(self.h, *scale)
         self.L.mco_set_iso(self.h, iso)
+        if repeat:
+            assert self.L.mco_set_repeat(self.h, 1, repeat)
         for i, (lhs, op, rhs) in enumerate(cons):
             assert self.L.mco_set_equation(self.h, i + 1, lhs.encode())
             assert self.L.mco_set_constraint(self.h, i, {">": 0, "<": 1, ">=": 2, "<=": 3}[op], rhs, 1)

@@ -44,6 +44,25 @@ def test_restatement_matches_reference_goldens(OB, golden):
             assert same_bits(o.normals(), golden[name + "/normals"]), name + " normal.h"
 
 
+def test_restatement_repeating_surface_mode_matches_reference_goldens(OB):
+    """marching.cpp:481-494 in the restatement: per-cube level for code and ambiguity, Marching::interp's own constant for
+    the points — against the unmodified reference's runs (tests/golden/repeat_cases.npz)."""
+    import json
+    rep = np.load(os.path.join(ROOT, "tests", "golden", "repeat_cases.npz"), allow_pickle=False)
+    for name, case in json.loads(bytes(rep["meta_json"]).decode()).items():
+        o = OB.Oracle(case["eq"], case["step"], tuple(case["scale"]), case["iso"], cons=[tuple(c) for c in case["cons"]], repeat=case["dist"])
+        sw = o.sweep(nthreads=4)
+        act = (rep[name + "/code"] != 0) & (rep[name + "/code"] != 255)
+        assert np.array_equal(sw["code"][act], rep[name + "/code"][act]) and np.array_equal((sw["code"] != 0) & (sw["code"] != 255), act), name
+        assert np.array_equal(sw["table_idx"][act], rep[name + "/table_idx"][act]), name
+        assert np.array_equal(sw["ntri"], rep[name + "/ntri"]), name
+        assert (sw["T"], sw["active"], sw["ambiguous"], sw["redirected"]) == (case["T"], case["active"], case["ambiguous"], case["redirected"]), name
+        assert same_bits(sw["soup"], rep[name + "/soup"]), name
+        v, t = o.recalculate(nthreads=2)   # the restatement carries the reference's global std::set, so the weld is the reference's too
+        assert same_bits(v, rep[name + "/vertex_list"]) and np.array_equal(t, rep[name + "/tri_list"]), name + " weld"
+        assert same_bits(o.normals(), rep[name + "/normals"]), name + " normal.h"
+
+
 def test_restatement_gradient_normals_match_numpy(OB, golden):
     """Two independent CPU statements of the product's normal definition (C in mc_oracle.c, numpy in mc_numpy.py)."""
     from .test_host_logic import _packed_rows
