@@ -867,16 +867,19 @@ int Run::stage_classify() {
         launches++;
         cw = ctx->d_cw;
     }
-    if (dV)
-        classify_kernel<true><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
-                                                                        ctx->d_status, ctx->d_ctr, ctx->d_F, cw);
-    else
-        classify_kernel<false><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc,
-                                                                         ctx->d_status, ctx->d_ctr, ctx->d_F, cw);
     const bool need_items = want_indexed || ctx->seed_on; /* per-word record index for the weld / the seed walk */
     if (need_items && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
-    compact_kernel<<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status, ctx->d_ctr,
-                                                 ctx->d_rec, ctx->d_trioff, ctx->cap_active, need_items ? ctx->d_item : nullptr, ctx->d_F, cw);
+    unsigned long long* items = need_items ? ctx->d_item : nullptr;
+#define MCB_CLASSIFY(HAS_V, REPEAT)                                                                                                   \
+    do {                                                                                                                              \
+        classify_kernel<HAS_V, REPEAT><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, \
+                                                                                 ctx->d_status, ctx->d_ctr, ctx->d_F, cw);               \
+        compact_kernel<REPEAT><<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,    \
+                                                             ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active, items, ctx->d_F, cw); \
+    } while (0)
+    if (cw) { if (dV) MCB_CLASSIFY(true, true); else MCB_CLASSIFY(false, true); }
+    else { if (dV) MCB_CLASSIFY(true, false); else MCB_CLASSIFY(false, false); }
+#undef MCB_CLASSIFY
     launches += 2;
     return MCB_OK;
 }
@@ -981,8 +984,10 @@ int Run::stage_weld() {
     int rc;
     if ((rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
     const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr, ctx->seed_on ? ctx->d_item : nullptr, cg.WC};
+    const WeldViewT<true> WR{W.g, W.cs, W.F, W.V, W.present, W.WC}; /* repeating-surface mode: same view, level checks compiled in */
     const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_item, ctx->d_vinfo, ctx->d_chunk_new, cg.WC};
-    weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
+    if (g.repeat) weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(WR, B, ctx->d_ctr, ctx->cap_active);
+    else weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
     weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
     weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);
     /* streaming: with a registered host destination and everything fitting, weld_emit runs range by range and
@@ -1004,12 +1009,12 @@ int Run::stage_weld() {
     for (int j = 0; j < (stream_out ? K : 1); j++) {
         const unsigned long long cb = stream_out ? ctx->h_bounds[3 * j] : 0ull, ce = stream_out ? ctx->h_bounds[3 * j + 3] : ~0ull;
         if (stream_out && cb == ce) continue;
-        if (ctx->normals == 1)
-            weld_emit_kernel<true><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
-                                                                       ctx->d_vlist, ctx->d_vnrm, ctx->d_tlist, cb, ce);
-        else
-            weld_emit_kernel<false><<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris,
-                                                                        ctx->d_vlist, nullptr, ctx->d_tlist, cb, ce);
+#define MCB_WELD_EMIT(NRM, VIEW)                                                                                              \
+    weld_emit_kernel<NRM><<<eblocks * 2, kWeldThreads, 0, s>>>(VIEW, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris, \
+                                                               ctx->d_vlist, NRM ? ctx->d_vnrm : nullptr, ctx->d_tlist, cb, ce)
+        if (ctx->normals == 1) { if (g.repeat) MCB_WELD_EMIT(true, WR); else MCB_WELD_EMIT(true, W); }
+        else { if (g.repeat) MCB_WELD_EMIT(false, WR); else MCB_WELD_EMIT(false, W); }
+#undef MCB_WELD_EMIT
         launches++;
         if (!stream_out) break;
         const unsigned long long v0 = ctx->h_bounds[3 * j + 1], v1 = ctx->h_bounds[3 * j + 4];

@@ -61,8 +61,7 @@ struct Grid {
  * floor and multiply-add order.  (i, j, k) = cube indices, k global.  The level decides the cube code and the
  * ambiguity test only: Marching::interp (marching.cpp:437-446) keeps interpolating towards the surface constant
  * itself, so in that mode the reference's crossing points are extrapolated along their edges; that is reproduced. */
-__device__ __forceinline__ float cube_iso(const Grid& g, const float* __restrict__ F, int i, int j, int k) {
-    if (!g.repeat) return g.iso;
+__device__ __noinline__ float cube_level(const Grid& g, const float* __restrict__ F, int i, int j, int k) {
     const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
     const float* f0 = F + (size_t)(k - g.kb + 1) * planep + (size_t)(j + 1) * rowp + (i + 1);
     float mx = __ldg(f0);
@@ -75,6 +74,10 @@ __device__ __forceinline__ float cube_iso(const Grid& g, const float* __restrict
     float a = (mx - g.iso) / g.rstep;
     a = floorf(a);
     return g.iso + g.rstep * a;
+}
+/* kept out of line: the plain mode pays one uniform branch for it, not its eight loads in every caller */
+__device__ __forceinline__ float cube_iso(const Grid& g, const float* __restrict__ F, int i, int j, int k) {
+    return g.repeat ? cube_level(g, F, i, j, k) : g.iso;
 }
 
 
@@ -592,16 +595,17 @@ repeat_words_kernel(const Grid g, const float* __restrict__ F, uint32_t WC, uint
     }
 }
 
+template <bool REPEAT>
 __device__ __forceinline__ void view_item(ItemView& it, uint32_t item_local, uint32_t j0, uint32_t kz0, const ClsGeom& q,
                                           const Grid& g, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
-                                          uint32_t plane, const uint32_t* __restrict__ Cw = nullptr) {
+                                          uint32_t plane, const uint32_t* __restrict__ Cw) {
     const uint32_t r = div_small(item_local, q.inv_wc);
     it.w = item_local - r * q.WC;
     const uint32_t jj = j0 + r, dk = div_small(jj, q.inv_m);
     it.j = jj - dk * (uint32_t)g.M;
     it.kz = kz0 + dk;
     const uint32_t idx = ((it.kz + 1u) * (uint32_t)g.NV + (it.j + 1u)) * (uint32_t)g.WP + it.w;
-    if (Cw != nullptr) repeat_item_words(Cw, ((size_t)it.kz * (uint32_t)g.M + it.j) * q.WC + it.w, it.c);
+    if (REPEAT) repeat_item_words(Cw, ((size_t)it.kz * (uint32_t)g.M + it.j) * q.WC + it.w, it.c);
     else {
         uint32_t lo[4], hi[4];
         vertex_row_words(S, idx, plane, lo);
@@ -619,7 +623,7 @@ struct ClsScratch {        /* global scratch handed from classify_kernel to comp
     uint32_t tile_items;   /* tile_rows * WC */
 };
 
-template <bool HAS_V>
+template <bool HAS_V, bool REPEAT /* repeating-surface mode: corner words from Cw instead of the sign planes */>
 __global__ void __launch_bounds__(kClsThreads, 4)
 classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
                 const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
@@ -648,7 +652,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
             const uint32_t colmask = column_mask(g, w);
             uint32_t kz = kz0 + (j0 + r) / M, j = (j0 + r) - (kz - kz0) * M;
             uint32_t item = r * q.WC + w;
-            while (Cw != nullptr && r < r_end) { /* repeating-surface mode: nothing is shared between cube rows */
+            while (REPEAT && r < r_end) { /* repeating-surface mode: nothing is shared between cube rows */
                 uint32_t c[8];
                 repeat_item_words(Cw, ((size_t)kz * M + j) * q.WC + w, c);
                 uint32_t m = active_mask(c, colmask);
@@ -724,7 +728,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
         if (k < nz) {
             const uint32_t item_local = list[k];
             ItemView it;
-            view_item(it, item_local, j0, kz0, q, g, S, V, plane, Cw);
+            view_item<REPEAT>(it, item_local, j0, kz0, q, g, S, V, plane, Cw);
             const uint32_t na = __popc(it.m);
             uint32_t nt = 0, mm = it.m;
             while (mm) {
@@ -735,7 +739,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
                 if (face >= 0) {
                     n_amb++;
                     const int ci = (int)it.w * 32 + b, cj = (int)it.j, ck = (int)it.kz + g.kb;
-                    if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, cube_iso(g, F, ci, cj, ck))) {
+                    if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, REPEAT ? cube_level(g, F, ci, cj, ck) : g.iso)) {
                         code = 255 - code;
                         n_red++;
                     }
@@ -766,6 +770,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
     }
 }
 
+template <bool REPEAT>
 __global__ void __launch_bounds__(kClsThreads)
 compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
                const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
@@ -879,7 +884,7 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
         unsigned long long ot = tile_t + chunk_t[kb >> 5] + ((inc - mine) >> 16);
         ItemView it;
         const uint32_t item_local = glist[k];
-        view_item(it, item_local, j0, kz0, q, g, S, V, plane, Cw);
+        view_item<REPEAT>(it, item_local, j0, kz0, q, g, S, V, plane, Cw);
         uint32_t m = it.m;
         if (item_info != nullptr) /* cube -> record look-up of the weld: first record of the word | its active mask */
             item_info[(size_t)tile * sc.tile_items + item_local] = (oa & 0xFFFFFFFFull) | ((unsigned long long)m << 32);
@@ -891,7 +896,7 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
             const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
             if (face >= 0) {
                 const int ci = (int)it.w * 32 + b, cj = (int)it.j, ck = (int)it.kz + g.kb;
-                if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, cube_iso(g, F, ci, cj, ck))) tidx = 255 - code;
+                if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, REPEAT ? cube_level(g, F, ci, cj, ck) : g.iso)) tidx = 255 - code;
             }
             if (oa < cap_active) {
                 rec[oa] = (unsigned long long)(it.w * 32 + b) | ((unsigned long long)it.j << 12) |
@@ -1068,7 +1073,11 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
  *     those counts in loop order is the reference's vertex numbering; weld_emit writes vertex_list (the inserting
  *     cube's own interpolation), tri_list and, optionally, gradient normals per welded vertex.
  * ------------------------------------------------------------------------------------------------------------- */
-struct WeldView {
+/* REPEAT = repeating-surface mode: only then a cube's level has to be looked at (cube_level); the plain instantiation
+ * carries none of it. */
+template <bool REPEAT>
+struct WeldViewT {
+    static constexpr bool kRepeat = REPEAT;
     Grid g;
     const float* __restrict__ cs;
     const float* __restrict__ F;
@@ -1078,6 +1087,10 @@ struct WeldView {
     const unsigned long long* __restrict__ present;
     uint32_t WC;
 };
+using WeldView = WeldViewT<false>;
+template <class WV>
+__device__ __forceinline__ float weld_level(const WV& W, int i, int j, int k) { return WV::kRepeat ? cube_level(W.g, W.F, i, j, k) : W.g.iso; }
+
 struct CubeEdge { /* an edge of a cube: who inserts a vertex, and as which of its edges */
     int i, j, k, e;
 };
@@ -1095,10 +1108,11 @@ __device__ __forceinline__ GridEdge grid_edge_of(int i, int j, int k, int e) {
 }
 /* `level`: repeating-surface mode only — the iso level of the cube that asks.  A neighbour polygonised with another level
  * puts no point on the shared grid edge at this level, so for this edge it does not exist. */
-__device__ __forceinline__ bool weld_cube_ok(const WeldView& W, int i, int j, int k, float level = 0.f) {
+template <class WV>
+__device__ __forceinline__ bool weld_cube_ok(const WV& W, int i, int j, int k, float level = 0.f) {
     const Grid& g = W.g;
     if (i < 0 || j < 0 || i >= g.M || j >= g.M || k < g.kb || k >= g.ke) return false;
-    if (g.repeat && !(cube_iso(g, W.F, i, j, k) == level)) return false;
+    if (WV::kRepeat && !(cube_level(g, W.F, i, j, k) == level)) return false;
     if (W.present != nullptr &&
         !(((uint32_t)(W.present[((size_t)(k - g.kb) * g.M + j) * W.WC + (i >> 5)] >> 32) >> (i & 31)) & 1u)) return false;
     if (W.V == nullptr) return true;
@@ -1111,7 +1125,8 @@ __device__ __forceinline__ bool weld_cube_ok(const WeldView& W, int i, int j, in
     return ok;
 }
 /* first cube in loop order (z slowest, then y, then x) that contains the grid edge and is visited by the loop */
-__device__ __forceinline__ bool weld_owner(const WeldView& W, const GridEdge& E, CubeEdge& o, float level) {
+template <class WV>
+__device__ __forceinline__ bool weld_owner(const WV& W, const GridEdge& E, CubeEdge& o, float level) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int hi = 1 - (q >> 1), lo = 1 - (q & 1); /* offsets in the slower / faster of the two other axes */
@@ -1124,14 +1139,15 @@ __device__ __forceinline__ bool weld_owner(const WeldView& W, const GridEdge& E,
 }
 /* crossing point of edge e of cube (i,j,k) along the edge's axis, interpolated in that cube's edge direction
  * (marching.cpp:557-583); crossing = the end points lie on different sides of iso */
-__device__ __forceinline__ float weld_edge_point(const WeldView& W, const CubeEdge& c, int axis, bool& crossing) {
+template <class WV>
+__device__ __forceinline__ float weld_edge_point(const WV& W, const CubeEdge& c, int axis, bool& crossing) {
     const Grid& g = W.g;
     const int oa = mcb_corner_ofs(mcb_edge_a(c.e)), ob = mcb_corner_ofs(mcb_edge_b(c.e));
     const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
     const float* f0 = W.F + (size_t)(c.k - g.kb + 1) * planep + (size_t)(c.j + 1) * rowp + (c.i + 1);
     const float f1 = __ldg(f0 + (oa >> 2) * planep + ((oa >> 1) & 1) * rowp + (oa & 1));
     const float f2 = __ldg(f0 + (ob >> 2) * planep + ((ob >> 1) & 1) * rowp + (ob & 1));
-    const float level = cube_iso(g, W.F, c.i, c.j, c.k);
+    const float level = weld_level(W, c.i, c.j, c.k);
     crossing = (f1 > level) != (f2 > level);
     const int base = (axis == 0 ? c.i : axis == 1 ? c.j : c.k) + 1;
     const float ca = W.cs[base + ((oa >> axis) & 1)], cb = W.cs[base + ((ob >> axis) & 1)];
@@ -1168,14 +1184,15 @@ __device__ __forceinline__ CubeEdge weld_unkey(const Grid& g, unsigned long long
  * that element is not less than it either.  At most 24 insertions, a handful of elements; only taken when the
  * owner's point lies within 1.5e-6 of an end point (the extra half tolerance covers the ulp-level differences
  * between the sharing cubes' interpolations). */
-__device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], unsigned long long target) {
+template <class WV>
+__device__ __noinline__ CubeEdge weld_replay(const WV& W, const int G[3], unsigned long long target) {
     const Grid& g = W.g;
     const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
     unsigned long long ekey[24];
     float ept[24]; /* coordinate along the edge's own axis; the other two are G's */
     int n = 0;
     const CubeEdge asking = weld_unkey(g, target);
-    const float iso = cube_iso(g, W.F, asking.i, asking.j, asking.k); /* repeating-surface mode: only this level's points can meet here */
+    const float iso = weld_level(W, asking.i, asking.j, asking.k); /* repeating-surface mode: only this level's points can meet here */
     for (int ax = 0; ax < 3; ax++)
         for (int side = 0; side < 2; side++) { /* side 0: G is the edge's upper end point, 1: its lower end point */
             GridEdge E2{ax, G[0], G[1], G[2]};
@@ -1238,9 +1255,10 @@ __device__ __noinline__ CubeEdge weld_replay(const WeldView& W, const int G[3], 
 
 /* Owner of a grid edge, closed form for the unconstrained grid: the first cube in loop order is the one furthest
  * back in the two other axes that still exists ((i,j) >= 0, k >= kb); with constraints, the candidate loop. */
-__device__ __forceinline__ void weld_owner_fast(const WeldView& W, const GridEdge& E, CubeEdge& o) {
-    if (W.V != nullptr || W.present != nullptr || W.g.repeat) { /* o comes in as the asking (cube, edge) */
-        weld_owner(W, E, o, cube_iso(W.g, W.F, o.i, o.j, o.k));
+template <class WV>
+__device__ __forceinline__ void weld_owner_fast(const WV& W, const GridEdge& E, CubeEdge& o) {
+    if (W.V != nullptr || W.present != nullptr || WV::kRepeat) { /* o comes in as the asking (cube, edge) */
+        weld_owner(W, E, o, weld_level(W, o.i, o.j, o.k));
         return;
     }
     const int kb = W.g.kb;
@@ -1259,7 +1277,8 @@ __device__ __forceinline__ void weld_owner_fast(const WeldView& W, const GridEdg
 /* Does the crossing point of (cube, edge), as this cube interpolates it, sit on a grid vertex?  The sharing cubes'
  * interpolations differ by an ulp or two (< 2.5e-7), so 1.5e-6 catches every edge any of whose versions is within
  * the reference's 1e-6.  Returns 0 (no), 1 (lower end point) or 2 (upper end point). */
-__device__ __forceinline__ int weld_on_vertex(const WeldView& W, int i, int j, int k, int e) {
+template <class WV>
+__device__ __forceinline__ int weld_on_vertex(const WV& W, int i, int j, int k, int e) {
     const GridEdge E = grid_edge_of(i, j, k, e);
     bool cr;
     const CubeEdge me{i, j, k, e};
@@ -1272,7 +1291,8 @@ __device__ __forceinline__ int weld_on_vertex(const WeldView& W, int i, int j, i
 
 /* (cube, crossing edge) -> the (cube, edge) whose insertion created the welded vertex the reference uses there.
  * on_vertex = weld_on_vertex() of this pair (computed once, in weld_count, and handed on in the vinfo words). */
-__device__ __forceinline__ CubeEdge weld_resolve(const WeldView& W, int i, int j, int k, int e, int on_vertex) {
+template <class WV>
+__device__ __forceinline__ CubeEdge weld_resolve(const WV& W, int i, int j, int k, int e, int on_vertex) {
     const GridEdge E = grid_edge_of(i, j, k, e);
     if (on_vertex == 0) { /* the up-to-four sharing cubes agree to within an ulp: the first inserter wins */
         CubeEdge own{i, j, k, e};
@@ -1350,8 +1370,9 @@ __device__ __forceinline__ uint32_t weld_load_chunk(WeldChunk& sh, const unsigne
 }
 
 /* marks, per active cube, the edges for which it inserts a new vertex and those whose point sits on a grid vertex */
+template <class WV>
 __global__ void __launch_bounds__(kWeldThreads)
-weld_count_kernel(const WeldView W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active) {
+weld_count_kernel(const WV W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active) {
     __shared__ WeldChunk sh;
     unsigned long long A = ctr->active;
     if (A > cap_active) A = cap_active;
@@ -1458,9 +1479,9 @@ __global__ void weld_bounds_kernel(const WeldBuffers B, const Counters* __restri
     out[3 * j + 2] = c < nchunks ? (unsigned long long)B.trioff[c * kWeldCubes] : ctr->triangles;
 }
 
-template <bool NORMALS>
+template <bool NORMALS, class WV>
 __global__ void __launch_bounds__(kWeldThreads)
-weld_emit_kernel(const WeldView W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active,
+weld_emit_kernel(const WV W, const WeldBuffers B, const Counters* __restrict__ ctr, unsigned long long cap_active,
                  unsigned long long cap_verts, unsigned long long cap_tris, float* __restrict__ vertex_list,
                  float* __restrict__ vertex_nrm, uint32_t* __restrict__ tri_list, unsigned long long chunk_begin,
                  unsigned long long chunk_end /* chunks [begin,end) of kWeldCubes cubes: the host streams the mesh out range by range */) {
