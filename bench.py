@@ -180,6 +180,7 @@ def run_ours(args):
     k0, k1 = mcb.slab_range(M, rank, world)
     ctx.set_slab(k0, k1)
     ctx.set_normals(1)
+    ctx.set_field_mode(mcb.FIELD_AUTO)  # what the drop-in class uses: the field write is dropped once the surface is known to be sparse
     slabs = importlib.import_module(PKG + ".slabs")
     placement = slabs.DeviceCounts(ctx, torch.device("cuda", local)) if world > 1 else None
 
@@ -201,7 +202,7 @@ def run_ours(args):
 
     # ---- timed region: device-resident inputs ---------------------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"ms_tables": 0.0, "ms_eval": 0.0, "ms_classify": 0.0, "ms_emit": 0.0}
+    stage = {"ms_tables": 0.0, "ms_eval": 0.0, "ms_classify": 0.0, "ms_emit": 0.0, "ms_fill": 0.0}
     launches = 0
     t0 = time.time()
     e0.record(stream)
@@ -239,26 +240,43 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = cubes / (ms_per_step * 1e-3) / 1e9
 
-    # ---- variant: sparse-field mode (signs everywhere, field values only around the surface); informational ----------
+    # ---- variants (informational): the field fully materialised; the bytecode interpreter ---------------------------------
     variants = {}
     if world == 1:
-        ctx.set_field_mode(mcb.FIELD_SPARSE)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nv = max(1, min(args.steps, 10))
+        ctx.set_field_mode(mcb.FIELD_DENSE)
         for _ in range(3):
             cs_ = ctx.polygonise()
         torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nv = max(1, min(args.steps, 10))
         ev0.record(stream)
         for _ in range(nv):
             cs_ = ctx.polygonise()
         ev1.record(stream)
         torch.cuda.synchronize()
-        sp_ms = ev0.elapsed_time(ev1) / nv
-        variants["sparse_field"] = {"value": float(cs_.cubes) / (sp_ms * 1e-3) / 1e9, "ms_per_step": sp_ms, "ms_eval_signs_only": cs_.ms_eval,
-                                    "ms_fill": cs_.ms_fill, "field_blocks": int(cs_.field_blocks), "steps": nv,
-                                    "what": "mcb_set_field_mode(MCB_FIELD_SPARSE): same outputs bit for bit, the 4 B/vertex field is not "
-                                            "written; not the default because it loses on dense surfaces (DESIGN.md)"}
-        ctx.set_field_mode(mcb.FIELD_DENSE)
+        dn_ms = ev0.elapsed_time(ev1) / nv
+        V_ = (M + 1) * (M + 1) * (k1 - k0 + 1)
+        variants["dense_field"] = {"value": float(cs_.cubes) / (dn_ms * 1e-3) / 1e9, "ms_per_step": dn_ms, "ms_eval": cs_.ms_eval, "steps": nv,
+                                   "eval_GBps": (4.0 * V_ + V_ / 8.0) / (cs_.ms_eval * 1e-3) / 1e9,
+                                   "what": "mcb_set_field_mode(MCB_FIELD_DENSE): every vertex's value written to HBM (4 B/vertex); "
+                                           "eval_GBps is that kernel's real write rate"}
+        # the bytecode interpreter instead of the kernel NVRTC compiled for this equation (same results bit for bit)
+        ctx.set_jit(mcb.JIT_OFF)
+        for _ in range(3):
+            ci_ = ctx.polygonise()
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(nv):
+            ci_ = ctx.polygonise()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        in_ms = ev0.elapsed_time(ev1) / nv
+        variants["interpreter"] = {"value": float(ci_.cubes) / (in_ms * 1e-3) / 1e9, "ms_per_step": in_ms, "ms_eval": ci_.ms_eval, "steps": nv,
+                                   "what": "mcb_set_jit(MCB_JIT_OFF): eval_field_kernel interpreting the fused bytecode"}
+        ctx.set_jit(mcb.JIT_AUTO)
+        ctx.set_field_mode(mcb.FIELD_AUTO)
+        for _ in range(2):
+            ctx.polygonise()
 
     # ---- e2e: through the reference-facing call with HOST buffers: equation text in, Poly_Data out ----------------
     # Marching::recalculate() leaves a welded, indexed mesh in Poly_Data (vertex_list + tri_list, marching.h:26-30);
@@ -336,15 +354,24 @@ def run_ours(args):
         V = (M + 1) * (M + 1) * (Ml + 1)
         A_r, T_r, C_r = float(c.active), float(c.triangles), float(c.cubes)
         per = {k: v / args.steps for k, v in stage.items()}
+        sparse_run = c.field_mode == mcb.FIELD_SPARSE
         kern = {
             # algorithmic bytes per launch, SURVEY.md §8(d) / DESIGN.md §roofline
             "eval_field": {"ms": per["ms_eval"], "bytes": 4.0 * V + V / 8.0,
-                           "what": "4 B field + 1 bit sign per grid vertex written"},
+                           "written_bytes": (V / 8.0) if sparse_run else (4.0 * V + V / 8.0),
+                           "what": "SURVEY 8(d) accounting: 4 B field + 1 bit sign per grid vertex (%s)%s" % (
+                               "mcb_eval_jit: the equation's program compiled by NVRTC" if c.jit else "eval_field_kernel: bytecode interpreter",
+                               "; sparse-field mode: every vertex is evaluated but only the sign bit is written, so this "
+                               "algorithmic rate exceeds the HBM peak - as SURVEY 8(d) anticipates for a variant that never "
+                               "writes the field; variants.dense_field.eval_GBps is the kernel that really writes 4 B/vertex" if sparse_run else "")},
             "classify+compact": {"ms": per["ms_classify"], "bytes": V / 8.0 + 12.0 * A_r,
                                  "what": "1 bit per vertex read + 12 B per active cube written (our layout; SURVEY's 4V+C accounting is in classify_scan_emit_vs_survey_bytes)"},
             "emit": {"ms": per["ms_emit"], "bytes": 12.0 * A_r + 32.0 * A_r + 96.0 * T_r,
                      "what": "12 B record + 8 corner values per active cube read, 96 B per triangle written"},
         }
+        if sparse_run:
+            kern["field_refill"] = {"ms": per["ms_fill"], "bytes": 2048.0 * float(c.field_blocks) + 8.0 * A_r,
+                                    "what": "sparse-field mode: records read, 32x4x4-vertex blocks around the active cubes evaluated again and written (4 B/vertex)"}
         for k, d in kern.items():
             d["GBps"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else None
             d["frac_of_hbm_peak"] = d["GBps"] / hbm if d["GBps"] else None
@@ -362,9 +389,12 @@ def run_ours(args):
             "metric": "Gvoxels/s", "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "mtriangles_per_s": tris / (ms_per_step * 1e-3) / 1e6,
-            "config": {"workload": "%s %s at %d^3 (step 2/%d, M=%d cubes/axis), iso 0, scale 1, positions+gradient normals, z-slabs over %d GPU(s)" % (
+            "config": {"workload": "%s %s at %d^3 (step 2/%d, M=%d cubes/axis), iso 0, scale 1, positions+gradient normals, field mode auto, z-slabs over %d GPU(s)" % (
                 args.workload, eq, n, n, M, world), "cubes": cubes, "triangles": tris, "active_cubes": active,
-                "l2": "inputs larger than L2 (field %.2f GB per GPU)" % (4.0 * (M + 3) ** 2 * (Ml + 3) / 1e9),
+                "field_mode": "sparse (MCB_FIELD_AUTO after the first run of this configuration)" if sparse_run else "dense",
+                "l2": ("nothing is read back between steps; per step the sign planes (%.2f GB) and the soup (%.2f GB) alone exceed L2, "
+                       "every grid vertex is re-evaluated" % ((M + 3) ** 2 * (Ml + 3) / 8e9, 96.0 * T_r / 1e9)) if sparse_run else
+                      "inputs larger than L2 (field %.2f GB per GPU)" % (4.0 * (M + 3) ** 2 * (Ml + 3) / 1e9),
                 "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": hbm, "unit": "GB/s",
                          "frac": kern[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,

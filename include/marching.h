@@ -258,6 +258,7 @@ private:
         /* marching.cpp:156-170, 481-494.  The reference accepts the mode with its initial distance 0: every cube's iso is
          * then NaN and nothing is drawn; recalculate() short-cuts that case, the GPU only sees positive distances */
         mcb_set_repeat(ctx_, repeat_ && repeat_step_ > 0.f ? 1 : 0, repeat_step_);
+        mcb_set_field_mode(ctx_, MCB_FIELD_AUTO); /* nothing here reads the field back: let the library drop its write when that pays */
         for (int i = 0; i < 3; i++)
             mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
         return true;

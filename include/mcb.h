@@ -63,6 +63,8 @@ typedef struct {
     float ms_fill;        /* sparse-field mode: device time of the block refill (flag, list, evaluate); else 0 */
     uint32_t field_mode;  /* MCB_FIELD_* this result was produced with */
     uint64_t field_blocks; /* sparse-field mode: 32 x 4 x 4 vertex blocks the field was written in */
+    uint32_t jit;         /* 1: the field was evaluated by the kernel compiled for this equation (mcb_set_jit) */
+    float ms_compile;     /* host milliseconds this call spent in NVRTC (0 when the equation's kernel was cached) */
 } mcb_counts;
 
 /* Where the scalar field lives (mcb_set_field_mode; default MCB_FIELD_DENSE). */
@@ -70,6 +72,9 @@ typedef struct {
 #define MCB_FIELD_SPARSE 1  /* every vertex is still evaluated, but only its sign is kept; the values are written again,
                                by the same arithmetic, in 32 x 4 x 4 vertex blocks around the active cubes.  Meshes,
                                normals and counts are bit-identical to MCB_FIELD_DENSE; mcb_get_field is unavailable */
+#define MCB_FIELD_AUTO 2    /* dense the first time a configuration (equation, grid, slab, iso, scaling, constraints) is
+                               polygonised; sparse from then on if it had at most 0.5 % active cubes, where dropping the
+                               field write pays (sphere at 1024^3: 1.20 -> 0.88 ms); mcb_counts::field_mode says which ran */
 
 /* What mcb_polygonise leaves in device memory (mcb_set_mesh_mode; default MCB_MESH_SOUP). */
 #define MCB_MESH_SOUP 1     /* triangle soup: 3 float4 positions (+ 3 float4 normals) per triangle, emission order */
@@ -167,8 +172,28 @@ int mcb_counts_device(mcb_ctx* ctx, const uint64_t** counts);
  * level sets.  distance must be > 0.  Forces MCB_FIELD_DENSE; not available together with seed mode. */
 int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance);
 
-/* MCB_FIELD_DENSE (default) or MCB_FIELD_SPARSE: whether mcb_polygonise writes the whole scalar field to device
- * memory or only the blocks of it that the mesh stages read.  Results are bit-identical. */
+/* Run-time specialisation of the evaluator.  The first mcb_polygonise after an equation change compiles
+ * that equation's fused grid program into a straight-line sm_100a kernel with NVRTC (libnvrtc.so.12, loaded on demand;
+ * 10-20 ms, reported in mcb_counts::ms_compile) and later calls reuse it.  The kernel executes the interpreter's fp32
+ * operations in the interpreter's order on the interpreter's tile, so every result is bit-identical; it just has no
+ * dispatch (torus 2.3 -> 1.5 ms, polynomial gyroid 1.3 -> 0.7 ms at 1024^3).  Constants, grid size and scaling are
+ * kernel arguments: only a new equation compiles again.
+ *   MCB_JIT_AUTO (default)  use it when NVRTC is there and the compile succeeds, else the bytecode interpreter — both
+ *                           are the same CUDA path with the same results; mcb_counts::jit says which one ran
+ *   MCB_JIT_ON              require it: mcb_polygonise returns MCB_E_STATE with the log in mcb_last_error otherwise
+ *   MCB_JIT_OFF             always interpret
+ * The sparse-field mode's kernels are always interpreted. */
+#define MCB_JIT_OFF 0
+#define MCB_JIT_ON 1
+#define MCB_JIT_AUTO 2
+int mcb_set_jit(mcb_ctx* ctx, int mode);
+/* Host-only: generate and compile the specialised kernel for `equation` (no GPU needed).  Returns the cubin size in
+ * bytes (> 0) and the generated CUDA source in `log`, or a negative status with the error / compile log in `log`. */
+int mcb_jit_check(const char* equation, char* log, size_t cap);
+
+/* MCB_FIELD_DENSE (default), MCB_FIELD_SPARSE or MCB_FIELD_AUTO: whether mcb_polygonise writes the whole scalar field to
+ * device memory or only the blocks of it that the mesh stages read.  Results are bit-identical.  The C++
+ * drop-in class, which never reads the field back, uses MCB_FIELD_AUTO. */
 int mcb_set_field_mode(mcb_ctx* ctx, int mode);
 
 /* MCB_MESH_SOUP, MCB_MESH_INDEXED or both (3).  The indexed mesh is what Marching::recalculate() leaves in

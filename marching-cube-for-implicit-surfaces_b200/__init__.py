@@ -23,7 +23,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcb200.so")
 
 MESH_SOUP, MESH_INDEXED = 1, 2
-FIELD_DENSE, FIELD_SPARSE = 0, 1
+FIELD_DENSE, FIELD_SPARSE, FIELD_AUTO = 0, 1, 2
+JIT_OFF, JIT_ON, JIT_AUTO = 0, 1, 2
 MCB_OK, MCB_E_PARSE, MCB_E_ARG, MCB_E_CUDA, MCB_E_NOMEM, MCB_E_STATE, MCB_E_CAPACITY, MCB_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
 
 
@@ -39,7 +40,7 @@ class Counts(C.Structure):
                 ("ms_tables", C.c_float), ("ms_eval", C.c_float), ("ms_classify", C.c_float), ("ms_emit", C.c_float),
                 ("ms_total", C.c_float), ("launches", C.c_uint32), ("reruns", C.c_uint32), ("ms_weld", C.c_float),
                 ("mesh_mode", C.c_uint32), ("vertices", C.c_uint64), ("ms_fill", C.c_float), ("field_mode", C.c_uint32),
-                ("field_blocks", C.c_uint64)]
+                ("field_blocks", C.c_uint64), ("jit", C.c_uint32), ("ms_compile", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -90,6 +91,8 @@ def _load():
         "mcb_counts_device": ([vp, C.POINTER(vp)], i),
         "mcb_set_mesh_mode": ([vp, i], i),
         "mcb_set_field_mode": ([vp, i], i),
+        "mcb_set_jit": ([vp, i], i),
+        "mcb_jit_check": ([cp, cp, sz], i),
         "mcb_get_indexed_mesh": ([vp, vp, vp, vp, u64, u64], i),
         "mcb_get_indexed_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i),
         "mcb_set_host_output": ([vp, vp, vp, vp, u64, u64], i),
@@ -138,6 +141,15 @@ def postfix(eq):
 
 def disassemble(eq, which=1):
     return _text(lib.mcb_disassemble, eq.encode(), which)
+
+
+def jit_check(eq, cap=1 << 18):
+    """Host-only: (cubin bytes, generated CUDA source) of the run-time specialised evaluator for `eq`; raises with the log."""
+    buf = C.create_string_buffer(cap)
+    rc = lib.mcb_jit_check(eq.encode(), buf, cap)
+    if rc <= 0:
+        raise McbError(rc, buf.value.decode(errors="replace"))
+    return rc, buf.value.decode(errors="replace")
 
 
 def grid_axis(step):
@@ -235,6 +247,11 @@ class Context:
         p = C.c_void_p()
         self._ck(lib.mcb_counts_device(self.h, C.byref(p)))
         return p.value
+
+    def set_jit(self, mode):
+        """JIT_AUTO (default) / JIT_ON / JIT_OFF: evaluate the field with a kernel NVRTC compiles for the equation
+        (bit-identical to the interpreter; compiled on first use, cached per equation)."""
+        self._ck(lib.mcb_set_jit(self.h, int(mode)))
 
     def set_field_mode(self, mode):
         """FIELD_DENSE (whole field in device memory) or FIELD_SPARSE (signs everywhere, values only around the surface)."""

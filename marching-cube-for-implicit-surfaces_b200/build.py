@@ -14,9 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcb200.so")
-SOURCES = ["mcb_api.cu", "mcb_lower.cpp"]
+SOURCES = ["mcb_api.cu", "mcb_lower.cpp", "mcb_jit.cpp"]
 HEADERS = [os.path.join("..", "..", "tools", "headless_main.cpp"), os.path.join("..", "..", "include", "marching.h"),
-           os.path.join("..", "..", "include", "evaluator.h"), "mcb_kernels.cuh", "mcb_bytecode.h", "mcb_pow.h", "mcb_tables.h", "mcb_tri_words.inc", "mcb_lower.h",
+           os.path.join("..", "..", "include", "evaluator.h"), "mcb_kernels.cuh", "mcb_jit.h", "mcb_bytecode.h", "mcb_pow.h", "mcb_tables.h", "mcb_tri_words.inc", "mcb_lower.h",
            os.path.join("..", "..", "include", "mcb.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
@@ -33,7 +33,10 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    # mcb_pow.h also travels inside the library as text: the run-time compiled evaluator (mcb_jit.cpp) includes it through NVRTC
+    with open(os.path.join(CSRC, "mcb_pow.h")) as f, open(os.path.join(CSRC, "mcb_pow_src.inc"), "w") as o:
+        o.write('R"MCBPOWSRC(' + f.read() + ')MCBPOWSRC"\n')
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

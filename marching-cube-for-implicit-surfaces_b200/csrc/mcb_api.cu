@@ -7,15 +7,18 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/mcb.h"
 #include "mcb_kernels.cuh"
+#include "mcb_jit.h"
 #include "mcb_lower.h"
 
 using namespace mcbk;
@@ -100,6 +103,14 @@ struct mcb_ctx {
     bool streamed = false;                  /* the last polygonise delivered the mesh to the registered buffers */
     /* seed mode (mcb_set_seed) */
     bool seed_on = false;
+    /* run-time specialised evaluator (mcb_set_jit): one cubin per distinct generated source, i.e. per equation */
+    int jit = MCB_JIT_AUTO;
+    std::string jit_note;          /* why MCB_JIT_AUTO stayed with the interpreter, if it did */
+    struct JitKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kernel = nullptr, fill = nullptr; };
+    const JitKernel* jit_cur = nullptr; /* the module the last evaluation used */
+    std::map<std::string, JitKernel> jit_cache;
+    bool jit_used = false;         /* the last polygonisation ran the specialised kernel */
+    float ms_compile = 0.f;        /* host time of the NVRTC compile it had to do (0 when cached) */
     bool repeat_on = false;        /* repeating-surface mode (mcb_set_repeat) */
     float repeat_step = 0.f;
     uint32_t* d_cw = nullptr;      /* [items][8] corner words of every 32-cube item, repeating-surface mode only */
@@ -127,6 +138,10 @@ struct mcb_ctx {
     cudaEvent_t ev[9] = {};
     /* sparse-field mode (mcb_set_field_mode): the field is only written in 32 x 4 x 4 vertex blocks around the surface */
     int field_mode = MCB_FIELD_DENSE;
+    /* MCB_FIELD_AUTO: what the last polygonisation of exactly this configuration found (signature over equation,
+     * grid, slab, iso, scaling, constraints): a sparse surface is cheaper without the 4 B/vertex field write */
+    uint64_t hint_signature = 0;
+    double hint_active_fraction = 1.0;
     bool field_is_sparse = false;  /* what the last polygonisation left in d_F */
     bool poison_field = false;     /* $MCB_POISON_FIELD: NaN-fill d_F first, so a read outside the blocks shows (tests) */
     uint8_t* d_fflags = nullptr;   /* [cap_fblocks] */
@@ -548,6 +563,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->eq) free_slot(s);
+    for (auto& kv : ctx->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw);
     cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
@@ -727,6 +743,7 @@ struct Run {
     int prepare_buffers();
     int encode_program(mcb_program& launch, bool& has_pow, bool blocks);
     int stage_fill();
+    int launch_eval_jit(bool store_field);
     int stage_tables();
     int stage_eval();
     int stage_classify();
@@ -819,6 +836,69 @@ int Run::stage_tables() {
     return MCB_OK;
 }
 
+/* The same evaluation by the kernel NVRTC compiled for this equation (mcb_jit.cpp): same tile, same launch geometry */
+int Run::launch_eval_jit(bool store_field) {
+    std::string err;
+    bool has_pow = false;
+    const std::string src = mcbjit::generate(eq.grid.code, eq.grid.n, &has_pow, &err);
+    if (src.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + err);
+    const std::string key = (store_field ? "F" : "S") + src;
+    auto it = ctx->jit_cache.find(key);
+    ctx->ms_compile = 0.f;
+    if (it == ctx->jit_cache.end()) {
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<char> cubin;
+        const std::string cerr = mcbjit::compile(src, has_pow, store_field, (int)sizeof(Grid), &cubin);
+        if (!cerr.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + cerr);
+        mcb_ctx::JitKernel jk;
+        MCB_CK(cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        MCB_CK(cudaLibraryGetKernel(&jk.kernel, jk.lib, "mcb_eval_jit"));
+        MCB_CK(cudaLibraryGetKernel(&jk.fill, jk.lib, "mcb_fill_jit"));
+        it = ctx->jit_cache.emplace(key, jk).first;
+        ctx->ms_compile = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY;
+    const dim3 blocks((unsigned)((g.P + kEvalTileX - 1) / kEvalTileX), (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)),
+                      (unsigned)g.NZ);
+    struct { float k[MCB_MAX_K]; } consts;
+    std::memcpy(consts.k, eq.grid.k, sizeof consts.k);
+    Grid garg = g;
+    const float* tables = ctx->d_tables;
+    float* F = ctx->d_F;
+    uint32_t* S = ctx->d_S;
+    int rg = rgpp, spa = eq.max_per_axis;
+    void* args[] = {&consts, &garg, &tables, &F, &S, &rg, &spa};
+    MCB_CK(cudaLaunchKernel((const void*)it->second.kernel, blocks, dim3(kEvalThreads), args, 0, s));
+    ctx->jit_cur = &it->second;
+    launches++;
+    return MCB_OK;
+}
+
+/* FNV-1a over everything the set of active cubes depends on */
+uint64_t config_signature(const mcb_ctx* ctx) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    for (int sl = 0; sl < 4; sl++) {
+        const EqSlot& e = ctx->eq[sl];
+        const int used = sl == 0 ? 1 : (ctx->cons[sl - 1].in_use && e.valid ? 1 : 0);
+        mix(&used, sizeof used);
+        if (!used) continue;
+        mix(&e.point.n, sizeof e.point.n);
+        mix(e.point.code, sizeof(uint32_t) * (size_t)e.point.n);
+        mix(e.point.k, sizeof e.point.k);
+        if (sl > 0) { mix(&ctx->cons[sl - 1].op, sizeof(int)); mix(&ctx->cons[sl - 1].rhs, sizeof(float)); }
+    }
+    const Grid& g = ctx->g;
+    const int geo[4] = {g.M, g.kb, g.ke, g.repeat};
+    const float par[6] = {ctx->step, g.sx, g.sy, g.sz, g.iso, g.rstep};
+    mix(geo, sizeof geo);
+    mix(par, sizeof par);
+    return h ? h : 1;
+}
+
 /* K1: field + sign bit-planes (+ K1b: constraint validity bit-planes) */
 int Run::stage_eval() {
     const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY; /* 4-row groups per plane */
@@ -829,9 +909,23 @@ int Run::stage_eval() {
     bool has_pow;
     int rc = encode_program(launch, has_pow, false);
     if (rc != MCB_OK) return rc;
-    const bool sparse = ctx->field_mode == MCB_FIELD_SPARSE && !g.repeat; /* per-cube iso levels read the field everywhere */
+    /* sparse field: asked for, or (auto) the last run of this very configuration had few active cubes; per-cube iso
+     * levels (repeat) read the field everywhere, and the seed walk's bookkeeping assumes the dense field too */
+    const uint64_t sig = config_signature(ctx);
+    const bool auto_sparse = ctx->field_mode == MCB_FIELD_AUTO && !ctx->seed_on && ctx->hint_signature == sig &&
+                             ctx->hint_active_fraction <= 0.005;
+    const bool sparse = (ctx->field_mode == MCB_FIELD_SPARSE || auto_sparse) && !g.repeat;
     if (sparse && ctx->poison_field) MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
-    if (sparse) {
+    ctx->jit_used = false;
+    if (ctx->jit != MCB_JIT_OFF) {
+        rc = launch_eval_jit(!sparse);
+        if (rc == MCB_OK) ctx->jit_used = true;
+        else if (ctx->jit == MCB_JIT_ON) return rc;      /* asked for explicitly: fail loudly */
+        else ctx->jit_note = ctx->err;                   /* auto: the interpreter below does the same work */
+    }
+    if (ctx->jit_used) {
+        launches--; /* counted below */
+    } else if (sparse) {
         if (has_pow) eval_field_kernel<true, false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
         else eval_field_kernel<false, false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
     } else {
@@ -908,7 +1002,18 @@ int Run::stage_fill() {
     MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb, s));
     field_flag_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(ctx->d_rec, g, ctx->d_ctr, ctx->cap_active, fb);
     field_list_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(fb, (unsigned)nb, ctx->d_ctr);
-    if (has_pow) eval_blocks_kernel<true><<<fill_ctas, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
+    if (ctx->jit_used && ctx->jit_cur && ctx->jit_cur->fill) { /* the refill kernel NVRTC compiled next to the evaluation kernel */
+        struct { float k[MCB_MAX_K]; } consts;
+        std::memcpy(consts.k, eq.grid.k, sizeof consts.k);
+        Grid garg = g;
+        const float* tables = ctx->d_tables;
+        float* F = ctx->d_F;
+        const uint32_t* list = ctx->d_flist;
+        const unsigned* count = &ctx->d_ctr->field_blocks;
+        int nbx = fb.nbx, nby = fb.nby, spa = eq.max_per_axis;
+        void* args[] = {&consts, &garg, &tables, &F, &list, &count, &nbx, &nby, &spa};
+        MCB_CK(cudaLaunchKernel((const void*)ctx->jit_cur->fill, dim3(fill_ctas), dim3(kEvalThreads), args, 0, s));
+    } else if (has_pow) eval_blocks_kernel<true><<<fill_ctas, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
     else eval_blocks_kernel<false><<<fill_ctas, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
     launches += 3;
     return MCB_OK;
@@ -1150,6 +1255,10 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     c.ms_classify -= c.ms_fill;
     c.field_mode = ctx->field_is_sparse ? MCB_FIELD_SPARSE : MCB_FIELD_DENSE;
     c.field_blocks = ctx->field_is_sparse ? ctx->h_ctr->field_blocks : 0;
+    ctx->hint_signature = config_signature(ctx);
+    ctx->hint_active_fraction = c.cubes ? (double)c.active / (double)c.cubes : 1.0;
+    c.jit = ctx->jit_used ? 1u : 0u;
+    c.ms_compile = ctx->jit_used ? ctx->ms_compile : 0.f;
     cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&c.ms_weld, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[5]);
@@ -1178,10 +1287,32 @@ int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles)
 }
 
 int mcb_set_field_mode(mcb_ctx* ctx, int mode) {
-    if (!ctx || (mode != MCB_FIELD_DENSE && mode != MCB_FIELD_SPARSE)) return MCB_E_ARG;
+    if (!ctx || mode < MCB_FIELD_DENSE || mode > MCB_FIELD_AUTO) return MCB_E_ARG;
     ctx->field_mode = mode;
     ctx->have_result = false;
     return MCB_OK;
+}
+
+int mcb_set_jit(mcb_ctx* ctx, int enabled) {
+    if (!ctx || enabled < MCB_JIT_OFF || enabled > MCB_JIT_AUTO) return MCB_E_ARG;
+    ctx->jit = enabled;
+    ctx->have_result = false;
+    return MCB_OK;
+}
+
+int mcb_jit_check(const char* equation, char* log, size_t cap) {
+    mcb::Compiled c;
+    int rc = mcb::compile(equation ? equation : "", c, nullptr);
+    if (rc != MCB_OK) return rc;
+    std::string err;
+    bool has_pow = false;
+    const std::string src = mcbjit::generate(c.grid_fused.data(), (int)c.grid_fused.size(), &has_pow, &err);
+    if (src.empty()) { copy_text(err, log, cap); return MCB_E_STATE; }
+    std::vector<char> cubin;
+    err = mcbjit::compile(src, has_pow, true, (int)sizeof(Grid), &cubin);
+    if (!err.empty()) { copy_text(err, log, cap); return MCB_E_STATE; }
+    copy_text(src, log, cap); /* best effort: a short buffer just truncates the listing */
+    return (int)cubin.size();
 }
 
 int mcb_set_mesh_mode(mcb_ctx* ctx, int mode) {

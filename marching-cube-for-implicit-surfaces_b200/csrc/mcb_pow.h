@@ -18,10 +18,17 @@
 #ifndef MCB_POW_H
 #define MCB_POW_H
 
+#if defined(__CUDACC_RTC__) /* run-time compilation (mcb_jit.cpp): no host headers, device code only */
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
 #include <string.h>
 #if !defined(__CUDACC__)
 #include <math.h>
+#endif
 #endif
 
 #if defined(__CUDACC__)

@@ -137,3 +137,31 @@ def test_sparse_field_has_no_dense_field_to_read(mcb, pair):
     sparse.polygonise()
     assert same_bits(sparse.get_field(), dense.get_field())
     sparse.set_field_mode(mcb.FIELD_SPARSE)
+
+
+def test_field_auto_goes_sparse_only_for_a_known_sparse_surface(mcb):
+    """MCB_FIELD_AUTO: dense on the first polygonisation of a configuration, sparse afterwards when it had <= 0.5 % active
+    cubes; re-sending the same equation keeps what was learnt, changing a parameter starts over; outputs identical."""
+    c = mcb.Context(0)
+    c.set_field_mode(mcb.FIELD_AUTO)
+    c.set_normals(1)
+    assert c.set_equation("x^2+y^2+z^2-0.49") == 0
+    c.set_grid_step(2.0 / 640)
+    first = c.polygonise()
+    p1, n1 = c.get_mesh(normals=True)
+    assert first.field_mode == mcb.FIELD_DENSE and first.active / first.cubes < 0.005
+    second = c.polygonise()
+    p2, n2 = c.get_mesh(normals=True)
+    assert second.field_mode == mcb.FIELD_SPARSE and second.field_blocks > 0
+    assert (first.active, first.triangles) == (second.active, second.triangles) and same_bits(p1, p2) and same_bits(n1, n2)
+    assert c.set_equation("x^2+y^2+z^2-0.49") == 0          # the same text again (a GUI refresh): nothing to relearn
+    c.set_grid_step(2.0 / 640)
+    assert c.polygonise().field_mode == mcb.FIELD_SPARSE
+    c.set_surface_constant(0.1)                               # another surface: dense once, then sparse again
+    assert c.polygonise().field_mode == mcb.FIELD_DENSE
+    assert c.polygonise().field_mode == mcb.FIELD_SPARSE
+    c.set_grid_step(2.0 / 24)                                 # a coarse grid: 4 % of the cubes are active, the field write stays
+    assert c.polygonise().field_mode == mcb.FIELD_DENSE
+    dense = c.polygonise()
+    assert dense.field_mode == mcb.FIELD_DENSE and dense.active / dense.cubes > 0.005
+    c.close()

@@ -200,3 +200,20 @@ def test_grid_limits(mcb):
     assert mcb.lib.mcb_grid_axis(2.0 / 5000, None, 0) < 0
     for bad in (0.0, -0.1, 1.5, float("nan"), float("inf")):
         assert mcb.lib.mcb_grid_axis(bad, None, 0) < 0
+
+
+def test_jit_source_compiles_for_every_golden_equation_without_a_gpu(mcb, golden):
+    """mcb_jit_check: generate the specialised evaluator of each golden equation and compile it with NVRTC for sm_100a
+    (no device needed).  The source depends on the equation's program only: same source for any constants/grid."""
+    from .helpers import load_meta
+    seen = {}
+    for name, case in load_meta(golden).items():
+        if case["eq"] in seen:
+            continue
+        nbytes, src = mcb.jit_check(case["eq"])
+        seen[case["eq"]] = nbytes
+        assert nbytes > 1000 and "mcb_eval_jit" in src and "op_" in src or "ty" in src
+    assert len(seen) >= 15
+    assert mcb.jit_check("x^2+y^2+z^2-0.49")[1] == mcb.jit_check("x^2+y^2+z^2-0.25")[1]   # constants are arguments
+    with pytest.raises(mcb.McbError):
+        mcb.jit_check("x+")                                                                 # parse error, not a crash
