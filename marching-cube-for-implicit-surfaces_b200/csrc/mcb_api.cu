@@ -106,7 +106,7 @@ struct mcb_ctx {
     /* run-time specialised evaluator (mcb_set_jit): one cubin per distinct generated source, i.e. per equation */
     int jit = MCB_JIT_AUTO;
     std::string jit_note;          /* why MCB_JIT_AUTO stayed with the interpreter, if it did */
-    struct JitKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kernel = nullptr, fill = nullptr; };
+    struct JitKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kernel = nullptr, signs = nullptr, fill = nullptr; };
     const JitKernel* jit_cur = nullptr; /* the module the last evaluation used */
     std::map<std::string, JitKernel> jit_cache;
     bool jit_used = false;         /* the last polygonisation ran the specialised kernel */
@@ -842,19 +842,19 @@ int Run::launch_eval_jit(bool store_field) {
     bool has_pow = false;
     const std::string src = mcbjit::generate(eq.grid.code, eq.grid.n, &has_pow, &err);
     if (src.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + err);
-    const std::string key = (store_field ? "F" : "S") + src;
-    auto it = ctx->jit_cache.find(key);
+    auto it = ctx->jit_cache.find(src);
     ctx->ms_compile = 0.f;
     if (it == ctx->jit_cache.end()) {
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<char> cubin;
-        const std::string cerr = mcbjit::compile(src, has_pow, store_field, (int)sizeof(Grid), &cubin);
+        const std::string cerr = mcbjit::compile(src, has_pow, (int)sizeof(Grid), &cubin);
         if (!cerr.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + cerr);
         mcb_ctx::JitKernel jk;
         MCB_CK(cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
         MCB_CK(cudaLibraryGetKernel(&jk.kernel, jk.lib, "mcb_eval_jit"));
+        MCB_CK(cudaLibraryGetKernel(&jk.signs, jk.lib, "mcb_signs_jit"));
         MCB_CK(cudaLibraryGetKernel(&jk.fill, jk.lib, "mcb_fill_jit"));
-        it = ctx->jit_cache.emplace(key, jk).first;
+        it = ctx->jit_cache.emplace(src, jk).first;
         ctx->ms_compile = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY;
@@ -868,7 +868,7 @@ int Run::launch_eval_jit(bool store_field) {
     uint32_t* S = ctx->d_S;
     int rg = rgpp, spa = eq.max_per_axis;
     void* args[] = {&consts, &garg, &tables, &F, &S, &rg, &spa};
-    MCB_CK(cudaLaunchKernel((const void*)it->second.kernel, blocks, dim3(kEvalThreads), args, 0, s));
+    MCB_CK(cudaLaunchKernel((const void*)(store_field ? it->second.kernel : it->second.signs), blocks, dim3(kEvalThreads), args, 0, s));
     ctx->jit_cur = &it->second;
     launches++;
     return MCB_OK;
@@ -1309,7 +1309,7 @@ int mcb_jit_check(const char* equation, char* log, size_t cap) {
     const std::string src = mcbjit::generate(c.grid_fused.data(), (int)c.grid_fused.size(), &has_pow, &err);
     if (src.empty()) { copy_text(err, log, cap); return MCB_E_STATE; }
     std::vector<char> cubin;
-    err = mcbjit::compile(src, has_pow, true, (int)sizeof(Grid), &cubin);
+    err = mcbjit::compile(src, has_pow, (int)sizeof(Grid), &cubin);
     if (!err.empty()) { copy_text(err, log, cap); return MCB_E_STATE; }
     copy_text(src, log, cap); /* best effort: a short buffer just truncates the listing */
     return (int)cubin.size();

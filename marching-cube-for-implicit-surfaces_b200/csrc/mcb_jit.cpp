@@ -36,7 +36,7 @@ __device__ __forceinline__ float op_pow(float a, float b) { /* as fused_op<MCB_F
 )SRC";
 const char* const kHeadPlane = R"SRC(
 extern "C" __global__ void __launch_bounds__(128, MCB_MIN_BLOCKS)
-mcb_eval_jit(const __grid_constant__ Consts C, const Grid g, const float* __restrict__ tables, float* __restrict__ F,
+MCB_KERNEL_NAME(const __grid_constant__ Consts C, const Grid g, const float* __restrict__ tables, float* __restrict__ F,
              unsigned int* __restrict__ S, int row_groups, int slots_per_axis) {
     const int lane = threadIdx.x & 31;
     const int cx = (int)blockIdx.x;
@@ -130,7 +130,8 @@ Nvrtc& nvrtc() {
 
 } /* namespace */
 
-static std::string generate_one(const uint32_t* code, int n, bool blocks, bool* has_pow, std::string* err) {
+static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane + field, 1 plane signs only, 2 blocks */, bool* has_pow, std::string* err) {
+    const bool blocks = kind == 2;
     std::ostringstream loads, body;
     bool pow = false;
     /* operand fetches, one declaration per distinct (axis, slot): exactly the loads of eval_step / LeafOperand */
@@ -214,25 +215,29 @@ static std::string generate_one(const uint32_t* code, int n, bool blocks, bool* 
     }
     if (acc.empty() || !stack.empty()) { *err = "program does not leave exactly one value"; return std::string(); }
     if (has_pow) *has_pow = pow;
-    std::string src = blocks ? kHeadBlocks : kHeadPlane;
+    std::string src = blocks ? "" : kind == 0 ? "#define MCB_KERNEL_NAME mcb_eval_jit\n#define MCB_STORE_F 1\n" : "#define MCB_KERNEL_NAME mcb_signs_jit\n#define MCB_STORE_F 0\n";
+    src += blocks ? kHeadBlocks : kHeadPlane;
     src += loads.str();
     src += body.str();
     src += "#define RESULT " + acc + "\n";
     src += blocks ? kTailBlocks : kTail;
-    if (!blocks) src += "#undef RESULT\n";
+    if (!blocks) src += "#undef RESULT\n#undef MCB_KERNEL_NAME\n#undef MCB_STORE_F\n";
     return src;
 }
 
 std::string generate(const uint32_t* code, int n, bool* has_pow, std::string* err) {
-    /* one translation unit, two kernels: mcb_eval_jit (plane tiles) and mcb_fill_jit (the sparse-field mode's blocks) */
-    const std::string plane = generate_one(code, n, false, has_pow, err);
-    if (plane.empty()) return plane;
-    const std::string fill = generate_one(code, n, true, has_pow, err);
-    if (fill.empty()) return fill;
-    return std::string(kHead) + plane + fill;
+    /* one translation unit, three kernels: mcb_eval_jit (plane tiles, field + signs), mcb_signs_jit (signs only) and
+     * mcb_fill_jit (the blocks of the sparse-field mode) — one compile per equation whatever mode runs later */
+    std::string out = kHead;
+    for (int kind = 0; kind < 3; kind++) {
+        const std::string part = generate_one(code, n, kind, has_pow, err);
+        if (part.empty()) return part;
+        out += part;
+    }
+    return out;
 }
 
-std::string compile(const std::string& source, bool pow, bool store_field, int grid_size, std::vector<char>* cubin) {
+std::string compile(const std::string& source, bool pow, int grid_size, std::vector<char>* cubin) {
     Nvrtc& N = nvrtc();
     if (!N.error.empty()) return N.error;
     void* prog = nullptr;
@@ -244,7 +249,7 @@ std::string compile(const std::string& source, bool pow, bool store_field, int g
     std::snprintf(grid_bytes, sizeof grid_bytes, "-DMCB_GRID_BYTES=%d", grid_size);
     std::snprintf(max_k, sizeof max_k, "-DMCB_MAX_K=%d", MCB_MAX_K);
     const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-default-device", grid_bytes, max_k,
-                          pow ? "-DMCB_MIN_BLOCKS=8" : "-DMCB_MIN_BLOCKS=10", store_field ? "-DMCB_STORE_F=1" : "-DMCB_STORE_F=0"};
+                          pow ? "-DMCB_MIN_BLOCKS=8" : "-DMCB_MIN_BLOCKS=10"};
     rc = N.CompileProgram(prog, (int)(sizeof opts / sizeof opts[0]), opts);
     std::string log;
     size_t ls = 0;
