@@ -1554,7 +1554,10 @@ weld_emit_kernel(const WV W, const WeldBuffers B, const Counters* __restrict__ c
                 const CubeEdge v = weld_resolve(W, i, j, k, e, onv);
                 unsigned long long vi;
                 if (v.i == i && v.j == j && v.k == k) vi = ((unsigned long long)m << 32) | vb_s[lc];
-                else vi = B.vinfo[weld_find_cube(B, g, v.i, v.j, v.k)];
+                else { /* the owner's record; beyond the (too small) buffers of a pass the host is about to repeat there is nothing to read */
+                    const uint32_t owner = weld_find_cube(B, g, v.i, v.j, v.k);
+                    vi = owner < A ? B.vinfo[owner] : 0ull;
+                }
                 idx = MCB_VINFO_BASE(vi) + (uint32_t)__popc(MCB_VINFO_NEW(vi) & ((1u << v.e) - 1u));
             }
             eidx[lc * 12 + e] = idx;
