@@ -217,3 +217,33 @@ def test_jit_source_compiles_for_every_golden_equation_without_a_gpu(mcb, golden
     assert mcb.jit_check("x^2+y^2+z^2-0.49")[1] == mcb.jit_check("x^2+y^2+z^2-0.25")[1]   # constants are arguments
     with pytest.raises(mcb.McbError):
         mcb.jit_check("x+")                                                                 # parse error, not a crash
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """The bench lines committed under profiles/ (what `python bench.py` and `bench.py --impl reference` printed on the
+    B200) have every key of the measurement contract, and the numbers hang together."""
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = sorted(glob.glob(os.path.join(root, "profiles", "r01_bench_step9_n*.json")))
+    assert len(ours) >= 4
+    for path in ours:
+        d = json.loads(open(path).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+            assert k in d, (path, k)
+        assert d["metric"] == d["unit"] == "Gvoxels/s" and d["scaling"] == "weak" and d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert abs(d["config"]["cubes"] / (d["ms_per_step"] * 1e-3) / 1e9 - d["value"]) < 1e-6 * d["value"]
+        for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert k in d["roofline"], (path, k)
+        assert abs(d["roofline"]["achieved"] / d["roofline"]["peak"] - d["roofline"]["frac"]) < 1e-9
+        for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert k in d["e2e"], (path, k)
+        assert d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["n_gpus"] == 1:
+            for k in ("value", "unit", "cores", "kind", "sample"):
+                assert k in d["cpu_baseline"], k
+    ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_step9_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == "Gvoxels/s" and ref["e2e"]["h2d_bytes_per_step"] == 0
+    assert ref["cpu_baseline"]["kind"] == "reference" and ref["cpu_baseline"]["cores"] >= 1
