@@ -371,6 +371,7 @@ class Marching:
         self._poly = PolyData(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
         self._normals = True
         self._ctx.set_mesh_mode(MESH_INDEXED)
+        self._ctx.set_field_mode(FIELD_AUTO)  # like include/marching.h: this class never reads the field back
         self.counts = None
 
     def set_evaluator(self, e):

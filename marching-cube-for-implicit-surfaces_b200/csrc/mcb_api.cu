@@ -989,7 +989,7 @@ int Run::stage_fill() {
         if (ctx->d_fflags) cudaFree(ctx->d_fflags);
         if (ctx->d_flist) cudaFree(ctx->d_flist);
         ctx->d_fflags = nullptr; ctx->d_flist = nullptr; ctx->cap_fblocks = 0;
-        if (cudaMalloc((void**)&ctx->d_fflags, nb) != cudaSuccess || cudaMalloc((void**)&ctx->d_flist, nb * sizeof(uint32_t)) != cudaSuccess)
+        if (cudaMalloc((void**)&ctx->d_fflags, nb + 16) != cudaSuccess || cudaMalloc((void**)&ctx->d_flist, (nb + 16) * sizeof(uint32_t)) != cudaSuccess)
             return fail(ctx, MCB_E_NOMEM, "cudaMalloc of the field-block list failed");
         ctx->cap_fblocks = nb;
     }
@@ -999,9 +999,9 @@ int Run::stage_fill() {
     if ((rc = encode_program(launch, has_pow, true)) != MCB_OK) return rc;
     const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
     const unsigned fill_ctas = (unsigned)ctx->sm_count * 16;
-    MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb, s));
+    MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb + 16, s)); /* + the padding field_list reads */
     field_flag_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(ctx->d_rec, g, ctx->d_ctr, ctx->cap_active, fb);
-    field_list_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(fb, (unsigned)nb, ctx->d_ctr);
+    field_list_kernel<<<(unsigned)((nb / 16 + 256) / 256), 256, 0, s>>>(fb, (unsigned)nb, ctx->d_ctr);
     if (ctx->jit_used && ctx->jit_cur && ctx->jit_cur->fill) { /* the refill kernel NVRTC compiled next to the evaluation kernel */
         struct { float k[MCB_MAX_K]; } consts;
         std::memcpy(consts.k, eq.grid.k, sizeof consts.k);

@@ -411,17 +411,34 @@ field_flag_kernel(const unsigned long long* __restrict__ rec, const Grid g, cons
                 for (int bx = bx0; bx <= bx1; bx++) fb.flags[((size_t)bz * fb.nby + by) * fb.nbx + bx] = 1;
     }
 }
+/* flags -> list of flagged block ids (any order).  A thread takes 16 flags (one 16-byte load; the flag array is padded
+ * and zero-filled to a multiple of 16), a warp reserves its entries with one atomic. */
 __global__ void __launch_bounds__(256)
 field_list_kernel(const FieldBlocks fb, unsigned nblocks, Counters* __restrict__ ctr) {
-    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool on = b < nblocks && fb.flags[b] != 0;
-    const unsigned m = __ballot_sync(0xffffffffu, on);
-    if (m == 0) return;
+    const unsigned g16 = blockIdx.x * blockDim.x + threadIdx.x; /* group of 16 flags */
     const int lane = threadIdx.x & 31;
+    uint4 f = make_uint4(0u, 0u, 0u, 0u);
+    if (g16 * 16u < nblocks) f = __ldg(reinterpret_cast<const uint4*>(fb.flags) + g16);
+    const uint32_t w[4] = {f.x, f.y, f.z, f.w};
+    uint32_t bits = 0; /* bit i = flag 16 * g16 + i */
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) bits |= ((w[q] >> (8 * b)) & 0xffu) ? 1u << (4 * q + b) : 0u;
+    const uint32_t mine = (uint32_t)__popc(bits);
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&ctr->field_blocks, (unsigned)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (on) fb.list[base + __popc(m & ((1u << lane) - 1u))] = b;
+    if (lane == 31) base = atomicAdd(&ctr->field_blocks, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + (inc - mine);
+    while (bits) {
+        const int i = __ffs(bits) - 1;
+        bits &= bits - 1;
+        fb.list[base++] = g16 * 16u + (unsigned)i;
+    }
 }
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
