@@ -178,8 +178,9 @@ int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance);
  * operations in the interpreter's order on the interpreter's tile, so every result is bit-identical; it just has no
  * dispatch (torus 2.3 -> 1.5 ms, polynomial gyroid 1.3 -> 0.7 ms at 1024^3).  Constants, grid size and scaling are
  * kernel arguments: only a new equation compiles again.
- *   MCB_JIT_AUTO (default)  use it when NVRTC is there and the compile succeeds, else the bytecode interpreter — both
- *                           are the same CUDA path with the same results; mcb_counts::jit says which one ran
+ *   MCB_JIT_AUTO (default)  use it when NVRTC is there, the compile succeeds and the program has at most 8 `^` left after
+ *                           hoisting (more: powf dominates either way and compile time grows), else the bytecode
+ *                           interpreter — both are the same CUDA path with the same results; mcb_counts::jit says which ran
  *   MCB_JIT_ON              require it: mcb_polygonise returns MCB_E_STATE with the log in mcb_last_error otherwise
  *   MCB_JIT_OFF             always interpret
  * The sparse-field mode's kernels are always interpreted. */

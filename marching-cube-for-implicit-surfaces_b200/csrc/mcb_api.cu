@@ -917,7 +917,14 @@ int Run::stage_eval() {
     const bool sparse = (ctx->field_mode == MCB_FIELD_SPARSE || auto_sparse) && !g.repeat;
     if (sparse && ctx->poison_field) MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
     ctx->jit_used = false;
-    if (ctx->jit != MCB_JIT_OFF) {
+    /* auto: a program full of general `^` is bound by powf either way, and each inlined powf site costs compile time
+     * (13 of them: seconds) — leave those to the interpreter */
+    int n_pow = 0;
+    for (int pc = 0; pc < eq.grid.n; pc++) {
+        const uint32_t fop = MCB_FINSN_OP(eq.grid.code[pc]);
+        n_pow += fop == MCB_F_POW || fop == MCB_F_RPOW;
+    }
+    if (ctx->jit == MCB_JIT_ON || (ctx->jit == MCB_JIT_AUTO && n_pow <= 8)) {
         rc = launch_eval_jit(!sparse);
         if (rc == MCB_OK) ctx->jit_used = true;
         else if (ctx->jit == MCB_JIT_ON) return rc;      /* asked for explicitly: fail loudly */

@@ -85,3 +85,18 @@ def test_jit_at_1024_matches_the_interpreter(mcb):
         res.append((cnt.triangles, cnt.active, cnt.ambiguous, pos, nrm, cnt.ms_eval))
         c.close()
     assert res[0][:3] == res[1][:3] and same_bits(res[0][3], res[1][3]) and same_bits(res[0][4], res[1][4])
+
+
+def test_auto_leaves_pow_heavy_programs_to_the_interpreter(mcb):
+    eq = "+".join("(x*%d.5+y*z)^%d" % (i, 2 + i % 3) for i in range(1, 11)) + "-3"
+    res = []
+    for mode in (mcb.JIT_AUTO, mcb.JIT_ON):
+        c = mcb.Context(0)
+        c.set_jit(mode)
+        assert c.set_equation(eq) == 0
+        c.set_grid_step(2.0 / 40)
+        cnt = c.polygonise()
+        res.append((cnt.jit, cnt.triangles, c.get_field()))
+        c.close()
+    assert res[0][0] == 0 and res[1][0] == 1          # 10 general powers: auto interprets, ON compiles anyway
+    assert res[0][1] == res[1][1] and same_bits(res[0][2], res[1][2])
