@@ -79,3 +79,18 @@ def test_headless_repeating_surface_mode(mcb, tmp_path):
     t = np.frombuffer(raw, np.uint32, nt * 3, 16 + nv * 12).reshape(-1, 3)
     assert same_bits(v, rep["rep_testdrawer/vertex_list"]) and np.array_equal(t, rep["rep_testdrawer/tri_list"])
     assert subprocess.run([EXE, "--levels", "0"], capture_output=True).returncode == 1
+
+
+@pytest.mark.gpu
+def test_headless_repeated_recalculate_switches_to_the_sparse_field_and_keeps_the_mesh(mcb, tmp_path):
+    """The drop-in class uses MCB_FIELD_AUTO: the first recalculate() of a configuration writes the whole field, the
+    following ones only its signs (sphere at 640^3: 0.36 % active cubes).  The Poly_Data must not notice."""
+    dumps = []
+    for rep in (1, 3):
+        dump = tmp_path / ("m%d.bin" % rep)
+        out = subprocess.check_output([EXE, "--eq", "x^2+y^2+z^2-0.49", "--res", "640", "--scale", "1", "1", "1", "--repeat", str(rep),
+                                       "--dump", str(dump)], text=True)
+        info = json.loads(out.strip().splitlines()[-1])
+        assert info["M"] == 641 and info["triangles"] > 1000000
+        dumps.append(dump.read_bytes())
+    assert dumps[0] == dumps[1]
