@@ -857,7 +857,9 @@ int Run::launch_eval_jit(bool store_field) {
         it = ctx->jit_cache.emplace(src, jk).first;
         ctx->ms_compile = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
-    const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY;
+    /* the field kernel holds a 128 x 4 tile per warp in registers; the signs-only kernel streams 128 x 16 row by row */
+    const int tile_rows = store_field ? kEvalTileY : 16;
+    const int rgpp = (g.NV + tile_rows - 1) / tile_rows;
     const dim3 blocks((unsigned)((g.P + kEvalTileX - 1) / kEvalTileX), (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)),
                       (unsigned)g.NZ);
     struct { float k[MCB_MAX_K]; } consts;

@@ -90,6 +90,36 @@ const char* const kTailBlocks = R"SRC(
 }
 )SRC";
 
+/* Signs only (sparse-field mode): nothing has to stay in registers, so a warp streams a 128-column x 16-row tile row
+ * by row — 4 values per lane at a time — and the per-tile prologue is shared by four times as many vertices.  The
+ * compiler hoists what does not depend on the row (x and z operands and their combinations). */
+const char* const kHeadSigns = R"SRC(
+extern "C" __global__ void __launch_bounds__(128, MCB_MIN_BLOCKS)
+mcb_signs_jit(const __grid_constant__ Consts C, const Grid g, const float* __restrict__ tables, float* __restrict__ F,
+              unsigned int* __restrict__ S, int row_groups /* of 16 rows */, int slots_per_axis) {
+    const int lane = threadIdx.x & 31;
+    const int cx = (int)blockIdx.x;
+    const int yq = (int)blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int pz = (int)blockIdx.z;
+    if (yq >= row_groups) return;
+    const int x0 = cx * 128 + lane, y0 = yq * 16, zi = pz + g.kb;
+    unsigned int* sw = S + ((size_t)pz * g.NV + y0) * g.WP + cx * 4;
+)SRC";
+const char* const kSignsRowOpen = R"SRC(
+MCB_ROW_UNROLL
+    for (int r = 0; r < 16; r++) {
+        if (y0 + r >= g.NV) break;
+)SRC";
+const char* const kTailSigns = R"SRC(
+        unsigned int w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) w[q] = __ballot_sync(0xffffffffu, RESULT[q] > g.iso);
+        if (lane == 0) *reinterpret_cast<uint4*>(sw + (size_t)r * g.WP) = make_uint4(w[0], w[1], w[2], w[3]);
+#undef RESULT
+    }
+}
+)SRC";
+
 struct Nvrtc {
     void* lib = nullptr;
     int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
@@ -131,8 +161,10 @@ Nvrtc& nvrtc() {
 } /* namespace */
 
 static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane + field, 1 plane signs only, 2 blocks */, bool* has_pow, std::string* err) {
-    const bool blocks = kind == 2;
-    std::ostringstream loads, body;
+    const bool blocks = kind == 2, stream = kind == 1;
+    const char* const N = stream ? "4" : "16";   /* values per lane alive at a time */
+    const char* const I = stream ? "q" : "e";    /* their index variable */
+    std::ostringstream loads, rowloads, body;
     bool pow = false;
     /* operand fetches, one declaration per distinct (axis, slot): exactly the loads of eval_step / LeafOperand */
     bool seen[3][256] = {};
@@ -153,6 +185,10 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
                 else
                     std::snprintf(d, sizeof d, "    const float* pz%u = tables + (size_t)(2 * slots_per_axis + %u) * g.P + z0;\n"
                                   "    const float tz%u[4] = {__ldg(pz%u), __ldg(pz%u + 1), __ldg(pz%u + 2), __ldg(pz%u + 3)};\n", arg, arg, arg, arg, arg, arg, arg);
+            } else if (stream && axis == 1) { /* one row at a time: the row's entry, the same for the whole warp */
+                std::snprintf(d, sizeof d, "        const float ty%u = __ldg(tables + (size_t)(1 * slots_per_axis + %u) * g.P + y0 + r);\n", arg, arg);
+                rowloads << d;
+                d[0] = 0;
             } else if (axis == 0)
                 std::snprintf(d, sizeof d, "    const float* px%u = tables + (size_t)(0 * slots_per_axis + %u) * g.P + x0;\n"
                               "    const float tx%u[4] = {__ldg(px%u), __ldg(px%u + 32), __ldg(px%u + 64), __ldg(px%u + 96)};\n", arg, arg, arg, arg, arg, arg, arg);
@@ -163,8 +199,8 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
                 std::snprintf(d, sizeof d, "    const float tz%u = __ldg(tables + (size_t)(2 * slots_per_axis + %u) * g.P + zi);\n", arg, arg);
             loads << d;
         }
-        if (axis == 0) std::snprintf(buf, sizeof buf, blocks ? "tx%u" : "tx%u[Q(e)]", arg);
-        else if (axis == 1) std::snprintf(buf, sizeof buf, "ty%u[R(e)]", arg);
+        if (axis == 0) std::snprintf(buf, sizeof buf, blocks ? "tx%u" : stream ? "tx%u[q]" : "tx%u[Q(e)]", arg);
+        else if (axis == 1) std::snprintf(buf, sizeof buf, stream ? "ty%u" : "ty%u[R(e)]", arg);
         else std::snprintf(buf, sizeof buf, blocks ? "tz%u[Q(e)]" : "tz%u", arg);
         return buf;
     };
@@ -177,14 +213,14 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
         if (fop == MCB_F_NEG) {
             if (acc.empty()) { *err = "NEG without a value"; return std::string(); }
             const std::string t = fresh();
-            body << "    float " << t << "[16];\n#pragma unroll\n    for (int e = 0; e < 16; e++) " << t << "[e] = -" << acc << "[e];\n";
+            body << "    float " << t << "[" << N << "];\n#pragma unroll\n    for (int " << I << " = 0; " << I << " < " << N << "; " << I << "++) " << t << "[" << I << "] = -" << acc << "[" << I << "];\n";
             acc = t;
             continue;
         }
         std::string v;
         if (src == MCB_SRC_POP) {
             if (stack.empty()) { *err = "POP from an empty stack"; return std::string(); }
-            v = stack.back() + "[e]";
+            v = stack.back() + "[" + I + "]";
             stack.pop_back();
         } else {
             v = operand(src, arg);
@@ -197,7 +233,7 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
             expr = v;
         } else {
             if (acc.empty()) { *err = "operator without an accumulator"; return std::string(); }
-            const std::string a = acc + "[e]";
+            const std::string a = acc + "[" + I + "]";
             switch (fop) {
                 case MCB_F_ADD: expr = "op_add(" + a + ", " + v + ")"; break;
                 case MCB_F_SUB: expr = "op_sub(" + a + ", " + v + ")"; break;
@@ -210,12 +246,28 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
                 default: *err = "unknown operation"; return std::string();
             }
         }
-        body << "    float " << t << "[16];\n#pragma unroll\n    for (int e = 0; e < 16; e++) " << t << "[e] = " << expr << ";\n";
+        body << "    float " << t << "[" << N << "];\n#pragma unroll\n    for (int " << I << " = 0; " << I << " < " << N << "; " << I << "++) " << t << "[" << I << "] = " << expr << ";\n";
         acc = t;
     }
     if (acc.empty() || !stack.empty()) { *err = "program does not leave exactly one value"; return std::string(); }
     if (has_pow) *has_pow = pow;
-    std::string src = blocks ? "" : kind == 0 ? "#define MCB_KERNEL_NAME mcb_eval_jit\n#define MCB_STORE_F 1\n" : "#define MCB_KERNEL_NAME mcb_signs_jit\n#define MCB_STORE_F 0\n";
+    std::string src;
+    if (stream) {
+        /* measured at 1024^3: unrolling the row loop by 4 is the sweet spot for programs without `^` (sphere 0.29 ms; 0.33 ms
+         * with the 4-row register tile, 0.36 ms fully unrolled); programs with `^` keep it rolled — every unrolled copy
+         * would inline the power's fast path again (torus 1.37 -> 1.23 ms) */
+        src = pow ? "#define MCB_ROW_UNROLL _Pragma(\"unroll 1\")\n" : "#define MCB_ROW_UNROLL _Pragma(\"unroll 4\")\n";
+        src += kHeadSigns;
+        src += loads.str();
+        src += kSignsRowOpen;
+        src += rowloads.str();
+        src += body.str();
+        src += "#define RESULT " + acc + "\n";
+        src += kTailSigns;
+        src += "#undef MCB_ROW_UNROLL\n";
+        return src;
+    }
+    src = blocks ? "" : "#define MCB_KERNEL_NAME mcb_eval_jit\n#define MCB_STORE_F 1\n";
     src += blocks ? kHeadBlocks : kHeadPlane;
     src += loads.str();
     src += body.str();
