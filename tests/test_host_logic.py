@@ -225,7 +225,7 @@ def test_committed_bench_lines_carry_every_contract_key():
     import glob
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    ours = sorted(glob.glob(os.path.join(root, "profiles", "r01_bench_step9_n*.json")))
+    ours = sorted(glob.glob(os.path.join(root, "profiles", "r01_bench_step11_n*.json")))
     assert len(ours) >= 4
     for path in ours:
         d = json.loads(open(path).read().strip().splitlines()[-1])
