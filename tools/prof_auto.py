@@ -1,3 +1,5 @@
+"""The command profiled under ncu for profiles/r01_ncu_full_summary_step9.txt: N indexed-mesh polygonisations of the sphere
+at 1024^3 in field mode auto (the first writes the whole field, the following ones only its signs); not a test, not a bench."""
 import importlib, sys
 sys.path.insert(0, ".")
 m = importlib.import_module("marching-cube-for-implicit-surfaces_b200")
