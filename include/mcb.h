@@ -173,8 +173,8 @@ int mcb_counts_device(mcb_ctx* ctx, const uint64_t** counts);
 int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance);
 
 /* Run-time specialisation of the evaluator.  The first mcb_polygonise after an equation change compiles
- * that equation's fused grid program into a straight-line sm_100a kernel with NVRTC (libnvrtc.so.12, loaded on demand;
- * 10-20 ms, reported in mcb_counts::ms_compile) and later calls reuse it.  The kernel executes the interpreter's fp32
+ * that equation's fused grid program into straight-line sm_100a kernels with NVRTC (libnvrtc.so.12, loaded on demand;
+ * some tens of milliseconds, reported in mcb_counts::ms_compile) and later calls reuse them.  The kernel executes the interpreter's fp32
  * operations in the interpreter's order on the interpreter's tile, so every result is bit-identical; it just has no
  * dispatch (torus 2.3 -> 1.5 ms, polynomial gyroid 1.3 -> 0.7 ms at 1024^3).  Constants, grid size and scaling are
  * kernel arguments: only a new equation compiles again.
