@@ -247,3 +247,17 @@ def test_committed_bench_lines_carry_every_contract_key():
     ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_step9_reference_arm.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["metric"] == "Gvoxels/s" and ref["e2e"]["h2d_bytes_per_step"] == 0
     assert ref["cpu_baseline"]["kind"] == "reference" and ref["cpu_baseline"]["cores"] >= 1
+
+
+def test_jit_source_has_the_three_kernels_and_keeps_power_programs_rolled(mcb):
+    """One module per equation: mcb_eval_jit (field + signs), mcb_signs_jit (signs only, 128 x 16 tile streamed row by row),
+    mcb_fill_jit (sparse-field refill).  The operations are spelled with the never-contracted intrinsics."""
+    _, plain = mcb.jit_check("x*y+z*(x-y)")
+    _, power = mcb.jit_check("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)")
+    for src in (plain, power):
+        for kernel in ("mcb_eval_jit", "mcb_signs_jit", "mcb_fill_jit"):
+            assert src.count('%s(const __grid_constant__ Consts C' % kernel) == 1 or ("define MCB_KERNEL_NAME " + kernel) in src, kernel
+        assert "__fadd_rn" in src and "__fmul_rn" in src and "__fdiv_rn" in src and "mcb_powf" in src
+    assert '_Pragma("unroll 4")' in plain and '_Pragma("unroll 1")' not in plain
+    assert '_Pragma("unroll 1")' in power
+    assert "op_pow(" in power and "op_pow(v" not in plain
