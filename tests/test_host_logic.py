@@ -261,3 +261,82 @@ def test_jit_source_has_the_three_kernels_and_keeps_power_programs_rolled(mcb):
     assert '_Pragma("unroll 4")' in plain and '_Pragma("unroll 1")' not in plain
     assert '_Pragma("unroll 1")' in power
     assert "op_pow(" in power and "op_pow(v" not in plain
+
+
+def _random_equation(rng, depth):
+    """A random string over the reference's grammar: variables, numbers, + - * / ^, brackets, unary minus and the
+    implicit-multiplication forms (2x, x(y), (x)(y))."""
+    r = rng.random()
+    if depth <= 0 or r < 0.25:
+        k = rng.integers(0, 6)
+        if k < 3:
+            return "xyz"[k]
+        if k == 3:
+            return str(int(rng.integers(0, 10)))
+        if k == 4:
+            return "%d.%d" % (rng.integers(0, 4), rng.integers(0, 100))
+        return "XYZ"[rng.integers(0, 3)]
+    if r < 0.45:
+        return "(" + _random_equation(rng, depth - 1) + ")"
+    if r < 0.52:
+        return "-" + _random_equation(rng, depth - 1)
+    if r < 0.60:
+        return _random_equation(rng, depth - 1) + "(" + _random_equation(rng, depth - 1) + ")"
+    if r < 0.65:
+        return str(int(rng.integers(2, 5))) + "xyz"[rng.integers(0, 3)]
+    return _random_equation(rng, depth - 1) + "+-*/^"[rng.integers(0, 5)] + _random_equation(rng, depth - 1)
+
+
+def test_random_equations_lower_bit_exactly(mcb, refbind):
+    """Fuzz of the front end against the compiled reference: 500 random (half of them mutated, so often malformed)
+    equations.  Accept/reject: the product never accepts what Evaluator::tokenize rejects; it additionally rejects
+    strings the reference tokenizes but cannot evaluate (a dangling operator pops its unchecked Simple_Stack empty:
+    undefined behaviour there), exactly the ones the plain-C restatement flags as operand underflow.  Values: for every
+    equation both accept, the bytecode run by the host build of the interpreter equals Evaluator::evaluate bit for
+    bit at random points and on a tensor grid (folding, hoisting, fusion)."""
+    from oracle import oraclebind
+    so = os.path.join(ROOT, "oracle", "libmcoracle_host.so")
+    if not os.path.exists(so) or not oraclebind.available():
+        pytest.skip("oracle libraries not built")
+    H = C.CDLL(so)
+    H.mcoh_eval_points.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_long]
+    H.mcoh_eval_grid.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(20261018)
+    pts = (rng.random((200, 3), dtype=np.float32) * 3 - 1.5).astype(np.float32)
+    pts[:8] = 0
+    pts[8:16] = 1
+    cx = np.linspace(-1.1, 1.2, 7, dtype=np.float32)
+    cy = np.linspace(-0.9, 1.3, 5, dtype=np.float32)
+    cz = np.linspace(-1, 1, 3, dtype=np.float32)
+    Z, Y, X = np.meshgrid(cz, cy, cx, indexing="ij")
+    gp = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
+    alphabet = "xyzXYZ0123456789.+-*/^() "
+    both = stricter = rejected = 0
+    for _ in range(500):
+        eq = _random_equation(rng, int(rng.integers(1, 6)))
+        if rng.random() < 0.5:
+            for _m in range(int(rng.integers(1, 3))):
+                i, k, ch = int(rng.integers(0, len(eq) + 1)), rng.integers(0, 3), alphabet[rng.integers(0, len(alphabet))]
+                eq = eq[:i] + eq[i + 1:] if k == 0 else eq[:i] + ch + eq[i:] if k == 1 else eq[:i] + ch + eq[i + 1:]
+        if not eq or len(eq) > 120:
+            continue
+        ref_ok, ours_ok = bool(refbind.lib().mcref_parse_ok(eq.encode())), mcb.parse_ok(eq)
+        assert ref_ok or not ours_ok, eq
+        if not ref_ok:
+            rejected += 1
+            continue
+        if not ours_ok:
+            assert not oraclebind.lib().mco_parse_ok(eq.encode()), eq
+            stricter += 1
+            continue
+        both += 1
+        ref = refbind.Ref(eq)
+        out = np.empty(len(pts), np.float32)
+        assert H.mcoh_eval_points(eq.encode(), pts.ctypes.data, out.ctypes.data, len(pts)) == 0, eq
+        r = ref.eval_points(pts)
+        assert np.all((r.view(np.uint32) == out.view(np.uint32)) | (np.isnan(r) & np.isnan(out))), eq
+        g = np.empty(len(gp), np.float32)
+        assert H.mcoh_eval_grid(eq.encode(), cx.ctypes.data, len(cx), cy.ctypes.data, len(cy), cz.ctypes.data, len(cz), g.ctypes.data) == 0, eq
+        rg = ref.eval_points(gp)
+        assert np.all((rg.view(np.uint32) == g.view(np.uint32)) | (np.isnan(rg) & np.isnan(g))), eq
+    assert both > 300 and rejected > 30 and stricter > 3, (both, rejected, stricter)
