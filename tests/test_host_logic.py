@@ -340,3 +340,17 @@ def test_random_equations_lower_bit_exactly(mcb, refbind):
         rg = ref.eval_points(gp)
         assert np.all((rg.view(np.uint32) == g.view(np.uint32)) | (np.isnan(rg) & np.isnan(g))), eq
     assert both > 300 and rejected > 30 and stricter > 3, (both, rejected, stricter)
+
+
+def test_random_equations_compile_at_run_time(mcb):
+    """The kernel generator takes whatever the lowering produces (deep stacks, NEG, reversed operators, powers): 25 random
+    well-formed equations go through generation and NVRTC without a device."""
+    rng = np.random.default_rng(77)
+    done = 0
+    while done < 25:
+        eq = _random_equation(rng, int(rng.integers(2, 6)))
+        if len(eq) > 100 or not mcb.parse_ok(eq):
+            continue
+        nbytes, src = mcb.jit_check(eq, cap=1 << 20)
+        assert nbytes > 1000 and src.count("__launch_bounds__") == 3, eq
+        done += 1
