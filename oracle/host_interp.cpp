@@ -3,6 +3,7 @@
  * The product never links or calls this; on the GPU the same programs are interpreted by mcb_kernels.cuh.
  * Built into oracle/libmcoracle_host.so by oracle/Makefile with -ffp-contract=off.
  */
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -68,6 +69,29 @@ int mcoh_eval_grid(const char* eq, const float* cx, int nx, const float* cy, int
                 out[((size_t)k * ny + j) * nx + i] = fused;
             }
     return MCB_OK;
+}
+
+/* What the product's K0 kernels leave on the device for a grid program: the folded constant pool (MCB_MAX_K floats) and
+ * the per-axis tables of the hoisted subtrees in the product's layout tables[(axis * spa + slot) * P + index], evaluated at
+ * the (already scaled) coordinates ax[axis][0..P).  Returns spa (slots per axis) or a negative status. */
+int mcoh_tables(const char* eq, const float* cx, const float* cy, const float* cz, int P, float* tables, int tables_cap, float* kpool) {
+    mcb::Compiled c;
+    int rc = mcb::compile(eq, c, nullptr);
+    if (rc != MCB_OK) return rc;
+    fold(c);
+    const int spa = std::max(1, std::max(c.n_axis_slots[0], std::max(c.n_axis_slots[1], c.n_axis_slots[2])));
+    if ((long)3 * spa * P > tables_cap) return MCB_E_CAPACITY;
+    const float* ax[3] = {cx, cy, cz};
+    for (const mcb::Slot& s : c.slots) {
+        if (s.axis < 0) continue;
+        for (int i = 0; i < P; i++) {
+            const float v = ax[s.axis][i];
+            tables[((size_t)s.axis * spa + s.kindex) * P + i] =
+                mcb_interp_scalar(c.slot_code.data() + s.code_begin, s.code_len, c.kpool.data(), v, v, v, nullptr, nullptr, nullptr);
+        }
+    }
+    for (size_t i = 0; i < c.kpool.size() && i < MCB_MAX_K; i++) kpool[i] = c.kpool[i];
+    return spa;
 }
 
 int mcoh_depths(const char* eq, int* point_depth, int* grid_depth, int* n_point, int* n_grid, int* n_slots) {

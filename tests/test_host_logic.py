@@ -354,3 +354,57 @@ def test_random_equations_compile_at_run_time(mcb):
         nbytes, src = mcb.jit_check(eq, cap=1 << 20)
         assert nbytes > 1000 and src.count("__launch_bounds__") == 3, eq
         done += 1
+
+
+class _HostGrid(C.Structure):  # mcbk::Grid / the Grid struct of the generated source (52 bytes)
+    _fields_ = [(n, C.c_int) for n in ("M", "NV", "P", "WP", "kb", "ke", "NZ")] + \
+               [(n, C.c_float) for n in ("sx", "sy", "sz", "iso")] + [("repeat", C.c_int), ("rstep", C.c_float)]
+
+
+def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, refbind, tmp_path):
+    """The CUDA source mcb_jit.cpp generates is also valid C++ under a small shim (tests/cpp/jit_host_shim.h): g++ compiles
+    it with -ffp-contract=off and mcb_fill_jit — the generated arithmetic without warp-wide operations — runs lane by
+    lane over every block of a small grid with random coordinates.  The field it writes equals Evaluator::evaluate of
+    the compiled reference bit for bit, for the bench equations and for random ones (deep stacks, reversed operators,
+    powers, unary minus)."""
+    import subprocess
+    so_host = os.path.join(ROOT, "oracle", "libmcoracle_host.so")
+    if not os.path.exists(so_host):
+        pytest.skip("oracle/libmcoracle_host.so not built")
+    H = C.CDLL(so_host)
+    H.mcoh_tables.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    NV, P, NZ = 11, 32, 9
+    rng = np.random.default_rng(3)
+    ax = [np.sort((rng.random(P, dtype=np.float32) * 3 - 1.5).astype(np.float32)) for _ in range(3)]
+    Z, Y, X = np.meshgrid(ax[2][:NZ], ax[1][:NV], ax[0][:NV], indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
+    eqs = [refbind.SPHERE, refbind.TORUS, refbind.EXAMPLE_EQUATIONS[8], refbind.GYR34, "x*y-z/(x+2.5)", "-x^2-(y-1)(z+2)/3", "2^x+y^z"]
+    while len(eqs) < 17:
+        eq = _random_equation(rng, int(rng.integers(2, 6)))
+        if len(eq) <= 100 and mcb.parse_ok(eq):
+            eqs.append(eq)
+    shim = os.path.join(ROOT, "tests", "cpp", "jit_host_shim.h")
+    tail = open(os.path.join(ROOT, "tests", "cpp", "jit_host_tail.inc")).read()
+    for n, eq in enumerate(eqs):
+        _, src = mcb.jit_check(eq, cap=1 << 20)
+        cpp, so = tmp_path / ("k%d.cpp" % n), tmp_path / ("k%d.so" % n)
+        cpp.write_text('#include "%s"\n' % shim + src + tail)
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, mcb.__name__, "csrc"),
+                            "-DMCB_GRID_BYTES=%d" % C.sizeof(_HostGrid), "-DMCB_MAX_K=128", "-DMCB_MIN_BLOCKS=8", str(cpp), "-o", str(so)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (eq, r.stderr[:2000])
+        L = C.CDLL(str(so))
+        L.run_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]
+        tables = np.zeros(3 * 64 * P + 256, np.float32)
+        kpool = np.zeros(128, np.float32)
+        spa = H.mcoh_tables(eq.encode(), ax[0].ctypes.data, ax[1].ctypes.data, ax[2].ctypes.data, P, tables.ctypes.data, len(tables) - 256,
+                            kpool.ctypes.data)
+        assert spa > 0, (eq, spa)
+        g = _HostGrid(M=NV - 3, NV=NV, P=P, WP=4, kb=0, ke=NZ - 3, NZ=NZ, sx=1, sy=1, sz=1, iso=0, repeat=0, rstep=0)
+        nbx, nby, nbz = P // 32, (NV + 3) // 4, (NZ + 3) // 4
+        blocks = np.arange(nbx * nby * nbz, dtype=np.uint32)
+        F = np.full((NZ, NV, P), np.nan, np.float32)
+        L.run_fill(kpool.ctypes.data, C.byref(g), tables.ctypes.data, F.ctypes.data, blocks.ctypes.data, len(blocks), nbx, nby, spa)
+        ref = refbind.Ref(eq).eval_points(pts).reshape(NZ, NV, NV)
+        got = F[:, :, :NV]
+        assert np.all((ref.view(np.uint32) == got.view(np.uint32)) | (np.isnan(ref) & np.isnan(got))), eq
