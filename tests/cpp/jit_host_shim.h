@@ -1,6 +1,8 @@
 /* TEST INFRASTRUCTURE ONLY.  Lets g++ compile the CUDA source that mcb_jit.cpp generates, so that the generated
- * arithmetic can be executed on the host in the CPU test tier (tests/test_host_logic.py).  Only mcb_fill_jit — the kernel
- * without warp-wide operations — is run; lanes execute one after the other.  Build with -ffp-contract=off. */
+ * kernels can be executed on the host in the CPU test tier (tests/test_host_logic.py).  Lanes execute one after the
+ * other; the only warp-wide operation, __ballot_sync, is emulated by running every warp twice: the first pass records
+ * each lane's predicate per ballot call (control flow is uniform across a warp, so the calls line up), the second
+ * returns the assembled masks.  Build with -ffp-contract=off. */
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -23,4 +25,10 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline void __stcs(float* p, float v) { *p = v; }
-static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; } /* the plane kernels are compiled, never run here */
+static int g_pass = 0, g_lane = 0, g_seq = 0;
+static unsigned g_masks[1024];
+static inline unsigned __ballot_sync(unsigned, bool p) {
+    const int s = g_seq++;
+    if (g_pass == 0) { if (p) g_masks[s] |= 1u << g_lane; return 0u; }
+    return g_masks[s];
+}

@@ -363,10 +363,10 @@ class _HostGrid(C.Structure):  # mcbk::Grid / the Grid struct of the generated s
 
 def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, refbind, tmp_path):
     """The CUDA source mcb_jit.cpp generates is also valid C++ under a small shim (tests/cpp/jit_host_shim.h): g++ compiles
-    it with -ffp-contract=off and mcb_fill_jit — the generated arithmetic without warp-wide operations — runs lane by
-    lane over every block of a small grid with random coordinates.  The field it writes equals Evaluator::evaluate of
-    the compiled reference bit for bit, for the bench equations and for random ones (deep stacks, reversed operators,
-    powers, unary minus)."""
+    it with -ffp-contract=off and all three kernels run lane by lane over a small grid with random coordinates (warp
+    ballots emulated by a two-pass trick).  The field they write equals Evaluator::evaluate of the compiled reference
+    bit for bit and the sign words equal `value > iso`, for the bench equations and for random ones (deep stacks,
+    reversed operators, powers, unary minus)."""
     import subprocess
     so_host = os.path.join(ROOT, "oracle", "libmcoracle_host.so")
     if not os.path.exists(so_host):
@@ -408,3 +408,21 @@ def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, 
         ref = refbind.Ref(eq).eval_points(pts).reshape(NZ, NV, NV)
         got = F[:, :, :NV]
         assert np.all((ref.view(np.uint32) == got.view(np.uint32)) | (np.isnan(ref) & np.isnan(got))), eq
+        # the plane kernels: mcb_eval_jit (128 x 4 tile in registers: field + sign words) and mcb_signs_jit (128 x 16 tile
+        # streamed row by row: sign words only), warp ballots emulated by the shim; sign bit = value > iso, strict, NaN -> 0
+        L.run_plane.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        g.iso = float(np.float32(np.nanmedian(ref[np.isfinite(ref)]))) if np.isfinite(ref).any() else 0.0
+        with np.errstate(invalid="ignore"):
+            want = ref > np.float32(g.iso)
+        xs = np.arange(NV)
+        for which in (0, 1):
+            F2 = np.full((NZ, NV, P), np.nan, np.float32)
+            S = np.zeros((NZ, NV, 4), np.uint32)
+            L.run_plane(which, kpool.ctypes.data, C.byref(g), tables.ctypes.data, F2.ctypes.data, S.ctypes.data, spa)
+            bits = ((S[:, :, xs >> 5] >> (xs & 31).astype(np.uint32)) & 1).astype(bool)
+            assert np.array_equal(bits, want), (eq, which)
+            if which == 0:
+                got2 = F2[:, :, :NV]
+                assert np.all((ref.view(np.uint32) == got2.view(np.uint32)) | (np.isnan(ref) & np.isnan(got2))), eq
+            else:
+                assert np.isnan(F2).all(), eq   # the signs-only kernel does not touch the field
