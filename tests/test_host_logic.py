@@ -373,11 +373,9 @@ def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, 
         pytest.skip("oracle/libmcoracle_host.so not built")
     H = C.CDLL(so_host)
     H.mcoh_tables.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
-    NV, P, NZ = 11, 32, 9
+    P = 32
     rng = np.random.default_rng(3)
     ax = [np.sort((rng.random(P, dtype=np.float32) * 3 - 1.5).astype(np.float32)) for _ in range(3)]
-    Z, Y, X = np.meshgrid(ax[2][:NZ], ax[1][:NV], ax[0][:NV], indexing="ij")
-    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
     eqs = [refbind.SPHERE, refbind.TORUS, refbind.EXAMPLE_EQUATIONS[8], refbind.GYR34, "x*y-z/(x+2.5)", "-x^2-(y-1)(z+2)/3", "2^x+y^z"]
     while len(eqs) < 17:
         eq = _random_equation(rng, int(rng.integers(2, 6)))
@@ -386,6 +384,10 @@ def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, 
     shim = os.path.join(ROOT, "tests", "cpp", "jit_host_shim.h")
     tail = open(os.path.join(ROOT, "tests", "cpp", "jit_host_tail.inc")).read()
     for n, eq in enumerate(eqs):
+        # geometry: vertices per axis, planes, first cube layer of the slab (the z tables are indexed by plane + kb)
+        NV, NZ, kb = ((11, 9, 0), (21, 6, 5), (16, 4, 2))[n % 3]
+        Z, Y, X = np.meshgrid(ax[2][kb:kb + NZ], ax[1][:NV], ax[0][:NV], indexing="ij")
+        pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
         _, src = mcb.jit_check(eq, cap=1 << 20)
         cpp, so = tmp_path / ("k%d.cpp" % n), tmp_path / ("k%d.so" % n)
         cpp.write_text('#include "%s"\n' % shim + src + tail)
@@ -400,7 +402,7 @@ def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, 
         spa = H.mcoh_tables(eq.encode(), ax[0].ctypes.data, ax[1].ctypes.data, ax[2].ctypes.data, P, tables.ctypes.data, len(tables) - 256,
                             kpool.ctypes.data)
         assert spa > 0, (eq, spa)
-        g = _HostGrid(M=NV - 3, NV=NV, P=P, WP=4, kb=0, ke=NZ - 3, NZ=NZ, sx=1, sy=1, sz=1, iso=0, repeat=0, rstep=0)
+        g = _HostGrid(M=NV - 3, NV=NV, P=P, WP=4, kb=kb, ke=kb + NZ - 3, NZ=NZ, sx=1, sy=1, sz=1, iso=0, repeat=0, rstep=0)
         nbx, nby, nbz = P // 32, (NV + 3) // 4, (NZ + 3) // 4
         blocks = np.arange(nbx * nby * nbz, dtype=np.uint32)
         F = np.full((NZ, NV, P), np.nan, np.float32)
