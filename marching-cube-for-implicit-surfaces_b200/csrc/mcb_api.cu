@@ -229,7 +229,7 @@ int install_equation(mcb_ctx* ctx, int slot, const char* equation) {
     MCB_CK(cudaMemcpyAsync(ns.d_kpool, c.kpool.data(), c.kpool.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     if (ns.n_const > 0) {
         /* constant subtrees are folded ON THE DEVICE by the same interpreter that evaluates the field */
-        fold_constants_kernel<<<1, 128, 0, ctx->stream>>>(ns.d_slot_code, ns.d_slots, (int)descs.size(), ns.d_kpool, ns.d_kpool);
+        MCB_LAUNCH((fold_constants_kernel), 1, 128, 0, ctx->stream, ns.d_slot_code, ns.d_slots, (int)descs.size(), ns.d_kpool, ns.d_kpool);
         MCB_CK(cudaGetLastError());
         MCB_CK(cudaMemcpyAsync(ns.c.kpool.data(), ns.d_kpool, ns.c.kpool.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -612,7 +612,7 @@ int mcb_eval_points(mcb_ctx* ctx, int slot, const float* xyz, float* out, size_t
     if (e != cudaSuccess) { cudaFree(d_in); return fail(ctx, MCB_E_NOMEM, "cudaMalloc"); }
     float sx = apply_scale ? ctx->scale[0] : 1.f, sy = apply_scale ? ctx->scale[1] : 1.f, sz = apply_scale ? ctx->scale[2] : 1.f;
     cudaMemcpyAsync(d_in, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    eval_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->eq[slot].point, d_in, d_out, (long long)n, sx, sy, sz);
+    MCB_LAUNCH((eval_points_kernel), (unsigned)((n + 127) / 128), 128, 0, ctx->stream, ctx->eq[slot].point, d_in, d_out, (long long)n, sx, sy, sz);
     cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     cudaError_t e2 = cudaGetLastError();
@@ -687,7 +687,7 @@ int mcb_inspect_cube(mcb_ctx* ctx, float x0, float y0, float z0, mcb_step_data* 
     }
     for (int sl = 0; sl < 4; sl++)
         if (ctx->eq[sl].valid) cudaMemcpyAsync(d_progs + sl, &ctx->eq[sl].point, sizeof(mcb_program), cudaMemcpyHostToDevice, ctx->stream);
-    inspect_cube_kernel<<<1, 1, 0, ctx->stream>>>(d_progs, cons, slots[0], slots[1], slots[2], x0, y0, z0, ctx->step, ctx->scale[0],
+    MCB_LAUNCH((inspect_cube_kernel), 1, 1, 0, ctx->stream, d_progs, cons, slots[0], slots[1], slots[2], x0, y0, z0, ctx->step, ctx->scale[0],
                                                   ctx->scale[1], ctx->scale[2], ctx->iso, ctx->repeat_on ? 1 : 0, ctx->repeat_step, ctx->d_cls, d_out);
     cudaMemcpyAsync(out, d_out, sizeof(StepOut), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -829,7 +829,7 @@ int Run::encode_program(mcb_program& launch, bool& has_pow, bool blocks) {
 int Run::stage_tables() {
     if (eq.n_axis > 0) {
         dim3 grid((g.P + 127) / 128, eq.n_axis);
-        axis_tables_kernel<<<grid, 128, 0, s>>>(eq.d_slot_code, eq.d_slots, eq.n_const, eq.d_kpool, ctx->d_cs, g.NV, g.P,
+        MCB_LAUNCH((axis_tables_kernel), grid, 128, 0, s, eq.d_slot_code, eq.d_slots, eq.n_const, eq.d_kpool, ctx->d_cs, g.NV, g.P,
                                                 eq.max_per_axis, g.sx, g.sy, g.sz, ctx->d_tables);
         launches++;
     }
@@ -935,11 +935,11 @@ int Run::stage_eval() {
     if (ctx->jit_used) {
         launches--; /* counted below */
     } else if (sparse) {
-        if (has_pow) eval_field_kernel<true, false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
-        else eval_field_kernel<false, false><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        if (has_pow) MCB_LAUNCH((eval_field_kernel<true, false>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        else MCB_LAUNCH((eval_field_kernel<false, false>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
     } else {
-        if (has_pow) eval_field_kernel<true, true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
-        else eval_field_kernel<false, true><<<blocks, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        if (has_pow) MCB_LAUNCH((eval_field_kernel<true, true>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        else MCB_LAUNCH((eval_field_kernel<false, true>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
     }
     ctx->field_is_sparse = sparse;
     launches++;
@@ -948,7 +948,7 @@ int Run::stage_eval() {
         int first = 1;
         for (int i = 0; i < 3; i++) {
             if (!(ctx->cons[i].in_use && ctx->eq[i + 1].valid)) continue;
-            eval_constraint_kernel<<<(unsigned)((words + 7) / 8), 256, 0, s>>>(ctx->eq[i + 1].point, g, ctx->d_cs, ctx->cons[i].op,
+            MCB_LAUNCH((eval_constraint_kernel), (unsigned)((words + 7) / 8), 256, 0, s, ctx->eq[i + 1].point, g, ctx->d_cs, ctx->cons[i].op,
                                                                                  ctx->cons[i].rhs, first, ctx->d_V, words);
             first = 0;
             launches++;
@@ -966,7 +966,7 @@ int Run::stage_classify() {
     if (g.repeat) { /* per-cube iso levels: the corner signs come from the field, item by item */
         const unsigned long long items = (unsigned long long)cg.total_rows * cg.WC;
         if ((rc = ensure(ctx, &ctx->d_cw, &ctx->cap_cw, (size_t)items * 8)) != MCB_OK) return rc;
-        repeat_words_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(g, ctx->d_F, cg.WC, ctx->d_cw, items);
+        MCB_LAUNCH((repeat_words_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, g, ctx->d_F, cg.WC, ctx->d_cw, items);
         launches++;
         cw = ctx->d_cw;
     }
@@ -975,9 +975,9 @@ int Run::stage_classify() {
     unsigned long long* items = need_items ? ctx->d_item : nullptr;
 #define MCB_CLASSIFY(HAS_V, REPEAT)                                                                                                   \
     do {                                                                                                                              \
-        classify_kernel<HAS_V, REPEAT><<<tiles, kClsThreads, kClsSmemBytes, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, \
+        MCB_LAUNCH((classify_kernel<HAS_V, REPEAT>), tiles, kClsThreads, kClsSmemBytes, s, eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, \
                                                                                  ctx->d_status, ctx->d_ctr, ctx->d_F, cw);               \
-        compact_kernel<REPEAT><<<tiles, kClsThreads, 0, s>>>(eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,    \
+        MCB_LAUNCH((compact_kernel<REPEAT>), tiles, kClsThreads, 0, s, eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,    \
                                                              ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active, items, ctx->d_F, cw); \
     } while (0)
     if (cw) { if (dV) MCB_CLASSIFY(true, true); else MCB_CLASSIFY(false, true); }
@@ -1009,8 +1009,8 @@ int Run::stage_fill() {
     const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
     const unsigned fill_ctas = (unsigned)ctx->sm_count * 16;
     MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb + 16, s)); /* + the padding field_list reads */
-    field_flag_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(ctx->d_rec, g, ctx->d_ctr, ctx->cap_active, fb);
-    field_list_kernel<<<(unsigned)((nb / 16 + 256) / 256), 256, 0, s>>>(fb, (unsigned)nb, ctx->d_ctr);
+    MCB_LAUNCH((field_flag_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, ctx->d_rec, g, ctx->d_ctr, ctx->cap_active, fb);
+    MCB_LAUNCH((field_list_kernel), (unsigned)((nb / 16 + 256) / 256), 256, 0, s, fb, (unsigned)nb, ctx->d_ctr);
     if (ctx->jit_used && ctx->jit_cur && ctx->jit_cur->fill) { /* the refill kernel NVRTC compiled next to the evaluation kernel */
         struct { float k[MCB_MAX_K]; } consts;
         std::memcpy(consts.k, eq.grid.k, sizeof consts.k);
@@ -1022,8 +1022,8 @@ int Run::stage_fill() {
         int nbx = fb.nbx, nby = fb.nby, spa = eq.max_per_axis;
         void* args[] = {&consts, &garg, &tables, &F, &list, &count, &nbx, &nby, &spa};
         MCB_CK(cudaLaunchKernel((const void*)ctx->jit_cur->fill, dim3(fill_ctas), dim3(kEvalThreads), args, 0, s));
-    } else if (has_pow) eval_blocks_kernel<true><<<fill_ctas, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
-    else eval_blocks_kernel<false><<<fill_ctas, kEvalThreads, smem, s>>>(launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
+    } else if (has_pow) MCB_LAUNCH((eval_blocks_kernel<true>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
+    else MCB_LAUNCH((eval_blocks_kernel<false>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
     launches += 3;
     return MCB_OK;
 }
@@ -1045,7 +1045,7 @@ int Run::stage_seed() {
         MCB_CK(cudaMemsetAsync(ctx->d_mark, 0, std::max<unsigned long long>(ctx->h_ctr->active, 1), s));
         MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
         if (sc3[0] >= 0 && sc3[1] >= 0 && sc3[2] >= g.kb && sc3[0] < g.M && sc3[1] < g.M && sc3[2] < g.ke) {
-            seed_init_kernel<<<1, 1, 0, s>>>(SB, g, ctx->d_ctr, ctx->cap_active, sc3[0], sc3[1], sc3[2]);
+            MCB_LAUNCH((seed_init_kernel), 1, 1, 0, s, SB, g, ctx->d_ctr, ctx->cap_active, sc3[0], sc3[1], sc3[2]);
             launches++;
         }
         for (int round = 0; round < 100000; round++) { /* monotone marking until nothing changes */
@@ -1055,26 +1055,26 @@ int Run::stage_seed() {
             if (!changed) break;
             MCB_CK(cudaMemsetAsync(ctx->d_changed, 0, 4, s));
             for (int q = 0; q < 8; q++) {
-                seed_sweep_kernel<<<sblocks, 256, 0, s>>>(SB, W, ctx->d_ctr, ctx->cap_active, 0.5 * (double)ctx->step);
+                MCB_LAUNCH((seed_sweep_kernel), sblocks, 256, 0, s, SB, W, ctx->d_ctr, ctx->cap_active, 0.5 * (double)ctx->step);
                 launches++;
             }
         }
         const unsigned long long* na = &ctx->d_ctr->active;
-        seed_flags_kernel<<<sblocks, 256, 0, s>>>(SB, ctx->d_cls, ctx->d_ctr, ctx->cap_active, keep, ktri);
-        scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, na, sums);
-        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
-        scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(keep, sums, na, pa);
-        scan_block_sums_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, na, sums);
-        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, na);
-        scan_apply_kernel<<<sblocks / 2, kScanBlock, 0, s>>>(ktri, sums, na, pt);
-        seed_scatter_kernel<<<sblocks, 256, 0, s>>>(SB, keep, ktri, pa, pt, ctx->d_ctr, ctx->cap_active, ctx->d_rec2, ctx->d_trioff2);
-        seed_commit_kernel<<<1, 1, 0, s>>>(ctx->d_ctr);
+        MCB_LAUNCH((seed_flags_kernel), sblocks, 256, 0, s, SB, ctx->d_cls, ctx->d_ctr, ctx->cap_active, keep, ktri);
+        MCB_LAUNCH((scan_block_sums_kernel), sblocks / 2, kScanBlock, 0, s, keep, na, sums);
+        MCB_LAUNCH((scan_sums_kernel), 1, kScanBlock, 0, s, sums, na);
+        MCB_LAUNCH((scan_apply_kernel), sblocks / 2, kScanBlock, 0, s, keep, sums, na, pa);
+        MCB_LAUNCH((scan_block_sums_kernel), sblocks / 2, kScanBlock, 0, s, ktri, na, sums);
+        MCB_LAUNCH((scan_sums_kernel), 1, kScanBlock, 0, s, sums, na);
+        MCB_LAUNCH((scan_apply_kernel), sblocks / 2, kScanBlock, 0, s, ktri, sums, na, pt);
+        MCB_LAUNCH((seed_scatter_kernel), sblocks, 256, 0, s, SB, keep, ktri, pa, pt, ctx->d_ctr, ctx->cap_active, ctx->d_rec2, ctx->d_trioff2);
+        MCB_LAUNCH((seed_commit_kernel), 1, 1, 0, s, ctx->d_ctr);
         std::swap(ctx->d_rec, ctx->d_rec2);
         std::swap(ctx->d_trioff, ctx->d_trioff2);
         launches += 9;
         if (want_indexed) { /* the weld must only see the kept cubes: rebuild the per-word look-up from scratch */
             MCB_CK(cudaMemsetAsync(ctx->d_item, 0, (size_t)(g.ke - g.kb) * g.M * cg.WC * 8, s));
-            seed_items_kernel<<<sblocks, 256, 0, s>>>(ctx->d_rec, g, cg.WC, ctx->d_ctr, ctx->d_item);
+            MCB_LAUNCH((seed_items_kernel), sblocks, 256, 0, s, ctx->d_rec, g, cg.WC, ctx->d_ctr, ctx->d_item);
             launches++;
         }
     }
@@ -1084,10 +1084,10 @@ int Run::stage_seed() {
 /* K3: interpolation + coalesced float4 emission of the triangle soup */
 int Run::stage_soup() {
     if (ctx->normals == 1)
-        emit_kernel<true><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
+        MCB_LAUNCH((emit_kernel<true>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
                                                            ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
     else
-        emit_kernel<false><<<eblocks, kEmitThreads, 0, s>>>(g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
+        MCB_LAUNCH((emit_kernel<false>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
                                                             ctx->cap_tris, ctx->d_pos, nullptr);
     launches++;
     return MCB_OK;
@@ -1100,17 +1100,17 @@ int Run::stage_weld() {
     const WeldView W{g, ctx->d_cs, ctx->d_F, any_constraint ? ctx->d_V : nullptr, ctx->seed_on ? ctx->d_item : nullptr, cg.WC};
     const WeldViewT<true> WR{W.g, W.cs, W.F, W.V, W.present, W.WC}; /* repeating-surface mode: same view, level checks compiled in */
     const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_item, ctx->d_vinfo, ctx->d_chunk_new, cg.WC};
-    if (g.repeat) weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(WR, B, ctx->d_ctr, ctx->cap_active);
-    else weld_count_kernel<<<eblocks * 2, kWeldThreads, 0, s>>>(W, B, ctx->d_ctr, ctx->cap_active);
-    weld_scan_kernel<<<1, 1024, 0, s>>>(ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
-    weld_base_kernel<<<eblocks * 2, kWeldCubes, 0, s>>>(B, ctx->d_ctr, ctx->cap_active);
+    if (g.repeat) MCB_LAUNCH((weld_count_kernel), eblocks * 2, kWeldThreads, 0, s, WR, B, ctx->d_ctr, ctx->cap_active);
+    else MCB_LAUNCH((weld_count_kernel), eblocks * 2, kWeldThreads, 0, s, W, B, ctx->d_ctr, ctx->cap_active);
+    MCB_LAUNCH((weld_scan_kernel), 1, 1024, 0, s, ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
+    MCB_LAUNCH((weld_base_kernel), eblocks * 2, kWeldCubes, 0, s, B, ctx->d_ctr, ctx->cap_active);
     /* streaming: with a registered host destination and everything fitting, weld_emit runs range by range and
      * each finished range of vertices / normals / triangles leaves over PCIe on the copy stream meanwhile */
     constexpr int K = 8;
     bool stream_out = ctx->h_out_v && ctx->h_out_t && ctx->normals != 2 && (ctx->normals == 0 || ctx->h_out_n);
     ctx->streamed = false;
     if (stream_out) {
-        weld_bounds_kernel<<<1, 32, 0, s>>>(B, ctx->d_ctr, ctx->cap_active, K, ctx->d_bounds);
+        MCB_LAUNCH((weld_bounds_kernel), 1, 32, 0, s, B, ctx->d_ctr, ctx->cap_active, K, ctx->d_bounds);
         MCB_CK(cudaMemcpyAsync(ctx->h_bounds, ctx->d_bounds, 3 * (K + 1) * 8, cudaMemcpyDeviceToHost, s));
         MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         MCB_CK(cudaStreamSynchronize(s));
@@ -1124,7 +1124,7 @@ int Run::stage_weld() {
         const unsigned long long cb = stream_out ? ctx->h_bounds[3 * j] : 0ull, ce = stream_out ? ctx->h_bounds[3 * j + 3] : ~0ull;
         if (stream_out && cb == ce) continue;
 #define MCB_WELD_EMIT(NRM, VIEW)                                                                                              \
-    weld_emit_kernel<NRM><<<eblocks * 2, kWeldThreads, 0, s>>>(VIEW, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris, \
+    MCB_LAUNCH((weld_emit_kernel<NRM>), eblocks * 2, kWeldThreads, 0, s, VIEW, B, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris, \
                                                                ctx->d_vlist, NRM ? ctx->d_vnrm : nullptr, ctx->d_tlist, cb, ce)
         if (ctx->normals == 1) { if (g.repeat) MCB_WELD_EMIT(true, WR); else MCB_WELD_EMIT(true, W); }
         else { if (g.repeat) MCB_WELD_EMIT(false, WR); else MCB_WELD_EMIT(false, W); }
@@ -1156,15 +1156,15 @@ int Run::stage_normal_h() {
     int rc;
     if ((rc = ensure_normal_h_scratch(ctx)) != MCB_OK) return rc;
     const unsigned long long* nv = &ctx->d_ctr->nh_vertices;
-    nh_gate_kernel<<<1, 1, 0, s>>>(ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris);
+    MCB_LAUNCH((nh_gate_kernel), 1, 1, 0, s, ctx->d_ctr, ctx->cap_active, ctx->cap_verts, ctx->cap_itris);
     MCB_CK(cudaMemsetAsync(ctx->d_nh_count, 0, ctx->cap_verts * 4, s));
     MCB_CK(cudaMemsetAsync(ctx->d_nh_cursor, 0, ctx->cap_verts * 4, s));
-    nh_face_normals_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_vlist, ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_fn, ctx->d_nh_count);
-    scan_block_sums_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, nv, ctx->d_nh_sums);
-    scan_sums_kernel<<<1, kScanBlock, 0, s>>>(ctx->d_nh_sums, nv);
-    scan_apply_kernel<<<eblocks, kScanBlock, 0, s>>>(ctx->d_nh_count, ctx->d_nh_sums, nv, ctx->d_nh_start);
-    nh_fill_kernel<<<eblocks * 2, 256, 0, s>>>(ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_nh_start, ctx->d_nh_cursor, ctx->d_nh_adj);
-    nh_accumulate_kernel<<<eblocks * 4, 128, 0, s>>>(ctx->d_fn, ctx->d_nh_start, ctx->d_nh_count, ctx->d_nh_adj, ctx->d_ctr, ctx->cap_verts, ctx->d_vnrm);
+    MCB_LAUNCH((nh_face_normals_kernel), eblocks * 2, 256, 0, s, ctx->d_vlist, ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_fn, ctx->d_nh_count);
+    MCB_LAUNCH((scan_block_sums_kernel), eblocks, kScanBlock, 0, s, ctx->d_nh_count, nv, ctx->d_nh_sums);
+    MCB_LAUNCH((scan_sums_kernel), 1, kScanBlock, 0, s, ctx->d_nh_sums, nv);
+    MCB_LAUNCH((scan_apply_kernel), eblocks, kScanBlock, 0, s, ctx->d_nh_count, ctx->d_nh_sums, nv, ctx->d_nh_start);
+    MCB_LAUNCH((nh_fill_kernel), eblocks * 2, 256, 0, s, ctx->d_tlist, ctx->d_ctr, ctx->cap_itris, ctx->d_nh_start, ctx->d_nh_cursor, ctx->d_nh_adj);
+    MCB_LAUNCH((nh_accumulate_kernel), eblocks * 4, 128, 0, s, ctx->d_fn, ctx->d_nh_start, ctx->d_nh_count, ctx->d_nh_adj, ctx->d_ctr, ctx->cap_verts, ctx->d_vnrm);
     launches += 7;
     return MCB_OK;
 }
@@ -1393,10 +1393,10 @@ int mcb_get_cases(mcb_ctx* ctx, uint8_t* cube_code, uint8_t* table_idx) {
     uint8_t *d_code = nullptr, *d_tidx = nullptr;
     MCB_CK(cudaMalloc((void**)&d_code, (size_t)n));
     if (cudaMalloc((void**)&d_tidx, (size_t)n) != cudaSuccess) { cudaFree(d_code); return fail(ctx, MCB_E_NOMEM, "cudaMalloc"); }
-    dense_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_S, any_constraint ? ctx->d_V : nullptr, d_code, d_tidx, n,
+    MCB_LAUNCH((dense_codes_kernel), (unsigned)((n + 255) / 256), 256, 0, ctx->stream, g, ctx->d_S, any_constraint ? ctx->d_V : nullptr, d_code, d_tidx, n,
                                                                              g.repeat ? ctx->d_cw : nullptr, (uint32_t)((g.M + 31) / 32));
     if (ctx->last.active)
-        scatter_tidx_kernel<<<(unsigned)((ctx->last.active + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_rec, ctx->last.active, d_tidx);
+        MCB_LAUNCH((scatter_tidx_kernel), (unsigned)((ctx->last.active + 255) / 256), 256, 0, ctx->stream, g, ctx->d_rec, ctx->last.active, d_tidx);
     if (cube_code) cudaMemcpyAsync(cube_code, d_code, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
     if (table_idx) cudaMemcpyAsync(table_idx, d_tidx, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);

@@ -32,6 +32,7 @@
 #include <stdint.h>
 
 #include "mcb_bytecode.h"
+#include "mcb_launch.h"
 #include "mcb_tables.h"
 
 namespace mcbk {
@@ -316,7 +317,7 @@ template <bool HAS_POW, bool STORE_F> /* programs without `^` (after hoisting) g
 __global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
 eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
                   float* __restrict__ F, uint32_t* __restrict__ S, int row_groups) {
-    extern __shared__ float stack_smem[]; /* [level][16][kEvalThreads] */
+    MCB_DYNAMIC_SMEM(float, stack_smem); /* [level][16][kEvalThreads] */
     const int lane = threadIdx.x & 31;
     const int cx = (int)blockIdx.x;                                            /* 128-column tile of the row */
     const int yq = (int)blockIdx.y * (kEvalThreads / 32) + (threadIdx.x >> 5); /* 4-row group */
@@ -368,7 +369,7 @@ template <bool HAS_POW>
 __global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
 eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
                    float* __restrict__ F, const FieldBlocks fb, const Counters* __restrict__ ctr) {
-    extern __shared__ float stack_smem[];
+    MCB_DYNAMIC_SMEM(float, stack_smem);
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * (kEvalThreads / 32);
     const unsigned n = ctr->field_blocks;
@@ -646,7 +647,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
                 const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
                 const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status, Counters* __restrict__ ctr,
                 const float* __restrict__ F, const uint32_t* __restrict__ Cw /* repeating-surface mode: corner words, else nullptr */) {
-    extern __shared__ uint32_t cls_smem[];
+    MCB_DYNAMIC_SMEM(uint32_t, cls_smem);
     uint32_t* bitmap = cls_smem;                                          /* [kClsChunkCap] one bit per item */
     uint16_t* list = reinterpret_cast<uint16_t*>(cls_smem + kClsChunkCap); /* [kClsItemCap] active items, loop order */
     __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];

@@ -19,7 +19,19 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def mcb():
+    if os.environ.get("MCB_TEST_EMU") == "1":
+        # developer switch: run the `-m gpu` tests' small cases against the kernels' source executed on the host
+        # (tests/emu).  Never set by the driver; the GPU tier always goes through libmcb200.so on a real device.
+        from tests import emu
+        return emu.load()
     return importlib.import_module("marching-cube-for-implicit-surfaces_b200")
+
+
+@pytest.fixture(scope="session")
+def mcb_emu():
+    """The package's ctypes mirror bound to tests/emu/_build/libmcb200_emu.so (device code executed on the host)."""
+    from tests import emu
+    return emu.load()
 
 
 @pytest.fixture(scope="session")
