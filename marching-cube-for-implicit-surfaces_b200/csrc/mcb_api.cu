@@ -71,10 +71,10 @@ struct mcb_ctx {
     ClsTables* d_cls = nullptr;
     Counters* d_ctr = nullptr;
     Counters* h_ctr = nullptr; /* pinned */
-    unsigned long long* d_status = nullptr; /* one look-back status word per classify tile */
-    uint16_t* d_tile_list = nullptr;        /* classify -> compact scratch: active items per tile, their counts */
-    uint16_t* d_tile_cnt = nullptr;
-    uint32_t* d_tile_nz = nullptr;
+    unsigned long long* d_ent = nullptr;    /* classify -> compact scratch: one entry per active item of every tile */
+    uint32_t* d_tile_u32 = nullptr;         /* [5][cap_tiles]: entries, active cubes, triangles, and the two exclusive prefixes */
+    unsigned long long* d_amb = nullptr;    /* [cap_amb][2] ambiguous cubes awaiting the face-centre test */
+    uint32_t cap_amb = 0;
     size_t cap_tile_entries = 0;
     size_t cap_tiles = 0;
     unsigned long long* d_rec = nullptr;
@@ -138,15 +138,16 @@ struct mcb_ctx {
     cudaEvent_t ev[9] = {};
     /* sparse-field mode (mcb_set_field_mode): the field is only written in 32 x 4 x 4 vertex blocks around the surface */
     int field_mode = MCB_FIELD_DENSE;
-    /* MCB_FIELD_AUTO: what the last polygonisation of exactly this configuration found (signature over equation,
-     * grid, slab, iso, scaling, constraints): a sparse surface is cheaper without the 4 B/vertex field write */
-    uint64_t hint_signature = 0;
-    double hint_active_fraction = 1.0;
-    bool field_is_sparse = false;  /* what the last polygonisation left in d_F */
+    bool field_is_sparse = false;  /* what the last polygonisation left in d_F: only the blocks around the surface */
     bool poison_field = false;     /* $MCB_POISON_FIELD: NaN-fill d_F first, so a read outside the blocks shows (tests) */
-    uint8_t* d_fflags = nullptr;   /* [cap_fblocks] */
-    uint32_t* d_flist = nullptr;   /* [cap_fblocks] */
-    size_t cap_fblocks = 0;
+    bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
+    uint8_t* d_fflags = nullptr;   /* [cap_fblocks] 2 = evaluated (undecided block), 1 = apron block to refill, 0 = untouched */
+    uint8_t* d_bcls = nullptr;     /* [cap_fblocks] interval class of every 32 x 4 x 4 vertex block */
+    uint32_t* d_flist = nullptr;   /* [cap_fblocks] apron blocks */
+    uint32_t* d_elist = nullptr;   /* [cap_fblocks] undecided blocks */
+    uint8_t* d_cand = nullptr;     /* [cap_cand] cube blocks that may hold an active cube */
+    mcb_ival* d_bounds_iv = nullptr; /* [3][slots][nb] table bounds per block of each axis */
+    size_t cap_fblocks = 0, cap_cand = 0, cap_bounds_iv = 0;
     mcb_counts last{};
     bool have_result = false;
 };
@@ -287,23 +288,23 @@ int setup_grid(mcb_ctx* ctx) {
     const ClsGeom cg0 = classify_geometry(ctx, g, &tiles_now);
     const size_t tiles = (size_t)tiles_now + 1;
     if (tiles > ctx->cap_tiles) {
-        if (ctx->d_status) cudaFree(ctx->d_status);
-        if (ctx->d_tile_nz) cudaFree(ctx->d_tile_nz);
-        ctx->d_status = nullptr; ctx->d_tile_nz = nullptr;
+        if (ctx->d_tile_u32) cudaFree(ctx->d_tile_u32);
+        ctx->d_tile_u32 = nullptr;
         ctx->cap_tiles = 0;
-        MCB_CK(cudaMalloc((void**)&ctx->d_status, tiles * 8));
-        MCB_CK(cudaMalloc((void**)&ctx->d_tile_nz, tiles * 4));
+        MCB_CK(cudaMalloc((void**)&ctx->d_tile_u32, 5 * tiles * 4));
         ctx->cap_tiles = tiles;
     }
     const size_t entries = tiles * (size_t)cg0.tile_rows * cg0.WC; /* worst case: every item active */
     if (entries > ctx->cap_tile_entries) {
-        if (ctx->d_tile_list) cudaFree(ctx->d_tile_list);
-        if (ctx->d_tile_cnt) cudaFree(ctx->d_tile_cnt);
-        ctx->d_tile_list = nullptr; ctx->d_tile_cnt = nullptr;
+        if (ctx->d_ent) cudaFree(ctx->d_ent);
+        ctx->d_ent = nullptr;
         ctx->cap_tile_entries = 0;
-        MCB_CK(cudaMalloc((void**)&ctx->d_tile_list, entries * 2));
-        MCB_CK(cudaMalloc((void**)&ctx->d_tile_cnt, entries * 2));
+        MCB_CK(cudaMalloc((void**)&ctx->d_ent, entries * 8));
         ctx->cap_tile_entries = entries;
+    }
+    if (!ctx->d_amb) {
+        ctx->cap_amb = 1u << 18;
+        MCB_CK(cudaMalloc((void**)&ctx->d_amb, (size_t)ctx->cap_amb * 16));
     }
     ctx->grid_dirty = false;
     return MCB_OK;
@@ -542,13 +543,14 @@ int mcb_create(int device, mcb_ctx** out) {
     if (cudaMemcpy(ctx->d_cls, &tb, sizeof tb, cudaMemcpyHostToDevice) != cudaSuccess) return bail(MCB_E_CUDA);
     {
         const int stack_bytes = MCB_MAX_STACK * kEvalRows * kEvalThreads * (int)sizeof(float);
-        const void* evals[] = {(const void*)eval_field_kernel<true, true>,  (const void*)eval_field_kernel<false, true>,
-                               (const void*)eval_field_kernel<true, false>, (const void*)eval_field_kernel<false, false>,
-                               (const void*)eval_blocks_kernel<true>,       (const void*)eval_blocks_kernel<false>};
+        const void* evals[] = {(const void*)eval_field_kernel<true, true>, (const void*)eval_field_kernel<false, true>,
+                               (const void*)eval_blocks_kernel<true>,      (const void*)eval_blocks_kernel<false>};
         for (const void* k : evals)
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, stack_bytes) != cudaSuccess) return bail(MCB_E_CUDA);
         const char* poison = std::getenv("MCB_POISON_FIELD");
         ctx->poison_field = poison && poison[0] == '1';
+        const char* noiv = std::getenv("MCB_NO_INTERVAL");
+        ctx->decide_blocks = !(noiv && noiv[0] == '1');
     }
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
@@ -564,11 +566,11 @@ void mcb_destroy(mcb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->eq) free_slot(s);
     for (auto& kv : ctx->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
-    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw);
+    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw); cudaFree(ctx->d_bcls); cudaFree(ctx->d_elist); cudaFree(ctx->d_cand);
+    cudaFree(ctx->d_bounds_iv); cudaFree(ctx->d_ent); cudaFree(ctx->d_tile_u32); cudaFree(ctx->d_amb);
     cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    cudaFree(ctx->d_status); cudaFree(ctx->d_tile_list); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_tile_nz);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_trioff); cudaFree(ctx->d_pos); cudaFree(ctx->d_nrm);
     cudaFree(ctx->d_vlist); cudaFree(ctx->d_vnrm); cudaFree(ctx->d_tlist); cudaFree(ctx->d_item); cudaFree(ctx->d_vinfo);
     cudaFree(ctx->d_chunk_new); cudaFree(ctx->d_fn); cudaFree(ctx->d_nh_count); cudaFree(ctx->d_nh_start); cudaFree(ctx->d_nh_cursor);
@@ -742,8 +744,11 @@ struct Run {
 
     int prepare_buffers();
     int encode_program(mcb_program& launch, bool& has_pow, bool blocks);
+    int ensure_block_buffers(FieldBlocks* fb, BlockDims* bd);
+    int launch_block_eval(const FieldBlocks& fb, const uint32_t* list, const unsigned* count);
+    int stage_eval_blocks();
     int stage_fill();
-    int launch_eval_jit(bool store_field);
+    int launch_eval_jit();
     int stage_tables();
     int stage_eval();
     int stage_classify();
@@ -836,14 +841,14 @@ int Run::stage_tables() {
     return MCB_OK;
 }
 
-/* The same evaluation by the kernel NVRTC compiled for this equation (mcb_jit.cpp): same tile, same launch geometry */
-int Run::launch_eval_jit(bool store_field) {
+/* The module NVRTC compiled for this equation (mcb_jit.cpp), from the per-context cache or compiled now.
+ * Returns MCB_OK with *out set, or a status with the reason in ctx->err. */
+int jit_module(mcb_ctx* ctx, const EqSlot& eq, const mcb_ctx::JitKernel** out) {
     std::string err;
     bool has_pow = false;
     const std::string src = mcbjit::generate(eq.grid.code, eq.grid.n, &has_pow, &err);
     if (src.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + err);
     auto it = ctx->jit_cache.find(src);
-    ctx->ms_compile = 0.f;
     if (it == ctx->jit_cache.end()) {
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<char> cubin;
@@ -851,15 +856,41 @@ int Run::launch_eval_jit(bool store_field) {
         if (!cerr.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + cerr);
         mcb_ctx::JitKernel jk;
         MCB_CK(cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-        MCB_CK(cudaLibraryGetKernel(&jk.kernel, jk.lib, "mcb_eval_jit"));
-        MCB_CK(cudaLibraryGetKernel(&jk.signs, jk.lib, "mcb_signs_jit"));
-        MCB_CK(cudaLibraryGetKernel(&jk.fill, jk.lib, "mcb_fill_jit"));
+        cudaError_t e = cudaLibraryGetKernel(&jk.kernel, jk.lib, "mcb_eval_jit");
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.fill, jk.lib, "mcb_fill_jit");
+        if (e != cudaSuccess) {
+            cudaLibraryUnload(jk.lib);
+            return fail(ctx, MCB_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
+        }
+        if (ctx->jit_cache.size() >= 64) { /* a long GUI session types many equations: keep the cache bounded */
+            for (auto& kv : ctx->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+            ctx->jit_cache.clear();
+            ctx->jit_cur = nullptr;
+        }
         it = ctx->jit_cache.emplace(src, jk).first;
-        ctx->ms_compile = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        ctx->ms_compile += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
-    /* the field kernel holds a 128 x 4 tile per warp in registers; the signs-only kernel streams 128 x 16 row by row */
-    const int tile_rows = store_field ? kEvalTileY : 16;
-    const int rgpp = (g.NV + tile_rows - 1) / tile_rows;
+    *out = &it->second;
+    return MCB_OK;
+}
+
+/* auto: a program full of general `^` is bound by powf either way, and each inlined powf site costs compile time
+ * (13 of them: seconds) — leave those to the interpreter */
+bool jit_wanted(const mcb_ctx* ctx, const EqSlot& eq) {
+    int n_pow = 0;
+    for (int pc = 0; pc < eq.grid.n; pc++) {
+        const uint32_t fop = MCB_FINSN_OP(eq.grid.code[pc]);
+        n_pow += fop == MCB_F_POW || fop == MCB_F_RPOW;
+    }
+    return ctx->jit == MCB_JIT_ON || (ctx->jit == MCB_JIT_AUTO && n_pow <= 8);
+}
+
+/* The dense evaluation by the kernel compiled for this equation: same tile, same launch geometry as eval_field_kernel */
+int Run::launch_eval_jit() {
+    const mcb_ctx::JitKernel* jk = nullptr;
+    int rc = jit_module(ctx, eq, &jk);
+    if (rc != MCB_OK) return rc;
+    const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY;
     const dim3 blocks((unsigned)((g.P + kEvalTileX - 1) / kEvalTileX), (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)),
                       (unsigned)g.NZ);
     struct { float k[MCB_MAX_K]; } consts;
@@ -870,98 +901,146 @@ int Run::launch_eval_jit(bool store_field) {
     uint32_t* S = ctx->d_S;
     int rg = rgpp, spa = eq.max_per_axis;
     void* args[] = {&consts, &garg, &tables, &F, &S, &rg, &spa};
-    MCB_CK(cudaLaunchKernel((const void*)(store_field ? it->second.kernel : it->second.signs), blocks, dim3(kEvalThreads), args, 0, s));
-    ctx->jit_cur = &it->second;
+    MCB_CK(cudaLaunchKernel((const void*)jk->kernel, blocks, dim3(kEvalThreads), args, 0, s));
+    ctx->jit_cur = jk;
     launches++;
     return MCB_OK;
 }
 
-/* FNV-1a over everything the set of active cubes depends on */
-uint64_t config_signature(const mcb_ctx* ctx) {
-    uint64_t h = 1469598103934665603ull;
-    auto mix = [&h](const void* p, size_t n) {
-        const unsigned char* b = static_cast<const unsigned char*>(p);
-        for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
-    };
-    for (int sl = 0; sl < 4; sl++) {
-        const EqSlot& e = ctx->eq[sl];
-        const int used = sl == 0 ? 1 : (ctx->cons[sl - 1].in_use && e.valid ? 1 : 0);
-        mix(&used, sizeof used);
-        if (!used) continue;
-        mix(&e.point.n, sizeof e.point.n);
-        mix(e.point.code, sizeof(uint32_t) * (size_t)e.point.n);
-        mix(e.point.k, sizeof e.point.k);
-        if (sl > 0) { mix(&ctx->cons[sl - 1].op, sizeof(int)); mix(&ctx->cons[sl - 1].rhs, sizeof(float)); }
+/* K1b: constraint validity bit-planes */
+int launch_constraints(Run& r) {
+    mcb_ctx* ctx = r.ctx;
+    if (!r.any_constraint) return MCB_OK;
+    const long long words = (long long)r.g.NZ * r.g.NV * r.g.WP;
+    int first = 1;
+    for (int i = 0; i < 3; i++) {
+        if (!(ctx->cons[i].in_use && ctx->eq[i + 1].valid)) continue;
+        MCB_LAUNCH((eval_constraint_kernel), (unsigned)((words + 7) / 8), 256, 0, r.s, ctx->eq[i + 1].point, r.g, ctx->d_cs, ctx->cons[i].op,
+                   ctx->cons[i].rhs, first, ctx->d_V, words);
+        first = 0;
+        r.launches++;
     }
-    const Grid& g = ctx->g;
-    const int geo[4] = {g.M, g.kb, g.ke, g.repeat};
-    const float par[6] = {ctx->step, g.sx, g.sy, g.sz, g.iso, g.rstep};
-    mix(geo, sizeof geo);
-    mix(par, sizeof par);
-    return h ? h : 1;
+    return MCB_OK;
 }
 
-/* K1: field + sign bit-planes (+ K1b: constraint validity bit-planes) */
+/* K1, MCB_FIELD_DENSE: field + sign bit-planes at every grid vertex */
 int Run::stage_eval() {
     const int rgpp = (g.NV + kEvalTileY - 1) / kEvalTileY; /* 4-row groups per plane */
     const dim3 blocks((unsigned)((g.P + kEvalTileX - 1) / kEvalTileX), (unsigned)((rgpp + kEvalThreads / 32 - 1) / (kEvalThreads / 32)),
                       (unsigned)g.NZ);
-    const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
-    mcb_program launch;
-    bool has_pow;
-    int rc = encode_program(launch, has_pow, false);
-    if (rc != MCB_OK) return rc;
-    /* sparse field: asked for, or (auto) the last run of this very configuration had few active cubes; per-cube iso
-     * levels (repeat) read the field everywhere, and the seed walk's bookkeeping assumes the dense field too */
-    const uint64_t sig = config_signature(ctx);
-    const bool auto_sparse = ctx->field_mode == MCB_FIELD_AUTO && !ctx->seed_on && ctx->hint_signature == sig &&
-                             ctx->hint_active_fraction <= 0.005;
-    const bool sparse = (ctx->field_mode == MCB_FIELD_SPARSE || auto_sparse) && !g.repeat;
-    if (sparse && ctx->poison_field) MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
     ctx->jit_used = false;
-    /* auto: a program full of general `^` is bound by powf either way, and each inlined powf site costs compile time
-     * (13 of them: seconds) — leave those to the interpreter */
-    int n_pow = 0;
-    for (int pc = 0; pc < eq.grid.n; pc++) {
-        const uint32_t fop = MCB_FINSN_OP(eq.grid.code[pc]);
-        n_pow += fop == MCB_F_POW || fop == MCB_F_RPOW;
-    }
-    if (ctx->jit == MCB_JIT_ON || (ctx->jit == MCB_JIT_AUTO && n_pow <= 8)) {
-        rc = launch_eval_jit(!sparse);
+    ctx->field_is_sparse = false;
+    int rc;
+    if (jit_wanted(ctx, eq)) {
+        rc = launch_eval_jit();
         if (rc == MCB_OK) ctx->jit_used = true;
         else if (ctx->jit == MCB_JIT_ON) return rc;      /* asked for explicitly: fail loudly */
         else ctx->jit_note = ctx->err;                   /* auto: the interpreter below does the same work */
     }
-    if (ctx->jit_used) {
-        launches--; /* counted below */
-    } else if (sparse) {
-        if (has_pow) MCB_LAUNCH((eval_field_kernel<true, false>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
-        else MCB_LAUNCH((eval_field_kernel<false, false>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
-    } else {
+    if (!ctx->jit_used) {
+        const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
+        mcb_program launch;
+        bool has_pow;
+        if ((rc = encode_program(launch, has_pow, false)) != MCB_OK) return rc;
         if (has_pow) MCB_LAUNCH((eval_field_kernel<true, true>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
         else MCB_LAUNCH((eval_field_kernel<false, true>), blocks, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, rgpp);
+        launches++;
     }
-    ctx->field_is_sparse = sparse;
-    launches++;
-    if (any_constraint) {
-        const long long words = (long long)g.NZ * g.NV * g.WP;
-        int first = 1;
-        for (int i = 0; i < 3; i++) {
-            if (!(ctx->cons[i].in_use && ctx->eq[i + 1].valid)) continue;
-            MCB_LAUNCH((eval_constraint_kernel), (unsigned)((words + 7) / 8), 256, 0, s, ctx->eq[i + 1].point, g, ctx->d_cs, ctx->cons[i].op,
-                                                                                 ctx->cons[i].rhs, first, ctx->d_V, words);
-            first = 0;
-            launches++;
-        }
+    return launch_constraints(*this);
+}
+
+/* the 32 x 4 x 4 vertex blocks of the slab and everything indexed by them */
+int Run::ensure_block_buffers(FieldBlocks* fb, BlockDims* bd) {
+    bd->nbx = g.P / kFieldBlockX;
+    bd->nby = (g.NV + kFieldBlockY - 1) / kFieldBlockY;
+    bd->nbz = (g.NZ + kFieldBlockZ - 1) / kFieldBlockZ;
+    bd->nb = std::max(bd->nbx, std::max(bd->nby, bd->nbz));
+    bd->spa = eq.max_per_axis;
+    const size_t nb = (size_t)bd->nbx * bd->nby * bd->nbz;
+    if (nb >= (1ull << 32)) return fail(ctx, MCB_E_CAPACITY, "too many field blocks: split the grid into more z-slabs");
+    if (ctx->cap_fblocks < nb) {
+        cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_bcls); cudaFree(ctx->d_elist);
+        ctx->d_fflags = nullptr; ctx->d_flist = nullptr; ctx->d_bcls = nullptr; ctx->d_elist = nullptr; ctx->cap_fblocks = 0;
+        if (cudaMalloc((void**)&ctx->d_fflags, nb + 16) != cudaSuccess || cudaMalloc((void**)&ctx->d_flist, (nb + 16) * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc((void**)&ctx->d_bcls, nb + 16) != cudaSuccess || cudaMalloc((void**)&ctx->d_elist, (nb + 16) * sizeof(uint32_t)) != cudaSuccess)
+            return fail(ctx, MCB_E_NOMEM, "cudaMalloc of the field-block lists failed");
+        MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb + 16, s)); /* the padding field_list_kernel reads stays zero */
+        ctx->cap_fblocks = nb;
     }
+    const size_t niv = (size_t)3 * bd->spa * bd->nb;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_bounds_iv, &ctx->cap_bounds_iv, niv)) != MCB_OK) return rc;
+    const size_t ncand = (size_t)cg.WC * ((g.M + 3) / 4) * ((g.ke - g.kb + 3) / 4);
+    if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, ncand)) != MCB_OK) return rc;
+    *fb = FieldBlocks{bd->nbx, bd->nby, bd->nbz, ctx->d_fflags, ctx->d_flist};
     return MCB_OK;
 }
 
-/* K2: classification + ambiguity (per tile, independent) -> look-back scan + compaction */
+/* field values + sign words of the listed blocks: the kernel compiled for the equation, or the interpreter */
+int Run::launch_block_eval(const FieldBlocks& fb, const uint32_t* list, const unsigned* count) {
+    const unsigned fill_ctas = (unsigned)ctx->sm_count * 16;
+    int rc;
+    if (ctx->jit_used && ctx->jit_cur && ctx->jit_cur->fill) {
+        struct { float k[MCB_MAX_K]; } consts;
+        std::memcpy(consts.k, eq.grid.k, sizeof consts.k);
+        Grid garg = g;
+        const float* tables = ctx->d_tables;
+        float* F = ctx->d_F;
+        uint32_t* S = ctx->d_S;
+        int nbx = fb.nbx, nby = fb.nby, spa = eq.max_per_axis;
+        void* args[] = {&consts, &garg, &tables, &F, &S, &list, &count, &nbx, &nby, &spa};
+        MCB_CK(cudaLaunchKernel((const void*)ctx->jit_cur->fill, dim3(fill_ctas), dim3(kEvalThreads), args, 0, s));
+    } else {
+        mcb_program launch;
+        bool has_pow;
+        if ((rc = encode_program(launch, has_pow, true)) != MCB_OK) return rc;
+        const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
+        if (has_pow) MCB_LAUNCH((eval_blocks_kernel<true>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, list, count, fb.nbx, fb.nby);
+        else MCB_LAUNCH((eval_blocks_kernel<false>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, list, count, fb.nbx, fb.nby);
+    }
+    launches++;
+    return MCB_OK;
+}
+
+/* K1, block-field mode (MCB_FIELD_SPARSE / MCB_FIELD_AUTO): interval classes per 32 x 4 x 4 vertex block, field values
+ * and signs only in the undecided blocks, the candidate map for classify (mcb_kernels.cuh, "decide, evaluate, skip") */
+int Run::stage_eval_blocks() {
+    FieldBlocks fb;
+    BlockDims bd;
+    int rc = ensure_block_buffers(&fb, &bd);
+    if (rc != MCB_OK) return rc;
+    if (ctx->poison_field) MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
+    ctx->field_is_sparse = true;
+    ctx->jit_used = false;
+    if (jit_wanted(ctx, eq)) {
+        const mcb_ctx::JitKernel* jk = nullptr;
+        rc = jit_module(ctx, eq, &jk);
+        if (rc == MCB_OK) { ctx->jit_used = true; ctx->jit_cur = jk; }
+        else if (ctx->jit == MCB_JIT_ON) return rc;
+        else ctx->jit_note = ctx->err;
+    }
+    const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz;
+    MCB_LAUNCH((axis_bounds_kernel), (unsigned)((3 * bd.spa * bd.nb + 127) / 128), 128, 0, s, ctx->d_tables, g, bd, eq.c.n_axis_slots[0],
+               eq.c.n_axis_slots[1], eq.c.n_axis_slots[2], ctx->d_bounds_iv);
+    MCB_LAUNCH((block_class_kernel), (nblocks + 255) / 256, 256, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->decide_blocks ? 1 : 0, ctx->d_bcls,
+               ctx->d_fflags, ctx->d_elist, ctx->d_S, ctx->d_ctr);
+    const int cjb = (g.M + 3) / 4, ckb = (g.ke - g.kb + 3) / 4;
+    MCB_LAUNCH((cube_cand_kernel), (unsigned)(((size_t)cg.WC * cjb * ckb + 255) / 256), 256, 0, s, ctx->d_bcls, bd, (int)cg.WC, cjb, ckb, ctx->d_cand);
+    launches += 3;
+    if ((rc = launch_block_eval(fb, ctx->d_elist, &ctx->d_ctr->eval_blocks)) != MCB_OK) return rc;
+    return launch_constraints(*this);
+}
+
+/* K2: classification (per tile, independent) -> face-centre tests of the ambiguous cubes -> scan of the tile totals ->
+ * compaction */
 int Run::stage_classify() {
     int rc;
-    MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
-    const ClsScratch sc{ctx->d_tile_list, ctx->d_tile_cnt, ctx->d_tile_nz, cg.tile_rows * cg.WC};
+    MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, kCountersClassifyBytes, s)); /* the evaluation stage's counters stay */
+    uint32_t* tu = ctx->d_tile_u32;
+    const size_t ct = ctx->cap_tiles;
+    const bool skip = ctx->field_is_sparse; /* the candidate map of the block-field mode */
+    const ClsScratch sc{ctx->d_ent, tu, tu + ct, tu + 2 * ct, tu + 3 * ct, tu + 4 * ct, ctx->d_amb, ctx->cap_amb, cg.tile_rows * cg.WC,
+                        skip ? ctx->d_cand : nullptr, (uint32_t)((g.M + 3) / 4)};
     const uint32_t* cw = nullptr;
     if (g.repeat) { /* per-cube iso levels: the corner signs come from the field, item by item */
         const unsigned long long items = (unsigned long long)cg.total_rows * cg.WC;
@@ -973,59 +1052,36 @@ int Run::stage_classify() {
     const bool need_items = want_indexed || ctx->seed_on; /* per-word record index for the weld / the seed walk */
     if (need_items && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
     unsigned long long* items = need_items ? ctx->d_item : nullptr;
+    const unsigned amb_ctas = (unsigned)ctx->sm_count * 2;
 #define MCB_CLASSIFY(HAS_V, REPEAT)                                                                                                   \
     do {                                                                                                                              \
-        MCB_LAUNCH((classify_kernel<HAS_V, REPEAT>), tiles, kClsThreads, kClsSmemBytes, s, eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, \
-                                                                                 ctx->d_status, ctx->d_ctr, ctx->d_F, cw);               \
-        MCB_LAUNCH((compact_kernel<REPEAT>), tiles, kClsThreads, 0, s, eq.point, g, ctx->d_cs, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_status,    \
-                                                             ctx->d_ctr, ctx->d_rec, ctx->d_trioff, ctx->cap_active, items, ctx->d_F, cw); \
+        MCB_LAUNCH((classify_kernel<HAS_V, REPEAT>), tiles, kClsThreads, kClsSmemBytes, s, g, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_ctr, cw); \
+        MCB_LAUNCH((ambiguity_kernel<REPEAT>), amb_ctas, 128, 0, s, eq.point, g, ctx->d_cs, ctx->d_cls, sc, ctx->d_ctr, ctx->d_F);          \
+        MCB_LAUNCH((tile_scan_kernel), 1, 1024, 0, s, sc, tiles, ctx->d_ctr);                                                             \
+        MCB_LAUNCH((compact_kernel<REPEAT>), tiles, kClsThreads, 0, s, g, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_rec, ctx->d_trioff,     \
+                   ctx->cap_active, items, cw);                                                                                        \
     } while (0)
     if (cw) { if (dV) MCB_CLASSIFY(true, true); else MCB_CLASSIFY(false, true); }
     else { if (dV) MCB_CLASSIFY(true, false); else MCB_CLASSIFY(false, false); }
 #undef MCB_CLASSIFY
-    launches += 2;
+    launches += 4;
     return MCB_OK;
 }
 
-/* Sparse-field mode: the field values the later stages read — the corners of the active cubes and their +-1
- * neighbours — are written now, block by block, by the same interpreter (the field is not materialised) */
+/* Block-field mode: the field values the mesh stages read — the corners of the active cubes and their +-1 neighbours
+ * (gradient stencil, the weld's look at neighbouring grid edges) — reach into blocks the interval test decided and the
+ * evaluation therefore skipped.  Those "apron" blocks are written now by the same evaluation kernel (their sign words
+ * come out as the constants they already are). */
 int Run::stage_fill() {
-    int rc;
-    const FieldBlocks shape{g.P / kFieldBlockX, (g.NV + kFieldBlockY - 1) / kFieldBlockY, (g.NZ + kFieldBlockZ - 1) / kFieldBlockZ, nullptr, nullptr};
-    const size_t nb = (size_t)shape.nbx * shape.nby * shape.nbz;
-    if (nb >= (1ull << 32)) return fail(ctx, MCB_E_CAPACITY, "too many field blocks: split the grid into more z-slabs");
-    if (ctx->cap_fblocks < nb) {
-        if (ctx->d_fflags) cudaFree(ctx->d_fflags);
-        if (ctx->d_flist) cudaFree(ctx->d_flist);
-        ctx->d_fflags = nullptr; ctx->d_flist = nullptr; ctx->cap_fblocks = 0;
-        if (cudaMalloc((void**)&ctx->d_fflags, nb + 16) != cudaSuccess || cudaMalloc((void**)&ctx->d_flist, (nb + 16) * sizeof(uint32_t)) != cudaSuccess)
-            return fail(ctx, MCB_E_NOMEM, "cudaMalloc of the field-block list failed");
-        ctx->cap_fblocks = nb;
-    }
-    const FieldBlocks fb{shape.nbx, shape.nby, shape.nbz, ctx->d_fflags, ctx->d_flist};
-    mcb_program launch;
-    bool has_pow;
-    if ((rc = encode_program(launch, has_pow, true)) != MCB_OK) return rc;
-    const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
-    const unsigned fill_ctas = (unsigned)ctx->sm_count * 16;
-    MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb + 16, s)); /* + the padding field_list reads */
+    FieldBlocks fb;
+    BlockDims bd;
+    int rc = ensure_block_buffers(&fb, &bd);
+    if (rc != MCB_OK) return rc;
+    const size_t nb = (size_t)fb.nbx * fb.nby * fb.nbz;
     MCB_LAUNCH((field_flag_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, ctx->d_rec, g, ctx->d_ctr, ctx->cap_active, fb);
     MCB_LAUNCH((field_list_kernel), (unsigned)((nb / 16 + 256) / 256), 256, 0, s, fb, (unsigned)nb, ctx->d_ctr);
-    if (ctx->jit_used && ctx->jit_cur && ctx->jit_cur->fill) { /* the refill kernel NVRTC compiled next to the evaluation kernel */
-        struct { float k[MCB_MAX_K]; } consts;
-        std::memcpy(consts.k, eq.grid.k, sizeof consts.k);
-        Grid garg = g;
-        const float* tables = ctx->d_tables;
-        float* F = ctx->d_F;
-        const uint32_t* list = ctx->d_flist;
-        const unsigned* count = &ctx->d_ctr->field_blocks;
-        int nbx = fb.nbx, nby = fb.nby, spa = eq.max_per_axis;
-        void* args[] = {&consts, &garg, &tables, &F, &list, &count, &nbx, &nby, &spa};
-        MCB_CK(cudaLaunchKernel((const void*)ctx->jit_cur->fill, dim3(fill_ctas), dim3(kEvalThreads), args, 0, s));
-    } else if (has_pow) MCB_LAUNCH((eval_blocks_kernel<true>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
-    else MCB_LAUNCH((eval_blocks_kernel<false>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, fb, ctx->d_ctr);
-    launches += 3;
-    return MCB_OK;
+    launches += 2;
+    return launch_block_eval(fb, ctx->d_flist, &ctx->d_ctr->field_blocks);
 }
 
 /* K6: keep the component of the seed cube (marching.cpp:42-137, 310-331) */
@@ -1196,10 +1252,16 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     cudaStream_t s = ctx->stream;
     uint32_t reruns = 0;
 
+    /* Where the field lives.  Dense: every vertex (the mcb_get_field hook, per-cube iso levels).  Otherwise the
+     * block-field mode: interval proof per 32 x 4 x 4 vertex block, evaluation of the undecided blocks only — decided
+     * from this call's own data, so a first or changed configuration is as fast as a repeated one. */
+    const bool blocks = ctx->field_mode != MCB_FIELD_DENSE && !g.repeat;
+    ctx->ms_compile = 0.f;
+    MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     MCB_CK(cudaEventRecord(ctx->ev[0], s));
     if ((rc = run.stage_tables()) != MCB_OK) return rc;
     MCB_CK(cudaEventRecord(ctx->ev[1], s));
-    if ((rc = run.stage_eval()) != MCB_OK) return rc;
+    if ((rc = blocks ? run.stage_eval_blocks() : run.stage_eval()) != MCB_OK) return rc;
     MCB_CK(cudaEventRecord(ctx->ev[2], s));
     MCB_CK(cudaGetLastError());
 
@@ -1234,6 +1296,15 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
             need_classify = true;
             again = true;
         }
+        if (ctx->h_ctr->amb_n > ctx->cap_amb) { /* more ambiguous cubes than the face-test list holds: counts are provisional */
+            const uint32_t want = ctx->h_ctr->amb_n + ctx->h_ctr->amb_n / 8 + 1024;
+            cudaFree(ctx->d_amb);
+            ctx->d_amb = nullptr; ctx->cap_amb = 0;
+            MCB_CK(cudaMalloc((void**)&ctx->d_amb, (size_t)want * 16));
+            ctx->cap_amb = want;
+            need_classify = true;
+            again = true;
+        }
         if (run.want_soup && needT > ctx->cap_tris) {
             if ((rc = ensure_soup(ctx, needT + needT / 8 + 1024, ctx->normals != 0)) != MCB_OK) return rc;
             again = true;
@@ -1263,9 +1334,7 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     cudaEventElapsedTime(&c.ms_fill, ctx->ev[6], ctx->ev[7]);
     c.ms_classify -= c.ms_fill;
     c.field_mode = ctx->field_is_sparse ? MCB_FIELD_SPARSE : MCB_FIELD_DENSE;
-    c.field_blocks = ctx->field_is_sparse ? ctx->h_ctr->field_blocks : 0;
-    ctx->hint_signature = config_signature(ctx);
-    ctx->hint_active_fraction = c.cubes ? (double)c.active / (double)c.cubes : 1.0;
+    c.field_blocks = ctx->field_is_sparse ? (uint64_t)ctx->h_ctr->field_blocks + ctx->h_ctr->eval_blocks : 0;
     c.jit = ctx->jit_used ? 1u : 0u;
     c.ms_compile = ctx->jit_used ? ctx->ms_compile : 0.f;
     cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);

@@ -69,7 +69,8 @@ const char* const kTail = R"SRC(
 const char* const kHeadBlocks = R"SRC(
 extern "C" __global__ void __launch_bounds__(128, MCB_MIN_BLOCKS)
 mcb_fill_jit(const __grid_constant__ Consts C, const Grid g, const float* __restrict__ tables, float* __restrict__ F,
-             const unsigned int* __restrict__ list, const unsigned int* __restrict__ count, int nbx, int nby, int slots_per_axis) {
+             unsigned int* __restrict__ S, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count, int nbx, int nby,
+             int slots_per_axis) {
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * 4, n = *count;
     for (unsigned b = blockIdx.x * 4 + (threadIdx.x >> 5); b < n; b += nwarps) {
@@ -78,6 +79,14 @@ mcb_fill_jit(const __grid_constant__ Consts C, const Grid g, const float* __rest
         const int xc = bx * 32 + lane, y0 = by * 4, z0 = bz * 4 + g.kb;
 )SRC";
 const char* const kTailBlocks = R"SRC(
+        unsigned int mine = 0; /* lane 4 r + q keeps the sign word of row r, plane q (as eval_blocks_kernel) */
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const unsigned int wv = __ballot_sync(0xffffffffu, RESULT[e] > g.iso);
+            if (lane == e) mine = wv;
+        }
+        if (lane < 16 && y0 + (lane >> 2) < g.NV && bz * 4 + (lane & 3) < g.NZ)
+            S[((size_t)(bz * 4 + (lane & 3)) * g.NV + (y0 + (lane >> 2))) * g.WP + bx] = mine;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             if (y0 + r >= g.NV) break;
@@ -85,36 +94,6 @@ const char* const kTailBlocks = R"SRC(
             for (int q = 0; q < 4; q++)
                 if (bz * 4 + q < g.NZ) F[((size_t)(bz * 4 + q) * g.NV + (y0 + r)) * g.P + xc] = RESULT[4 * r + q];
         }
-#undef RESULT
-    }
-}
-)SRC";
-
-/* Signs only (sparse-field mode): nothing has to stay in registers, so a warp streams a 128-column x 16-row tile row
- * by row — 4 values per lane at a time — and the per-tile prologue is shared by four times as many vertices.  The
- * compiler hoists what does not depend on the row (x and z operands and their combinations). */
-const char* const kHeadSigns = R"SRC(
-extern "C" __global__ void __launch_bounds__(128, MCB_MIN_BLOCKS)
-mcb_signs_jit(const __grid_constant__ Consts C, const Grid g, const float* __restrict__ tables, float* __restrict__ F,
-              unsigned int* __restrict__ S, int row_groups /* of 16 rows */, int slots_per_axis) {
-    const int lane = threadIdx.x & 31;
-    const int cx = (int)blockIdx.x;
-    const int yq = (int)blockIdx.y * 4 + (threadIdx.x >> 5);
-    const int pz = (int)blockIdx.z;
-    if (yq >= row_groups) return;
-    const int x0 = cx * 128 + lane, y0 = yq * 16, zi = pz + g.kb;
-    unsigned int* sw = S + ((size_t)pz * g.NV + y0) * g.WP + cx * 4;
-)SRC";
-const char* const kSignsRowOpen = R"SRC(
-MCB_ROW_UNROLL
-    for (int r = 0; r < 16; r++) {
-        if (y0 + r >= g.NV) break;
-)SRC";
-const char* const kTailSigns = R"SRC(
-        unsigned int w[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) w[q] = __ballot_sync(0xffffffffu, RESULT[q] > g.iso);
-        if (lane == 0) *reinterpret_cast<uint4*>(sw + (size_t)r * g.WP) = make_uint4(w[0], w[1], w[2], w[3]);
 #undef RESULT
     }
 }
@@ -160,11 +139,11 @@ Nvrtc& nvrtc() {
 
 } /* namespace */
 
-static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane + field, 1 plane signs only, 2 blocks */, bool* has_pow, std::string* err) {
-    const bool blocks = kind == 2, stream = kind == 1;
-    const char* const N = stream ? "4" : "16";   /* values per lane alive at a time */
-    const char* const I = stream ? "q" : "e";    /* their index variable */
-    std::ostringstream loads, rowloads, body;
+static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane tiles (dense field), 1 listed 32 x 4 x 4 blocks */, bool* has_pow, std::string* err) {
+    const bool blocks = kind == 1;
+    const char* const N = "16";   /* values per lane */
+    const char* const I = "e";    /* their index variable */
+    std::ostringstream loads, body;
     bool pow = false;
     /* operand fetches, one declaration per distinct (axis, slot): exactly the loads of eval_step / LeafOperand */
     bool seen[3][256] = {};
@@ -185,10 +164,6 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
                 else
                     std::snprintf(d, sizeof d, "    const float* pz%u = tables + (size_t)(2 * slots_per_axis + %u) * g.P + z0;\n"
                                   "    const float tz%u[4] = {__ldg(pz%u), __ldg(pz%u + 1), __ldg(pz%u + 2), __ldg(pz%u + 3)};\n", arg, arg, arg, arg, arg, arg, arg);
-            } else if (stream && axis == 1) { /* one row at a time: the row's entry, the same for the whole warp */
-                std::snprintf(d, sizeof d, "        const float ty%u = __ldg(tables + (size_t)(1 * slots_per_axis + %u) * g.P + y0 + r);\n", arg, arg);
-                rowloads << d;
-                d[0] = 0;
             } else if (axis == 0)
                 std::snprintf(d, sizeof d, "    const float* px%u = tables + (size_t)(0 * slots_per_axis + %u) * g.P + x0;\n"
                               "    const float tx%u[4] = {__ldg(px%u), __ldg(px%u + 32), __ldg(px%u + 64), __ldg(px%u + 96)};\n", arg, arg, arg, arg, arg, arg, arg);
@@ -199,8 +174,8 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
                 std::snprintf(d, sizeof d, "    const float tz%u = __ldg(tables + (size_t)(2 * slots_per_axis + %u) * g.P + zi);\n", arg, arg);
             loads << d;
         }
-        if (axis == 0) std::snprintf(buf, sizeof buf, blocks ? "tx%u" : stream ? "tx%u[q]" : "tx%u[Q(e)]", arg);
-        else if (axis == 1) std::snprintf(buf, sizeof buf, stream ? "ty%u" : "ty%u[R(e)]", arg);
+        if (axis == 0) std::snprintf(buf, sizeof buf, blocks ? "tx%u" : "tx%u[Q(e)]", arg);
+        else if (axis == 1) std::snprintf(buf, sizeof buf, "ty%u[R(e)]", arg);
         else std::snprintf(buf, sizeof buf, blocks ? "tz%u[Q(e)]" : "tz%u", arg);
         return buf;
     };
@@ -252,21 +227,6 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
     if (acc.empty() || !stack.empty()) { *err = "program does not leave exactly one value"; return std::string(); }
     if (has_pow) *has_pow = pow;
     std::string src;
-    if (stream) {
-        /* measured at 1024^3: unrolling the row loop by 4 is the sweet spot for programs without `^` (sphere 0.29 ms; 0.33 ms
-         * with the 4-row register tile, 0.36 ms fully unrolled); programs with `^` keep it rolled — every unrolled copy
-         * would inline the power's fast path again (torus 1.37 -> 1.23 ms) */
-        src = pow ? "#define MCB_ROW_UNROLL _Pragma(\"unroll 1\")\n" : "#define MCB_ROW_UNROLL _Pragma(\"unroll 4\")\n";
-        src += kHeadSigns;
-        src += loads.str();
-        src += kSignsRowOpen;
-        src += rowloads.str();
-        src += body.str();
-        src += "#define RESULT " + acc + "\n";
-        src += kTailSigns;
-        src += "#undef MCB_ROW_UNROLL\n";
-        return src;
-    }
     src = blocks ? "" : "#define MCB_KERNEL_NAME mcb_eval_jit\n#define MCB_STORE_F 1\n";
     src += blocks ? kHeadBlocks : kHeadPlane;
     src += loads.str();
@@ -278,10 +238,11 @@ static std::string generate_one(const uint32_t* code, int n, int kind /* 0 plane
 }
 
 std::string generate(const uint32_t* code, int n, bool* has_pow, std::string* err) {
-    /* one translation unit, three kernels: mcb_eval_jit (plane tiles, field + signs), mcb_signs_jit (signs only) and
-     * mcb_fill_jit (the blocks of the sparse-field mode) — one compile per equation whatever mode runs later */
+    /* one translation unit, two kernels: mcb_eval_jit (plane tiles: the whole field + signs, MCB_FIELD_DENSE) and
+     * mcb_fill_jit (listed 32 x 4 x 4 vertex blocks: field + signs, the block-field mode) — one compile per equation
+     * whatever mode runs later */
     std::string out = kHead;
-    for (int kind = 0; kind < 3; kind++) {
+    for (int kind = 0; kind < 2; kind++) {
         const std::string part = generate_one(code, n, kind, has_pow, err);
         if (part.empty()) return part;
         out += part;

@@ -29,9 +29,11 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "mcb_bytecode.h"
+#include "mcb_interval.h"
 #include "mcb_launch.h"
 #include "mcb_tables.h"
 
@@ -91,9 +93,12 @@ struct Counters {
     unsigned long long seed_active, seed_triangles; /* seed mode: counts of the kept component */
     unsigned int tile_ticket;
     unsigned int error; /* 2 = 2^31 or more triangles in the slab */
-    unsigned int field_blocks, pad_; /* sparse-field mode: 32 x 4 x 4 vertex blocks the field was written in */
+    unsigned int field_blocks, amb_n; /* blocks the apron refill wrote; ambiguous cubes appended to the face-test list */
     unsigned long long nh_vertices, nh_triangles; /* what the normal.h stage works on: the mesh, or nothing when it is truncated */
+    /* ---- everything above is reset before every classify pass; what follows belongs to the evaluation stage ---- */
+    unsigned int eval_blocks, pad2_; /* block-field mode: 32 x 4 x 4 vertex blocks the interval test could not decide */
 };
+constexpr size_t kCountersClassifyBytes = offsetof(Counters, eval_blocks);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K0a  fold_constants: evaluate every maximal constant subtree once (same interpreter, same arithmetic as the
@@ -368,15 +373,16 @@ struct FieldBlocks {
 template <bool HAS_POW>
 __global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
 eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
-                   float* __restrict__ F, const FieldBlocks fb, const Counters* __restrict__ ctr) {
+                   float* __restrict__ F, uint32_t* __restrict__ S, const uint32_t* __restrict__ list,
+                   const unsigned* __restrict__ count, int nbx, int nby) {
     MCB_DYNAMIC_SMEM(float, stack_smem);
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * (kEvalThreads / 32);
-    const unsigned n = ctr->field_blocks;
+    const unsigned n = *count;
     for (unsigned b = blockIdx.x * (kEvalThreads / 32) + (threadIdx.x >> 5); b < n; b += nwarps) {
-        const uint32_t id = fb.list[b];
-        const int bx = (int)(id % (unsigned)fb.nbx), by = (int)(id / (unsigned)fb.nbx % (unsigned)fb.nby);
-        const int bz = (int)(id / ((unsigned)fb.nbx * (unsigned)fb.nby));
+        const uint32_t id = list[b];
+        const int bx = (int)(id % (unsigned)nbx), by = (int)(id / (unsigned)nbx % (unsigned)nby);
+        const int bz = (int)(id / ((unsigned)nbx * (unsigned)nby));
         EvalLane L;
         L.tables = tables;
         L.x0 = bz * kFieldBlockZ + g.kb; /* class 1: the z tables, consecutive planes */
@@ -384,6 +390,12 @@ eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const
         L.zi = bx * kFieldBlockX + lane; /* class 3: the x tables, this lane's column */
         float acc[kEvalRows];
         eval_run<HAS_POW, 1>(prog, L, acc, stack_smem + threadIdx.x);
+        uint32_t mine = 0; /* lane 4 r + q keeps the sign word of row r, plane q: bit = this column's value > iso */
+#pragma unroll
+        for (int e = 0; e < kEvalRows; e++) {
+            const uint32_t wv = __ballot_sync(0xffffffffu, acc[e] > g.iso);
+            if (lane == e) mine = wv;
+        }
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int y = L.y0 + r;
@@ -393,6 +405,10 @@ eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const
                 const int pz = bz * kFieldBlockZ + q;
                 if (pz < g.NZ) F[((size_t)pz * g.NV + y) * g.P + L.zi] = acc[4 * r + q];
             }
+        }
+        if (lane < kEvalRows) {
+            const int y = L.y0 + (lane >> 2), pz = bz * kFieldBlockZ + (lane & 3);
+            if (y < g.NV && pz < g.NZ) S[((size_t)pz * g.NV + y) * g.WP + bx] = mine;
         }
     }
 }
@@ -409,10 +425,13 @@ field_flag_kernel(const unsigned long long* __restrict__ rec, const Grid g, cons
         const int bx0 = i >> 5, bx1 = (i + 3) >> 5, by0 = j >> 2, by1 = (j + 3) >> 2, bz0 = pz >> 2, bz1 = (pz + 3) >> 2;
         for (int bz = bz0; bz <= bz1; bz++)
             for (int by = by0; by <= by1; by++)
-                for (int bx = bx0; bx <= bx1; bx++) fb.flags[((size_t)bz * fb.nby + by) * fb.nbx + bx] = 1;
+                for (int bx = bx0; bx <= bx1; bx++) {
+                    uint8_t* f = fb.flags + ((size_t)bz * fb.nby + by) * fb.nbx + bx;
+                    if (*f == 0) *f = 1; /* 2 = already evaluated (block_class_kernel); racing writers all store 1 */
+                }
     }
 }
-/* flags -> list of flagged block ids (any order).  A thread takes 16 flags (one 16-byte load; the flag array is padded
+/* flags == 1 -> list of the flagged, not yet evaluated block ids (any order).  A thread takes 16 flags (one 16-byte load; the flag array is padded
  * and zero-filled to a multiple of 16), a warp reserves its entries with one atomic. */
 __global__ void __launch_bounds__(256)
 field_list_kernel(const FieldBlocks fb, unsigned nblocks, Counters* __restrict__ ctr) {
@@ -425,7 +444,7 @@ field_list_kernel(const FieldBlocks fb, unsigned nblocks, Counters* __restrict__
 #pragma unroll
     for (int q = 0; q < 4; q++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) bits |= ((w[q] >> (8 * b)) & 0xffu) ? 1u << (4 * q + b) : 0u;
+        for (int b = 0; b < 4; b++) bits |= ((w[q] >> (8 * b)) & 0xffu) == 1u ? 1u << (4 * q + b) : 0u;
     const uint32_t mine = (uint32_t)__popc(bits);
     uint32_t inc = mine;
 #pragma unroll
@@ -440,6 +459,112 @@ field_list_kernel(const FieldBlocks fb, unsigned nblocks, Counters* __restrict__
         bits &= bits - 1;
         fb.list[base++] = g16 * 16u + (unsigned)i;
     }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K1 (block-field mode, the default of the drop-in): decide, evaluate, skip.
+ *   axis_bounds   minimum and maximum of every axis table over each 32-column / 4-row / 4-plane block of its axis;
+ *   block_class   one thread per 32 x 4 x 4 vertex block runs the fused grid program on those intervals
+ *                 (mcb_interval.h: an exact proof, rounding included).  A block proven to lie entirely on one side of
+ *                 the iso value gets its sixteen sign words written as constants and is never evaluated; the others
+ *                 ("unknown") are appended to the evaluation list, which eval_blocks_kernel / mcb_fill_jit turn into
+ *                 field values and sign words;
+ *   cube_cand     one byte per 32 x 4 x 4 CUBE block: can it contain an active cube, i.e. is one of the (up to) eight
+ *                 vertex blocks its corners touch unknown, or do they differ in their proven sign?  classify skips the
+ *                 rest of the grid four cube rows at a time.
+ * The work of a polygonisation is then proportional to the surface, not to the grid, for any equation — no earlier
+ * run of the same configuration is needed to find that out.
+ * ------------------------------------------------------------------------------------------------------------- */
+struct BlockDims {
+    int nbx, nby, nbz; /* vertex blocks per axis: P/32, ceil(NV/4), ceil(NZ/4) */
+    int nb;            /* max of the three: stride of the bounds arrays */
+    int spa;           /* table slots per axis */
+};
+__global__ void __launch_bounds__(128)
+axis_bounds_kernel(const float* __restrict__ tables, const Grid g, const BlockDims bd, int nsx, int nsy, int nsz,
+                   mcb_ival* __restrict__ B) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * bd.spa * bd.nb) return;
+    const int b = idx % bd.nb, slot = (idx / bd.nb) % bd.spa, axis = idx / (bd.nb * bd.spa);
+    const int ns = axis == 0 ? nsx : axis == 1 ? nsy : nsz, nbk = axis == 0 ? bd.nbx : axis == 1 ? bd.nby : bd.nbz;
+    if (slot >= ns || b >= nbk) return;
+    int i0, i1; /* table entries of this block: x columns, y rows, or the slab's planes (vertex kb-1+pz at entry kb+pz) */
+    if (axis == 0) { i0 = b * kFieldBlockX; i1 = i0 + kFieldBlockX; }
+    else if (axis == 1) { i0 = b * kFieldBlockY; i1 = min(i0 + kFieldBlockY, g.NV); }
+    else { i0 = g.kb + b * kFieldBlockZ; i1 = g.kb + min(b * kFieldBlockZ + kFieldBlockZ, g.NZ); }
+    const float* t = tables + ((size_t)axis * bd.spa + slot) * g.P;
+    float lo = __ldg(t + i0), hi = lo;
+    bool ok = mcb_iv_finite(lo) != 0;
+    for (int i = i0 + 1; i < i1; i++) {
+        const float v = __ldg(t + i);
+        ok = ok && mcb_iv_finite(v);
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    mcb_ival r;
+    r.lo = ok ? lo : -INFINITY;
+    r.hi = ok ? hi : INFINITY;
+    B[idx] = r;
+}
+
+__global__ void __launch_bounds__(256)
+block_class_kernel(const __grid_constant__ mcb_program prog /* fused grid program, slot numbers as arguments */, const Grid g,
+                   const BlockDims bd, const mcb_ival* __restrict__ B, int decide /* 0: every block is "unknown" (tests) */,
+                   uint8_t* __restrict__ cls, uint8_t* __restrict__ flags, uint32_t* __restrict__ list,
+                   uint32_t* __restrict__ S, Counters* __restrict__ ctr) {
+    const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int c = 0;
+    int bx = 0, by = 0, bz = 0;
+    if (idx < nblocks) {
+        bx = (int)(idx % (unsigned)bd.nbx); by = (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nby);
+        bz = (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nby));
+        if (decide) c = mcb_interval_class(prog.code, prog.n, prog.k, B, bd.spa, bd.nb, bx, by, bz, g.iso, nullptr);
+        cls[idx] = (uint8_t)c;
+        flags[idx] = c == 0 ? 2 : 0; /* 2 = on the evaluation list; the apron refill later turns some 0 into 1 */
+    }
+    const bool unknown = idx < nblocks && c == 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, unknown);
+    if (m) { /* a warp reserves its list entries with one atomic */
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&ctr->eval_blocks, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (unknown) list[base + __popc(m & ((1u << lane) - 1u))] = idx;
+    }
+    if (idx < nblocks && c != 0) {
+        const uint32_t word = c == 2 ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int q = 0; q < kFieldBlockZ; q++) {
+            const int pz = bz * kFieldBlockZ + q;
+            if (pz >= g.NZ) break;
+#pragma unroll
+            for (int r = 0; r < kFieldBlockY; r++) {
+                const int y = by * kFieldBlockY + r;
+                if (y < g.NV) S[((size_t)pz * g.NV + y) * g.WP + bx] = word;
+            }
+        }
+    }
+}
+
+/* cube (i, j, kz) reads the stored vertices (i+1..i+2, j+1..j+2, kz+1..kz+2): cube block (w, jb, kq) touches vertex
+ * blocks {w, w+1} x {jb, jb+1} x {kq, kq+1} (those that exist) */
+__global__ void __launch_bounds__(256)
+cube_cand_kernel(const uint8_t* __restrict__ cls, const BlockDims bd, int WC, int cjb, int ckb, uint8_t* __restrict__ cand) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)WC * (unsigned)cjb * (unsigned)ckb) return;
+    const int w = (int)(idx % (unsigned)WC), jb = (int)(idx / (unsigned)WC % (unsigned)cjb), kq = (int)(idx / ((unsigned)WC * (unsigned)cjb));
+    int first = -1;
+    bool can = false;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const int bx = w + (d & 1), by = jb + ((d >> 1) & 1), bz = kq + (d >> 2);
+        if (bx >= bd.nbx || by >= bd.nby || bz >= bd.nbz) continue;
+        const int c = (int)cls[((size_t)bz * bd.nby + by) * bd.nbx + bx];
+        if (first < 0) first = c;
+        can = can || c == 0 || c != first;
+    }
+    cand[idx] = can ? 1 : 0;
 }
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
@@ -466,8 +591,8 @@ eval_constraint_kernel(const __grid_constant__ mcb_program prog, const Grid g, c
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K2  classify + compact: sign bit-planes -> cube codes -> ambiguity redirect -> per-cube triangle counts ->
- *     device-wide exclusive scan (decoupled look-back) of (active cubes, triangles) -> compacted, loop-ordered
- *     active-cube records with their triangle offsets.
+ *     device-wide exclusive scan of (active cubes, triangles) -> compacted, loop-ordered active-cube records with
+ *     their triangle offsets.
  *
  *     Work item = one 32-cube word of a cube row; items are numbered in the reference's loop order (z slowest,
  *     then y, then x).  A tile is a run of whole cube rows (<= kClsItemCap items).
@@ -475,20 +600,22 @@ eval_constraint_kernel(const __grid_constant__ mcb_program prog, const Grid g, c
  *     classify_kernel (one block per tile, no dependency between tiles):
  *       A  every thread walks one word column down a strip of rows, carrying the sign words of the vertex row it
  *          shares with the next cube row (4 loads and ~30 instructions per 32 cubes), and sets a bit in a
- *          shared-memory bitmap for every item that has an active cube.  This is the only work done per voxel;
- *          everything below is proportional to the surface.
+ *          shared-memory bitmap for every item that has an active cube.  With the candidate map of the block-field
+ *          mode (cube_cand_kernel) it steps over four cube rows at a time wherever the interval test has already
+ *          proven that no sign changes: this is the only work done per voxel, and it is then done per 128 voxels;
  *       B  the bitmap is turned into the list of active items in loop order (popc + block scan);
- *       C1 one lane per ACTIVE item: rebuild its corner words, per cube code -> ambiguity face test
- *          (marching.cpp:521-549) -> triangle count.  The list, the per-item counts and the tile aggregate go to
- *          global scratch; the aggregate is the tile's look-back status word
- *              [63:62] 0 = nothing yet, 1 = tile aggregate, 2 = inclusive prefix  [61:31] triangles  [30:0] active
- *     compact_kernel (tiles by atomic ticket):
- *       S  warp 0 runs the decoupled look-back over the status words (single 8-byte accesses, no fence between
- *          value and flag) and publishes the tile's inclusive prefix at once — all the expensive, data-dependent
- *          work (face-centre evaluations) happened in classify_kernel, so a slow tile never stalls the chain;
- *          the other warps meanwhile scan the tile's per-item counts in chunks of 32;
- *       C2 one lane per active item: packed shuffle scan inside the chunk, then the records are written in loop
- *          order at tile base + chunk base + lane offset.
+ *       C1 one lane per ACTIVE item: rebuild its corner words, per cube code -> triangle count.  A cube whose code
+ *          has a redirect entry (marching_lookup.h:329-587) is counted with its own row for now and appended to the
+ *          ambiguity list.  One 64-bit entry per active item goes to global scratch:
+ *              [5:0] active cubes  [13:6] triangles  [26:14] tile-local item  [63:32] redirected cubes (bit per cube)
+ *     ambiguity_kernel (one thread per listed cube): the face-centre test of marching.cpp:521-549 — one evaluation of
+ *          the field — and, when it redirects, the bit in the item's entry and the triangle-count difference of row
+ *          255-code, applied to the entry and to the tile total with atomics.  Dense lanes: a tile with one
+ *          ambiguous cube no longer holds up a whole block, and the test is evaluated once, not twice.
+ *     tile_scan_kernel (one block): exclusive scan of the per-tile totals; grand totals to the counters.
+ *     compact_kernel (one block per tile; tiles without an active item leave at once):
+ *       C2 per chunk of 32 list entries a packed shuffle scan, then one lane per active item writes its cubes'
+ *          records in loop order at tile base + chunk base + lane offset.
  * ------------------------------------------------------------------------------------------------------------- */
 constexpr int kClsWarps = kClsThreads / 32;
 constexpr int kClsItemCap = 8192; /* items per tile: bitmap 1 KB + active-item list 16 KB of shared memory */
@@ -506,13 +633,6 @@ struct ClsGeom {
 };
 /* floor(n / d) for n * d < 2^32 (tile-local indices), inv = ceil(2^32 / d) */
 __device__ __forceinline__ uint32_t div_small(uint32_t n, uint32_t inv) { return inv ? __umulhi(n, inv) : n; }
-
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
-    return *(const volatile unsigned long long*)p;
-}
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
-    *(volatile unsigned long long*)p = v;
-}
 
 struct ClsTables { /* built once per context on the host (mcb_tables.h); read through the read-only path */
     uint64_t tri[256];
@@ -634,19 +754,29 @@ __device__ __forceinline__ void view_item(ItemView& it, uint32_t item_local, uin
     if (V != nullptr && it.m) it.m &= valid_mask(V, idx, (uint32_t)g.WP, plane);
 }
 
-struct ClsScratch {        /* global scratch handed from classify_kernel to compact_kernel */
-    uint16_t* list;        /* [tiles][tile_items]  active items of the tile, loop order (tile-local item index) */
-    uint16_t* cnt;         /* [tiles][tile_items]  active cubes | triangles << 6 of list entry k */
-    uint32_t* nz;          /* [tiles]              number of list entries */
-    uint32_t tile_items;   /* tile_rows * WC */
+struct ClsScratch {          /* global scratch handed from classify_kernel to ambiguity / tile_scan / compact */
+    unsigned long long* ent; /* [tiles][tile_items]  one entry per active item of the tile, loop order (layout above) */
+    uint32_t* nz;            /* [tiles]  number of entries */
+    uint32_t* tile_a;        /* [tiles]  active cubes of the tile */
+    uint32_t* tile_t;        /* [tiles]  triangles of the tile (ambiguity_kernel corrects it) */
+    uint32_t* base_a;        /* [tiles]  exclusive prefixes (tile_scan_kernel) */
+    uint32_t* base_t;
+    unsigned long long* amb; /* [cap_amb][2]  entry index | bit << 40 | face << 45 | code << 48 ;  i | j << 12 | k << 24 */
+    uint32_t cap_amb;
+    uint32_t tile_items;     /* tile_rows * WC */
+    const uint8_t* cand;     /* [ckb][cjb][WC] cube blocks that may hold an active cube, or nullptr: look everywhere */
+    uint32_t cjb;            /* ceil(M / 4) */
 };
+#define MCB_ENT_NA(e) ((uint32_t)(e) & 63u)
+#define MCB_ENT_NT(e) (((uint32_t)(e) >> 6) & 255u)
+#define MCB_ENT_ITEM(e) (((uint32_t)(e) >> 14) & 8191u)
+#define MCB_ENT_RED(e) ((uint32_t)((e) >> 32))
 
 template <bool HAS_V, bool REPEAT /* repeating-surface mode: corner words from Cw instead of the sign planes */>
 __global__ void __launch_bounds__(kClsThreads, 4)
-classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
-                const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
-                const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status, Counters* __restrict__ ctr,
-                const float* __restrict__ F, const uint32_t* __restrict__ Cw /* repeating-surface mode: corner words, else nullptr */) {
+classify_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
+                const ClsGeom q, const ClsScratch sc, Counters* __restrict__ ctr,
+                const uint32_t* __restrict__ Cw /* repeating-surface mode: corner words, else nullptr */) {
     MCB_DYNAMIC_SMEM(uint32_t, cls_smem);
     uint32_t* bitmap = cls_smem;                                          /* [kClsChunkCap] one bit per item */
     uint16_t* list = reinterpret_cast<uint16_t*>(cls_smem + kClsChunkCap); /* [kClsItemCap] active items, loop order */
@@ -682,12 +812,26 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
             }
             while (r < r_end) {
                 uint32_t idx = ((kz + 1u) * (uint32_t)g.NV + (j + 1u)) * WP + w;
-                uint32_t lo[4];
-                vertex_row_words(S, idx, plane, lo);
-                uint32_t any_lo = lo[0] | lo[1] | lo[2] | lo[3], all_lo = lo[0] & lo[1] & lo[2] & lo[3];
                 const uint32_t n = min(r_end - r, M - j); /* rows left in this strip and in this plane */
-#pragma unroll 4
-                for (uint32_t t = 0; t < n; t++) {
+                const uint8_t* cand_row = sc.cand ? sc.cand + (size_t)(kz >> 2) * sc.cjb * q.WC + w : nullptr;
+                uint32_t any_lo = 0, all_lo = 0;
+                bool have_lo = false, look = true;
+                uint32_t t = 0;
+                while (t < n) {
+                    const uint32_t jj = j + t;
+                    if (cand_row != nullptr && (t == 0 || (jj & 3u) == 0u)) look = cand_row[(size_t)(jj >> 2) * q.WC] != 0;
+                    if (!look) { /* proven: no cube of these (up to) four rows of this word column is active */
+                        const uint32_t skip = min(4u - (jj & 3u), n - t);
+                        t += skip; idx += skip * WP; item += skip * q.WC;
+                        have_lo = false;
+                        continue;
+                    }
+                    if (!have_lo) {
+                        uint32_t lo[4];
+                        vertex_row_words(S, idx, plane, lo);
+                        any_lo = lo[0] | lo[1] | lo[2] | lo[3]; all_lo = lo[0] & lo[1] & lo[2] & lo[3];
+                        have_lo = true;
+                    }
                     uint32_t hi[4];
                     vertex_row_words(S, idx + WP, plane, hi);
                     const uint32_t any_hi = hi[0] | hi[1] | hi[2] | hi[3], all_hi = hi[0] & hi[1] & hi[2] & hi[3];
@@ -697,6 +841,7 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
                     any_lo = any_hi; all_lo = all_hi;
                     idx += WP;
                     item += q.WC;
+                    t++;
                 }
                 r += n;
                 j = 0; kz++; /* only reached again when the strip continues on the next plane */
@@ -736,11 +881,14 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
         }
     }
     __syncthreads();
+    if (nz == 0) { /* uniform per block: most tiles of a sparse surface end here */
+        if (threadIdx.x == 0) { sc.nz[tile] = 0; sc.tile_a[tile] = 0; sc.tile_t[tile] = 0; }
+        return;
+    }
 
-    /* ---- C1: per active item: cube codes, ambiguity, triangle counts ------------------------------------------ */
-    uint16_t* glist = sc.list + (size_t)tile * sc.tile_items;
-    uint16_t* gcnt = sc.cnt + (size_t)tile * sc.tile_items;
-    uint32_t n_amb = 0, n_red = 0, sum_a = 0, sum_t = 0;
+    /* ---- C1: per active item: cube codes, triangle counts, the ambiguity list ---------------------------------- */
+    unsigned long long* gent = sc.ent + (size_t)tile * sc.tile_items;
+    uint32_t sum_a = 0, sum_t = 0;
     for (uint32_t kb = (uint32_t)warp * 32u; kb < nz; kb += kClsThreads) {
         const uint32_t k = kb + (uint32_t)lane;
         if (k < nz) {
@@ -752,103 +900,114 @@ classify_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, co
             while (mm) {
                 const int b = __ffs(mm) - 1;
                 mm &= mm - 1;
-                int code = code_of(it.c, b);
+                const int code = code_of(it.c, b);
                 const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
-                if (face >= 0) {
-                    n_amb++;
-                    const int ci = (int)it.w * 32 + b, cj = (int)it.j, ck = (int)it.kz + g.kb;
-                    if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, REPEAT ? cube_level(g, F, ci, cj, ck) : g.iso)) {
-                        code = 255 - code;
-                        n_red++;
+                if (face >= 0) { /* marching.cpp:521-549: decided by ambiguity_kernel */
+                    const uint32_t slot = atomicAdd(&ctr->amb_n, 1u);
+                    if (slot < sc.cap_amb) {
+                        sc.amb[2 * (size_t)slot] = ((unsigned long long)tile * sc.tile_items + k) | ((unsigned long long)b << 40) |
+                                                   ((unsigned long long)face << 45) | ((unsigned long long)code << 48);
+                        sc.amb[2 * (size_t)slot + 1] = (unsigned long long)(it.w * 32 + b) | ((unsigned long long)it.j << 12) |
+                                                       ((unsigned long long)(it.kz + g.kb) << 24);
                     }
                 }
                 nt += __ldg(gtb->ntri + code);
             }
-            glist[k] = (uint16_t)item_local;
-            gcnt[k] = (uint16_t)(na | (nt << 6)); /* na <= 32, nt <= 160 */
+            gent[k] = (unsigned long long)(na | (nt << 6) | (item_local << 14)); /* na <= 32, nt <= 160, item < 8192 */
             sum_a += na; sum_t += nt;
         }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) { sum_a += __shfl_xor_sync(0xffffffffu, sum_a, d); sum_t += __shfl_xor_sync(0xffffffffu, sum_t, d); }
     if (lane == 0) { warp_x[warp] = sum_a; warp_y[warp] = sum_t; }
-    if (__any_sync(0xffffffffu, n_amb != 0)) { /* statistics: one atomic per warp, only when needed */
-        uint32_t sa = n_amb, sr = n_red;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, d); sr += __shfl_xor_sync(0xffffffffu, sr, d); }
-        if (lane == 0) { atomicAdd(&ctr->ambiguous, (unsigned long long)sa); if (sr) atomicAdd(&ctr->redirected, (unsigned long long)sr); }
-    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long ta = 0, tt = 0;
+        uint32_t ta = 0, tt = 0;
 #pragma unroll
         for (int w2 = 0; w2 < kClsWarps; w2++) { ta += warp_x[w2]; tt += warp_y[w2]; }
         sc.nz[tile] = nz;
-        status[tile] = (1ull << 62) | (tt << 31) | ta; /* tile aggregate: < 2^19 cubes, < 2^22 triangles */
+        sc.tile_a[tile] = ta;                  /* < 2^19 cubes */
+        sc.tile_t[tile] = tt;                  /* ambiguity_kernel corrects it afterwards */
+    }
+}
+
+/* One thread per ambiguous cube: the face-centre test, evaluated once. */
+template <bool REPEAT>
+__global__ void __launch_bounds__(128)
+ambiguity_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
+                 const ClsTables* __restrict__ gtb, const ClsScratch sc, Counters* __restrict__ ctr, const float* __restrict__ F) {
+    const uint32_t n = min(ctr->amb_n, sc.cap_amb);
+    uint32_t redirected = 0;
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const unsigned long long e0 = sc.amb[2 * (size_t)a], e1 = sc.amb[2 * (size_t)a + 1];
+        const unsigned long long entry = e0 & ((1ull << 40) - 1ull);
+        const int b = (int)((e0 >> 40) & 31u), face = (int)((e0 >> 45) & 7u), code = (int)((e0 >> 48) & 255u);
+        const int ci = (int)(e1 & 0xFFFu), cj = (int)((e1 >> 12) & 0xFFFu), ck = (int)((e1 >> 24) & 0xFFFu);
+        if (!ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, REPEAT ? cube_level(g, F, ci, cj, ck) : g.iso)) continue;
+        redirected++;
+        const int delta = (int)__ldg(gtb->ntri + (255 - code)) - (int)__ldg(gtb->ntri + code);
+        /* one atomic sets the cube's redirect bit and moves the item's triangle count: the count field cannot underflow,
+         * every partial sum of corrections is at least minus the triangles counted for those cubes */
+        atomicAdd(sc.ent + entry, (1ull << (32 + b)) + (unsigned long long)((long long)delta * 64));
+        if (delta) atomicAdd(sc.tile_t + entry / sc.tile_items, (uint32_t)delta);
+    }
+    if (redirected) atomicAdd(&ctr->redirected, (unsigned long long)redirected);
+}
+
+/* Exclusive scan of the per-tile totals: a few thousand tiles, one block.  Grand totals -> counters. */
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const ClsScratch sc, uint32_t tiles, Counters* __restrict__ ctr) {
+    __shared__ unsigned long long warp_a[32], warp_t[32];
+    __shared__ unsigned long long carry_a, carry_t;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) { carry_a = 0; carry_t = 0; }
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < tiles; b0 += 1024) {
+        const uint32_t i = b0 + t;
+        const unsigned long long va = i < tiles ? sc.tile_a[i] : 0ull, vt = i < tiles ? sc.tile_t[i] : 0ull;
+        unsigned long long ia = va, it = vt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long ua = __shfl_up_sync(0xffffffffu, ia, d), ut = __shfl_up_sync(0xffffffffu, it, d);
+            if (lane >= d) { ia += ua; it += ut; }
+        }
+        if (lane == 31) { warp_a[warp] = ia; warp_t[warp] = it; }
+        __syncthreads();
+        unsigned long long ba = carry_a, bt = carry_t;
+        for (int w2 = 0; w2 < warp; w2++) { ba += warp_a[w2]; bt += warp_t[w2]; }
+        if (i < tiles) { sc.base_a[i] = (uint32_t)(ba + ia - va); sc.base_t[i] = (uint32_t)(bt + it - vt); }
+        __syncthreads();
+        if (t == 1023) { carry_a = ba + ia; carry_t = bt + it; }
+        __syncthreads();
+    }
+    if (t == 0) {
+        ctr->active = carry_a;
+        ctr->triangles = carry_t;
+        ctr->ambiguous = ctr->amb_n;
+        if (carry_t >= (1ull << 31)) ctr->error = 2u; /* >= 2^31 triangles in one slab: beyond any output buffer */
     }
 }
 
 template <bool REPEAT>
 __global__ void __launch_bounds__(kClsThreads)
-compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, const float* __restrict__ cs,
-               const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
-               const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ status,
-               Counters* __restrict__ ctr, unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
+compact_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
+               const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
                unsigned long long cap_active, unsigned long long* __restrict__ item_info /* nullptr unless the weld needs it */,
-               const float* __restrict__ F, const uint32_t* __restrict__ Cw /* repeating-surface mode, else nullptr */) {
+               const uint32_t* __restrict__ Cw /* repeating-surface mode, else nullptr */) {
     __shared__ uint32_t chunk_a[kClsChunkCap], chunk_t[kClsChunkCap]; /* per 32 list entries */
     __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];
-    __shared__ unsigned long long base_a_s, base_t_s;
-    __shared__ uint32_t tile_s;
 
-    if (threadIdx.x == 0) tile_s = atomicAdd(&ctr->tile_ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = tile_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
     const uint32_t nz = sc.nz[tile];
-    const uint16_t* __restrict__ glist = sc.list + (size_t)tile * sc.tile_items;
-    const uint16_t* __restrict__ gcnt = sc.cnt + (size_t)tile * sc.tile_items;
-    const uint32_t row0 = tile * q.tile_rows;
-    const uint32_t rows = min(q.tile_rows, q.total_rows - row0);
-
-    /* ---- S: look-back (warp 0) while every warp reduces its chunks of the per-item counts ---------------------- */
-    if (warp == 0) {
-        constexpr unsigned long long kField = 0x7fffffffull;
-        const unsigned long long own = ld_status(status + tile);
-        unsigned long long pa = 0, pt = 0;
-        if (tile > 0) {
-            long long basei = (long long)tile - 1;
-            for (;;) {
-                const long long idx = basei - lane;
-                const unsigned long long sv = idx >= 0 ? ld_status(status + idx) : (2ull << 62);
-                /* every status word is at least an aggregate: classify_kernel finished before this kernel started */
-                const uint32_t pmask = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
-                const int first = pmask ? __ffs(pmask) - 1 : 32;
-                unsigned long long va = 0, vt = 0;
-                if (lane <= first) { va = sv & kField; vt = (sv >> 31) & kField; } /* aggregates up to, and including, the first inclusive prefix */
-#pragma unroll
-                for (int d = 16; d; d >>= 1) { va += __shfl_xor_sync(0xffffffffu, va, d); vt += __shfl_xor_sync(0xffffffffu, vt, d); }
-                pa += va; pt += vt;
-                if (pmask) break;
-                basei -= 32;
-            }
-        }
-        if (lane == 0) {
-            const unsigned long long ia = pa + (own & kField), it = pt + ((own >> 31) & kField);
-            if (it > kField) atomicExch(&ctr->error, 2u); /* >= 2^31 triangles in one slab: beyond any output buffer */
-            st_status(status + tile, (2ull << 62) | ((it & kField) << 31) | (ia & kField));
-            base_a_s = pa; base_t_s = pt;
-            if (row0 + rows >= q.total_rows) { /* last tile: grand totals */
-                ctr->active = ia;
-                ctr->triangles = it;
-            }
-        }
-    }
     if (nz == 0) return; /* uniform per block */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long* __restrict__ gent = sc.ent + (size_t)tile * sc.tile_items;
+    const uint32_t row0 = tile * q.tile_rows;
+
     for (uint32_t kb = (uint32_t)warp * 32u; kb < nz; kb += kClsThreads) {
         const uint32_t k = kb + (uint32_t)lane;
-        const uint32_t c = k < nz ? (uint32_t)gcnt[k] : 0u;
-        uint32_t na = c & 63u, nt = c >> 6;
+        const unsigned long long e = k < nz ? gent[k] : 0ull;
+        uint32_t na = MCB_ENT_NA(e), nt = MCB_ENT_NT(e);
 #pragma unroll
         for (int d = 16; d; d >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, d); nt += __shfl_xor_sync(0xffffffffu, nt, d); }
         if (lane == 0) { chunk_a[kb >> 5] = na; chunk_t[kb >> 5] = nt; }
@@ -889,11 +1048,11 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
     /* ---- C2: write the compacted records in loop order -------------------------------------------------------- */
     const uint32_t WP = (uint32_t)g.WP, plane = (uint32_t)g.NV * WP, M = (uint32_t)g.M;
     const uint32_t kz0 = row0 / M, j0 = row0 - kz0 * M;
-    const unsigned long long tile_a = base_a_s, tile_t = base_t_s;
+    const unsigned long long tile_a = sc.base_a[tile], tile_t = sc.base_t[tile];
     for (uint32_t kb = (uint32_t)warp * 32u; kb < nz; kb += kClsThreads) {
         const uint32_t k = kb + (uint32_t)lane;
-        const uint32_t c = k < nz ? (uint32_t)gcnt[k] : 0u;
-        const uint32_t mine = (c & 63u) | ((c >> 6) << 16);
+        const unsigned long long e = k < nz ? gent[k] : 0ull;
+        const uint32_t mine = MCB_ENT_NA(e) | (MCB_ENT_NT(e) << 16);
         uint32_t inc = mine; /* <= 32 | 160 << 16 per lane: a chunk's sum stays below 2^16 per field */
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
@@ -901,7 +1060,7 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
         unsigned long long oa = tile_a + chunk_a[kb >> 5] + ((inc - mine) & 0xffffu);
         unsigned long long ot = tile_t + chunk_t[kb >> 5] + ((inc - mine) >> 16);
         ItemView it;
-        const uint32_t item_local = glist[k];
+        const uint32_t item_local = MCB_ENT_ITEM(e), red = MCB_ENT_RED(e);
         view_item<REPEAT>(it, item_local, j0, kz0, q, g, S, V, plane, Cw);
         uint32_t m = it.m;
         if (item_info != nullptr) /* cube -> record look-up of the weld: first record of the word | its active mask */
@@ -910,12 +1069,7 @@ compact_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, con
             const int b = __ffs(m) - 1;
             m &= m - 1;
             const int code = code_of(it.c, b);
-            int tidx = code;
-            const int face = (int)(int8_t)__ldg((const signed char*)gtb->face + code);
-            if (face >= 0) {
-                const int ci = (int)it.w * 32 + b, cj = (int)it.j, ck = (int)it.kz + g.kb;
-                if (ambiguity_redirects(point_prog, g, cs, face, ci, cj, ck, REPEAT ? cube_level(g, F, ci, cj, ck) : g.iso)) tidx = 255 - code;
-            }
+            const int tidx = ((red >> b) & 1u) ? 255 - code : code; /* marching.cpp:545-547 */
             if (oa < cap_active) {
                 rec[oa] = (unsigned long long)(it.w * 32 + b) | ((unsigned long long)it.j << 12) |
                           ((unsigned long long)(it.kz + g.kb) << 24) | ((unsigned long long)code << 36) |

@@ -1,9 +1,10 @@
-"""-m gpu: MCB_FIELD_SPARSE (signs for every vertex, field values only in blocks around the surface)
-against MCB_FIELD_DENSE, which the other -m gpu tests pin to the unmodified reference.
+"""-m gpu: the block-field mode (MCB_FIELD_SPARSE / MCB_FIELD_AUTO: an interval proof per 32 x 4 x 4 vertex block decides
+which blocks can hold a sign change; only those are evaluated, classify skips the rest) against
+MCB_FIELD_DENSE, which the other -m gpu tests pin to the unmodified reference.
 
 Bar: every output — counts, triangle soup, gradient normals, welded Poly_Data, normal.h normals, seed-mode component,
 constrained and slabbed runs — is byte for byte what the dense mode produces.  The sparse contexts run with
-$MCB_POISON_FIELD=1: the field buffer is NaN-filled before every run, so a read outside the refilled blocks cannot
+$MCB_POISON_FIELD=1: the field buffer is NaN-filled before every run, so a read outside the evaluated blocks cannot
 go unnoticed.
 """
 import os
@@ -66,7 +67,7 @@ def test_sparse_field_equals_dense_on_the_golden_cases(mcb, pair, golden, name, 
     d, s = run_both(pair, lambda c: configure(c, case), normals)
     assert_same(d, s)
     assert s[0].field_mode == mcb.FIELD_SPARSE and d[0].field_mode == mcb.FIELD_DENSE
-    assert (s[0].field_blocks > 0) == (s[0].active > 0)
+    assert s[0].field_blocks > 0 or s[0].active == 0   # undecided blocks need not hold a sign change, active cubes need blocks
 
 
 EQS = {
@@ -139,29 +140,69 @@ def test_sparse_field_has_no_dense_field_to_read(mcb, pair):
     sparse.set_field_mode(mcb.FIELD_SPARSE)
 
 
-def test_field_auto_goes_sparse_only_for_a_known_sparse_surface(mcb):
-    """MCB_FIELD_AUTO: dense on the first polygonisation of a configuration, sparse afterwards when it had <= 0.5 % active
-    cubes; re-sending the same equation keeps what was learnt, changing a parameter starts over; outputs identical."""
+def test_field_auto_is_the_block_mode_from_the_first_call(mcb):
+    """MCB_FIELD_AUTO needs no earlier run of a configuration: the first polygonisation of a new equation, a moved iso
+    value and a coarse grid all run the block-field mode, with the dense mode's outputs."""
     c = mcb.Context(0)
+    d = mcb.Context(0)
     c.set_field_mode(mcb.FIELD_AUTO)
-    c.set_normals(1)
-    assert c.set_equation("x^2+y^2+z^2-0.49") == 0
-    c.set_grid_step(2.0 / 640)
-    first = c.polygonise()
-    p1, n1 = c.get_mesh(normals=True)
-    assert first.field_mode == mcb.FIELD_DENSE and first.active / first.cubes < 0.005
-    second = c.polygonise()
-    p2, n2 = c.get_mesh(normals=True)
-    assert second.field_mode == mcb.FIELD_SPARSE and second.field_blocks > 0
-    assert (first.active, first.triangles) == (second.active, second.triangles) and same_bits(p1, p2) and same_bits(n1, n2)
-    assert c.set_equation("x^2+y^2+z^2-0.49") == 0          # the same text again (a GUI refresh): nothing to relearn
-    c.set_grid_step(2.0 / 640)
-    assert c.polygonise().field_mode == mcb.FIELD_SPARSE
-    c.set_surface_constant(0.1)                               # another surface: dense once, then sparse again
-    assert c.polygonise().field_mode == mcb.FIELD_DENSE
-    assert c.polygonise().field_mode == mcb.FIELD_SPARSE
-    c.set_grid_step(2.0 / 24)                                 # a coarse grid: 4 % of the cubes are active, the field write stays
-    assert c.polygonise().field_mode == mcb.FIELD_DENSE
-    dense = c.polygonise()
-    assert dense.field_mode == mcb.FIELD_DENSE and dense.active / dense.cubes > 0.005
+    d.set_field_mode(mcb.FIELD_DENSE)
+    for x in (c, d):
+        x.set_normals(1)
+
+    def both():
+        a, b = c.polygonise(), d.polygonise()
+        pa, na = c.get_mesh(normals=True)
+        pb, nb = d.get_mesh(normals=True)
+        assert a.field_mode == mcb.FIELD_SPARSE and b.field_mode == mcb.FIELD_DENSE
+        assert (a.active, a.triangles, a.ambiguous, a.redirected) == (b.active, b.triangles, b.ambiguous, b.redirected)
+        assert same_bits(pa, pb) and same_bits(na, nb)
+        return a
+    for x in (c, d):
+        assert x.set_equation("x^2+y^2+z^2-0.49") == 0
+        x.set_grid_step(2.0 / 320)
+    first = both()
+    nblocks = ((first.M + 3 + 31) // 32) * ((first.M + 3 + 3) // 4) ** 2
+    assert 0 < first.field_blocks < 0.25 * nblocks        # most of the grid is proven empty, not evaluated
+    for x in (c, d):
+        x.set_surface_constant(0.1)                        # another surface of the same equation
+    both()
+    for x in (c, d):
+        assert x.set_equation("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)") == 0   # another equation
+    both()
+    for x in (c, d):
+        x.set_grid_step(2.0 / 24)                          # a coarse grid: the surface is everywhere
+    both()
     c.close()
+    d.close()
+
+
+@pytest.mark.parametrize("eq,n", [("x^2+y^2+z^2-0.49", 200), ("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)", 160),
+                                  ("x^2-y/z+x*y^3", 130), ("x/(y*y+0.01)-z^3", 96), ("(x*y)^3+z", 96), ("2^(x*y)-z-1", 64)])
+def test_the_interval_proof_changes_nothing(mcb, eq, n):
+    """Deciding blocks by interval arithmetic against evaluating every block ($MCB_NO_INTERVAL=1): identical outputs;
+    includes programs the proof has to give up on (division by an interval around zero, a variable exponent)."""
+    decided = mcb.Context(0)
+    os.environ["MCB_NO_INTERVAL"] = "1"
+    try:
+        everything = mcb.Context(0)
+    finally:
+        del os.environ["MCB_NO_INTERVAL"]
+    out = []
+    for c in (decided, everything):
+        c.set_field_mode(mcb.FIELD_SPARSE)
+        c.set_mesh_mode(mcb.MESH_SOUP | mcb.MESH_INDEXED)
+        c.set_normals(1)
+        assert c.set_equation(eq) == 0
+        c.set_grid_step(2.0 / n)
+        cnt = c.polygonise()
+        out.append((cnt, c.get_active(), c.get_mesh(normals=True), c.get_indexed_mesh(normals=True), c.get_cases()))
+    (ca, ra, ma, ia, ka), (cb, rb, mb, ib, kb) = out
+    assert (ca.active, ca.triangles, ca.ambiguous, ca.redirected, ca.vertices) == (cb.active, cb.triangles, cb.ambiguous, cb.redirected, cb.vertices)
+    assert ca.field_blocks <= cb.field_blocks
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    assert same_bits(ma[0], mb[0]) and same_bits(ma[1], mb[1])
+    assert same_bits(ia[0], ib[0]) and np.array_equal(ia[1], ib[1]) and same_bits(ia[2], ib[2])
+    assert np.array_equal(ka[0], kb[0]) and np.array_equal(ka[1], kb[1])
+    decided.close()
+    everything.close()
