@@ -1,0 +1,78 @@
+"""-m "not gpu": the product's DEVICE CODE executed on the host (tests/emu: csrc/mcb_api.cu + mcb_kernels.cuh compiled by g++
+against an emulated CUDA runtime, every CUDA thread a fiber) through the same C ABI and ctypes mirror the GPU tests use.
+
+This is test infrastructure for the build container, which has no GPU: kernel logic (tiling, scans, ballots, the block
+skipping of the block-field mode, the ambiguity list, the weld) is checked here against the golden vectors of the
+unmodified reference at small sizes; the -m gpu tier repeats it, and everything at size, on the real device through
+libmcb200.so.  The product never loads the emulated library."""
+import numpy as np
+import pytest
+
+from .helpers import configure, load_meta, same_bits
+
+CASES = ["eq1_gui", "eq8_ctor", "sphere_17", "gyr78_17", "constraint_2", "quirk_div", "saddle_17", "torus_33", "sphere_33_iso", "nonuniform_scale"]
+
+
+@pytest.fixture(scope="module")
+def ctx(mcb_emu):
+    c = mcb_emu.Context(0)
+    c.set_mesh_mode(mcb_emu.MESH_SOUP | mcb_emu.MESH_INDEXED)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", ["dense", "blocks"])
+def test_golden_cases_through_the_emulated_kernels(mcb_emu, ctx, golden, name, mode):
+    case = load_meta(golden)[name]
+    configure(ctx, case)
+    ctx.set_field_mode(mcb_emu.FIELD_DENSE if mode == "dense" else mcb_emu.FIELD_AUTO)
+    ctx.set_normals(2)
+    cnt = ctx.polygonise()
+    assert cnt.field_mode == (mcb_emu.FIELD_DENSE if mode == "dense" else mcb_emu.FIELD_SPARSE)
+    code, tidx = ctx.get_cases()
+    pos, _ = ctx.get_mesh(normals=False)
+    vl, tl, vn = ctx.get_indexed_mesh(normals=True)
+    assert np.array_equal(code, golden[name + "/code"]) and np.array_equal(tidx, golden[name + "/table_idx"])
+    assert cnt.triangles == case["T"]
+    assert same_bits(pos[:, :, :3], golden[name + "/soup"])
+    assert same_bits(vl, golden[name + "/vertex_list"].reshape(-1, 3)) and np.array_equal(tl, golden[name + "/tri_list"].reshape(-1, 3))
+    assert same_bits(vn, golden[name + "/normals"].reshape(-1, 3))
+
+
+GYR78 = ("((x*(-7+x^2*(56+x^2*(-112+64*x^2))))*(1+y^2*(-32+y^2*(160+y^2*(-256+128*y^2)))))"
+         "+((y*(-7+y^2*(56+y^2*(-112+64*y^2))))*(1+z^2*(-32+z^2*(160+z^2*(-256+128*z^2)))))"
+         "+((z*(-7+z^2*(56+z^2*(-112+64*z^2))))*(1+x^2*(-32+x^2*(160+x^2*(-256+128*x^2)))))")
+
+
+@pytest.mark.parametrize("eq,n,expect", [("x^2+y^2+z^2-0.49", 64, None), (GYR78, 64, (155478, 338, 163))])
+def test_block_mode_skips_space_and_equals_dense_at_65_cubed(mcb_emu, ctx, eq, n, expect):
+    """large enough for whole 32 x 4 x 4 blocks to be proven empty and skipped; slab with a halo on both sides too.
+    gyr78 at M = 65: triangle / ambiguous / redirected counts of the unmodified reference (SURVEY.md §8d cfg 4)."""
+    res = {}
+    for mode in (mcb_emu.FIELD_DENSE, mcb_emu.FIELD_AUTO):
+        for slab in (None, (7, 22)):
+            assert ctx.set_equation(eq) == 0
+            M = ctx.set_grid_step(2.0 / n)
+            ctx.set_scaling(1, 1, 1); ctx.set_surface_constant(0.0)
+            for i in range(3):
+                ctx.set_constraint(i, ">", 0.0, False)
+            if slab:
+                ctx.set_slab(*slab)
+            ctx.set_field_mode(mode)
+            ctx.set_normals(1)
+            cnt = ctx.polygonise()
+            res[(mode, slab)] = (cnt, ctx.get_active(), ctx.get_mesh(normals=True), ctx.get_indexed_mesh(normals=True))
+    for slab in (None, (7, 22)):
+        (cd, rd, md, idd), (cb, rb, mb, ib) = res[(mcb_emu.FIELD_DENSE, slab)], res[(mcb_emu.FIELD_AUTO, slab)]
+        assert (cd.active, cd.triangles, cd.ambiguous, cd.redirected, cd.vertices) == (cb.active, cb.triangles, cb.ambiguous, cb.redirected, cb.vertices)
+        assert np.array_equal(rd[0], rb[0]) and np.array_equal(rd[1], rb[1])
+        assert same_bits(md[0], mb[0]) and same_bits(md[1], mb[1])
+        assert same_bits(idd[0], ib[0]) and np.array_equal(idd[1], ib[1]) and same_bits(idd[2], ib[2])
+    full = res[(mcb_emu.FIELD_AUTO, None)][0]
+    nblocks = ((full.M + 3 + 31) // 32) * ((full.M + 3 + 3) // 4) ** 2
+    assert 0 < full.field_blocks <= nblocks
+    if expect is None:
+        assert full.field_blocks < 0.5 * nblocks   # the sphere leaves most blocks decided, i.e. skipped
+    if expect:
+        assert (full.triangles, full.ambiguous, full.redirected) == expect

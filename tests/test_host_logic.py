@@ -249,17 +249,16 @@ def test_committed_bench_lines_carry_every_contract_key():
     assert ref["cpu_baseline"]["kind"] == "reference" and ref["cpu_baseline"]["cores"] >= 1
 
 
-def test_jit_source_has_the_three_kernels_and_keeps_power_programs_rolled(mcb):
-    """One module per equation: mcb_eval_jit (field + signs), mcb_signs_jit (signs only, 128 x 16 tile streamed row by row),
-    mcb_fill_jit (sparse-field refill).  The operations are spelled with the never-contracted intrinsics."""
+def test_jit_source_has_both_kernels(mcb):
+    """One module per equation: mcb_eval_jit (plane tiles: the whole field + signs) and mcb_fill_jit (listed 32 x 4 x 4 blocks:
+    field + signs, the block-field mode).  The operations are spelled with the never-contracted intrinsics."""
     _, plain = mcb.jit_check("x*y+z*(x-y)")
     _, power = mcb.jit_check("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)")
     for src in (plain, power):
-        for kernel in ("mcb_eval_jit", "mcb_signs_jit", "mcb_fill_jit"):
+        for kernel in ("mcb_eval_jit", "mcb_fill_jit"):
             assert src.count('%s(const __grid_constant__ Consts C' % kernel) == 1 or ("define MCB_KERNEL_NAME " + kernel) in src, kernel
+        assert "mcb_signs_jit" not in src
         assert "__fadd_rn" in src and "__fmul_rn" in src and "__fdiv_rn" in src and "mcb_powf" in src
-    assert '_Pragma("unroll 4")' in plain and '_Pragma("unroll 1")' not in plain
-    assert '_Pragma("unroll 1")' in power
     assert "op_pow(" in power and "op_pow(v" not in plain
 
 
@@ -352,7 +351,7 @@ def test_random_equations_compile_at_run_time(mcb):
         if len(eq) > 100 or not mcb.parse_ok(eq):
             continue
         nbytes, src = mcb.jit_check(eq, cap=1 << 20)
-        assert nbytes > 1000 and src.count("__launch_bounds__") == 3, eq
+        assert nbytes > 1000 and src.count("__launch_bounds__") == 2, eq
         done += 1
 
 
@@ -363,7 +362,7 @@ class _HostGrid(C.Structure):  # mcbk::Grid / the Grid struct of the generated s
 
 def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, refbind, tmp_path):
     """The CUDA source mcb_jit.cpp generates is also valid C++ under a small shim (tests/cpp/jit_host_shim.h): g++ compiles
-    it with -ffp-contract=off and all three kernels run lane by lane over a small grid with random coordinates (warp
+    it with -ffp-contract=off and both kernels run lane by lane over a small grid with random coordinates (warp
     ballots emulated by a two-pass trick).  The field they write equals Evaluator::evaluate of the compiled reference
     bit for bit and the sign words equal `value > iso`, for the bench equations and for random ones (deep stacks,
     reversed operators, powers, unary minus)."""
@@ -396,35 +395,34 @@ def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, 
                            capture_output=True, text=True)
         assert r.returncode == 0, (eq, r.stderr[:2000])
         L = C.CDLL(str(so))
-        L.run_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]
+        L.run_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]
         tables = np.zeros(3 * 64 * P + 256, np.float32)
         kpool = np.zeros(128, np.float32)
         spa = H.mcoh_tables(eq.encode(), ax[0].ctypes.data, ax[1].ctypes.data, ax[2].ctypes.data, P, tables.ctypes.data, len(tables) - 256,
                             kpool.ctypes.data)
         assert spa > 0, (eq, spa)
         g = _HostGrid(M=NV - 3, NV=NV, P=P, WP=4, kb=kb, ke=kb + NZ - 3, NZ=NZ, sx=1, sy=1, sz=1, iso=0, repeat=0, rstep=0)
-        nbx, nby, nbz = P // 32, (NV + 3) // 4, (NZ + 3) // 4
-        blocks = np.arange(nbx * nby * nbz, dtype=np.uint32)
-        F = np.full((NZ, NV, P), np.nan, np.float32)
-        L.run_fill(kpool.ctypes.data, C.byref(g), tables.ctypes.data, F.ctypes.data, blocks.ctypes.data, len(blocks), nbx, nby, spa)
         ref = refbind.Ref(eq).eval_points(pts).reshape(NZ, NV, NV)
-        got = F[:, :, :NV]
-        assert np.all((ref.view(np.uint32) == got.view(np.uint32)) | (np.isnan(ref) & np.isnan(got))), eq
-        # the plane kernels: mcb_eval_jit (128 x 4 tile in registers: field + sign words) and mcb_signs_jit (128 x 16 tile
-        # streamed row by row: sign words only), warp ballots emulated by the shim; sign bit = value > iso, strict, NaN -> 0
-        L.run_plane.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         g.iso = float(np.float32(np.nanmedian(ref[np.isfinite(ref)]))) if np.isfinite(ref).any() else 0.0
         with np.errstate(invalid="ignore"):
-            want = ref > np.float32(g.iso)
+            want = ref > np.float32(g.iso)   # sign bit = value > iso, strict, NaN -> 0
         xs = np.arange(NV)
-        for which in (0, 1):
-            F2 = np.full((NZ, NV, P), np.nan, np.float32)
-            S = np.zeros((NZ, NV, 4), np.uint32)
-            L.run_plane(which, kpool.ctypes.data, C.byref(g), tables.ctypes.data, F2.ctypes.data, S.ctypes.data, spa)
-            bits = ((S[:, :, xs >> 5] >> (xs & 31).astype(np.uint32)) & 1).astype(bool)
-            assert np.array_equal(bits, want), (eq, which)
-            if which == 0:
-                got2 = F2[:, :, :NV]
-                assert np.all((ref.view(np.uint32) == got2.view(np.uint32)) | (np.isnan(ref) & np.isnan(got2))), eq
-            else:
-                assert np.isnan(F2).all(), eq   # the signs-only kernel does not touch the field
+        nbx, nby, nbz = P // 32, (NV + 3) // 4, (NZ + 3) // 4
+        blocks = np.arange(nbx * nby * nbz, dtype=np.uint32)
+        # mcb_fill_jit: every block listed; field and sign words (warp ballots emulated by the shim)
+        F = np.full((NZ, NV, P), np.nan, np.float32)
+        S = np.zeros((NZ, NV, 4), np.uint32)
+        L.run_fill(kpool.ctypes.data, C.byref(g), tables.ctypes.data, F.ctypes.data, S.ctypes.data, blocks.ctypes.data, len(blocks), nbx, nby, spa)
+        got = F[:, :, :NV]
+        assert np.all((ref.view(np.uint32) == got.view(np.uint32)) | (np.isnan(ref) & np.isnan(got))), eq
+        bits = ((S[:, :, xs >> 5] >> (xs & 31).astype(np.uint32)) & 1).astype(bool)
+        assert np.array_equal(bits, want), (eq, "fill")
+        # mcb_eval_jit: 128 x 4 tile in registers, field + sign words
+        L.run_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        F2 = np.full((NZ, NV, P), np.nan, np.float32)
+        S2 = np.zeros((NZ, NV, 4), np.uint32)
+        L.run_plane(kpool.ctypes.data, C.byref(g), tables.ctypes.data, F2.ctypes.data, S2.ctypes.data, spa)
+        bits = ((S2[:, :, xs >> 5] >> (xs & 31).astype(np.uint32)) & 1).astype(bool)
+        assert np.array_equal(bits, want), (eq, "plane")
+        got2 = F2[:, :, :NV]
+        assert np.all((ref.view(np.uint32) == got2.view(np.uint32)) | (np.isnan(ref) & np.isnan(got2))), eq
