@@ -63,6 +63,7 @@ struct mcb_ctx {
     Grid g{};
     bool grid_dirty = true;
     float* d_cs = nullptr;
+    size_t rinv_ofs = 0; /* d_cs + rinv_ofs: 1 / (c[v+1] - c[v-1]) per stored coordinate */
     float* d_F = nullptr;
     uint32_t* d_S = nullptr;
     uint32_t* d_V = nullptr;
@@ -141,6 +142,8 @@ struct mcb_ctx {
     bool field_is_sparse = false;  /* what the last polygonisation left in d_F: only the blocks around the surface */
     bool poison_field = false;     /* $MCB_POISON_FIELD: NaN-fill d_F first, so a read outside the blocks shows (tests) */
     bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
+    int emit_variant = 2;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk),
+                                      9 = second generation with 24 edge slots (tests: forces chunks to be emitted in several runs) */
     uint8_t* d_fflags = nullptr;   /* [cap_fblocks] 2 = evaluated (undecided block), 1 = apron block to refill, 0 = untouched */
     uint8_t* d_bcls = nullptr;     /* [cap_fblocks] interval class of every 32 x 4 x 4 vertex block */
     uint32_t* d_flist = nullptr;   /* [cap_fblocks] apron blocks */
@@ -271,11 +274,14 @@ int setup_grid(mcb_ctx* ctx) {
     g.ke = ctx->ke;
     g.NZ = (g.ke - g.kb) + 3;
     /* coordinates with the apron: cs[v+1] = c[v]; c[-1] = c[0]-step, c[M+1] = c[M]+step (fp32, like the loop) */
-    std::vector<float> cs((size_t)g.P + 64, 0.f);
+    const size_t ncs = (size_t)g.P + 64;
+    std::vector<float> cs(2 * ncs, 0.f); /* coordinates, then 1 / (c[v+1] - c[v-1]): the central-difference denominators */
     cs[0] = ctx->axis[0] - ctx->step;
     for (int v = 0; v <= g.M; v++) cs[v + 1] = ctx->axis[v];
     cs[g.M + 2] = ctx->axis[g.M] + ctx->step;
-    for (size_t q = g.NV; q < cs.size(); q++) cs[q] = cs[g.NV - 1];
+    for (size_t q = g.NV; q < ncs; q++) cs[q] = cs[g.NV - 1];
+    for (int v = 1; v + 1 < g.NV; v++) cs[ncs + v] = 1.0f / (cs[v + 1] - cs[v - 1]);
+    ctx->rinv_ofs = ncs;
     int rc;
     if ((rc = ensure(ctx, &ctx->d_cs, &ctx->cap_cs, cs.size())) != MCB_OK) return rc;
     MCB_CK(cudaMemcpyAsync(ctx->d_cs, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -538,6 +544,8 @@ int mcb_create(int device, mcb_ctx** out) {
         tb.tri[q] = MCB_TRI_WORDS[q];
         tb.face[q] = face[q];
         tb.ntri[q] = (uint8_t)mcb_tri_count(MCB_TRI_WORDS[q]);
+        tb.emask[q] = 0;
+        for (int e = 0; e < 12; e++) tb.emask[q] |= (uint16_t)((((q >> mcb_edge_a(e)) ^ (q >> mcb_edge_b(e))) & 1) << e);
     }
     if (cudaMalloc((void**)&ctx->d_cls, sizeof(ClsTables)) != cudaSuccess) return bail(MCB_E_NOMEM);
     if (cudaMemcpy(ctx->d_cls, &tb, sizeof tb, cudaMemcpyHostToDevice) != cudaSuccess) return bail(MCB_E_CUDA);
@@ -551,6 +559,8 @@ int mcb_create(int device, mcb_ctx** out) {
         ctx->poison_field = poison && poison[0] == '1';
         const char* noiv = std::getenv("MCB_NO_INTERVAL");
         ctx->decide_blocks = !(noiv && noiv[0] == '1');
+        const char* ev = std::getenv("MCB_EMIT");
+        if (ev && (ev[0] == '1' || ev[0] == '2' || ev[0] == '3' || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
     }
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
@@ -1139,12 +1149,23 @@ int Run::stage_seed() {
 
 /* K3: interpolation + coalesced float4 emission of the triangle soup */
 int Run::stage_soup() {
-    if (ctx->normals == 1)
-        MCB_LAUNCH((emit_kernel<true>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
-                                                           ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
-    else
-        MCB_LAUNCH((emit_kernel<false>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
-                                                            ctx->cap_tris, ctx->d_pos, nullptr);
+    const float* rinv = ctx->d_cs + ctx->rinv_ofs;
+#define MCB_EMIT2(NRM, CUBES, THREADS, CAP, MINB, MULT)                                                                               \
+    MCB_LAUNCH((emit2_kernel<NRM, CUBES, THREADS, CAP, MINB>), eblocks * MULT, THREADS, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, \
+               ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, NRM ? ctx->d_nrm : nullptr)
+    const bool nrm = ctx->normals == 1;
+    switch (ctx->emit_variant) {
+        case 1:
+            if (nrm) MCB_LAUNCH((emit_kernel<true>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
+                                ctx->cap_tris, ctx->d_pos, ctx->d_nrm);
+            else MCB_LAUNCH((emit_kernel<false>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
+                            ctx->cap_tris, ctx->d_pos, nullptr);
+            break;
+        case 3: if (nrm) MCB_EMIT2(true, 64, 128, 512, 10, 4); else MCB_EMIT2(false, 64, 128, 512, 10, 4); break;
+        case 9: if (nrm) MCB_EMIT2(true, 128, 256, 24, 2, 1); else MCB_EMIT2(false, 128, 256, 24, 2, 1); break;
+        default: if (nrm) MCB_EMIT2(true, 128, 256, 1024, 6, 2); else MCB_EMIT2(false, 128, 256, 1024, 6, 2); break;
+    }
+#undef MCB_EMIT2
     launches++;
     return MCB_OK;
 }

@@ -638,6 +638,7 @@ struct ClsTables { /* built once per context on the host (mcb_tables.h); read th
     uint64_t tri[256];
     int8_t face[256];
     uint8_t ntri[256];
+    uint16_t emask[256]; /* bit e: edge e joins corners on different sides (marching.cpp:563-566), from the raw cube code */
 };
 
 /* Sign words of one vertex row as seen by the 32 cubes of an item: the vertex x-index of corner dx of cube i is
@@ -1220,6 +1221,178 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
                     __stcs(nrm + ov, make_float4(en[0], en[1], en[2], 0.0f));
                 }
             }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K3, second generation (the default; the kernel above stays for A/B runs with $MCB_EMIT=1).  Same three phases, same
+ * results for the positions bit for bit, less work per edge and per output vertex:
+ *   - an edge is parallel to an axis, so Marching::interp (marching.cpp:437-446) changes ONE coordinate; for the other
+ *     two, t * 0 is 0 or NaN and both the sum and the fallback return the end point's own grid coordinate exactly.
+ *     One interp per edge instead of three, and a crossing edge is a float4 in shared memory (its coordinate + the
+ *     normal), in compact slots: first slot of the cube + rank of the edge among the cube's crossing edges;
+ *   - the gradient normals are the product's own definition, checked to 1e-5 (north_star), not bit for bit: central
+ *     differences multiply by a per-coordinate table of 1 / (c[v+1] - c[v-1]) (built once per grid on the host) instead
+ *     of six IEEE divisions per edge, and the normalisation is rsqrtf;
+ *   - the crossing-edge set of a cube code is one table load; chunk-local 32-bit arithmetic in the output phase
+ *     (no 64-bit division per output vertex).
+ * A chunk whose crossing edges exceed the slot capacity (never on a surface; a degenerate field can) is emitted in
+ * several runs of whole cubes.
+ * ------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void gradient_normal(const float* __restrict__ pa, const float* __restrict__ pb, size_t rowp, size_t planep,
+                                                const float* __restrict__ rinv, int xa, int ya, int za, int xb, int yb, int zb,
+                                                float tq, float& ox, float& oy, float& oz) {
+    const float gxa = (__ldg(pa + 1) - __ldg(pa - 1)) * __ldg(rinv + xa);
+    const float gya = (__ldg(pa + rowp) - __ldg(pa - rowp)) * __ldg(rinv + ya);
+    const float gza = (__ldg(pa + planep) - __ldg(pa - planep)) * __ldg(rinv + za);
+    const float gxb = (__ldg(pb + 1) - __ldg(pb - 1)) * __ldg(rinv + xb);
+    const float gyb = (__ldg(pb + rowp) - __ldg(pb - rowp)) * __ldg(rinv + yb);
+    const float gzb = (__ldg(pb + planep) - __ldg(pb - planep)) * __ldg(rinv + zb);
+    float tt = tq;
+    if (isinf(tt) || isnan(tt)) tt = 0.5f;
+    const float nx = gxa + tt * (gxb - gxa);
+    const float ny = gya + tt * (gyb - gya);
+    const float nz = gza + tt * (gzb - gza);
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+    ox = nx * inv; oy = ny * inv; oz = nz * inv;
+}
+
+template <bool NORMALS, int CUBES, int THREADS, int CAP /* edge slots per chunk run */, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict__ rinv, const float* __restrict__ F,
+             const ClsTables* __restrict__ gtb, const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ trioff,
+             const Counters* __restrict__ ctr, unsigned long long cap_active, unsigned long long cap_tris,
+             float4* __restrict__ pos, float4* __restrict__ nrm) {
+    static_assert(CAP >= 12 && CUBES <= 256 && CUBES <= THREADS, "a cube's edges fit one run; a thread per cube in phase 1");
+    __shared__ float4 eslot[NORMALS ? CAP : 1];     /* crossing edge: coordinate along its axis, normal */
+    __shared__ float epos_only[NORMALS ? 1 : CAP];
+    __shared__ float ccoord[CUBES * 6];             /* x0 x1 y0 y1 z0 z1 of the cube */
+    __shared__ uint32_t off_s[CUBES + 1];           /* first triangle of the cube */
+    __shared__ uint64_t triw_s[CUBES];
+    __shared__ uint32_t ijk_s[CUBES];               /* i | j << 12 */
+    __shared__ uint16_t k_s[CUBES];
+    __shared__ uint16_t emask_s[CUBES];
+    __shared__ uint16_t ebase_s[CUBES + 1];         /* exclusive prefix of the crossing-edge counts */
+    __shared__ uint16_t work_s[CUBES * 12];         /* local cube << 4 | edge, one per crossing edge, (cube, edge) order */
+    __shared__ uint8_t tri2cube[CUBES * 5];         /* chunk-local triangle -> local cube (a cube has at most 5) */
+    __shared__ uint32_t warp_s[THREADS / 32];
+
+    unsigned long long A = ctr->active;
+    const unsigned long long T = ctr->triangles;
+    const bool whole = A <= cap_active;
+    if (!whole) A = cap_active; /* the host re-runs with larger buffers when counts exceed capacity */
+    const unsigned long long nchunks = (A + CUBES - 1) / CUBES;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+
+    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();
+        const unsigned long long c0 = chunk * CUBES;
+        const int n = (int)((A - c0) < (unsigned long long)CUBES ? (A - c0) : CUBES);
+
+        /* ---- 1: records -> per-cube state and the edge work list ---- */
+        uint32_t emask = 0;
+        if (t < n) {
+            const unsigned long long r = rec[c0 + t];
+            const int code = (int)((r >> 36) & 0xFF), tidx = (int)((r >> 44) & 0xFF);
+            const int i = (int)(r & 0xFFF), j = (int)((r >> 12) & 0xFFF), k = (int)((r >> 24) & 0xFFF);
+            off_s[t] = trioff[c0 + t];
+            triw_s[t] = mcb_tri_word(tidx);
+            ijk_s[t] = (uint32_t)(r & 0xFFFFFF);
+            k_s[t] = (uint16_t)k;
+            emask = __ldg(gtb->emask + code);
+            emask_s[t] = (uint16_t)emask;
+            ccoord[6 * t + 0] = __ldg(cs + i + 1); ccoord[6 * t + 1] = __ldg(cs + i + 2);
+            ccoord[6 * t + 2] = __ldg(cs + j + 1); ccoord[6 * t + 3] = __ldg(cs + j + 2);
+            ccoord[6 * t + 4] = __ldg(cs + k + 1); ccoord[6 * t + 5] = __ldg(cs + k + 2);
+        }
+        const uint32_t nv = __popc(emask);
+        uint32_t inc = nv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_s[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = inc - nv;
+#pragma unroll
+        for (int w2 = 0; w2 < THREADS / 32; w2++) if (w2 < warp) wbase += warp_s[w2];
+        if (t < n) ebase_s[t] = (uint16_t)wbase;
+        if (t == n - 1) ebase_s[n] = (uint16_t)(wbase + nv);
+        while (emask) {
+            const int e = __ffs(emask) - 1;
+            emask &= emask - 1;
+            work_s[wbase++] = (uint16_t)((t << 4) | e);
+        }
+        if (t == 0) /* end of the chunk's output range; a capacity-truncated run is repeated by the host anyway */
+            off_s[n] = (c0 + n < A) ? trioff[c0 + n] : (whole ? (uint32_t)T : off_s[n - 1]);
+        __syncthreads();
+        if (t < n) { /* off_s is complete here */
+            const uint32_t first = off_s[t] - off_s[0], cnt = off_s[t + 1] - off_s[t];
+            for (uint32_t q2 = 0; q2 < cnt && q2 < 5u; q2++) tri2cube[first + q2] = (uint8_t)t;
+        }
+
+        /* runs of whole cubes whose crossing edges fit the slots (one run, except on degenerate fields) */
+        for (int cb = 0; cb < n;) {
+            int ce = n;
+            if ((int)ebase_s[n] - (int)ebase_s[cb] > CAP) { /* uniform: everyone reads the same prefix array */
+                ce = cb + 1;
+                while (ce < n && (int)ebase_s[ce + 1] - (int)ebase_s[cb] <= CAP) ce++;
+            }
+            const uint32_t q0 = ebase_s[cb], q1 = ebase_s[ce];
+
+            /* ---- 2: one thread per crossing edge ---- */
+            for (uint32_t q = q0 + t; q < q1; q += THREADS) {
+                const uint32_t wk = work_s[q];
+                const int lc = (int)(wk >> 4), e = (int)(wk & 15u);
+                const uint32_t ij = ijk_s[lc];
+                const int i = (int)(ij & 0xFFF), j = (int)(ij >> 12), k = (int)k_s[lc];
+                const int a = mcb_edge_a(e), b = mcb_edge_b(e);
+                const int oa = mcb_corner_ofs(a), ob = mcb_corner_ofs(b);
+                const int axis = e >= 8 ? 2 : (e & 1);
+                /* vertex indices into cs (apron: +1) of the two end points */
+                const int xa = i + 1 + (oa & 1), ya = j + 1 + ((oa >> 1) & 1), za = k + 1 + ((oa >> 2) & 1);
+                const int xb = i + 1 + (ob & 1), yb = j + 1 + ((ob >> 1) & 1), zb = k + 1 + ((ob >> 2) & 1);
+                const float* pa = F + (size_t)(za - g.kb) * planep + (size_t)ya * rowp + xa;
+                const float* pb = F + (size_t)(zb - g.kb) * planep + (size_t)yb * rowp + xb;
+                const float f1 = __ldg(pa), f2 = __ldg(pb);
+                const float tq = (g.iso - f1) / (f2 - f1); /* Marching::interp uses the surface constant itself, also in repeating-surface mode */
+                const float* cc = ccoord + 6 * lc + 2 * axis;
+                const float ca = cc[(oa >> axis) & 1], cb2 = cc[(ob >> axis) & 1];
+                const float p = interp_ref(ca, cb2, tq);
+                if (NORMALS) {
+                    float nx, ny, nz;
+                    gradient_normal(pa, pb, rowp, planep, rinv, xa, ya, za, xb, yb, zb, tq, nx, ny, nz);
+                    eslot[q - q0] = make_float4(p, nx, ny, nz);
+                } else epos_only[q - q0] = p;
+            }
+            __syncthreads();
+
+            /* ---- 3: coalesced float4 emission of the cubes [cb, ce) ---- */
+            const uint32_t tri0 = off_s[0];
+            const uint32_t lv_begin = 3u * (off_s[cb] - tri0), lv_end = 3u * (off_s[ce] - tri0);
+            for (uint32_t lv = lv_begin + t; lv < lv_end; lv += THREADS) {
+                const uint32_t ltri = lv / 3u;
+                const int corner = (int)(lv - 3u * ltri);
+                const int lo = (int)tri2cube[ltri];
+                const int lt = (int)(ltri - (off_s[lo] - tri0));
+                const int e = (int)((triw_s[lo] >> (4 * (3 * lt + corner))) & 0xF);
+                const uint32_t slot = (uint32_t)ebase_s[lo] - q0 + (uint32_t)__popc((uint32_t)emask_s[lo] & ((1u << e) - 1u));
+                const int oa = mcb_corner_ofs(mcb_edge_a(e));
+                const int axis = e >= 8 ? 2 : (e & 1);
+                const float* cc = ccoord + 6 * lo;
+                float x = cc[oa & 1], y = cc[2 + ((oa >> 1) & 1)], z = cc[4 + ((oa >> 2) & 1)];
+                float4 en = make_float4(0.f, 0.f, 0.f, 0.f);
+                float p;
+                if (NORMALS) { en = eslot[slot]; p = en.x; } else p = epos_only[slot];
+                if (axis == 0) x = p; else if (axis == 1) y = p; else z = p;
+                const unsigned long long ov = 3ull * tri0 + lv;
+                if ((unsigned long long)tri0 + ltri < cap_tris) {
+                    __stcs(pos + ov, make_float4(x, y, z, 1.0f));
+                    if (NORMALS) __stcs(nrm + ov, make_float4(en.y, en.z, en.w, 0.0f));
+                }
+            }
+            cb = ce;
+            if (cb < n) __syncthreads(); /* the slots are reused by the next run */
         }
     }
 }

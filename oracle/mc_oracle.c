@@ -343,9 +343,11 @@ static void calc_cube(const mco* m, int i, int j, int k, Cube* q, int want_grad)
             const int o = mcb_corner_ofs(v);
             const int xi = i + 1 + (o & 1), yi = j + 1 + ((o >> 1) & 1), zi = k + 1 + ((o >> 2) & 1); /* cs indices */
             const float X = m->cs[xi], Y = m->cs[yi], Z = m->cs[zi];
-            g[v][0] = (march_eval(m, 0, m->cs[xi + 1], Y, Z) - march_eval(m, 0, m->cs[xi - 1], Y, Z)) / (m->cs[xi + 1] - m->cs[xi - 1]);
-            g[v][1] = (march_eval(m, 0, X, m->cs[yi + 1], Z) - march_eval(m, 0, X, m->cs[yi - 1], Z)) / (m->cs[yi + 1] - m->cs[yi - 1]);
-            g[v][2] = (march_eval(m, 0, X, Y, m->cs[zi + 1]) - march_eval(m, 0, X, Y, m->cs[zi - 1])) / (m->cs[zi + 1] - m->cs[zi - 1]);
+            /* the difference times the fp32 reciprocal of the coordinate difference (one table of reciprocals per grid) */
+            const float rx = 1.0f / (m->cs[xi + 1] - m->cs[xi - 1]), ry = 1.0f / (m->cs[yi + 1] - m->cs[yi - 1]), rz = 1.0f / (m->cs[zi + 1] - m->cs[zi - 1]);
+            g[v][0] = (march_eval(m, 0, m->cs[xi + 1], Y, Z) - march_eval(m, 0, m->cs[xi - 1], Y, Z)) * rx;
+            g[v][1] = (march_eval(m, 0, X, m->cs[yi + 1], Z) - march_eval(m, 0, X, m->cs[yi - 1], Z)) * ry;
+            g[v][2] = (march_eval(m, 0, X, Y, m->cs[zi + 1]) - march_eval(m, 0, X, Y, m->cs[zi - 1])) * rz;
         }
         for (int n = 0; n < q->nedges; n++) {
             const int a = mcb_edge_a(q->edges[n]), b = mcb_edge_b(q->edges[n]);

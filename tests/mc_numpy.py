@@ -29,9 +29,10 @@ def soup_gradient_normals(field_ext, cs, iso, cubes, tri_rows):
             for (dx, dy, dz) in CORNER:
                 x, y, z = i + 1 + dx, j + 1 + dy, k + 1 + dz
                 val.append(F[z, y, x])
-                gx = f32(f32(F[z, y, x + 1] - F[z, y, x - 1]) / f32(cs[x + 1] - cs[x - 1]))
-                gy = f32(f32(F[z, y + 1, x] - F[z, y - 1, x]) / f32(cs[y + 1] - cs[y - 1]))
-                gz = f32(f32(F[z + 1, y, x] - F[z - 1, y, x]) / f32(cs[z + 1] - cs[z - 1]))
+                # the product's definition: the difference times the fp32 reciprocal of the coordinate difference
+                gx = f32(f32(F[z, y, x + 1] - F[z, y, x - 1]) * f32(f32(1.0) / f32(cs[x + 1] - cs[x - 1])))
+                gy = f32(f32(F[z, y + 1, x] - F[z, y - 1, x]) * f32(f32(1.0) / f32(cs[y + 1] - cs[y - 1])))
+                gz = f32(f32(F[z + 1, y, x] - F[z - 1, y, x]) * f32(f32(1.0) / f32(cs[z + 1] - cs[z - 1])))
                 grad.append((gx, gy, gz))
             enrm = {}
             for e in range(12):
