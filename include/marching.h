@@ -82,7 +82,10 @@ public:
         for (int i = 0; i < 3; i++) { cons_valid_[i] = cons_use_[i] = false; cons_op_[i] = NAO; cons_rhs_[i] = 0.f; }
         counts_ = mcb_counts();
     }
-    ~Marching() { if (ctx_) mcb_destroy(ctx_); }
+    ~Marching() {
+        unpin_all();
+        if (ctx_) mcb_destroy(ctx_);
+    }
     Marching(const Marching&) = delete;
     Marching& operator=(const Marching&) = delete;
 
@@ -92,9 +95,11 @@ public:
 
     bool recalculate() {
         if (!ensure_ctx()) return false;
-        if (step_mode_ && !seed_mode_) return step_once(); /* marching.cpp:386-428 */
-        reset_all_data();
-        if (!evaluator_) return true; /* Marching::evaluate returns 0 without an evaluator: nothing is above iso */
+        if (step_mode_ && !seed_mode_) { unpin_all(); return step_once(); } /* marching.cpp:386-428 */
+        /* reset_all_data() of the reference (marching.cpp:293-305), except that vertex_list / tri_list keep their storage
+         * AND their size until the new mesh is in: the GPU streams the new Poly_Data straight into them (below) */
+        reset_step_data();
+        if (!evaluator_) { poly_data.vertex_list.clear(); poly_data.tri_list.clear(); return true; } /* Marching::evaluate returns 0 without an evaluator */
         if (!push_parameters()) return false;
         /* welded: the GPU builds Poly_Data's own layout (vertex_list + tri_list, numbered and welded like
          * add_step_to_poly_data, marching.cpp:599-654); unwelded: the float4 triangle soup */
@@ -106,17 +111,35 @@ public:
             poly_data.step_data.step_i = -1;
             return true;
         }
-        if (mcb_polygonise(ctx_, &counts_) != MCB_OK) return false;
-        const size_t T = (size_t)counts_.triangles;
         if (weld_) {
-            const size_t nv = (size_t)counts_.vertices;
-            poly_data.vertex_list.resize(nv * 3);
+            /* Poly_Data's vectors, page-locked where they are, are the destination of the device's copy engine: while the
+             * later parts of the mesh are still being welded the earlier ones are already crossing PCIe, and the call
+             * returns with Poly_Data filled (drawer.cpp:795-801 reads it next).  That needs the vectors to be large
+             * enough before the mesh size is known: they are whenever the mesh did not grow since the last call — a
+             * repeated or shrinking configuration; a growing one takes the plain copy below once, then streams again. */
+            const size_t cv = poly_data.vertex_list.size() / 3, ct = poly_data.tri_list.size() / 3;
+            const bool with_n = normals_ && !reference_normals_;
+            bool stream = cv > 0 && ct > 0 && !(normals_ && reference_normals_) && (!with_n || vertex_normals_.size() / 3 >= cv);
+            if (stream) stream = pin(pin_v_, poly_data.vertex_list) && pin(pin_t_, poly_data.tri_list) && (!with_n || pin(pin_n_, vertex_normals_));
+            mcb_set_host_output(ctx_, stream ? poly_data.vertex_list.data() : nullptr, stream ? poly_data.tri_list.data() : nullptr,
+                                stream && with_n ? vertex_normals_.data() : nullptr, stream ? cv : 0, stream ? ct : 0);
+            if (mcb_polygonise(ctx_, &counts_) != MCB_OK) return false;
+            const size_t T = (size_t)counts_.triangles, nv = (size_t)counts_.vertices;
+            const bool filled = stream && mcb_host_output_filled(ctx_) != 0;
+            if (nv * 3 > poly_data.vertex_list.capacity() || T * 3 > poly_data.tri_list.capacity() ||
+                (normals_ && nv * 3 > vertex_normals_.capacity()))
+                unpin_all(); /* a vector is about to move: its old storage must not stay page-locked */
+            poly_data.vertex_list.resize(nv * 3); /* shrinks (free) when the mesh was streamed, grows otherwise */
             poly_data.tri_list.resize(T * 3);
             if (normals_) vertex_normals_.resize(nv * 3); else vertex_normals_.clear();
             soup_.clear(); normals_soup_.clear();
-            if (T && mcb_get_indexed_mesh(ctx_, poly_data.vertex_list.data(), poly_data.tri_list.data(),
-                                          normals_ ? vertex_normals_.data() : nullptr, nv, T) != MCB_OK) return false;
+            if (!filled && T && mcb_get_indexed_mesh(ctx_, poly_data.vertex_list.data(), poly_data.tri_list.data(),
+                                                     normals_ ? vertex_normals_.data() : nullptr, nv, T) != MCB_OK) return false;
         } else {
+            unpin_all();
+            mcb_set_host_output(ctx_, nullptr, nullptr, nullptr, 0, 0);
+            if (mcb_polygonise(ctx_, &counts_) != MCB_OK) return false;
+            const size_t T = (size_t)counts_.triangles;
             soup_.resize(T * 12);
             if (normals_) normals_soup_.resize(T * 12); else normals_soup_.clear();
             vertex_normals_.clear();
@@ -127,12 +150,9 @@ public:
         return true;
     }
 
-    void reset_all_data() {
+    void reset_all_data() { /* marching.cpp:293-305 */
         poly_data.tri_list.clear(); poly_data.vertex_list.clear();
-        poly_data.step_data.intersect_coord.clear(); poly_data.step_data.tri_vlist.clear(); poly_data.step_data.edge_list.clear();
-        seed_queue_.clear();
-        vertex_set_.clear();
-        reset_step();
+        reset_step_data();
     }
 
     bool set_grid_step_size(float v) { /* [0.001, 0.5], marching.cpp:226-238 */
@@ -200,6 +220,7 @@ public:
         return true;
     }
     bool load_poly_from_file() {
+        unpin_all();
         reset_all_data();
         FILE* fp = std::fopen(mesh_file(), "r");
         if (!fp) return false;
@@ -241,6 +262,26 @@ public:
     const std::vector<float>& get_vertex_normals() const { return vertex_normals_; }
 
 private:
+    void reset_step_data() {
+        poly_data.step_data.intersect_coord.clear(); poly_data.step_data.tri_vlist.clear(); poly_data.step_data.edge_list.clear();
+        seed_queue_.clear();
+        vertex_set_.clear();
+        reset_step();
+    }
+    /* a vector's storage, page-locked in place (mcb_host_register = cudaHostRegister) for as long as it stays where it is */
+    struct Pinned { void* ptr = nullptr; size_t bytes = 0; };
+    static void unpin(Pinned& p) { if (p.ptr) mcb_host_unregister(p.ptr); p.ptr = nullptr; p.bytes = 0; }
+    void unpin_all() { unpin(pin_v_); unpin(pin_t_); unpin(pin_n_); }
+    template <class T>
+    static bool pin(Pinned& p, std::vector<T>& v) {
+        void* ptr = v.data();
+        const size_t bytes = v.capacity() * sizeof(T);
+        if (p.ptr == ptr && p.bytes == bytes) return true;
+        unpin(p);
+        if (!ptr || !bytes || mcb_host_register(ptr, bytes) != MCB_OK) return false;
+        p.ptr = ptr; p.bytes = bytes;
+        return true;
+    }
     bool ensure_ctx() {
         if (!ctx_) {
             const char* d = std::getenv("MCB_DEVICE");
@@ -346,6 +387,7 @@ private:
     std::deque<xyz> seed_queue_;
     std::set<xyz> vertex_set_; /* step-by-step mode only (marching.h:149) */
     std::vector<float> soup_, normals_soup_, vertex_normals_;
+    Pinned pin_v_, pin_t_, pin_n_;
     mcb_counts counts_;
 };
 

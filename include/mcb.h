@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MCB_ABI_VERSION 3
+#define MCB_ABI_VERSION 4
 
 typedef enum {
     MCB_OK = 0,
@@ -68,13 +68,15 @@ typedef struct {
 } mcb_counts;
 
 /* Where the scalar field lives (mcb_set_field_mode; default MCB_FIELD_DENSE). */
-#define MCB_FIELD_DENSE 0   /* every grid vertex's value is written to device memory (4 B per vertex) */
-#define MCB_FIELD_SPARSE 1  /* every vertex is still evaluated, but only its sign is kept; the values are written again,
-                               by the same arithmetic, in 32 x 4 x 4 vertex blocks around the active cubes.  Meshes,
-                               normals and counts are bit-identical to MCB_FIELD_DENSE; mcb_get_field is unavailable */
-#define MCB_FIELD_AUTO 2    /* dense the first time a configuration (equation, grid, slab, iso, scaling, constraints) is
-                               polygonised; sparse from then on if it had at most 0.5 % active cubes, where dropping the
-                               field write pays (sphere at 1024^3: 1.20 -> 0.88 ms); mcb_counts::field_mode says which ran */
+#define MCB_FIELD_DENSE 0   /* every grid vertex is evaluated and its value written to device memory (4 B per vertex) */
+#define MCB_FIELD_SPARSE 1  /* block-field mode: an interval evaluation of the equation per 32 x 4 x 4 vertex block (an exact
+                               proof, csrc/mcb_interval.h) decides which blocks can hold a sign change; only those, and the
+                               blocks the mesh stages read next to them, are evaluated, and classification visits nothing
+                               else.  Decided inside the call from its own data: a first or changed configuration costs
+                               the same as a repeated one.  Meshes, normals and counts are bit-identical to
+                               MCB_FIELD_DENSE; mcb_get_field is unavailable; mcb_counts::field_blocks = blocks evaluated */
+#define MCB_FIELD_AUTO 2    /* MCB_FIELD_SPARSE wherever it applies (everything except the repeating-surface mode, whose
+                               per-cube iso levels read the field everywhere); mcb_counts::field_mode says which ran */
 
 /* What mcb_polygonise leaves in device memory (mcb_set_mesh_mode; default MCB_MESH_SOUP). */
 #define MCB_MESH_SOUP 1     /* triangle soup: 3 float4 positions (+ 3 float4 normals) per triangle, emission order */
@@ -83,6 +85,9 @@ typedef struct {
 /* ---- library / host-only helpers (no GPU needed) ---------------------------------------------------------- */
 
 int mcb_abi_version(void);
+/* sha256 (hex) over the sources the loaded library was built from (csrc/, include/mcb.h): lets a test or a deployment
+ * check that the binary in use is the build of the sources next to it */
+const char* mcb_build_stamp(void);
 /* sizeof of the structs that cross the boundary, so a binding can check its mirror: 0 = mcb_counts, 1 = mcb_step_data */
 int mcb_struct_size(int which);
 const char* mcb_status_string(int status);
@@ -142,8 +147,13 @@ int mcb_set_scaling(mcb_ctx* ctx, float sx, float sy, float sz); /* marching.cpp
 int mcb_set_constraint(mcb_ctx* ctx, int i, int op, float rhs, int in_use);
 /* Seed mode (Marching::seed_mode + set_seed, marching.cpp:42-137, 310-331): polygonise only the cubes connected to
  * the cube containing (x,y,z) — a point of [-1,1]^3, else MCB_E_ARG — through cube faces that carry a crossing edge.
- * Same set of cubes and triangles as the reference's BFS, emitted in the full-grid loop order instead of BFS order.
- * With z-slabs the walk stays inside the context's slab.  enabled = 0 switches back to the full grid. */
+ * The set of cubes and triangles of the reference's BFS on dyadic grid steps, emitted in the full-grid loop order instead
+ * of BFS order.  Deviation: the reference's walk derives its cube origins from the seed (-1 + floor(d) * h, then +-h per
+ * move: marching.cpp:76-79, 104-113), not from the accumulated loop coordinates; for non-dyadic steps such as the GUI's
+ * 0.2 its positions therefore differ from the full-grid ones by ~2e-6 and tests/test_gpu_seed.py compares with a
+ * tolerance there.  The walk stays inside the context's slab: seed mode is a single-context feature — with z-slabs a rank
+ * without the seed emits nothing and a component that leaves and re-enters a slab is cut (mcb_comm_init refuses seed mode).
+ * enabled = 0 switches back to the full grid. */
 int mcb_set_seed(mcb_ctx* ctx, int enabled, float x, float y, float z);
 /* 0 = positions only; 1 = also normals from central-difference field gradients (per soup vertex and per welded
  * vertex; DESIGN.md, normals); 2 = CalculateNormal of the reference (normal.h:3-42: area-weighted face normals summed
@@ -154,6 +164,10 @@ int mcb_set_normals(mcb_ctx* ctx, int mode);
  * On return the triangle soup is resident in device memory in the reference's emission order (cube loop order
  * x fastest, then y, then z; tri_table order inside a cube) and *out holds the counts. */
 int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out);
+
+/* The per-stage device times in the counts struct, ms_tables .. ms_total, come from CUDA events recorded between the stages:
+ * enabled by default; 0 drops the events (the fields read 0), which shortens the gaps between the short kernels. */
+int mcb_set_stage_timing(mcb_ctx* ctx, int enabled);
 
 /* Copy the soup to host memory: pos4 / nrm4 = 3*triangles float4 (x,y,z,1) / (nx,ny,nz,0); either may be NULL.
  * cap_triangles = capacity of the buffers in triangles. */
@@ -183,7 +197,7 @@ int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance);
  *                           interpreter — both are the same CUDA path with the same results; mcb_counts::jit says which ran
  *   MCB_JIT_ON              require it: mcb_polygonise returns MCB_E_STATE with the log in mcb_last_error otherwise
  *   MCB_JIT_OFF             always interpret
- * The sparse-field mode's kernels are always interpreted. */
+ * One module per equation holds the kernel of the dense mode and the block kernel of the block-field mode. */
 #define MCB_JIT_OFF 0
 #define MCB_JIT_ON 1
 #define MCB_JIT_AUTO 2
@@ -192,9 +206,9 @@ int mcb_set_jit(mcb_ctx* ctx, int mode);
  * bytes (> 0) and the generated CUDA source in `log`, or a negative status with the error / compile log in `log`. */
 int mcb_jit_check(const char* equation, char* log, size_t cap);
 
-/* MCB_FIELD_DENSE (default), MCB_FIELD_SPARSE or MCB_FIELD_AUTO: whether mcb_polygonise writes the whole scalar field to
- * device memory or only the blocks of it that the mesh stages read.  Results are bit-identical.  The C++
- * drop-in class, which never reads the field back, uses MCB_FIELD_AUTO. */
+/* MCB_FIELD_DENSE (default), MCB_FIELD_SPARSE or MCB_FIELD_AUTO: whether mcb_polygonise evaluates and writes the whole
+ * scalar field or only the blocks of it around the surface.  Results are bit-identical.  The C++ drop-in
+ * class, which never reads the field back, uses MCB_FIELD_AUTO. */
 int mcb_set_field_mode(mcb_ctx* ctx, int mode);
 
 /* MCB_MESH_SOUP, MCB_MESH_INDEXED or both (3).  The indexed mesh is what Marching::recalculate() leaves in
@@ -215,6 +229,44 @@ int mcb_get_indexed_mesh_device(mcb_ctx* ctx, const float** vertex_list, const u
 int mcb_set_host_output(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices,
                         uint64_t cap_triangles);
 int mcb_host_output_filled(const mcb_ctx* ctx);
+
+/* ---- z-slabs over several GPUs (BASELINE.json configs[4]) ---------------------------------------
+ * One context per GPU, each with its slab of cube layers (mcb_set_slab); the field is analytic, so every slab recomputes
+ * its halo planes and the only exchange of the path is one integer per rank: the slab's triangle count, all-gathered
+ * over NCCL (NVLink / NVSwitch) so that every rank knows its offset in the global triangle list (the reference emits z
+ * slowest, marching.cpp:375-383: concatenating the slabs in rank order reproduces its order).  libnccl.so.2 is loaded
+ * on first use, like NVRTC; without it these calls return MCB_E_STATE and the single-GPU path is unaffected.
+ * The ranks may be processes (one GPU each, the id travelling by any out-of-band means) or threads of one process
+ * (include/marching.h: Marching::set_devices). */
+/* Triangles per cube layer of this context's slab in the last polygonisation, k_end - k_begin values. */
+int mcb_layer_triangles(mcb_ctx* ctx, uint32_t* per_layer);
+/* Host only: cut M cube layers into nranks contiguous slabs of (nearly) equal cost, cost(layer) = triangles_per_layer[k]
+ * + fixed_cost_per_layer (< 0: the default, 0.0015 * M * M — what a layer costs before it emits anything, in
+ * triangles).  cuts[0..nranks]: rank r takes layers [cuts[r], cuts[r+1]).  Every slab gets at least one layer. */
+int mcb_balance_slabs(int M, int nranks, const uint32_t* triangles_per_layer, double fixed_cost_per_layer, int* cuts);
+/* ncclGetUniqueId into 128 bytes: call on one rank, hand the bytes to the others. */
+int mcb_comm_unique_id(void* id128);
+/* Join the communicator (ncclCommInitRank on the context's device) and take the balanced-by-layer-count slab of `rank`
+ * (mcb_slab_range).  Collective over the nranks contexts. */
+int mcb_comm_init(mcb_ctx* ctx, const void* id128, int rank, int nranks);
+/* Enqueue the all-gather of this slab's triangle count, straight from the device counters of the last mcb_polygonise,
+ * on a side stream: the next polygonisation does not wait for the slowest rank.  Collective. */
+int mcb_comm_exchange(mcb_ctx* ctx);
+/* Result of the last exchange (waits for it): offset of this slab in the global triangle list, the global total, and the
+ * per-rank counts (nranks values; may be NULL). */
+int mcb_comm_offsets(mcb_ctx* ctx, uint64_t* offset, uint64_t* total, uint64_t* per_rank);
+/* Re-cut the slabs so that every rank carries the same cost: all-reduce (NCCL) of the per-layer triangle counts of the
+ * last polygonisation, mcb_balance_slabs on every rank, mcb_set_slab with this rank's share.  Collective; the new slab
+ * is returned in *k_begin / *k_end (either may be NULL).  A configuration is profiled once with the uniform slabs and
+ * polygonised with the balanced ones from then on. */
+int mcb_comm_balance(mcb_ctx* ctx, double fixed_cost_per_layer, int* k_begin, int* k_end);
+/* Leave the communicator (also done by mcb_destroy). */
+int mcb_comm_finalize(mcb_ctx* ctx);
+
+/* Page-lock host memory the caller owns (cudaHostRegister / cudaHostUnregister), so that mcb_set_host_output can stream
+ * into it at full PCIe speed: what the C++ drop-in does with the storage of its Poly_Data vectors. */
+int mcb_host_register(void* ptr, size_t bytes);
+int mcb_host_unregister(void* ptr);
 
 /* Marching::calculate_step(x_0, y_0, z_0) (marching.cpp:456-595) for ONE cube with origin (x0,y0,z0) and the context's
  * step, scale, iso, equation and constraints: the Step_Data (marching.h:15-23) the GUI's step-by-step / movie mode

@@ -61,6 +61,7 @@ def _load():
     vp, cp, i, f, u64, sz = C.c_void_p, C.c_char_p, C.c_int, C.c_float, C.c_uint64, C.c_size_t
     sigs = {
         "mcb_abi_version": ([], i),
+        "mcb_build_stamp": ([], cp),
         "mcb_struct_size": ([i], i),
         "mcb_status_string": ([i], cp),
         "mcb_parse": ([cp], i),
@@ -91,6 +92,7 @@ def _load():
         "mcb_counts_device": ([vp, C.POINTER(vp)], i),
         "mcb_set_mesh_mode": ([vp, i], i),
         "mcb_set_field_mode": ([vp, i], i),
+        "mcb_set_stage_timing": ([vp, i], i),
         "mcb_set_jit": ([vp, i], i),
         "mcb_jit_check": ([cp, cp, sz], i),
         "mcb_get_indexed_mesh": ([vp, vp, vp, vp, u64, u64], i),
@@ -100,6 +102,16 @@ def _load():
         "mcb_get_cases": ([vp, vp, vp], i),
         "mcb_get_field": ([vp, vp], i),
         "mcb_get_active": ([vp, vp, vp, u64], i),
+        "mcb_layer_triangles": ([vp, vp], i),
+        "mcb_balance_slabs": ([i, i, vp, C.c_double, vp], i),
+        "mcb_comm_unique_id": ([vp], i),
+        "mcb_comm_init": ([vp, vp, i, i], i),
+        "mcb_comm_exchange": ([vp], i),
+        "mcb_comm_offsets": ([vp, C.POINTER(u64), C.POINTER(u64), vp], i),
+        "mcb_comm_balance": ([vp, C.c_double, C.POINTER(i), C.POINTER(i)], i),
+        "mcb_comm_finalize": ([vp], i),
+        "mcb_host_register": ([vp, sz], i),
+        "mcb_host_unregister": ([vp], i),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what include/mcb.h declares
@@ -168,6 +180,25 @@ def slab_range(M, rank, nranks):
     if rc != MCB_OK:
         raise McbError(rc)
     return a.value, b.value
+
+
+def balance_slabs(triangles_per_layer, nranks, fixed_cost_per_layer=-1.0):
+    """Host-only: cut points [nranks+1] of contiguous z-slabs of (nearly) equal cost (mcb_balance_slabs)."""
+    t = np.ascontiguousarray(triangles_per_layer, np.uint32)
+    cuts = np.zeros(nranks + 1, np.int32)
+    rc = lib.mcb_balance_slabs(len(t), nranks, t.ctypes.data_as(C.c_void_p), float(fixed_cost_per_layer), cuts.ctypes.data_as(C.c_void_p))
+    if rc != MCB_OK:
+        raise McbError(rc)
+    return [int(x) for x in cuts]
+
+
+def comm_unique_id():
+    """128 bytes of ncclGetUniqueId: made on one rank, handed to the others out of band."""
+    buf = C.create_string_buffer(128)
+    rc = lib.mcb_comm_unique_id(buf)
+    if rc != MCB_OK:
+        raise McbError(rc, "mcb_comm_unique_id (is libnccl.so.2 there?)")
+    return buf.raw
 
 
 class Context:
@@ -257,6 +288,10 @@ class Context:
         """FIELD_DENSE (whole field in device memory) or FIELD_SPARSE (signs everywhere, values only around the surface)."""
         self._ck(lib.mcb_set_field_mode(self.h, int(mode)))
 
+    def set_stage_timing(self, enabled):
+        """CUDA events around the stages (Counts.ms_*): on by default; off shortens the gaps between the short kernels."""
+        self._ck(lib.mcb_set_stage_timing(self.h, int(bool(enabled))))
+
     def set_mesh_mode(self, mode):
         """MESH_SOUP (float4 triangle soup), MESH_INDEXED (welded Poly_Data layout) or both (3)."""
         self._ck(lib.mcb_set_mesh_mode(self.h, int(mode)))
@@ -316,6 +351,31 @@ class Context:
         out = np.empty((c.k_end - c.k_begin + 1, n1, n1), np.float32)
         self._ck(lib.mcb_get_field(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def layer_triangles(self):
+        """Triangles per cube layer of this slab in the last polygonisation (uint32[k_end - k_begin])."""
+        c = self.counts
+        out = np.zeros(c.k_end - c.k_begin, np.uint32)
+        self._ck(lib.mcb_layer_triangles(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ---- z-slabs over several GPUs: the NCCL exchange behind the C ABI (mcb_comm_*) ----
+    def comm_init(self, id128, rank, nranks):
+        self._ck(lib.mcb_comm_init(self.h, C.c_char_p(id128), rank, nranks))
+
+    def comm_exchange(self):
+        self._ck(lib.mcb_comm_exchange(self.h))
+
+    def comm_offsets(self, nranks):
+        off, tot = C.c_uint64(0), C.c_uint64(0)
+        per = np.zeros(nranks, np.uint64)
+        self._ck(lib.mcb_comm_offsets(self.h, C.byref(off), C.byref(tot), per.ctypes.data_as(C.c_void_p)))
+        return int(off.value), int(tot.value), [int(x) for x in per]
+
+    def comm_balance(self, fixed_cost_per_layer=-1.0):
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(lib.mcb_comm_balance(self.h, float(fixed_cost_per_layer), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def get_active(self):
         A = int(self.counts.active)

@@ -30,7 +30,25 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS) or os.path.getmtime(__file__) > t
 
 
+def source_stamp():
+    """sha256 over every source the library is built from, in a fixed order (mcb_build_stamp() returns it)."""
+    import hashlib
+    h = hashlib.sha256()
+    names = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h")) or f == "mcb_tri_words.inc")
+    for f in names + [os.path.join("..", "..", "include", "mcb.h")]:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
+    stamp = source_stamp()
+    stamp_file = os.path.join(CSRC, "mcb_build_stamp.inc")
+    old = open(stamp_file).read() if os.path.exists(stamp_file) else ""
+    if old != '"%s"\n' % stamp:
+        with open(stamp_file, "w") as o:
+            o.write('"%s"\n' % stamp)
+        force = True  # a source changed since the library was built, whatever the mtimes say
     if not force and not stale():
         return LIB
     # mcb_pow.h also travels inside the library as text: the run-time compiled evaluator (mcb_jit.cpp) includes it through NVRTC

@@ -5,6 +5,7 @@
  * computes field values, cases or triangles on the host.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -12,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -117,6 +119,17 @@ struct mcb_ctx {
     uint32_t* d_cw = nullptr;      /* [items][8] corner words of every 32-cube item, repeating-surface mode only */
     size_t cap_cw = 0;
     float seed[3] = {0.f, 0.f, 0.f};
+    /* z-slabs over several GPUs (mcb_comm_*): the NCCL communicator and the device-side placement of this slab */
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_nranks = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t comm_ready = nullptr, comm_done = nullptr;
+    unsigned long long* d_comm = nullptr;   /* [2 + nranks]: two staging slots for this slab's count, then the gathered counts */
+    unsigned long long* h_comm = nullptr;   /* pinned copy of the gathered counts */
+    int comm_flip = 0;
+    bool comm_pending = false;
+    uint32_t* d_layer_hist = nullptr;       /* [cap_layer_hist] triangles per global cube layer */
+    size_t cap_layer_hist = 0;
     uint8_t* d_mark = nullptr;
     uint32_t* d_changed = nullptr;
     uint32_t* d_seed_u32 = nullptr; /* keep | ktri | pa | pt, cap_seed entries each, then the block sums */
@@ -142,6 +155,8 @@ struct mcb_ctx {
     bool field_is_sparse = false;  /* what the last polygonisation left in d_F: only the blocks around the surface */
     bool poison_field = false;     /* $MCB_POISON_FIELD: NaN-fill d_F first, so a read outside the blocks shows (tests) */
     bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
+    bool stage_timing = true;      /* mcb_set_stage_timing: CUDA events around the stages (mcb_counts::ms_*) */
+    bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
     int emit_variant = 2;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk),
                                       9 = second generation with 24 edge slots (tests: forces chunks to be emitted in several runs) */
     uint8_t* d_fflags = nullptr;   /* [cap_fblocks] 2 = evaluated (undecided block), 1 = apron block to refill, 0 = untouched */
@@ -149,6 +164,9 @@ struct mcb_ctx {
     uint32_t* d_flist = nullptr;   /* [cap_fblocks] apron blocks */
     uint32_t* d_elist = nullptr;   /* [cap_fblocks] undecided blocks */
     uint8_t* d_cand = nullptr;     /* [cap_cand] cube blocks that may hold an active cube */
+    uint8_t* d_scls = nullptr;     /* [cap_scls] interval class of every 32 x 16 x 16 super-block */
+    size_t cap_scls = 0;
+    BlockDims bd{};                /* block geometry of the last block-field run (mcb_get_cases completes the sign words with it) */
     mcb_ival* d_bounds_iv = nullptr; /* [3][slots][nb] table bounds per block of each axis */
     size_t cap_fblocks = 0, cap_cand = 0, cap_bounds_iv = 0;
     mcb_counts last{};
@@ -214,6 +232,10 @@ int install_equation(mcb_ctx* ctx, int slot, const char* equation) {
     if (rc != MCB_OK) return fail(ctx, rc, err);
 
     EqSlot ns;
+    struct Guard { /* frees the new slot's device memory on every early return */
+        EqSlot* s;
+        ~Guard() { if (s) free_slot(*s); }
+    } guard{&ns};
     ns.c = c;
     ns.valid = true;
     std::vector<SlotDesc> descs;
@@ -242,6 +264,7 @@ int install_equation(mcb_ctx* ctx, int slot, const char* equation) {
     fill_program(ns.grid, ns.c.grid_fused, ns.c.kpool);
     free_slot(ctx->eq[slot]);
     ctx->eq[slot] = ns;
+    guard.s = nullptr; /* the slot owns the allocations now */
     ctx->have_result = false;
     return MCB_OK;
 }
@@ -439,6 +462,12 @@ extern "C" {
 
 int mcb_abi_version(void) { return MCB_ABI_VERSION; }
 
+const char* mcb_build_stamp(void) {
+    return
+#include "mcb_build_stamp.inc" /* sha256 over the sources this library was built from, written by build.py */
+        ;
+}
+
 int mcb_struct_size(int which) { return which == 0 ? (int)sizeof(mcb_counts) : which == 1 ? (int)sizeof(mcb_step_data) : MCB_E_ARG; }
 
 const char* mcb_status_string(int s) {
@@ -559,6 +588,8 @@ int mcb_create(int device, mcb_ctx** out) {
         ctx->poison_field = poison && poison[0] == '1';
         const char* noiv = std::getenv("MCB_NO_INTERVAL");
         ctx->decide_blocks = !(noiv && noiv[0] == '1');
+        const char* we = std::getenv("MCB_WELD_EXACT");
+        ctx->weld_exact_only = we && we[0] == '1';
         const char* ev = std::getenv("MCB_EMIT");
         if (ev && (ev[0] == '1' || ev[0] == '2' || ev[0] == '3' || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
     }
@@ -576,7 +607,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->eq) free_slot(s);
     for (auto& kv : ctx->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
-    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw); cudaFree(ctx->d_bcls); cudaFree(ctx->d_elist); cudaFree(ctx->d_cand);
+    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw); cudaFree(ctx->d_bcls); cudaFree(ctx->d_elist); cudaFree(ctx->d_cand); cudaFree(ctx->d_scls);
     cudaFree(ctx->d_bounds_iv); cudaFree(ctx->d_ent); cudaFree(ctx->d_tile_u32); cudaFree(ctx->d_amb);
     cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
@@ -589,6 +620,8 @@ void mcb_destroy(mcb_ctx* ctx) {
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->seg_ev) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    mcb_comm_finalize(ctx);
+    cudaFree(ctx->d_layer_hist);
     cudaFree(ctx->d_bounds);
     if (ctx->h_bounds) cudaFreeHost(ctx->h_bounds);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -824,8 +857,8 @@ int Run::encode_program(mcb_program& launch, bool& has_pow, bool blocks) {
                     uint32_t arg_b;
                     if (!resolve(nsrc, MCB_FINSN_ARG(nx), &arg_b)) return fail(ctx, MCB_E_CAPACITY, "axis tables too large for the operand field");
                     has_pow |= nop == MCB_F_POW || nop == MCB_F_RPOW;
+                    if (n + 2 + (fop == MCB_F_PUSH ? 1 : 0) > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
                     if (fop == MCB_F_PUSH) launch.code[n++] = MCB_HANDLER_SPILL;
-                    if (n + 2 > MCB_MAX_CODE) return fail(ctx, MCB_E_CAPACITY, "program too long");
                     launch.code[n++] = (uint32_t)MCB_HANDLER_PAIR(nop, leaf_class(src), leaf_class(nsrc)) | (arg << 8);
                     launch.code[n++] = arg_b;
                     pc++;
@@ -964,8 +997,13 @@ int Run::ensure_block_buffers(FieldBlocks* fb, BlockDims* bd) {
     bd->nbx = g.P / kFieldBlockX;
     bd->nby = (g.NV + kFieldBlockY - 1) / kFieldBlockY;
     bd->nbz = (g.NZ + kFieldBlockZ - 1) / kFieldBlockZ;
+    bd->nsy = (bd->nby + kSuper - 1) / kSuper;
+    bd->nsz = (bd->nbz + kSuper - 1) / kSuper;
     bd->nb = std::max(bd->nbx, std::max(bd->nby, bd->nbz));
     bd->spa = eq.max_per_axis;
+    bd->WC = (int)cg.WC;
+    bd->cjb = (g.M + 3) / 4;
+    bd->ckb = (g.ke - g.kb + 3) / 4;
     const size_t nb = (size_t)bd->nbx * bd->nby * bd->nbz;
     if (nb >= (1ull << 32)) return fail(ctx, MCB_E_CAPACITY, "too many field blocks: split the grid into more z-slabs");
     if (ctx->cap_fblocks < nb) {
@@ -977,12 +1015,12 @@ int Run::ensure_block_buffers(FieldBlocks* fb, BlockDims* bd) {
         MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb + 16, s)); /* the padding field_list_kernel reads stays zero */
         ctx->cap_fblocks = nb;
     }
-    const size_t niv = (size_t)3 * bd->spa * bd->nb;
     int rc;
-    if ((rc = ensure(ctx, &ctx->d_bounds_iv, &ctx->cap_bounds_iv, niv)) != MCB_OK) return rc;
-    const size_t ncand = (size_t)cg.WC * ((g.M + 3) / 4) * ((g.ke - g.kb + 3) / 4);
-    if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, ncand)) != MCB_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_bounds_iv, &ctx->cap_bounds_iv, (size_t)2 * 3 * bd->spa * bd->nb)) != MCB_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (size_t)bd->WC * bd->cjb * bd->ckb)) != MCB_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_scls, &ctx->cap_scls, (size_t)bd->nbx * bd->nsy * bd->nsz)) != MCB_OK) return rc;
     *fb = FieldBlocks{bd->nbx, bd->nby, bd->nbz, ctx->d_fflags, ctx->d_flist};
+    ctx->bd = *bd;
     return MCB_OK;
 }
 
@@ -1019,7 +1057,10 @@ int Run::stage_eval_blocks() {
     BlockDims bd;
     int rc = ensure_block_buffers(&fb, &bd);
     if (rc != MCB_OK) return rc;
-    if (ctx->poison_field) MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
+    if (ctx->poison_field) { /* tests: a read of a field value or a sign word nobody wrote must show */
+        MCB_CK(cudaMemsetAsync(ctx->d_F, 0xff, (size_t)g.NZ * g.NV * g.P * sizeof(float), s));
+        MCB_CK(cudaMemsetAsync(ctx->d_S, 0x5a, (size_t)g.NZ * g.NV * g.WP * sizeof(uint32_t), s));
+    }
     ctx->field_is_sparse = true;
     ctx->jit_used = false;
     if (jit_wanted(ctx, eq)) {
@@ -1029,14 +1070,15 @@ int Run::stage_eval_blocks() {
         else if (ctx->jit == MCB_JIT_ON) return rc;
         else ctx->jit_note = ctx->err;
     }
-    const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz;
-    MCB_LAUNCH((axis_bounds_kernel), (unsigned)((3 * bd.spa * bd.nb + 127) / 128), 128, 0, s, ctx->d_tables, g, bd, eq.c.n_axis_slots[0],
+    const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz, nsuper = (unsigned)bd.nbx * (unsigned)bd.nsy * (unsigned)bd.nsz;
+    MCB_CK(cudaMemsetAsync(ctx->d_cand, 0, (size_t)bd.WC * bd.cjb * bd.ckb, s));
+    MCB_LAUNCH((axis_bounds_kernel), dim3((unsigned)((3 * bd.spa * bd.nb + 127) / 128), 2u), 128, 0, s, ctx->d_tables, g, bd, eq.c.n_axis_slots[0],
                eq.c.n_axis_slots[1], eq.c.n_axis_slots[2], ctx->d_bounds_iv);
-    MCB_LAUNCH((block_class_kernel), (nblocks + 255) / 256, 256, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->decide_blocks ? 1 : 0, ctx->d_bcls,
-               ctx->d_fflags, ctx->d_elist, ctx->d_S, ctx->d_ctr);
-    const int cjb = (g.M + 3) / 4, ckb = (g.ke - g.kb + 3) / 4;
-    MCB_LAUNCH((cube_cand_kernel), (unsigned)(((size_t)cg.WC * cjb * ckb + 255) / 256), 256, 0, s, ctx->d_bcls, bd, (int)cg.WC, cjb, ckb, ctx->d_cand);
-    launches += 3;
+    MCB_LAUNCH((super_class_kernel), (nsuper + 127) / 128, 128, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->d_scls);
+    MCB_LAUNCH((block_class_kernel), (nblocks + 255) / 256, 256, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->d_scls, ctx->decide_blocks ? 1 : 0,
+               ctx->d_bcls, ctx->d_fflags, ctx->d_elist, ctx->d_cand, ctx->d_ctr);
+    MCB_LAUNCH((decided_signs_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, g, bd, ctx->d_elist, ctx->d_ctr, ctx->d_bcls, ctx->d_S);
+    launches += 4;
     if ((rc = launch_block_eval(fb, ctx->d_elist, &ctx->d_ctr->eval_blocks)) != MCB_OK) return rc;
     return launch_constraints(*this);
 }
@@ -1063,13 +1105,14 @@ int Run::stage_classify() {
     if (need_items && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
     unsigned long long* items = need_items ? ctx->d_item : nullptr;
     const unsigned amb_ctas = (unsigned)ctx->sm_count * 2;
+    const FieldBlocks apron = skip ? FieldBlocks{ctx->bd.nbx, ctx->bd.nby, ctx->bd.nbz, ctx->d_fflags, ctx->d_flist} : FieldBlocks{0, 0, 0, nullptr, nullptr};
 #define MCB_CLASSIFY(HAS_V, REPEAT)                                                                                                   \
     do {                                                                                                                              \
         MCB_LAUNCH((classify_kernel<HAS_V, REPEAT>), tiles, kClsThreads, kClsSmemBytes, s, g, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_ctr, cw); \
         MCB_LAUNCH((ambiguity_kernel<REPEAT>), amb_ctas, 128, 0, s, eq.point, g, ctx->d_cs, ctx->d_cls, sc, ctx->d_ctr, ctx->d_F);          \
         MCB_LAUNCH((tile_scan_kernel), 1, 1024, 0, s, sc, tiles, ctx->d_ctr);                                                             \
         MCB_LAUNCH((compact_kernel<REPEAT>), tiles, kClsThreads, 0, s, g, ctx->d_cls, ctx->d_S, dV, cg, sc, ctx->d_rec, ctx->d_trioff,     \
-                   ctx->cap_active, items, cw);                                                                                        \
+                   ctx->cap_active, items, cw, apron);                                                                                 \
     } while (0)
     if (cw) { if (dV) MCB_CLASSIFY(true, true); else MCB_CLASSIFY(false, true); }
     else { if (dV) MCB_CLASSIFY(true, false); else MCB_CLASSIFY(false, false); }
@@ -1088,9 +1131,8 @@ int Run::stage_fill() {
     int rc = ensure_block_buffers(&fb, &bd);
     if (rc != MCB_OK) return rc;
     const size_t nb = (size_t)fb.nbx * fb.nby * fb.nbz;
-    MCB_LAUNCH((field_flag_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, ctx->d_rec, g, ctx->d_ctr, ctx->cap_active, fb);
-    MCB_LAUNCH((field_list_kernel), (unsigned)((nb / 16 + 256) / 256), 256, 0, s, fb, (unsigned)nb, ctx->d_ctr);
-    launches += 2;
+    MCB_LAUNCH((field_list_kernel), (unsigned)((nb / 16 + 256) / 256), 256, 0, s, fb, (unsigned)nb, ctx->d_ctr); /* the blocks compact_kernel marked */
+    launches += 1;
     return launch_block_eval(fb, ctx->d_flist, &ctx->d_ctr->field_blocks);
 }
 
@@ -1178,7 +1220,8 @@ int Run::stage_weld() {
     const WeldViewT<true> WR{W.g, W.cs, W.F, W.V, W.present, W.WC}; /* repeating-surface mode: same view, level checks compiled in */
     const WeldBuffers B{ctx->d_rec, ctx->d_trioff, ctx->d_item, ctx->d_vinfo, ctx->d_chunk_new, cg.WC};
     if (g.repeat) MCB_LAUNCH((weld_count_kernel), eblocks * 2, kWeldThreads, 0, s, WR, B, ctx->d_ctr, ctx->cap_active);
-    else MCB_LAUNCH((weld_count_kernel), eblocks * 2, kWeldThreads, 0, s, W, B, ctx->d_ctr, ctx->cap_active);
+    else if (W.V != nullptr || W.present != nullptr || ctx->weld_exact_only) MCB_LAUNCH((weld_count_kernel), eblocks * 2, kWeldThreads, 0, s, W, B, ctx->d_ctr, ctx->cap_active);
+    else MCB_LAUNCH((weld_count_fast_kernel), eblocks * 4, kWeldCubes, 0, s, W, B, ctx->d_cls, ctx->d_ctr, ctx->cap_active);
     MCB_LAUNCH((weld_scan_kernel), 1, 1024, 0, s, ctx->d_chunk_new, ctx->d_ctr, ctx->cap_active);
     MCB_LAUNCH((weld_base_kernel), eblocks * 2, kWeldCubes, 0, s, B, ctx->d_ctr, ctx->cap_active);
     /* streaming: with a registered host destination and everything fitting, weld_emit runs range by range and
@@ -1261,6 +1304,8 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     g.repeat = ctx->repeat_on ? 1 : 0;
     g.rstep = ctx->repeat_step;
     if (ctx->repeat_on && ctx->seed_on) return fail(ctx, MCB_E_STATE, "repeating-surface mode and seed mode cannot be combined");
+    if (ctx->seed_on && ctx->nccl_comm && ctx->comm_nranks > 1)
+        return fail(ctx, MCB_E_STATE, "seed mode follows one component through the whole grid: it cannot be combined with z-slabs over several GPUs");
     if (ctx->normals == 2 && !(ctx->mesh_mode & MCB_MESH_INDEXED))
         return fail(ctx, MCB_E_STATE, "normal.h normals (mode 2) are defined on the welded mesh: request MCB_MESH_INDEXED");
 
@@ -1277,32 +1322,33 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
      * block-field mode: interval proof per 32 x 4 x 4 vertex block, evaluation of the undecided blocks only — decided
      * from this call's own data, so a first or changed configuration is as fast as a repeated one. */
     const bool blocks = ctx->field_mode != MCB_FIELD_DENSE && !g.repeat;
+    const bool timing = ctx->stage_timing;
     ctx->ms_compile = 0.f;
     MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
-    MCB_CK(cudaEventRecord(ctx->ev[0], s));
+    if (timing) MCB_CK(cudaEventRecord(ctx->ev[0], s));
     if ((rc = run.stage_tables()) != MCB_OK) return rc;
-    MCB_CK(cudaEventRecord(ctx->ev[1], s));
+    if (timing) MCB_CK(cudaEventRecord(ctx->ev[1], s));
     if ((rc = blocks ? run.stage_eval_blocks() : run.stage_eval()) != MCB_OK) return rc;
-    MCB_CK(cudaEventRecord(ctx->ev[2], s));
+    if (timing) MCB_CK(cudaEventRecord(ctx->ev[2], s));
     MCB_CK(cudaGetLastError());
 
     bool need_classify = true;
     for (;;) { /* repeated only when an output buffer had to grow (mcb_counts::reruns) */
         if (need_classify) {
             if ((rc = run.stage_classify()) != MCB_OK) return rc;
-            MCB_CK(cudaEventRecord(ctx->ev[6], s));
+            if (timing) MCB_CK(cudaEventRecord(ctx->ev[6], s));
             if (ctx->field_is_sparse && (rc = run.stage_fill()) != MCB_OK) return rc;
-            MCB_CK(cudaEventRecord(ctx->ev[7], s));
+            if (timing) MCB_CK(cudaEventRecord(ctx->ev[7], s));
             if (ctx->seed_on && (rc = run.stage_seed()) != MCB_OK) return rc;
-            MCB_CK(cudaEventRecord(ctx->ev[3], s));
+            if (timing) MCB_CK(cudaEventRecord(ctx->ev[3], s));
         }
         if (run.want_soup && (rc = run.stage_soup()) != MCB_OK) return rc;
-        MCB_CK(cudaEventRecord(ctx->ev[4], s));
+        if (timing) MCB_CK(cudaEventRecord(ctx->ev[4], s));
         if (run.want_indexed) {
             if ((rc = run.stage_weld()) != MCB_OK) return rc;
             if (ctx->normals == 2 && (rc = run.stage_normal_h()) != MCB_OK) return rc;
         }
-        MCB_CK(cudaEventRecord(ctx->ev[5], s));
+        if (timing) MCB_CK(cudaEventRecord(ctx->ev[5], s));
         if (run.want_indexed && ctx->streamed) MCB_CK(cudaStreamWaitEvent(s, ctx->seg_ev[8], 0)); /* return when the mesh is on the host */
         MCB_CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         MCB_CK(cudaStreamSynchronize(s));
@@ -1349,18 +1395,20 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     c.ambiguous = ctx->h_ctr->ambiguous;
     c.redirected = ctx->h_ctr->redirected;
     c.M = g.M; c.k_begin = g.kb; c.k_end = g.ke;
-    cudaEventElapsedTime(&c.ms_tables, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&c.ms_eval, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&c.ms_classify, ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&c.ms_fill, ctx->ev[6], ctx->ev[7]);
-    c.ms_classify -= c.ms_fill;
+    if (timing) {
+        cudaEventElapsedTime(&c.ms_tables, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&c.ms_eval, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&c.ms_classify, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&c.ms_fill, ctx->ev[6], ctx->ev[7]);
+        c.ms_classify -= c.ms_fill;
+        cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&c.ms_weld, ctx->ev[4], ctx->ev[5]);
+        cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[5]);
+    }
     c.field_mode = ctx->field_is_sparse ? MCB_FIELD_SPARSE : MCB_FIELD_DENSE;
     c.field_blocks = ctx->field_is_sparse ? (uint64_t)ctx->h_ctr->field_blocks + ctx->h_ctr->eval_blocks : 0;
     c.jit = ctx->jit_used ? 1u : 0u;
     c.ms_compile = ctx->jit_used ? ctx->ms_compile : 0.f;
-    cudaEventElapsedTime(&c.ms_emit, ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&c.ms_weld, ctx->ev[4], ctx->ev[5]);
-    cudaEventElapsedTime(&c.ms_total, ctx->ev[0], ctx->ev[5]);
     c.vertices = run.want_indexed ? ctx->h_ctr->vertices : 0;
     c.mesh_mode = (uint32_t)ctx->mesh_mode;
     c.launches = run.launches;
@@ -1382,6 +1430,12 @@ int mcb_get_mesh(mcb_ctx* ctx, float* pos4, float* nrm4, uint64_t cap_triangles)
     if (pos4) MCB_CK(cudaMemcpyAsync(pos4, ctx->d_pos, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     if (nrm4) MCB_CK(cudaMemcpyAsync(nrm4, ctx->d_nrm, T * 3 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_set_stage_timing(mcb_ctx* ctx, int enabled) {
+    if (!ctx) return MCB_E_ARG;
+    ctx->stage_timing = enabled != 0;
     return MCB_OK;
 }
 
@@ -1480,6 +1534,10 @@ int mcb_get_cases(mcb_ctx* ctx, uint8_t* cube_code, uint8_t* table_idx) {
     const long long n = (long long)ctx->last.cubes;
     bool any_constraint = false;
     for (int i = 0; i < 3; i++) any_constraint |= ctx->cons[i].in_use && ctx->eq[i + 1].valid;
+    if (ctx->field_is_sparse) { /* block-field mode: only the decided blocks next to the surface carry their sign words so far */
+        const unsigned nblocks = (unsigned)ctx->bd.nbx * (unsigned)ctx->bd.nby * (unsigned)ctx->bd.nbz;
+        MCB_LAUNCH((decided_signs_all_kernel), (nblocks + 255) / 256, 256, 0, ctx->stream, g, ctx->bd, ctx->d_bcls, ctx->d_S);
+    }
     uint8_t *d_code = nullptr, *d_tidx = nullptr;
     MCB_CK(cudaMalloc((void**)&d_code, (size_t)n));
     if (cudaMalloc((void**)&d_tidx, (size_t)n) != cudaSuccess) { cudaFree(d_code); return fail(ctx, MCB_E_NOMEM, "cudaMalloc"); }
@@ -1530,3 +1588,205 @@ int mcb_get_active(mcb_ctx* ctx, uint64_t* records, uint32_t* tri_offsets, uint6
 }
 
 } /* extern "C" */
+
+/* ---- z-slabs over several GPUs --------------------------------------------------------------------------------- */
+namespace {
+
+/* libnccl.so.2, loaded on first use (in a torchrun process this is the copy torch already mapped) */
+struct NcclId { char internal[128]; };
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string error;
+};
+constexpr int kNcclUint32 = 3, kNcclUint64 = 5, kNcclSum = 0; /* ncclDataType_t / ncclRedOp_t values (nccl.h) */
+
+Nccl& nccl() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (n.lib) break;
+        }
+        if (!n.lib) { n.error = "libnccl.so.2 not found: the multi-GPU exchange is unavailable"; return; }
+#define MCB_SYM(field, sym)                                                \
+    n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.lib, sym));      \
+    if (!n.field) n.error = std::string("libnccl lacks ") + sym;
+        MCB_SYM(GetUniqueId, "ncclGetUniqueId")
+        MCB_SYM(CommInitRank, "ncclCommInitRank")
+        MCB_SYM(CommDestroy, "ncclCommDestroy")
+        MCB_SYM(AllGather, "ncclAllGather")
+        MCB_SYM(AllReduce, "ncclAllReduce")
+        MCB_SYM(GetErrorString, "ncclGetErrorString")
+#undef MCB_SYM
+    });
+    return n;
+}
+
+#define MCB_NCCL(call)                                                                                                  \
+    do {                                                                                                                \
+        const int r_ = (call);                                                                                          \
+        if (r_ != 0) return fail(ctx, MCB_E_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r_));                \
+    } while (0)
+
+} /* namespace */
+
+extern "C" {
+
+int mcb_balance_slabs(int M, int nranks, const uint32_t* tri, double fixed, int* cuts) {
+    if (M <= 0 || nranks <= 0 || nranks > M || !tri || !cuts) return MCB_E_ARG;
+    if (fixed < 0) fixed = 0.0015 * (double)M * (double)M;
+    double total = 0;
+    for (int k = 0; k < M; k++) total += (double)tri[k] + fixed;
+    cuts[0] = 0;
+    double run = 0;
+    int k = 0;
+    for (int r = 1; r < nranks; r++) {
+        const double want = total * (double)r / (double)nranks;
+        /* take layers while that brings the prefix closer to the target */
+        while (k < M && run + 0.5 * ((double)tri[k] + fixed) <= want) { run += (double)tri[k] + fixed; k++; }
+        int c = std::max(k, cuts[r - 1] + 1);            /* at least one layer per slab ... */
+        c = std::min(c, M - (nranks - r));               /* ... for the ranks still to come as well */
+        while (k < c) { run += (double)tri[k] + fixed; k++; }
+        cuts[r] = c;
+    }
+    cuts[nranks] = M;
+    return MCB_OK;
+}
+
+int mcb_layer_triangles(mcb_ctx* ctx, uint32_t* per_layer) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change");
+    if (!per_layer) return fail(ctx, MCB_E_ARG, "null buffer");
+    const size_t M = (size_t)ctx->g.M;
+    if ((rc = ensure(ctx, &ctx->d_layer_hist, &ctx->cap_layer_hist, M)) != MCB_OK) return rc;
+    MCB_CK(cudaMemsetAsync(ctx->d_layer_hist, 0, M * 4, ctx->stream));
+    MCB_LAUNCH((layer_hist_kernel), (unsigned)ctx->sm_count * 4, 256, 0, ctx->stream, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->d_layer_hist);
+    MCB_CK(cudaMemcpyAsync(per_layer, ctx->d_layer_hist + ctx->g.kb, (size_t)(ctx->g.ke - ctx->g.kb) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    MCB_CK(cudaGetLastError());
+    return MCB_OK;
+}
+
+int mcb_comm_unique_id(void* id128) {
+    if (!id128) return MCB_E_ARG;
+    Nccl& N = nccl();
+    if (!N.error.empty()) return MCB_E_STATE;
+    NcclId id;
+    if (N.GetUniqueId(&id) != 0) return MCB_E_CUDA;
+    std::memcpy(id128, &id, sizeof id);
+    return MCB_OK;
+}
+
+int mcb_comm_finalize(mcb_ctx* ctx) {
+    if (!ctx) return MCB_E_ARG;
+    if (ctx->nccl_comm) {
+        cudaSetDevice(ctx->device);
+        if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+        nccl().CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
+    if (ctx->comm_ready) { cudaEventDestroy(ctx->comm_ready); ctx->comm_ready = nullptr; }
+    if (ctx->comm_done) { cudaEventDestroy(ctx->comm_done); ctx->comm_done = nullptr; }
+    cudaFree(ctx->d_comm); ctx->d_comm = nullptr;
+    if (ctx->h_comm) { cudaFreeHost(ctx->h_comm); ctx->h_comm = nullptr; }
+    ctx->comm_nranks = 1; ctx->comm_rank = 0; ctx->comm_pending = false;
+    return MCB_OK;
+}
+
+int mcb_comm_init(mcb_ctx* ctx, const void* id128, int rank, int nranks) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, MCB_E_ARG, "rank / nranks out of range");
+    Nccl& N = nccl();
+    if (!N.error.empty()) return fail(ctx, MCB_E_STATE, N.error);
+    mcb_comm_finalize(ctx);
+    NcclId id;
+    std::memcpy(&id, id128, sizeof id);
+    MCB_NCCL(N.CommInitRank(&ctx->nccl_comm, nranks, id, rank));
+    ctx->comm_rank = rank; ctx->comm_nranks = nranks;
+    MCB_CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    MCB_CK(cudaEventCreateWithFlags(&ctx->comm_ready, cudaEventDisableTiming));
+    MCB_CK(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+    MCB_CK(cudaMalloc((void**)&ctx->d_comm, (size_t)(2 + nranks) * 8));
+    MCB_CK(cudaMallocHost((void**)&ctx->h_comm, (size_t)nranks * 8));
+    int k0, k1;
+    if ((rc = mcb_slab_range(ctx->M, rank, nranks, &k0, &k1)) != MCB_OK) return fail(ctx, rc, "fewer cube layers than ranks");
+    return mcb_set_slab(ctx, k0, k1);
+}
+
+int mcb_comm_exchange(mcb_ctx* ctx) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->nccl_comm) return fail(ctx, MCB_E_STATE, "mcb_comm_init has not been called");
+    /* the next polygonisation resets the live counters: the count is first copied aside, in stream order */
+    unsigned long long* stg = ctx->d_comm + ctx->comm_flip;
+    ctx->comm_flip ^= 1;
+    MCB_CK(cudaMemcpyAsync(stg, &ctx->d_ctr->triangles, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MCB_CK(cudaEventRecord(ctx->comm_ready, ctx->stream));
+    MCB_CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ready, 0));
+    MCB_NCCL(nccl().AllGather(stg, ctx->d_comm + 2, 1, kNcclUint64, ctx->nccl_comm, ctx->comm_stream));
+    MCB_CK(cudaMemcpyAsync(ctx->h_comm, ctx->d_comm + 2, (size_t)ctx->comm_nranks * 8, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    MCB_CK(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+    ctx->comm_pending = true;
+    return MCB_OK;
+}
+
+int mcb_comm_offsets(mcb_ctx* ctx, uint64_t* offset, uint64_t* total, uint64_t* per_rank) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->nccl_comm || !ctx->comm_pending) return fail(ctx, MCB_E_STATE, "no exchange to wait for");
+    MCB_CK(cudaEventSynchronize(ctx->comm_done));
+    uint64_t off = 0, tot = 0;
+    for (int r = 0; r < ctx->comm_nranks; r++) {
+        if (r < ctx->comm_rank) off += ctx->h_comm[r];
+        tot += ctx->h_comm[r];
+        if (per_rank) per_rank[r] = ctx->h_comm[r];
+    }
+    if (offset) *offset = off;
+    if (total) *total = tot;
+    return MCB_OK;
+}
+
+int mcb_comm_balance(mcb_ctx* ctx, double fixed_cost_per_layer, int* k_begin, int* k_end) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->nccl_comm) return fail(ctx, MCB_E_STATE, "mcb_comm_init has not been called");
+    if (!ctx->have_result) return fail(ctx, MCB_E_STATE, "mcb_polygonise has not run since the last change: nothing to balance by");
+    const size_t M = (size_t)ctx->g.M;
+    if ((rc = ensure(ctx, &ctx->d_layer_hist, &ctx->cap_layer_hist, M)) != MCB_OK) return rc;
+    MCB_CK(cudaMemsetAsync(ctx->d_layer_hist, 0, M * 4, ctx->stream));
+    MCB_LAUNCH((layer_hist_kernel), (unsigned)ctx->sm_count * 4, 256, 0, ctx->stream, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->d_layer_hist);
+    /* every rank's layers are disjoint: the sum over ranks is the whole grid's histogram */
+    MCB_NCCL(nccl().AllReduce(ctx->d_layer_hist, ctx->d_layer_hist, M, kNcclUint32, kNcclSum, ctx->nccl_comm, ctx->stream));
+    std::vector<uint32_t> hist(M);
+    MCB_CK(cudaMemcpyAsync(hist.data(), ctx->d_layer_hist, M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> cuts((size_t)ctx->comm_nranks + 1);
+    if ((rc = mcb_balance_slabs((int)M, ctx->comm_nranks, hist.data(), fixed_cost_per_layer, cuts.data())) != MCB_OK) return fail(ctx, rc, "mcb_balance_slabs");
+    const int k0 = cuts[(size_t)ctx->comm_rank], k1 = cuts[(size_t)ctx->comm_rank + 1];
+    if (k_begin) *k_begin = k0;
+    if (k_end) *k_end = k1;
+    return mcb_set_slab(ctx, k0, k1);
+}
+
+int mcb_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return MCB_E_ARG;
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) == cudaSuccess ? MCB_OK : MCB_E_CUDA;
+}
+
+int mcb_host_unregister(void* ptr) {
+    if (!ptr) return MCB_E_ARG;
+    return cudaHostUnregister(ptr) == cudaSuccess ? MCB_OK : MCB_E_CUDA;
+}
+
+} /* extern "C" */
+

@@ -413,24 +413,6 @@ eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const
     }
 }
 
-/* blocks touched by the field reads around an active cube: its corners and their +-1 neighbours along each axis
- * (gradient normals, the weld's look at the neighbouring grid edges) = stored vertices [i,i+3] x [j,j+3] x [k-kb,k-kb+3] */
-__global__ void __launch_bounds__(256)
-field_flag_kernel(const unsigned long long* __restrict__ rec, const Grid g, const Counters* __restrict__ ctr,
-                  unsigned long long cap_active, const FieldBlocks fb) {
-    const unsigned long long n = min(ctr->active, cap_active);
-    for (unsigned long long a = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long rc = rec[a];
-        const int i = (int)(rc & 0xfffu), j = (int)((rc >> 12) & 0xfffu), pz = (int)((rc >> 24) & 0xfffu) - g.kb;
-        const int bx0 = i >> 5, bx1 = (i + 3) >> 5, by0 = j >> 2, by1 = (j + 3) >> 2, bz0 = pz >> 2, bz1 = (pz + 3) >> 2;
-        for (int bz = bz0; bz <= bz1; bz++)
-            for (int by = by0; by <= by1; by++)
-                for (int bx = bx0; bx <= bx1; bx++) {
-                    uint8_t* f = fb.flags + ((size_t)bz * fb.nby + by) * fb.nbx + bx;
-                    if (*f == 0) *f = 1; /* 2 = already evaluated (block_class_kernel); racing writers all store 1 */
-                }
-    }
-}
 /* flags == 1 -> list of the flagged, not yet evaluated block ids (any order).  A thread takes 16 flags (one 16-byte load; the flag array is padded
  * and zero-filled to a multiple of 16), a warp reserves its entries with one atomic. */
 __global__ void __launch_bounds__(256)
@@ -463,36 +445,44 @@ field_list_kernel(const FieldBlocks fb, unsigned nblocks, Counters* __restrict__
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K1 (block-field mode, the default of the drop-in): decide, evaluate, skip.
- *   axis_bounds   minimum and maximum of every axis table over each 32-column / 4-row / 4-plane block of its axis;
- *   block_class   one thread per 32 x 4 x 4 vertex block runs the fused grid program on those intervals
- *                 (mcb_interval.h: an exact proof, rounding included).  A block proven to lie entirely on one side of
- *                 the iso value gets its sixteen sign words written as constants and is never evaluated; the others
- *                 ("unknown") are appended to the evaluation list, which eval_blocks_kernel / mcb_fill_jit turn into
- *                 field values and sign words;
- *   cube_cand     one byte per 32 x 4 x 4 CUBE block: can it contain an active cube, i.e. is one of the (up to) eight
- *                 vertex blocks its corners touch unknown, or do they differ in their proven sign?  classify skips the
- *                 rest of the grid four cube rows at a time.
+ *   axis_bounds    minimum and maximum of every axis table over each block of its axis, at two levels: the 32 x 4 x 4
+ *                  vertex blocks and the 32 x 16 x 16 super-blocks (1 x 4 x 4 blocks).  A block's range is EXTENDED by
+ *                  one vertex at its far end on every axis, so the boxes of neighbouring blocks share vertices: two
+ *                  neighbouring blocks that are both decided are decided with the same sign;
+ *   super_class    one thread per super-block runs the fused grid program on those intervals (mcb_interval.h: an exact
+ *                  proof, rounding included): 1 = no vertex above iso, 2 = every vertex above iso, 0 = undecided;
+ *   block_class    one thread per block: the super-block's verdict, or its own interval evaluation when that was
+ *                  undecided.  An undecided block goes on the evaluation list (eval_blocks_kernel / mcb_fill_jit turn it
+ *                  into field values and sign words) and marks the (up to) eight 32 x 4 x 4 CUBE blocks whose corners
+ *                  reach into it as candidates; classify looks nowhere else, because a cube block that touches decided
+ *                  blocks only sees one sign (the shared vertices above);
+ *   decided_signs  the decided neighbours of the undecided blocks — the only decided blocks classify reads sign words
+ *                  of — get their sixteen constant words written.
  * The work of a polygonisation is then proportional to the surface, not to the grid, for any equation — no earlier
  * run of the same configuration is needed to find that out.
  * ------------------------------------------------------------------------------------------------------------- */
 struct BlockDims {
     int nbx, nby, nbz; /* vertex blocks per axis: P/32, ceil(NV/4), ceil(NZ/4) */
-    int nb;            /* max of the three: stride of the bounds arrays */
+    int nsy, nsz;      /* super-blocks per axis in y and z: ceil(nby/4), ceil(nbz/4) */
+    int nb;            /* max(nbx, nby, nbz): stride of both bounds arrays */
     int spa;           /* table slots per axis */
+    int WC, cjb, ckb;  /* cube blocks: words per row, ceil(M/4), ceil(layers/4) */
 };
+constexpr int kSuper = 4; /* blocks per super-block in y and z */
 __global__ void __launch_bounds__(128)
 axis_bounds_kernel(const float* __restrict__ tables, const Grid g, const BlockDims bd, int nsx, int nsy, int nsz,
-                   mcb_ival* __restrict__ B) {
+                   mcb_ival* __restrict__ B /* [2][3][spa][nb]: level 0 blocks, level 1 super-blocks */) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int level = blockIdx.y;
     if (idx >= 3 * bd.spa * bd.nb) return;
     const int b = idx % bd.nb, slot = (idx / bd.nb) % bd.spa, axis = idx / (bd.nb * bd.spa);
-    const int ns = axis == 0 ? nsx : axis == 1 ? nsy : nsz, nbk = axis == 0 ? bd.nbx : axis == 1 ? bd.nby : bd.nbz;
+    const int ns = axis == 0 ? nsx : axis == 1 ? nsy : nsz;
+    const int nbk = axis == 0 ? bd.nbx : axis == 1 ? (level ? bd.nsy : bd.nby) : (level ? bd.nsz : bd.nbz);
     if (slot >= ns || b >= nbk) return;
-    int i0, i1; /* table entries of this block: x columns, y rows, or the slab's planes (vertex kb-1+pz at entry kb+pz) */
-    if (axis == 0) { i0 = b * kFieldBlockX; i1 = i0 + kFieldBlockX; }
-    else if (axis == 1) { i0 = b * kFieldBlockY; i1 = min(i0 + kFieldBlockY, g.NV); }
-    else { i0 = g.kb + b * kFieldBlockZ; i1 = g.kb + min(b * kFieldBlockZ + kFieldBlockZ, g.NZ); }
-    const float* t = tables + ((size_t)axis * bd.spa + slot) * g.P;
+    const int span = axis == 0 ? kFieldBlockX : (level ? kSuper : 1) * (axis == 1 ? kFieldBlockY : kFieldBlockZ);
+    const int count = axis == 0 ? g.P : axis == 1 ? g.NV : g.NZ; /* table entries that exist on this axis */
+    const int i0 = b * span, i1 = min(i0 + span + 1, count);      /* one past the block: the shared vertex */
+    const float* t = tables + ((size_t)axis * bd.spa + slot) * g.P + (axis == 2 ? g.kb : 0); /* plane pz is entry kb + pz */
     float lo = __ldg(t + i0), hi = lo;
     bool ok = mcb_iv_finite(lo) != 0;
     for (int i = i0 + 1; i < i1; i++) {
@@ -504,14 +494,24 @@ axis_bounds_kernel(const float* __restrict__ tables, const Grid g, const BlockDi
     mcb_ival r;
     r.lo = ok ? lo : -INFINITY;
     r.hi = ok ? hi : INFINITY;
-    B[idx] = r;
+    B[(size_t)level * 3 * bd.spa * bd.nb + idx] = r;
+}
+
+__global__ void __launch_bounds__(128)
+super_class_kernel(const __grid_constant__ mcb_program prog /* fused grid program, slot numbers as arguments */, const Grid g,
+                   const BlockDims bd, const mcb_ival* __restrict__ B, uint8_t* __restrict__ scls) {
+    const unsigned n = (unsigned)bd.nbx * (unsigned)bd.nsy * (unsigned)bd.nsz;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int bx = (int)(idx % (unsigned)bd.nbx), sy = (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nsy), sz = (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nsy));
+    scls[idx] = (uint8_t)mcb_interval_class(prog.code, prog.n, prog.k, B + (size_t)3 * bd.spa * bd.nb, bd.spa, bd.nb, bx, sy, sz, g.iso, nullptr);
 }
 
 __global__ void __launch_bounds__(256)
-block_class_kernel(const __grid_constant__ mcb_program prog /* fused grid program, slot numbers as arguments */, const Grid g,
-                   const BlockDims bd, const mcb_ival* __restrict__ B, int decide /* 0: every block is "unknown" (tests) */,
+block_class_kernel(const __grid_constant__ mcb_program prog, const Grid g, const BlockDims bd, const mcb_ival* __restrict__ B,
+                   const uint8_t* __restrict__ scls, int decide /* 0: every block is "undecided" (tests) */,
                    uint8_t* __restrict__ cls, uint8_t* __restrict__ flags, uint32_t* __restrict__ list,
-                   uint32_t* __restrict__ S, Counters* __restrict__ ctr) {
+                   uint8_t* __restrict__ cand /* zeroed before this kernel */, Counters* __restrict__ ctr) {
     const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -520,51 +520,78 @@ block_class_kernel(const __grid_constant__ mcb_program prog /* fused grid progra
     if (idx < nblocks) {
         bx = (int)(idx % (unsigned)bd.nbx); by = (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nby);
         bz = (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nby));
-        if (decide) c = mcb_interval_class(prog.code, prog.n, prog.k, B, bd.spa, bd.nb, bx, by, bz, g.iso, nullptr);
-        cls[idx] = (uint8_t)c;
-        flags[idx] = c == 0 ? 2 : 0; /* 2 = on the evaluation list; the apron refill later turns some 0 into 1 */
-    }
-    const bool unknown = idx < nblocks && c == 0;
-    const uint32_t m = __ballot_sync(0xffffffffu, unknown);
-    if (m) { /* a warp reserves its list entries with one atomic */
-        unsigned base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&ctr->eval_blocks, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (unknown) list[base + __popc(m & ((1u << lane) - 1u))] = idx;
-    }
-    if (idx < nblocks && c != 0) {
-        const uint32_t word = c == 2 ? 0xffffffffu : 0u;
-#pragma unroll
-        for (int q = 0; q < kFieldBlockZ; q++) {
-            const int pz = bz * kFieldBlockZ + q;
-            if (pz >= g.NZ) break;
-#pragma unroll
-            for (int r = 0; r < kFieldBlockY; r++) {
-                const int y = by * kFieldBlockY + r;
-                if (y < g.NV) S[((size_t)pz * g.NV + y) * g.WP + bx] = word;
-            }
+        if (decide) {
+            c = (int)__ldg(scls + ((size_t)(bz / kSuper) * bd.nsy + by / kSuper) * bd.nbx + bx);
+            if (c == 0) c = mcb_interval_class(prog.code, prog.n, prog.k, B, bd.spa, bd.nb, bx, by, bz, g.iso, nullptr);
         }
+        cls[idx] = (uint8_t)c;
+        flags[idx] = c == 0 ? 2 : 0; /* 2 = on the evaluation list; compact_kernel turns the apron blocks' 0 into 1 */
+    }
+    const bool undecided = idx < nblocks && c == 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, undecided);
+    if (m == 0u) return;
+    unsigned base = 0; /* a warp reserves its list entries with one atomic */
+    if (lane == __ffs(m) - 1) base = atomicAdd(&ctr->eval_blocks, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (!undecided) return;
+    list[base + __popc(m & ((1u << lane) - 1u))] = idx;
+    /* cube (i, j, kz) reads the stored vertices (i+1..i+2, j+1..j+2, kz+1..kz+2): the cube blocks reaching into this
+     * vertex block are (bx-1..bx, by-1..by, bz-1..bz) */
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const int w = bx - (d & 1), jb = by - ((d >> 1) & 1), kq = bz - (d >> 2);
+        if (w < 0 || jb < 0 || kq < 0 || w >= bd.WC || jb >= bd.cjb || kq >= bd.ckb) continue;
+        cand[((size_t)kq * bd.cjb + jb) * bd.WC + w] = 1;
     }
 }
 
-/* cube (i, j, kz) reads the stored vertices (i+1..i+2, j+1..j+2, kz+1..kz+2): cube block (w, jb, kq) touches vertex
- * blocks {w, w+1} x {jb, jb+1} x {kq, kq+1} (those that exist) */
-__global__ void __launch_bounds__(256)
-cube_cand_kernel(const uint8_t* __restrict__ cls, const BlockDims bd, int WC, int cjb, int ckb, uint8_t* __restrict__ cand) {
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (unsigned)WC * (unsigned)cjb * (unsigned)ckb) return;
-    const int w = (int)(idx % (unsigned)WC), jb = (int)(idx / (unsigned)WC % (unsigned)cjb), kq = (int)(idx / ((unsigned)WC * (unsigned)cjb));
-    int first = -1;
-    bool can = false;
+/* sign words of a decided block: sixteen constants */
+__device__ __forceinline__ void write_decided_signs(const Grid& g, uint32_t* __restrict__ S, int bx, int by, int bz, int c) {
+    const uint32_t word = (c & 3) == 2 ? 0xffffffffu : 0u;
 #pragma unroll
-    for (int d = 0; d < 8; d++) {
-        const int bx = w + (d & 1), by = jb + ((d >> 1) & 1), bz = kq + (d >> 2);
-        if (bx >= bd.nbx || by >= bd.nby || bz >= bd.nbz) continue;
-        const int c = (int)cls[((size_t)bz * bd.nby + by) * bd.nbx + bx];
-        if (first < 0) first = c;
-        can = can || c == 0 || c != first;
+    for (int q = 0; q < kFieldBlockZ; q++) {
+        const int pz = bz * kFieldBlockZ + q;
+        if (pz >= g.NZ) break;
+#pragma unroll
+        for (int r = 0; r < kFieldBlockY; r++) {
+            const int y = by * kFieldBlockY + r;
+            if (y < g.NV) S[((size_t)pz * g.NV + y) * g.WP + bx] = word;
+        }
     }
-    cand[idx] = can ? 1 : 0;
+}
+/* A warp per undecided block, a lane per neighbour: a decided neighbour whose words nobody has written yet gets them
+ * (bit 2 of its class byte remembers that; two writers racing store the same words).  These are all the decided
+ * blocks a candidate cube block can reach into. */
+__global__ void __launch_bounds__(256)
+decided_signs_kernel(const Grid g, const BlockDims bd, const uint32_t* __restrict__ list, const Counters* __restrict__ ctr,
+                     uint8_t* __restrict__ cls, uint32_t* __restrict__ S) {
+    const unsigned n = ctr->eval_blocks;
+    const int lane = threadIdx.x & 31;
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n; b += nwarps) {
+        if (lane >= 27 || lane == 13) continue; /* 13 = the block itself */
+        const uint32_t id = list[b];
+        const int bx = (int)(id % (unsigned)bd.nbx) + lane % 3 - 1, by = (int)(id / (unsigned)bd.nbx % (unsigned)bd.nby) + (lane / 3) % 3 - 1;
+        const int bz = (int)(id / ((unsigned)bd.nbx * (unsigned)bd.nby)) + lane / 9 - 1;
+        if (bx < 0 || by < 0 || bz < 0 || bx >= bd.nbx || by >= bd.nby || bz >= bd.nbz) continue;
+        uint8_t* pc = cls + ((size_t)bz * bd.nby + by) * bd.nbx + bx;
+        const int c = (int)*pc;
+        if (c == 0 || (c & 4)) continue;
+        *pc = (uint8_t)(c | 4);
+        write_decided_signs(g, S, bx, by, bz, c);
+    }
+}
+/* the parity hook mcb_get_cases reads every sign word: write those of all decided blocks */
+__global__ void __launch_bounds__(256)
+decided_signs_all_kernel(const Grid g, const BlockDims bd, uint8_t* __restrict__ cls, uint32_t* __restrict__ S) {
+    const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nblocks) return;
+    const int c = (int)cls[idx];
+    if (c == 0 || (c & 4)) return;
+    cls[idx] = (uint8_t)(c | 4);
+    write_decided_signs(g, S, (int)(idx % (unsigned)bd.nbx), (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nby),
+                        (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nby)), c);
 }
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
@@ -782,6 +809,7 @@ classify_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t*
     uint32_t* bitmap = cls_smem;                                          /* [kClsChunkCap] one bit per item */
     uint16_t* list = reinterpret_cast<uint16_t*>(cls_smem + kClsChunkCap); /* [kClsItemCap] active items, loop order */
     __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];
+    __shared__ uint32_t ncand_s;
 
     for (int i = threadIdx.x; i < kClsChunkCap; i += kClsThreads) bitmap[i] = 0u;
     __syncthreads();
@@ -792,60 +820,78 @@ classify_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t*
     const uint32_t rows = min(q.tile_rows, q.total_rows - row0);
     const uint32_t kz0 = row0 / M, j0 = row0 - kz0 * M;
 
-    /* ---- A: one bit per item ------------------------------------------------------------------------------- */
+    /* ---- A: one bit per item -------------------------------------------------------------------------------
+     * The tile's rows are taken four at a time: a CELL is one word column of the (up to) four cube rows with the same
+     * j / 4 of one layer — the footprint of a cube block of the candidate map.  First the cells worth looking at are
+     * listed (all of them without a map), then a thread per listed cell walks its rows, carrying the sign words of the
+     * vertex row two cube rows share.  Dense lanes and independent loads: the time goes with the number of candidate
+     * cells, not with the volume. */
     {
-        const uint32_t strip = div_small(threadIdx.x, q.inv_wc), w = threadIdx.x - strip * q.WC;
-        uint32_t r = strip * q.strip_rows;
-        const uint32_t r_end = strip < q.nstrips ? min(r + q.strip_rows, rows) : 0u;
-        if (r < r_end) {
-            const uint32_t colmask = column_mask(g, w);
-            uint32_t kz = kz0 + (j0 + r) / M, j = (j0 + r) - (kz - kz0) * M;
-            uint32_t item = r * q.WC + w;
-            while (REPEAT && r < r_end) { /* repeating-surface mode: nothing is shared between cube rows */
-                uint32_t c[8];
-                repeat_item_words(Cw, ((size_t)kz * M + j) * q.WC + w, c);
-                uint32_t m = active_mask(c, colmask);
-                if (HAS_V && m) m &= valid_mask(V, ((kz + 1u) * (uint32_t)g.NV + (j + 1u)) * WP + w, WP, plane);
-                if (m) atomicOr(&bitmap[item >> 5], 1u << (item & 31u));
-                item += q.WC;
-                r++;
-                if (++j == M) { j = 0; kz++; }
+        const uint32_t cjb = sc.cjb;
+        const uint32_t r_last = row0 + rows - 1u, kz1 = r_last / M, j1 = r_last - kz1 * M;
+        const uint32_t G0 = kz0 * cjb + (j0 >> 2), G1 = kz1 * cjb + (j1 >> 2);
+        const uint32_t ncell = (G1 - G0 + 1u) * q.WC;
+        uint16_t* cells = list; /* free until phase B */
+        uint32_t ncand = ncell;
+        const bool mapped = !REPEAT && sc.cand != nullptr;
+        if (mapped) {
+            if (threadIdx.x == 0) ncand_s = 0u;
+            __syncthreads();
+            for (uint32_t c0 = 0; c0 < ncell; c0 += kClsThreads) {
+                const uint32_t c = c0 + threadIdx.x;
+                bool look = false;
+                if (c < ncell) {
+                    const uint32_t gq = div_small(c, q.inv_wc), w = c - gq * q.WC, G = G0 + gq, kz = G / cjb, jb = G - kz * cjb;
+                    look = __ldg(sc.cand + ((size_t)(kz >> 2) * cjb + jb) * q.WC + w) != 0;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, look);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&ncand_s, (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (look) cells[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)c;
+                }
             }
-            while (r < r_end) {
-                uint32_t idx = ((kz + 1u) * (uint32_t)g.NV + (j + 1u)) * WP + w;
-                const uint32_t n = min(r_end - r, M - j); /* rows left in this strip and in this plane */
-                const uint8_t* cand_row = sc.cand ? sc.cand + (size_t)(kz >> 2) * sc.cjb * q.WC + w : nullptr;
-                uint32_t any_lo = 0, all_lo = 0;
-                bool have_lo = false, look = true;
-                uint32_t t = 0;
-                while (t < n) {
-                    const uint32_t jj = j + t;
-                    if (cand_row != nullptr && (t == 0 || (jj & 3u) == 0u)) look = cand_row[(size_t)(jj >> 2) * q.WC] != 0;
-                    if (!look) { /* proven: no cube of these (up to) four rows of this word column is active */
-                        const uint32_t skip = min(4u - (jj & 3u), n - t);
-                        t += skip; idx += skip * WP; item += skip * q.WC;
-                        have_lo = false;
-                        continue;
-                    }
-                    if (!have_lo) {
-                        uint32_t lo[4];
-                        vertex_row_words(S, idx, plane, lo);
-                        any_lo = lo[0] | lo[1] | lo[2] | lo[3]; all_lo = lo[0] & lo[1] & lo[2] & lo[3];
-                        have_lo = true;
-                    }
-                    uint32_t hi[4];
-                    vertex_row_words(S, idx + WP, plane, hi);
-                    const uint32_t any_hi = hi[0] | hi[1] | hi[2] | hi[3], all_hi = hi[0] & hi[1] & hi[2] & hi[3];
-                    uint32_t m = (any_lo | any_hi) & ~(all_lo & all_hi) & colmask;
+            __syncthreads();
+            ncand = ncand_s;
+        }
+        for (uint32_t q2 = threadIdx.x; q2 < ncand; q2 += kClsThreads) {
+            const uint32_t c = mapped ? (uint32_t)cells[q2] : q2;
+            const uint32_t gq = div_small(c, q.inv_wc), w = c - gq * q.WC, G = G0 + gq, kz = G / cjb, jb = G - kz * cjb;
+            uint32_t R_lo = kz * M + 4u * jb, R_hi = kz * M + min(4u * jb + 4u, M); /* slab-local cube rows of the cell */
+            R_lo = max(R_lo, row0); R_hi = min(R_hi, row0 + rows);
+            if (R_lo >= R_hi) continue;
+            const uint32_t n = R_hi - R_lo, j = R_lo - kz * M;
+            const uint32_t colmask = column_mask(g, w);
+            uint32_t item = (R_lo - row0) * q.WC + w;
+            uint32_t idx = ((kz + 1u) * (uint32_t)g.NV + (j + 1u)) * WP + w;
+            if (REPEAT) { /* repeating-surface mode: nothing is shared between cube rows */
+                for (uint32_t t = 0; t < n; t++) {
+                    uint32_t cw8[8];
+                    repeat_item_words(Cw, ((size_t)kz * M + (j + t)) * q.WC + w, cw8);
+                    uint32_t m = active_mask(cw8, colmask);
                     if (HAS_V && m) m &= valid_mask(V, idx, WP, plane);
                     if (m) atomicOr(&bitmap[item >> 5], 1u << (item & 31u));
-                    any_lo = any_hi; all_lo = all_hi;
                     idx += WP;
                     item += q.WC;
-                    t++;
                 }
-                r += n;
-                j = 0; kz++; /* only reached again when the strip continues on the next plane */
+                continue;
+            }
+            uint32_t lo[4];
+            vertex_row_words(S, idx, plane, lo);
+            uint32_t any_lo = lo[0] | lo[1] | lo[2] | lo[3], all_lo = lo[0] & lo[1] & lo[2] & lo[3];
+#pragma unroll 4
+            for (uint32_t t = 0; t < n; t++) {
+                uint32_t hi[4];
+                vertex_row_words(S, idx + WP, plane, hi);
+                const uint32_t any_hi = hi[0] | hi[1] | hi[2] | hi[3], all_hi = hi[0] & hi[1] & hi[2] & hi[3];
+                uint32_t m = (any_lo | any_hi) & ~(all_lo & all_hi) & colmask;
+                if (HAS_V && m) m &= valid_mask(V, idx, WP, plane);
+                if (m) atomicOr(&bitmap[item >> 5], 1u << (item & 31u));
+                any_lo = any_hi; all_lo = all_hi;
+                idx += WP;
+                item += q.WC;
             }
         }
     }
@@ -994,7 +1040,8 @@ __global__ void __launch_bounds__(kClsThreads)
 compact_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t* __restrict__ S, const uint32_t* __restrict__ V,
                const ClsGeom q, const ClsScratch sc, unsigned long long* __restrict__ rec, uint32_t* __restrict__ trioff,
                unsigned long long cap_active, unsigned long long* __restrict__ item_info /* nullptr unless the weld needs it */,
-               const uint32_t* __restrict__ Cw /* repeating-surface mode, else nullptr */) {
+               const uint32_t* __restrict__ Cw /* repeating-surface mode, else nullptr */,
+               const FieldBlocks fb /* block-field mode: flags != nullptr, the apron blocks are marked here */) {
     __shared__ uint32_t chunk_a[kClsChunkCap], chunk_t[kClsChunkCap]; /* per 32 list entries */
     __shared__ uint32_t warp_x[kClsWarps], warp_y[kClsWarps];
 
@@ -1066,6 +1113,19 @@ compact_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t* 
         uint32_t m = it.m;
         if (item_info != nullptr) /* cube -> record look-up of the weld: first record of the word | its active mask */
             item_info[(size_t)tile * sc.tile_items + item_local] = (oa & 0xFFFFFFFFull) | ((unsigned long long)m << 32);
+        if (fb.flags != nullptr) {
+            /* the mesh stages read the field at the corners of the active cubes and their +-1 neighbours: stored vertices
+             * [i, i+3] x [j, j+3] x [kz, kz+3].  Blocks of that range the evaluation skipped (flag 0) are marked for the
+             * apron refill.  Per item: the cubes of a word share j and kz, and span at most two blocks in x. */
+            const int bx0 = (int)it.w, bx1 = (m >> 29) ? min((int)it.w + 1, fb.nbx - 1) : (int)it.w; /* a cube with i % 32 >= 29 reaches x + 3 in the next block */
+            const int by0 = (int)it.j >> 2, by1 = ((int)it.j + 3) >> 2, bz0 = (int)it.kz >> 2, bz1 = ((int)it.kz + 3) >> 2;
+            for (int bz = bz0; bz <= bz1; bz++)
+                for (int by = by0; by <= by1; by++)
+                    for (int bx = bx0; bx <= bx1; bx++) {
+                        uint8_t* f = fb.flags + ((size_t)bz * fb.nby + by) * fb.nbx + bx;
+                        if (*f == 0) *f = 1; /* 2 = already evaluated; racing writers all store 1 */
+                    }
+        }
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
@@ -1756,7 +1816,82 @@ weld_count_kernel(const WV W, const WeldBuffers B, const Counters* __restrict__ 
     }
 }
 
-/* exclusive scan of the per-chunk new-vertex counts (one block: a few thousand to a few hundred thousand chunks) */
+/* The same marks for the plain grid (no constraints, no seed mode, no per-cube levels), a thread per CUBE instead of a
+ * thread per crossing edge.  There the owner of a grid edge has a closed form (weld_owner_fast): a cube is the first in
+ * loop order to contain the edges on its far faces, and those on its near faces only where the grid or the slab begins —
+ * pure index arithmetic.  What needs field values is the rare case of a crossing point sitting on a grid vertex, where
+ * the replay decides: a multiplication-only test on the cube's eight corner values rules it out for nearly every edge
+ * (a point within 1.5e-6 of an end point has |t| h or |1 - t| h below 3e-6, with t = (iso - f_a) / (f_b - f_a)), and only
+ * the edges it cannot rule out take the exact functions above.  Same vinfo words, a fraction of the work. */
+__global__ void __launch_bounds__(kWeldCubes)
+weld_count_fast_kernel(const WeldView W, const WeldBuffers B, const ClsTables* __restrict__ gtb, const Counters* __restrict__ ctr,
+                       unsigned long long cap_active) {
+    __shared__ uint32_t warp_s[kWeldCubes / 32];
+    const Grid& g = W.g;
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    const unsigned long long nchunks = (A + kWeldCubes - 1) / kWeldCubes;
+    const int t = threadIdx.x;
+    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();
+        const unsigned long long a = chunk * kWeldCubes + t;
+        uint32_t bits = 0;
+        if (a < A) {
+            const unsigned long long r = B.rec[a];
+            const int i = (int)(r & 0xFFF), j = (int)((r >> 12) & 0xFFF), k = (int)((r >> 24) & 0xFFF), code = (int)((r >> 36) & 0xFF);
+            const uint32_t emask = __ldg(gtb->emask + code);
+            const uint32_t X0 = i == 0, Y0 = j == 0, Z0 = k == g.kb;
+            /* edges 5, 6, 10 lie on the far faces; the others need the cube to be first along the axes they are near on */
+            uint32_t own = (1u << 5) | (1u << 6) | (1u << 10) | ((Y0 & Z0) << 0) | (Z0 << 2) | (Y0 << 4) | (Z0 << 1) | ((X0 & Z0) << 3) |
+                           (X0 << 7) | ((X0 & Y0) << 8) | (Y0 << 9) | (X0 << 11);
+            const float* f0 = W.F + (size_t)(k - g.kb + 1) * planep + (size_t)(j + 1) * rowp + (i + 1);
+            float f[8];
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                const int o = mcb_corner_ofs(v);
+                f[v] = __ldg(f0 + (size_t)(o >> 2) * planep + (size_t)((o >> 1) & 1) * rowp + (o & 1));
+            }
+            const float hx = W.cs[i + 2] - W.cs[i + 1], hy = W.cs[j + 2] - W.cs[j + 1], hz = W.cs[k + 2] - W.cs[k + 1];
+            uint32_t maybe = 0; /* crossing edges whose point may sit on a grid vertex */
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                const float fa = f[mcb_edge_a(e)], fb = f[mcb_edge_b(e)];
+                const float h = fabsf(e >= 8 ? hz : (e & 1) ? hy : hx);
+                const float d1 = fabsf(g.iso - fa), d2 = fabsf(fb - fa), d3 = fabsf(fb - g.iso);
+                const bool clear = d1 * h > 3e-6f * d2 && d3 * h > 3e-6f * d2; /* NaN / inf / zero denominators compare false */
+                maybe |= clear ? 0u : 1u << e;
+            }
+            maybe &= emask;
+            bits = emask & own;
+            while (maybe) { /* rare: the exact path of weld_count_kernel for this edge */
+                const int e = __ffs(maybe) - 1;
+                maybe &= maybe - 1;
+                const int onv = weld_on_vertex(W, i, j, k, e);
+                if (onv == 0) continue;
+                const CubeEdge v = weld_resolve(W, i, j, k, e, onv);
+                bits |= 1u << (12 + e);
+                if (v.i == i && v.j == j && v.k == k && v.e == e) bits |= 1u << e; else bits &= ~(1u << e);
+            }
+            B.vinfo[a] = (unsigned long long)bits << 32;
+        }
+        uint32_t mine = __popc(bits & 0xFFFu);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+        if ((t & 31) == 0) warp_s[t >> 5] = mine;
+        __syncthreads();
+        if (t == 0) {
+            uint32_t s2 = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < kWeldCubes / 32; w2++) s2 += warp_s[w2];
+            B.chunk_new[chunk] = s2;
+        }
+    }
+}
+
+/* exclusive scan of the per-chunk new-vertex counts (one block; a thread takes kWeldScanPer consecutive chunks, so the
+ * 19 000 chunks of a 1024^3 sphere are four rounds of the block) */
+constexpr int kWeldScanPer = 8;
 __global__ void __launch_bounds__(1024)
 weld_scan_kernel(uint32_t* __restrict__ chunk_new, Counters* __restrict__ ctr, unsigned long long cap_active) {
     __shared__ unsigned long long warp_tot[32];
@@ -1767,17 +1902,22 @@ weld_scan_kernel(uint32_t* __restrict__ chunk_new, Counters* __restrict__ ctr, u
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) carry_s = 0;
     __syncthreads();
-    for (unsigned long long b0 = 0; b0 < nchunks; b0 += 1024) {
-        const unsigned long long c = b0 + t;
-        const unsigned long long v = c < nchunks ? chunk_new[c] : 0ull;
-        unsigned long long inc = v;
+    for (unsigned long long b0 = 0; b0 < nchunks; b0 += 1024ull * kWeldScanPer) {
+        const unsigned long long c0 = b0 + (unsigned long long)t * kWeldScanPer;
+        uint32_t v[kWeldScanPer];
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int q = 0; q < kWeldScanPer; q++) { v[q] = c0 + q < nchunks ? chunk_new[c0 + q] : 0u; mine += v[q]; }
+        unsigned long long inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
         if (lane == 31) warp_tot[warp] = inc;
         __syncthreads();
         unsigned long long base = carry_s;
         for (int w2 = 0; w2 < warp; w2++) base += warp_tot[w2];
-        if (c < nchunks) chunk_new[c] = (uint32_t)(base + inc - v);
+        unsigned long long run = base + inc - mine;
+#pragma unroll
+        for (int q = 0; q < kWeldScanPer; q++) { if (c0 + q < nchunks) chunk_new[c0 + q] = (uint32_t)run; run += v[q]; }
         __syncthreads();
         if (t == 1023) carry_s = base + inc;
         __syncthreads();
@@ -2262,6 +2402,36 @@ __global__ void inspect_cube_kernel(const mcb_program* __restrict__ progs /* [0]
         }
     }
     *out = o;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Slab balancing (SURVEY §8e "optionally by measured active count"): triangles per cube layer of the last
+ * polygonisation.  The records are in loop order, so a warp's 32 cubes nearly always share their layer: one atomic
+ * per warp then.
+ * ------------------------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256)
+layer_hist_kernel(const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ trioff, const Counters* __restrict__ ctr,
+                  unsigned long long cap_active, uint32_t* __restrict__ hist /* [M], indexed by the global layer */) {
+    unsigned long long A = ctr->active;
+    const unsigned long long T = ctr->triangles;
+    if (A > cap_active) A = cap_active;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, a0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long base = a0 - lane; base < A; base += stride) { /* whole warps stay in the loop together */
+        const unsigned long long a = base + lane;
+        int layer = -1;
+        uint32_t cnt = 0;
+        if (a < A) {
+            layer = (int)((rec[a] >> 24) & 0xFFFu);
+            cnt = (a + 1 < A ? trioff[a + 1] : (uint32_t)T) - trioff[a];
+        }
+        const int first = __shfl_sync(0xffffffffu, layer, 0);
+        if (__all_sync(0xffffffffu, layer == first || layer < 0)) {
+#pragma unroll
+            for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            if (lane == 0 && first >= 0) atomicAdd(hist + first, cnt);
+        } else if (layer >= 0) atomicAdd(hist + layer, cnt);
+    }
 }
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -31,13 +31,36 @@ def exchange_counts(local_triangles, device=None, group=None):
     return sum(counts[:rank]), sum(counts), counts
 
 
+def balanced_slab(layer_triangles, k0, M, fixed_cost_per_layer=-1.0, group=None, device=None):
+    """Slabs of equal cost instead of equal thickness (SURVEY §8e "optionally by measured active count"): every rank
+    contributes the triangles per cube layer of the slab [k0, k0 + len) it has just polygonised, the histogram of the whole
+    grid is all-reduced, and every rank makes the same cut (mcb_balance_slabs).  Returns this rank's (k_begin, k_end) and the
+    cut points of all ranks.  The torch.distributed twin of mcb_comm_balance (which does the same over NCCL behind the C ABI)."""
+    from . import balance_slabs
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if world > 1 and dist.get_backend(group) == "nccl" else torch.device("cpu")
+    hist = torch.zeros(M, dtype=torch.int64, device=device)
+    lt = torch.as_tensor([int(x) for x in layer_triangles], dtype=torch.int64, device=device)
+    hist[k0:k0 + len(lt)] = lt
+    if world > 1:
+        dist.all_reduce(hist, group=group)
+    cuts = balance_slabs(hist.cpu().numpy().astype("uint32"), world, fixed_cost_per_layer)
+    return (cuts[rank], cuts[rank + 1]), cuts
+
+
 class DeviceCounts:
     """The same exchange without a host round trip (NCCL only): the slab's triangle count is all-gathered straight from
     the context's device counters, and the placement (offset of this slab, total) stays on the device as int64
     tensors.  The collective runs on a side stream, so the next polygonisation does not wait for the slowest rank's
-    count; a consumer of `offset` / `total` calls `wait()` (stream order) or `result()` (Python ints) first."""
+    count; a consumer of `offset` / `total` calls `wait()` (stream order) or `result()` (Python ints) first.
+    The context is switched to torch's current stream (mcb_set_stream): its counters are read in that stream's order.
+    mcb_comm_exchange / mcb_comm_offsets do the same behind the C ABI without torch."""
 
     def __init__(self, ctx, device):
+        # the staging copy below and the context's next counter reset must be ordered: both go on torch's current stream
+        ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
         self.device = device
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()

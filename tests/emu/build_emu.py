@@ -31,6 +31,10 @@ def build(force=False):
     if not os.path.exists(inc):  # normally written by the product build
         with open(os.path.join(CSRC, "mcb_pow.h")) as f, open(inc, "w") as o:
             o.write('R"MCBPOWSRC(' + f.read() + ')MCBPOWSRC"\n')
+    stamp = os.path.join(CSRC, "mcb_build_stamp.inc")
+    if not os.path.exists(stamp):  # normally written by the product build
+        with open(stamp, "w") as o:
+            o.write('"emulated build"\n')
     objs = []
     for s in SOURCES:
         o = os.path.join(OUT_DIR, s + ".o")

@@ -76,3 +76,31 @@ def test_block_mode_skips_space_and_equals_dense_at_65_cubed(mcb_emu, ctx, eq, n
         assert full.field_blocks < 0.5 * nblocks   # the sphere leaves most blocks decided, i.e. skipped
     if expect:
         assert (full.triangles, full.ambiguous, full.redirected) == expect
+
+
+def test_cpp_dropin_class_over_the_emulated_library(golden, tmp_path, mcb_emu):
+    """include/marching.h + include/evaluator.h (the reference-facing classes) linked against the emulated library: one
+    Marching object polygonises the golden cases one after the other — growing, shrinking and repeated meshes, i.e. both
+    the streamed path into the page-locked Poly_Data vectors and the plain copy — and Poly_Data equals the unmodified
+    reference's byte for byte (FNV-1a-64 of vertex_list / tri_list)."""
+    import os
+    import subprocess
+    from .test_cpp_dropin import ROOT, fnv1a64
+    from . import emu
+    lib_dir = os.path.join(ROOT, "tests", "emu", "_build")
+    exe = str(tmp_path / "dropin_emu")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-o", exe, "-L", lib_dir, "-lmcb200_emu",
+                           "-Wl,-rpath," + lib_dir])
+    meta = load_meta(golden)
+    names = ["sphere_17", "eq1_gui", "gyr78_17", "gyr78_17", "eq8_ctor", "torus_33", "sphere_17", "sphere_33_iso", "sphere_33_iso"]
+    args = []
+    for n in names:
+        c = meta[n]
+        args += [n, c["eq"], repr(c["step"]), repr(c["scale"][0]), repr(c["scale"][1]), repr(c["scale"][2]), repr(c["iso"])]
+    out = subprocess.check_output([exe] + args, text=True)
+    got = [l.split() for l in out.strip().splitlines()]
+    for n, line in zip(names, got):
+        v, t = golden[n + "/vertex_list"], golden[n + "/tri_list"]
+        assert line[0] == n and line[1:3] == [str(len(v)), str(len(t))], (n, line)
+        assert line[3] == fnv1a64(v.tobytes()) and line[4] == fnv1a64(t.tobytes()), n

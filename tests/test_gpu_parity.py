@@ -93,7 +93,8 @@ def test_case_against_golden(mcb, ctx, golden, name):
         nref = mc_numpy.soup_gradient_normals(golden[name + "/field_ext"], cs, case["iso"], cubes, tri_rows())
         ok = np.isfinite(nref).all(axis=2)
         assert rel_close(nrm[:, :, :3][ok], nref[ok], 1e-5)
-        assert np.array_equal(np.isnan(nrm[:, :, :3]).any(axis=2), ~ok) or True
+        # where the restatement's normal is not finite (zero or overflowing gradient) the device's is not a number either
+        assert not np.isfinite(nrm[:, :, :3][~ok]).all(axis=-1).any() if (~ok).any() else True
 
 
 def test_eval_points_against_reference(mcb, ctx, refbind):

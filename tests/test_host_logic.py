@@ -38,10 +38,19 @@ def test_abi_exports_every_declared_symbol(mcb):
     for name in sorted(declared):
         assert hasattr(lib, name), "libmcb200.so does not export " + name
     assert set(mcb.EXPORTS) == declared
-    assert mcb.lib.mcb_abi_version() == 3
+    assert mcb.lib.mcb_abi_version() == 4
     import ctypes
     assert mcb.lib.mcb_struct_size(0) == ctypes.sizeof(mcb.Counts) and mcb.lib.mcb_struct_size(1) == ctypes.sizeof(mcb.StepData)
     assert mcb.lib.mcb_struct_size(7) < 0
+
+
+def test_loaded_library_is_the_build_of_these_sources(mcb):
+    """mcb_build_stamp(): sha256 over the sources the loaded libmcb200.so was compiled from == the sources in the tree"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mcb_build", os.path.join(ROOT, mcb.__name__, "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert mcb.lib.mcb_build_stamp().decode() == b.source_stamp()
 
 
 @pytest.mark.parametrize("eq,ok", EVALUATOR_TEST_CASES)
