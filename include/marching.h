@@ -30,6 +30,7 @@
 #include <deque>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "evaluator.h"
@@ -84,6 +85,7 @@ public:
     }
     ~Marching() {
         unpin_all();
+        release_devices();
         if (ctx_) mcb_destroy(ctx_);
     }
     Marching(const Marching&) = delete;
@@ -96,6 +98,7 @@ public:
     bool recalculate() {
         if (!ensure_ctx()) return false;
         if (step_mode_ && !seed_mode_) { unpin_all(); return step_once(); } /* marching.cpp:386-428 */
+        if (devices_ > 1 && weld_ && !seed_mode_ && !(repeat_ && !(repeat_step_ > 0.f))) return recalculate_on_devices();
         /* reset_all_data() of the reference (marching.cpp:293-305), except that vertex_list / tri_list keep their storage
          * AND their size until the new mesh is in: the GPU streams the new Poly_Data straight into them (below) */
         reset_step_data();
@@ -248,6 +251,16 @@ public:
     }
 
     /* ---- extensions ---- */
+    /* Several GPUs of one box: the grid is cut into z-slabs, one mcb context and one host thread per
+     * device 0..n-1.  The slabs' triangle counts are all-gathered over NCCL (mcb_comm_exchange) into global offsets; the
+     * first recalculate() of a configuration also measures the triangles per layer and re-cuts the slabs to equal cost
+     * (mcb_comm_balance).  Poly_Data is the slabs' welded meshes one after the other — triangles in the reference's order,
+     * vertices on a plane shared by two slabs present once per slab.  Seed mode and step mode stay on device 0. */
+    bool set_devices(int n) {
+        if (n < 1 || n > 64) return false;
+        if (n != devices_) { release_devices(); devices_ = n; }
+        return true;
+    }
     void set_weld(bool b) { weld_ = b; }
     void set_normals(bool b) { normals_ = b; }
     /* true: get_vertex_normals() returns what CalculateNormal(get_poly_data()) would (normal.h:3-42), computed on the GPU,
@@ -291,19 +304,131 @@ private:
         if (have_slab_ && mcb_set_slab(ctx_, slab_[0], slab_[1]) != MCB_OK) return false;
         return true;
     }
-    bool push_parameters() {
-        if (mcb_set_equation(ctx_, 0, evaluator_->equation().c_str()) != MCB_OK) return false;
-        mcb_set_surface_constant(ctx_, iso_);
-        mcb_set_scaling(ctx_, sx_, sy_, sz_);
-        mcb_set_normals(ctx_, normals_ ? (weld_ && reference_normals_ ? 2 : 1) : 0);
+    bool push_parameters() { return push_parameters(ctx_); }
+    bool push_parameters(mcb_ctx* c) {
+        if (mcb_set_equation(c, 0, evaluator_->equation().c_str()) != MCB_OK) return false;
+        mcb_set_surface_constant(c, iso_);
+        mcb_set_scaling(c, sx_, sy_, sz_);
+        mcb_set_normals(c, normals_ ? (weld_ && reference_normals_ ? 2 : 1) : 0);
         /* marching.cpp:156-170, 481-494.  The reference accepts the mode with its initial distance 0: every cube's iso is
          * then NaN and nothing is drawn; recalculate() short-cuts that case, the GPU only sees positive distances */
-        mcb_set_repeat(ctx_, repeat_ && repeat_step_ > 0.f ? 1 : 0, repeat_step_);
-        mcb_set_field_mode(ctx_, MCB_FIELD_AUTO); /* nothing here reads the field back: let the library drop its write when that pays */
+        mcb_set_repeat(c, repeat_ && repeat_step_ > 0.f ? 1 : 0, repeat_step_);
+        mcb_set_field_mode(c, MCB_FIELD_AUTO); /* nothing here reads the field back: only the blocks around the surface are evaluated */
         for (int i = 0; i < 3; i++)
-            mcb_set_constraint(ctx_, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
+            mcb_set_constraint(c, i, cons_op_[i] == NAO ? 0 : (int)cons_op_[i], cons_rhs_[i], cons_valid_[i] && cons_use_[i]);
         return true;
     }
+
+    /* ---- several GPUs: one context + one host thread per device ---- */
+    void release_devices() {
+        for (size_t r = 1; r < dev_ctx_.size(); r++) if (dev_ctx_[r]) mcb_destroy(dev_ctx_[r]);
+        if (!dev_ctx_.empty() && dev_ctx_[0]) mcb_comm_finalize(dev_ctx_[0]);
+        dev_ctx_.clear();
+        comm_ready_ = false;
+        balanced_key_.clear();
+    }
+    std::string configuration_key() const {
+        char b[256];
+        std::snprintf(b, sizeof b, "|%a|%a|%a|%a|%a|%d|%a", (double)step_, (double)iso_, (double)sx_, (double)sy_, (double)sz_, (int)repeat_, (double)repeat_step_);
+        std::string k = evaluator_->equation() + b;
+        for (int i = 0; i < 3; i++) { std::snprintf(b, sizeof b, "|%d%d%d%a", (int)cons_valid_[i], (int)cons_use_[i], (int)cons_op_[i], (double)cons_rhs_[i]); k += b; }
+        return k;
+    }
+    bool recalculate_on_devices() {
+        reset_step_data();
+        unpin_all();
+        if (!evaluator_) { poly_data.vertex_list.clear(); poly_data.tri_list.clear(); return true; }
+        const int n = devices_;
+        dev_ctx_.resize((size_t)n, nullptr);
+        dev_ctx_[0] = ctx_; /* ensure_ctx() made it */
+        char id[128];
+        if (!comm_ready_ && mcb_comm_unique_id(id) != MCB_OK) return false; /* libnccl.so.2 is needed for more than one device */
+        const std::string key = configuration_key();
+        const bool rebalance = key != balanced_key_;
+        std::vector<mcb_counts> cnt((size_t)n);
+        std::vector<uint64_t> tri_off((size_t)n, 0);
+        std::vector<int> ok((size_t)n, 1);
+        auto per_device = [&](int r) {
+            mcb_ctx*& c = dev_ctx_[(size_t)r];
+            if (!c && mcb_create(r, &c) != MCB_OK) { c = nullptr; ok[(size_t)r] = 0; }
+            /* every thread keeps going through the collectives below even after a local failure would deadlock the
+             * others: creation failures are therefore checked before the first collective */
+        };
+        {
+            std::vector<std::thread> th;
+            for (int r = 1; r < n; r++) th.emplace_back(per_device, r);
+            for (auto& t : th) t.join();
+            for (int r = 0; r < n; r++) if (!ok[(size_t)r]) return false;
+        }
+        auto run = [&](int r) {
+            mcb_ctx* c = dev_ctx_[(size_t)r];
+            bool good = mcb_set_grid_step(c, step_) >= 0 && push_parameters(c);
+            mcb_set_seed(c, 0, 0.f, 0.f, 0.f);
+            mcb_set_mesh_mode(c, MCB_MESH_INDEXED);
+            mcb_set_host_output(c, nullptr, nullptr, nullptr, 0, 0);
+            if (!comm_ready_) good = mcb_comm_init(c, id, r, n) == MCB_OK && good;          /* collective; sets the uniform slab */
+            else if (rebalance) { int k0, k1; good = mcb_slab_range(cnt_M(c), r, n, &k0, &k1) == MCB_OK && mcb_set_slab(c, k0, k1) == MCB_OK && good; }
+            else good = mcb_set_slab(c, cuts_[(size_t)r], cuts_[(size_t)r + 1]) == MCB_OK && good;
+            good = mcb_polygonise(c, &cnt[(size_t)r]) == MCB_OK && good;
+            if (rebalance) { /* measured triangles per layer -> slabs of equal cost, then the real run */
+                int k0 = 0, k1 = 0;
+                good = mcb_comm_balance(c, -1.0, &k0, &k1) == MCB_OK && good;                   /* collective */
+                cuts_r_[(size_t)r] = k0; cuts_end_ = r == n - 1 ? k1 : cuts_end_;
+                good = mcb_polygonise(c, &cnt[(size_t)r]) == MCB_OK && good;
+            }
+            good = mcb_comm_exchange(c) == MCB_OK && good;                                      /* collective: NCCL all-gather */
+            good = mcb_comm_offsets(c, &tri_off[(size_t)r], nullptr, nullptr) == MCB_OK && good;
+            ok[(size_t)r] = good ? 1 : 0;
+        };
+        cuts_r_.assign((size_t)n, 0);
+        {
+            std::vector<std::thread> th;
+            for (int r = 1; r < n; r++) th.emplace_back(run, r);
+            run(0);
+            for (auto& t : th) t.join();
+        }
+        comm_ready_ = true;
+        for (int r = 0; r < n; r++) if (!ok[(size_t)r]) return false;
+        if (rebalance) {
+            cuts_.assign(cuts_r_.begin(), cuts_r_.end());
+            cuts_.push_back(cuts_end_);
+            balanced_key_ = key;
+        }
+        /* Poly_Data: the slabs one after the other */
+        std::vector<size_t> v_off((size_t)n + 1, 0);
+        size_t T = 0;
+        for (int r = 0; r < n; r++) { v_off[(size_t)r + 1] = v_off[(size_t)r] + (size_t)cnt[(size_t)r].vertices; T += (size_t)cnt[(size_t)r].triangles; }
+        poly_data.vertex_list.resize(v_off[(size_t)n] * 3);
+        poly_data.tri_list.resize(T * 3);
+        if (normals_) vertex_normals_.resize(v_off[(size_t)n] * 3); else vertex_normals_.clear();
+        soup_.clear(); normals_soup_.clear();
+        auto fetch = [&](int r) {
+            const mcb_counts& c = cnt[(size_t)r];
+            if (!c.triangles) return;
+            unsigned* tl = poly_data.tri_list.data() + 3 * (size_t)tri_off[(size_t)r];
+            if (mcb_get_indexed_mesh(dev_ctx_[(size_t)r], poly_data.vertex_list.data() + 3 * v_off[(size_t)r], tl,
+                                     normals_ ? vertex_normals_.data() + 3 * v_off[(size_t)r] : nullptr, c.vertices, c.triangles) != MCB_OK) { ok[(size_t)r] = 0; return; }
+            const unsigned base = (unsigned)v_off[(size_t)r];
+            if (base) for (size_t q = 0; q < 3 * (size_t)c.triangles; q++) tl[q] += base;
+        };
+        {
+            std::vector<std::thread> th;
+            for (int r = 1; r < n; r++) th.emplace_back(fetch, r);
+            fetch(0);
+            for (auto& t : th) t.join();
+        }
+        counts_ = cnt[0];
+        for (int r = 1; r < n; r++) {
+            counts_.cubes += cnt[(size_t)r].cubes; counts_.active += cnt[(size_t)r].active; counts_.triangles += cnt[(size_t)r].triangles;
+            counts_.ambiguous += cnt[(size_t)r].ambiguous; counts_.redirected += cnt[(size_t)r].redirected; counts_.vertices += cnt[(size_t)r].vertices;
+            if (cnt[(size_t)r].ms_total > counts_.ms_total) counts_.ms_total = cnt[(size_t)r].ms_total;
+            counts_.k_end = cnt[(size_t)r].k_end;
+        }
+        poly_data.step_data.step_i = -1;
+        for (int r = 0; r < n; r++) if (!ok[(size_t)r]) return false;
+        return true;
+    }
+    int cnt_M(mcb_ctx*) const { return mcb_grid_axis(step_, nullptr, 0); }
 
     /* Step-by-step mode (marching.cpp:386-428): one cube per recalculate() call, in the reference's own traversal
      * (x fastest, coordinates carried over from the previous cube's corners, `< 1.0` bounds).  The cube itself is
@@ -388,6 +513,12 @@ private:
     std::set<xyz> vertex_set_; /* step-by-step mode only (marching.h:149) */
     std::vector<float> soup_, normals_soup_, vertex_normals_;
     Pinned pin_v_, pin_t_, pin_n_;
+    int devices_ = 1;
+    std::vector<mcb_ctx*> dev_ctx_;       /* [devices_]; [0] = ctx_ */
+    bool comm_ready_ = false;
+    std::string balanced_key_;            /* configuration the slab cuts below were measured for */
+    std::vector<int> cuts_, cuts_r_;
+    int cuts_end_ = 0;
     mcb_counts counts_;
 };
 

@@ -69,7 +69,7 @@ def build_headless():
     root = os.path.dirname(HERE)
     exe = os.path.join(HERE, "mcb_headless")
     cmd = [os.environ.get("CXX", "g++"), "-std=c++14", "-O2", "-Wall", "-I", os.path.join(root, "include"),
-           os.path.join(root, "tools", "headless_main.cpp"), "-o", exe, "-L", HERE, "-lmcb200", "-Wl,-rpath,$ORIGIN"]
+           os.path.join(root, "tools", "headless_main.cpp"), "-o", exe, "-L", HERE, "-lmcb200", "-Wl,-rpath,$ORIGIN", "-pthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -163,7 +163,8 @@ struct mcb_ctx {
     uint8_t* d_bcls = nullptr;     /* [cap_fblocks] interval class of every 32 x 4 x 4 vertex block */
     uint32_t* d_flist = nullptr;   /* [cap_fblocks] apron blocks */
     uint32_t* d_elist = nullptr;   /* [cap_fblocks] undecided blocks */
-    uint8_t* d_cand = nullptr;     /* [cap_cand] cube blocks that may hold an active cube */
+    unsigned long long* d_cand = nullptr; /* [cap_cand] one bit per cube block that may hold an active cube */
+    uint32_t* d_slist = nullptr;   /* [cap_scls] undecided super-blocks */
     uint8_t* d_scls = nullptr;     /* [cap_scls] interval class of every 32 x 16 x 16 super-block */
     size_t cap_scls = 0;
     BlockDims bd{};                /* block geometry of the last block-field run (mcb_get_cases completes the sign words with it) */
@@ -607,7 +608,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->eq) free_slot(s);
     for (auto& kv : ctx->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
-    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw); cudaFree(ctx->d_bcls); cudaFree(ctx->d_elist); cudaFree(ctx->d_cand); cudaFree(ctx->d_scls);
+    cudaFree(ctx->d_fflags); cudaFree(ctx->d_flist); cudaFree(ctx->d_cw); cudaFree(ctx->d_bcls); cudaFree(ctx->d_elist); cudaFree(ctx->d_cand); cudaFree(ctx->d_scls); cudaFree(ctx->d_slist);
     cudaFree(ctx->d_bounds_iv); cudaFree(ctx->d_ent); cudaFree(ctx->d_tile_u32); cudaFree(ctx->d_amb);
     cudaFree(ctx->d_cs); cudaFree(ctx->d_F); cudaFree(ctx->d_S); cudaFree(ctx->d_V); cudaFree(ctx->d_tables);
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
@@ -1013,12 +1014,20 @@ int Run::ensure_block_buffers(FieldBlocks* fb, BlockDims* bd) {
             cudaMalloc((void**)&ctx->d_bcls, nb + 16) != cudaSuccess || cudaMalloc((void**)&ctx->d_elist, (nb + 16) * sizeof(uint32_t)) != cudaSuccess)
             return fail(ctx, MCB_E_NOMEM, "cudaMalloc of the field-block lists failed");
         MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nb + 16, s)); /* the padding field_list_kernel reads stays zero */
+        MCB_CK(cudaMemsetAsync(ctx->d_bcls, 0, nb + 16, s));
         ctx->cap_fblocks = nb;
     }
     int rc;
     if ((rc = ensure(ctx, &ctx->d_bounds_iv, &ctx->cap_bounds_iv, (size_t)2 * 3 * bd->spa * bd->nb)) != MCB_OK) return rc;
-    if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (size_t)bd->WC * bd->cjb * bd->ckb)) != MCB_OK) return rc;
-    if ((rc = ensure(ctx, &ctx->d_scls, &ctx->cap_scls, (size_t)bd->nbx * bd->nsy * bd->nsz)) != MCB_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (size_t)((bd->WC + 63) / 64) * bd->cjb * bd->ckb)) != MCB_OK) return rc;
+    const size_t nsup = (size_t)bd->nbx * bd->nsy * bd->nsz;
+    if (ctx->cap_scls < nsup) {
+        cudaFree(ctx->d_scls); cudaFree(ctx->d_slist);
+        ctx->d_scls = nullptr; ctx->d_slist = nullptr; ctx->cap_scls = 0;
+        MCB_CK(cudaMalloc((void**)&ctx->d_scls, nsup));
+        MCB_CK(cudaMalloc((void**)&ctx->d_slist, nsup * sizeof(uint32_t)));
+        ctx->cap_scls = nsup;
+    }
     *fb = FieldBlocks{bd->nbx, bd->nby, bd->nbz, ctx->d_fflags, ctx->d_flist};
     ctx->bd = *bd;
     return MCB_OK;
@@ -1035,16 +1044,16 @@ int Run::launch_block_eval(const FieldBlocks& fb, const uint32_t* list, const un
         const float* tables = ctx->d_tables;
         float* F = ctx->d_F;
         uint32_t* S = ctx->d_S;
-        int nbx = fb.nbx, nby = fb.nby, spa = eq.max_per_axis;
-        void* args[] = {&consts, &garg, &tables, &F, &S, &list, &count, &nbx, &nby, &spa};
+        int spa = eq.max_per_axis;
+        void* args[] = {&consts, &garg, &tables, &F, &S, &list, &count, &spa};
         MCB_CK(cudaLaunchKernel((const void*)ctx->jit_cur->fill, dim3(fill_ctas), dim3(kEvalThreads), args, 0, s));
     } else {
         mcb_program launch;
         bool has_pow;
         if ((rc = encode_program(launch, has_pow, true)) != MCB_OK) return rc;
         const size_t smem = (size_t)std::max(1, eq.c.grid_fused_depth) * kEvalRows * kEvalThreads * sizeof(float);
-        if (has_pow) MCB_LAUNCH((eval_blocks_kernel<true>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, list, count, fb.nbx, fb.nby);
-        else MCB_LAUNCH((eval_blocks_kernel<false>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, list, count, fb.nbx, fb.nby);
+        if (has_pow) MCB_LAUNCH((eval_blocks_kernel<true>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, list, count);
+        else MCB_LAUNCH((eval_blocks_kernel<false>), fill_ctas, kEvalThreads, smem, s, launch, g, ctx->d_tables, ctx->d_F, ctx->d_S, list, count);
     }
     launches++;
     return MCB_OK;
@@ -1070,14 +1079,18 @@ int Run::stage_eval_blocks() {
         else if (ctx->jit == MCB_JIT_ON) return rc;
         else ctx->jit_note = ctx->err;
     }
-    const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz, nsuper = (unsigned)bd.nbx * (unsigned)bd.nsy * (unsigned)bd.nsz;
-    MCB_CK(cudaMemsetAsync(ctx->d_cand, 0, (size_t)bd.WC * bd.cjb * bd.ckb, s));
+    const size_t nblocks = (size_t)bd.nbx * bd.nby * bd.nbz;
+    const unsigned nsuper = (unsigned)bd.nbx * (unsigned)bd.nsy * (unsigned)bd.nsz;
+    MCB_CK(cudaMemsetAsync(ctx->d_cand, 0, (size_t)((bd.WC + 63) / 64) * bd.cjb * bd.ckb * 8, s));
+    MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nblocks, s));
+    MCB_CK(cudaMemsetAsync(ctx->d_bcls, 0xFF, nblocks, s)); /* kClsInherit: the super-block's verdict holds unless the fine pass says otherwise */
     MCB_LAUNCH((axis_bounds_kernel), dim3((unsigned)((3 * bd.spa * bd.nb + 127) / 128), 2u), 128, 0, s, ctx->d_tables, g, bd, eq.c.n_axis_slots[0],
                eq.c.n_axis_slots[1], eq.c.n_axis_slots[2], ctx->d_bounds_iv);
-    MCB_LAUNCH((super_class_kernel), (nsuper + 127) / 128, 128, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->d_scls);
-    MCB_LAUNCH((block_class_kernel), (nblocks + 255) / 256, 256, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->d_scls, ctx->decide_blocks ? 1 : 0,
+    MCB_LAUNCH((super_class_kernel), (nsuper + 127) / 128, 128, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->decide_blocks ? 1 : 0, ctx->d_scls,
+               ctx->d_slist, ctx->d_ctr);
+    MCB_LAUNCH((block_class_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->d_slist, ctx->decide_blocks ? 1 : 0,
                ctx->d_bcls, ctx->d_fflags, ctx->d_elist, ctx->d_cand, ctx->d_ctr);
-    MCB_LAUNCH((decided_signs_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, g, bd, ctx->d_elist, ctx->d_ctr, ctx->d_bcls, ctx->d_S);
+    MCB_LAUNCH((decided_signs_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, g, bd, ctx->d_elist, ctx->d_ctr, ctx->d_bcls, ctx->d_scls, ctx->d_S);
     launches += 4;
     if ((rc = launch_block_eval(fb, ctx->d_elist, &ctx->d_ctr->eval_blocks)) != MCB_OK) return rc;
     return launch_constraints(*this);
@@ -1092,7 +1105,7 @@ int Run::stage_classify() {
     const size_t ct = ctx->cap_tiles;
     const bool skip = ctx->field_is_sparse; /* the candidate map of the block-field mode */
     const ClsScratch sc{ctx->d_ent, tu, tu + ct, tu + 2 * ct, tu + 3 * ct, tu + 4 * ct, ctx->d_amb, ctx->cap_amb, cg.tile_rows * cg.WC,
-                        skip ? ctx->d_cand : nullptr, (uint32_t)((g.M + 3) / 4)};
+                        skip ? ctx->d_cand : nullptr, (uint32_t)((g.M + 3) / 4), (uint32_t)((cg.WC + 63) / 64)};
     const uint32_t* cw = nullptr;
     if (g.repeat) { /* per-cube iso levels: the corner signs come from the field, item by item */
         const unsigned long long items = (unsigned long long)cg.total_rows * cg.WC;
@@ -1192,9 +1205,12 @@ int Run::stage_seed() {
 /* K3: interpolation + coalesced float4 emission of the triangle soup */
 int Run::stage_soup() {
     const float* rinv = ctx->d_cs + ctx->rinv_ofs;
-#define MCB_EMIT2(NRM, CUBES, THREADS, CAP, MINB, MULT)                                                                               \
-    MCB_LAUNCH((emit2_kernel<NRM, CUBES, THREADS, CAP, MINB>), eblocks * MULT, THREADS, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, \
+    const bool idx32 = (unsigned long long)g.NZ * g.NV * g.P < (1ull << 32) - 2ull * g.NV * g.P; /* offsets +- one plane stay below 2^32 */
+#define MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, I32)                                                                         \
+    MCB_LAUNCH((emit2_kernel<NRM, CUBES, THREADS, CAP, MINB, I32>), eblocks * MULT, THREADS, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, \
                ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, NRM ? ctx->d_nrm : nullptr)
+#define MCB_EMIT2(NRM, CUBES, THREADS, CAP, MINB, MULT)                                                                               \
+    do { if (idx32) MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, true); else MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, false); } while (0)
     const bool nrm = ctx->normals == 1;
     switch (ctx->emit_variant) {
         case 1:
@@ -1208,6 +1224,7 @@ int Run::stage_soup() {
         default: if (nrm) MCB_EMIT2(true, 128, 256, 1024, 6, 2); else MCB_EMIT2(false, 128, 256, 1024, 6, 2); break;
     }
 #undef MCB_EMIT2
+#undef MCB_EMIT2_
     launches++;
     return MCB_OK;
 }
@@ -1536,7 +1553,7 @@ int mcb_get_cases(mcb_ctx* ctx, uint8_t* cube_code, uint8_t* table_idx) {
     for (int i = 0; i < 3; i++) any_constraint |= ctx->cons[i].in_use && ctx->eq[i + 1].valid;
     if (ctx->field_is_sparse) { /* block-field mode: only the decided blocks next to the surface carry their sign words so far */
         const unsigned nblocks = (unsigned)ctx->bd.nbx * (unsigned)ctx->bd.nby * (unsigned)ctx->bd.nbz;
-        MCB_LAUNCH((decided_signs_all_kernel), (nblocks + 255) / 256, 256, 0, ctx->stream, g, ctx->bd, ctx->d_bcls, ctx->d_S);
+        MCB_LAUNCH((decided_signs_all_kernel), (nblocks + 255) / 256, 256, 0, ctx->stream, g, ctx->bd, ctx->d_bcls, ctx->d_scls, ctx->d_S);
     }
     uint8_t *d_code = nullptr, *d_tidx = nullptr;
     MCB_CK(cudaMalloc((void**)&d_code, (size_t)n));

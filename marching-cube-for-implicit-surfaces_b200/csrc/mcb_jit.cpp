@@ -69,13 +69,13 @@ const char* const kTail = R"SRC(
 const char* const kHeadBlocks = R"SRC(
 extern "C" __global__ void __launch_bounds__(128, MCB_MIN_BLOCKS)
 mcb_fill_jit(const __grid_constant__ Consts C, const Grid g, const float* __restrict__ tables, float* __restrict__ F,
-             unsigned int* __restrict__ S, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count, int nbx, int nby,
-             int slots_per_axis) {
+             unsigned int* __restrict__ S, const unsigned int* __restrict__ list /* bx | by << 8 | bz << 20 */,
+             const unsigned int* __restrict__ count, int slots_per_axis) {
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * 4, n = *count;
     for (unsigned b = blockIdx.x * 4 + (threadIdx.x >> 5); b < n; b += nwarps) {
         const unsigned id = list[b];
-        const int bx = (int)(id % (unsigned)nbx), by = (int)(id / (unsigned)nbx % (unsigned)nby), bz = (int)(id / ((unsigned)nbx * (unsigned)nby));
+        const int bx = (int)(id & 0xFFu), by = (int)((id >> 8) & 0xFFFu), bz = (int)(id >> 20);
         const int xc = bx * 32 + lane, y0 = by * 4, z0 = bz * 4 + g.kb;
 )SRC";
 const char* const kTailBlocks = R"SRC(
@@ -85,20 +85,27 @@ const char* const kTailBlocks = R"SRC(
             const unsigned int wv = __ballot_sync(0xffffffffu, RESULT[e] > g.iso);
             if (lane == e) mine = wv;
         }
-        if (lane < 16 && y0 + (lane >> 2) < g.NV && bz * 4 + (lane & 3) < g.NZ)
-            S[((size_t)(bz * 4 + (lane & 3)) * g.NV + (y0 + (lane >> 2))) * g.WP + bx] = mine;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if (y0 + r >= g.NV) break;
+        const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+        float* fb = F + (size_t)(bz * 4) * planep + (size_t)y0 * rowp + xc;
+        const int ny = min(4, g.NV - y0), nz = min(4, g.NZ - bz * 4);
+        if (ny == 4 && nz == 4) { /* a whole block: sixteen 128-byte lines */
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (bz * 4 + q < g.NZ) F[((size_t)(bz * 4 + q) * g.NV + (y0 + r)) * g.P + xc] = RESULT[4 * r + q];
+#pragma unroll
+                for (int r = 0; r < 4; r++) fb[q * planep + r * rowp] = RESULT[4 * r + q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (q < nz && r < ny) fb[q * planep + r * rowp] = RESULT[4 * r + q];
         }
+        if (lane < 16 && (lane >> 2) < ny && (lane & 3) < nz)
+            S[((size_t)(bz * 4 + (lane & 3)) * g.NV + (y0 + (lane >> 2))) * g.WP + bx] = mine;
 #undef RESULT
     }
 }
 )SRC";
-
 struct Nvrtc {
     void* lib = nullptr;
     int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;

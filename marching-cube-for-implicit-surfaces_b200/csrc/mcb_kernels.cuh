@@ -32,6 +32,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "mcb_bytecode.h"
 #include "mcb_interval.h"
 #include "mcb_launch.h"
@@ -96,7 +98,7 @@ struct Counters {
     unsigned int field_blocks, amb_n; /* blocks the apron refill wrote; ambiguous cubes appended to the face-test list */
     unsigned long long nh_vertices, nh_triangles; /* what the normal.h stage works on: the mesh, or nothing when it is truncated */
     /* ---- everything above is reset before every classify pass; what follows belongs to the evaluation stage ---- */
-    unsigned int eval_blocks, pad2_; /* block-field mode: 32 x 4 x 4 vertex blocks the interval test could not decide */
+    unsigned int eval_blocks, eval_supers; /* block-field mode: 32 x 4 x 4 vertex blocks / 32 x 16 x 16 super-blocks the interval test could not decide */
 };
 constexpr size_t kCountersClassifyBytes = offsetof(Counters, eval_blocks);
 
@@ -365,6 +367,8 @@ eval_field_kernel(const __grid_constant__ mcb_program prog, const Grid g, const 
  * is one x column and holds 4 rows x 4 planes, so the host swaps the operand classes of the x and z tables when it
  * encodes this kernel's launch program (class 1 = z, stride 1; class 2 = y; class 3 = x, per lane). */
 constexpr int kFieldBlockX = 32, kFieldBlockY = 4, kFieldBlockZ = 4;
+/* a block on a list: bx | by << 8 | bz << 20 (bx <= 129, by, bz <= 1025 for M <= 4094): no divisions to unpack */
+__device__ __forceinline__ uint32_t pack_block(int bx, int by, int bz) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 20); }
 struct FieldBlocks {
     int nbx, nby, nbz;            /* blocks per axis: P/32, ceil(NV/4), ceil(NZ/4) */
     uint8_t* flags;               /* [nbz][nby][nbx] */
@@ -373,16 +377,15 @@ struct FieldBlocks {
 template <bool HAS_POW>
 __global__ void __launch_bounds__(kEvalThreads, HAS_POW ? 8 : 10)
 eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const float* __restrict__ tables,
-                   float* __restrict__ F, uint32_t* __restrict__ S, const uint32_t* __restrict__ list,
-                   const unsigned* __restrict__ count, int nbx, int nby) {
+                   float* __restrict__ F, uint32_t* __restrict__ S, const uint32_t* __restrict__ list /* pack_block */,
+                   const unsigned* __restrict__ count) {
     MCB_DYNAMIC_SMEM(float, stack_smem);
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * (kEvalThreads / 32);
     const unsigned n = *count;
     for (unsigned b = blockIdx.x * (kEvalThreads / 32) + (threadIdx.x >> 5); b < n; b += nwarps) {
         const uint32_t id = list[b];
-        const int bx = (int)(id % (unsigned)nbx), by = (int)(id / (unsigned)nbx % (unsigned)nby);
-        const int bz = (int)(id / ((unsigned)nbx * (unsigned)nby));
+        const int bx = (int)(id & 0xFFu), by = (int)((id >> 8) & 0xFFFu), bz = (int)(id >> 20);
         EvalLane L;
         L.tables = tables;
         L.x0 = bz * kFieldBlockZ + g.kb; /* class 1: the z tables, consecutive planes */
@@ -396,20 +399,23 @@ eval_blocks_kernel(const __grid_constant__ mcb_program prog, const Grid g, const
             const uint32_t wv = __ballot_sync(0xffffffffu, acc[e] > g.iso);
             if (lane == e) mine = wv;
         }
+        const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+        float* fb = F + (size_t)(bz * kFieldBlockZ) * planep + (size_t)L.y0 * rowp + L.zi;
+        const int ny = min(kFieldBlockY, g.NV - L.y0), nz = min(kFieldBlockZ, g.NZ - bz * kFieldBlockZ); /* uniform per warp */
+        if (ny == kFieldBlockY && nz == kFieldBlockZ) { /* a whole block: sixteen 128-byte lines */
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int y = L.y0 + r;
-            if (y >= g.NV) break;
+            for (int q = 0; q < 4; q++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int pz = bz * kFieldBlockZ + q;
-                if (pz < g.NZ) F[((size_t)pz * g.NV + y) * g.P + L.zi] = acc[4 * r + q];
-            }
+                for (int r = 0; r < 4; r++) fb[q * planep + r * rowp] = acc[4 * r + q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (q < nz && r < ny) fb[q * planep + r * rowp] = acc[4 * r + q];
         }
-        if (lane < kEvalRows) {
-            const int y = L.y0 + (lane >> 2), pz = bz * kFieldBlockZ + (lane & 3);
-            if (y < g.NV && pz < g.NZ) S[((size_t)pz * g.NV + y) * g.WP + bx] = mine;
-        }
+        if (lane < kEvalRows && (lane >> 2) < ny && (lane & 3) < nz)
+            S[((size_t)(bz * kFieldBlockZ + (lane & 3)) * g.NV + (L.y0 + (lane >> 2))) * g.WP + bx] = mine;
     }
 }
 
@@ -439,7 +445,8 @@ field_list_kernel(const FieldBlocks fb, unsigned nblocks, Counters* __restrict__
     while (bits) {
         const int i = __ffs(bits) - 1;
         bits &= bits - 1;
-        fb.list[base++] = g16 * 16u + (unsigned)i;
+        const unsigned id = g16 * 16u + (unsigned)i, plane = (unsigned)fb.nbx * (unsigned)fb.nby, bz = id / plane, rem = id - bz * plane;
+        fb.list[base++] = pack_block((int)(rem % (unsigned)fb.nbx), (int)(rem / (unsigned)fb.nbx), (int)bz);
     }
 }
 
@@ -497,101 +504,132 @@ axis_bounds_kernel(const float* __restrict__ tables, const Grid g, const BlockDi
     B[(size_t)level * 3 * bd.spa * bd.nb + idx] = r;
 }
 
-__global__ void __launch_bounds__(128)
-super_class_kernel(const __grid_constant__ mcb_program prog /* fused grid program, slot numbers as arguments */, const Grid g,
-                   const BlockDims bd, const mcb_ival* __restrict__ B, uint8_t* __restrict__ scls) {
-    const unsigned n = (unsigned)bd.nbx * (unsigned)bd.nsy * (unsigned)bd.nsz;
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const int bx = (int)(idx % (unsigned)bd.nbx), sy = (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nsy), sz = (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nsy));
-    scls[idx] = (uint8_t)mcb_interval_class(prog.code, prog.n, prog.k, B + (size_t)3 * bd.spa * bd.nb, bd.spa, bd.nb, bx, sy, sz, g.iso, nullptr);
+/* Class of a block as its readers see it: the explicit byte, or — 0xFF, a block of a decided super-block, which the fine
+ * pass never visits — the super-block's verdict.  Bit 2 = "its constant sign words are written". */
+constexpr uint8_t kClsInherit = 0xFF;
+__device__ __forceinline__ int block_class_of(const uint8_t* __restrict__ cls, const uint8_t* __restrict__ scls, const BlockDims& bd,
+                                              int bx, int by, int bz) {
+    const int c = (int)cls[((size_t)bz * bd.nby + by) * bd.nbx + bx];
+    return c != kClsInherit ? c : (int)scls[((size_t)(bz / kSuper) * bd.nsy + by / kSuper) * bd.nbx + bx];
 }
 
-__global__ void __launch_bounds__(256)
-block_class_kernel(const __grid_constant__ mcb_program prog, const Grid g, const BlockDims bd, const mcb_ival* __restrict__ B,
-                   const uint8_t* __restrict__ scls, int decide /* 0: every block is "undecided" (tests) */,
-                   uint8_t* __restrict__ cls, uint8_t* __restrict__ flags, uint32_t* __restrict__ list,
-                   uint8_t* __restrict__ cand /* zeroed before this kernel */, Counters* __restrict__ ctr) {
-    const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz;
+__global__ void __launch_bounds__(128)
+super_class_kernel(const __grid_constant__ mcb_program prog /* fused grid program, slot numbers as arguments */, const Grid g,
+                   const BlockDims bd, const mcb_ival* __restrict__ B, int decide /* 0: everything is "undecided" (tests) */,
+                   uint8_t* __restrict__ scls, uint32_t* __restrict__ slist, Counters* __restrict__ ctr) {
+    const unsigned n = (unsigned)bd.nbx * (unsigned)bd.nsy * (unsigned)bd.nsz;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int c = 0;
-    int bx = 0, by = 0, bz = 0;
-    if (idx < nblocks) {
-        bx = (int)(idx % (unsigned)bd.nbx); by = (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nby);
-        bz = (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nby));
-        if (decide) {
-            c = (int)__ldg(scls + ((size_t)(bz / kSuper) * bd.nsy + by / kSuper) * bd.nbx + bx);
-            if (c == 0) c = mcb_interval_class(prog.code, prog.n, prog.k, B, bd.spa, bd.nb, bx, by, bz, g.iso, nullptr);
-        }
-        cls[idx] = (uint8_t)c;
-        flags[idx] = c == 0 ? 2 : 0; /* 2 = on the evaluation list; compact_kernel turns the apron blocks' 0 into 1 */
+    if (idx < n) {
+        const int bx = (int)(idx % (unsigned)bd.nbx), sy = (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nsy), sz = (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nsy));
+        if (decide) c = mcb_interval_class(prog.code, prog.n, prog.k, B + (size_t)3 * bd.spa * bd.nb, bd.spa, bd.nb, bx, sy, sz, g.iso, nullptr);
+        scls[idx] = (uint8_t)c;
     }
-    const bool undecided = idx < nblocks && c == 0;
+    /* the undecided super-blocks are what the fine pass looks at: a warp reserves its list entries with one atomic */
+    const bool undecided = idx < n && c == 0;
     const uint32_t m = __ballot_sync(0xffffffffu, undecided);
     if (m == 0u) return;
-    unsigned base = 0; /* a warp reserves its list entries with one atomic */
-    if (lane == __ffs(m) - 1) base = atomicAdd(&ctr->eval_blocks, (unsigned)__popc(m));
+    unsigned base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&ctr->eval_supers, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (!undecided) return;
-    list[base + __popc(m & ((1u << lane) - 1u))] = idx;
-    /* cube (i, j, kz) reads the stored vertices (i+1..i+2, j+1..j+2, kz+1..kz+2): the cube blocks reaching into this
-     * vertex block are (bx-1..bx, by-1..by, bz-1..bz) */
+    if (undecided) slist[base + __popc(m & ((1u << lane) - 1u))] = idx;
+}
+
+/* The fine pass: sixteen threads per undecided super-block, one per block. */
+__global__ void __launch_bounds__(256)
+block_class_kernel(const __grid_constant__ mcb_program prog, const Grid g, const BlockDims bd, const mcb_ival* __restrict__ B,
+                   const uint32_t* __restrict__ slist, int decide, uint8_t* __restrict__ cls /* preset to kClsInherit */,
+                   uint8_t* __restrict__ flags /* preset to 0 */, uint32_t* __restrict__ list,
+                   unsigned long long* __restrict__ cand /* preset to 0: one bit per cube block, cmw words per (layer group, row group) */,
+                   Counters* __restrict__ ctr) {
+    const unsigned nsuper = ctr->eval_supers;
+    const int lane = threadIdx.x & 31;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned total = (nsuper * 16u + 31u) & ~31u; /* whole warps stay in the loop: the ballot below needs them */
+    const int cmw = (bd.WC + 63) / 64;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const unsigned si = t >> 4, sub = t & 15u;
+        bool undecided = false;
+        int bx = 0, by = 0, bz = 0;
+        if (si < nsuper) {
+            const unsigned sidx = slist[si];
+            bx = (int)(sidx % (unsigned)bd.nbx);
+            by = (int)(sidx / (unsigned)bd.nbx % (unsigned)bd.nsy) * kSuper + (int)(sub & 3u);
+            bz = (int)(sidx / ((unsigned)bd.nbx * (unsigned)bd.nsy)) * kSuper + (int)(sub >> 2);
+            if (by < bd.nby && bz < bd.nbz) {
+                const int c = decide ? mcb_interval_class(prog.code, prog.n, prog.k, B, bd.spa, bd.nb, bx, by, bz, g.iso, nullptr) : 0;
+                const size_t id = ((size_t)bz * bd.nby + by) * bd.nbx + bx;
+                cls[id] = (uint8_t)c;
+                undecided = c == 0;
+                if (undecided) flags[id] = 2; /* 2 = on the evaluation list; compact_kernel turns the apron blocks' 0 into 1 */
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, undecided);
+        if (m == 0u) continue;
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&ctr->eval_blocks, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (!undecided) continue;
+        list[base + __popc(m & ((1u << lane) - 1u))] = pack_block(bx, by, bz);
+        /* cube (i, j, kz) reads the stored vertices (i+1..i+2, j+1..j+2, kz+1..kz+2): the cube blocks reaching into this
+         * vertex block are (bx-1..bx, by-1..by, bz-1..bz) */
 #pragma unroll
-    for (int d = 0; d < 8; d++) {
-        const int w = bx - (d & 1), jb = by - ((d >> 1) & 1), kq = bz - (d >> 2);
-        if (w < 0 || jb < 0 || kq < 0 || w >= bd.WC || jb >= bd.cjb || kq >= bd.ckb) continue;
-        cand[((size_t)kq * bd.cjb + jb) * bd.WC + w] = 1;
+        for (int d = 0; d < 4; d++) {
+            const int jb = by - (d & 1), kq = bz - (d >> 1);
+            if (jb < 0 || kq < 0 || jb >= bd.cjb || kq >= bd.ckb) continue;
+            unsigned long long* row = cand + ((size_t)kq * bd.cjb + jb) * cmw;
+            if (bx < bd.WC) atomicOr(row + (bx >> 6), 1ull << (bx & 63));
+            if (bx >= 1 && bx - 1 < bd.WC) atomicOr(row + ((bx - 1) >> 6), 1ull << ((bx - 1) & 63));
+        }
     }
 }
 
-/* sign words of a decided block: sixteen constants */
-__device__ __forceinline__ void write_decided_signs(const Grid& g, uint32_t* __restrict__ S, int bx, int by, int bz, int c) {
-    const uint32_t word = (c & 3) == 2 ? 0xffffffffu : 0u;
-#pragma unroll
-    for (int q = 0; q < kFieldBlockZ; q++) {
-        const int pz = bz * kFieldBlockZ + q;
-        if (pz >= g.NZ) break;
-#pragma unroll
-        for (int r = 0; r < kFieldBlockY; r++) {
-            const int y = by * kFieldBlockY + r;
-            if (y < g.NV) S[((size_t)pz * g.NV + y) * g.WP + bx] = word;
-        }
-    }
+/* sign words of a decided block: sixteen constants, written by sixteen lanes (lane = 4 r + q: row r, plane q) */
+__device__ __forceinline__ void write_decided_signs(const Grid& g, uint32_t* __restrict__ S, int bx, int by, int bz, int c, int lane16) {
+    const int y = by * kFieldBlockY + (lane16 >> 2), pz = bz * kFieldBlockZ + (lane16 & 3);
+    if (y < g.NV && pz < g.NZ) S[((size_t)pz * g.NV + y) * g.WP + bx] = (c & 3) == 2 ? 0xffffffffu : 0u;
 }
-/* A warp per undecided block, a lane per neighbour: a decided neighbour whose words nobody has written yet gets them
- * (bit 2 of its class byte remembers that; two writers racing store the same words).  These are all the decided
- * blocks a candidate cube block can reach into. */
+/* A warp per undecided block: its 26 neighbours are probed by 26 lanes; those that are decided and whose words nobody has
+ * written yet (bit 2 of the class byte remembers; two warps racing store the same words) are then written one after the
+ * other by sixteen lanes each.  These are all the decided blocks a candidate cube block can reach into. */
 __global__ void __launch_bounds__(256)
 decided_signs_kernel(const Grid g, const BlockDims bd, const uint32_t* __restrict__ list, const Counters* __restrict__ ctr,
-                     uint8_t* __restrict__ cls, uint32_t* __restrict__ S) {
+                     uint8_t* __restrict__ cls, const uint8_t* __restrict__ scls, uint32_t* __restrict__ S) {
     const unsigned n = ctr->eval_blocks;
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
     for (unsigned b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n; b += nwarps) {
-        if (lane >= 27 || lane == 13) continue; /* 13 = the block itself */
         const uint32_t id = list[b];
-        const int bx = (int)(id % (unsigned)bd.nbx) + lane % 3 - 1, by = (int)(id / (unsigned)bd.nbx % (unsigned)bd.nby) + (lane / 3) % 3 - 1;
-        const int bz = (int)(id / ((unsigned)bd.nbx * (unsigned)bd.nby)) + lane / 9 - 1;
-        if (bx < 0 || by < 0 || bz < 0 || bx >= bd.nbx || by >= bd.nby || bz >= bd.nbz) continue;
-        uint8_t* pc = cls + ((size_t)bz * bd.nby + by) * bd.nbx + bx;
-        const int c = (int)*pc;
-        if (c == 0 || (c & 4)) continue;
-        *pc = (uint8_t)(c | 4);
-        write_decided_signs(g, S, bx, by, bz, c);
+        const int bx = (int)(id & 0xFFu) + lane % 3 - 1, by = (int)((id >> 8) & 0xFFFu) + (lane / 3) % 3 - 1, bz = (int)(id >> 20) + lane / 9 - 1;
+        int c = 0;
+        if (lane < 27 && lane != 13 && bx >= 0 && by >= 0 && bz >= 0 && bx < bd.nbx && by < bd.nby && bz < bd.nbz) {
+            c = block_class_of(cls, scls, bd, bx, by, bz);
+            if (c & 4) c = 0;                                                             /* written already */
+            else if (c != 0) cls[((size_t)bz * bd.nby + by) * bd.nbx + bx] = (uint8_t)(c | 4);
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, c != 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int nx = __shfl_sync(0xffffffffu, bx, src), ny = __shfl_sync(0xffffffffu, by, src), nz = __shfl_sync(0xffffffffu, bz, src);
+            const int nc = __shfl_sync(0xffffffffu, c, src);
+            if (lane < 16) write_decided_signs(g, S, nx, ny, nz, nc, lane);
+        }
     }
 }
 /* the parity hook mcb_get_cases reads every sign word: write those of all decided blocks */
 __global__ void __launch_bounds__(256)
-decided_signs_all_kernel(const Grid g, const BlockDims bd, uint8_t* __restrict__ cls, uint32_t* __restrict__ S) {
+decided_signs_all_kernel(const Grid g, const BlockDims bd, uint8_t* __restrict__ cls, const uint8_t* __restrict__ scls, uint32_t* __restrict__ S) {
     const unsigned nblocks = (unsigned)bd.nbx * (unsigned)bd.nby * (unsigned)bd.nbz;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nblocks) return;
-    const int c = (int)cls[idx];
+    const int bx = (int)(idx % (unsigned)bd.nbx), by = (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nby), bz = (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nby));
+    const int c = block_class_of(cls, scls, bd, bx, by, bz);
     if (c == 0 || (c & 4)) return;
     cls[idx] = (uint8_t)(c | 4);
-    write_decided_signs(g, S, (int)(idx % (unsigned)bd.nbx), (int)(idx / (unsigned)bd.nbx % (unsigned)bd.nby),
-                        (int)(idx / ((unsigned)bd.nbx * (unsigned)bd.nby)), c);
+#pragma unroll
+    for (int l = 0; l < 16; l++) write_decided_signs(g, S, bx, by, bz, c, l);
 }
 
 /* K1b  constraint validity bit-plane: V &= (lhs(sx*x,sy*y,sz*z) op rhs), one launch per constraint in use. */
@@ -628,7 +666,7 @@ eval_constraint_kernel(const __grid_constant__ mcb_program prog, const Grid g, c
  *       A  every thread walks one word column down a strip of rows, carrying the sign words of the vertex row it
  *          shares with the next cube row (4 loads and ~30 instructions per 32 cubes), and sets a bit in a
  *          shared-memory bitmap for every item that has an active cube.  With the candidate map of the block-field
- *          mode (cube_cand_kernel) it steps over four cube rows at a time wherever the interval test has already
+ *          mode (block_class_kernel) it steps over four cube rows at a time wherever the interval test has already
  *          proven that no sign changes: this is the only work done per voxel, and it is then done per 128 voxels;
  *       B  the bitmap is turned into the list of active items in loop order (popc + block scan);
  *       C1 one lane per ACTIVE item: rebuild its corner words, per cube code -> triangle count.  A cube whose code
@@ -792,8 +830,9 @@ struct ClsScratch {          /* global scratch handed from classify_kernel to am
     unsigned long long* amb; /* [cap_amb][2]  entry index | bit << 40 | face << 45 | code << 48 ;  i | j << 12 | k << 24 */
     uint32_t cap_amb;
     uint32_t tile_items;     /* tile_rows * WC */
-    const uint8_t* cand;     /* [ckb][cjb][WC] cube blocks that may hold an active cube, or nullptr: look everywhere */
+    const unsigned long long* cand; /* [ckb][cjb][cmw] one bit per cube block that may hold an active cube, or nullptr: look everywhere */
     uint32_t cjb;            /* ceil(M / 4) */
+    uint32_t cmw;            /* 64-bit words per row group: ceil(WC / 64) */
 };
 #define MCB_ENT_NA(e) ((uint32_t)(e) & 63u)
 #define MCB_ENT_NT(e) (((uint32_t)(e) >> 6) & 255u)
@@ -834,23 +873,32 @@ classify_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t*
         uint16_t* cells = list; /* free until phase B */
         uint32_t ncand = ncell;
         const bool mapped = !REPEAT && sc.cand != nullptr;
-        if (mapped) {
+        if (mapped) { /* a thread per (row group, 64 word columns): one load says which of its cells are candidates */
             if (threadIdx.x == 0) ncand_s = 0u;
             __syncthreads();
-            for (uint32_t c0 = 0; c0 < ncell; c0 += kClsThreads) {
-                const uint32_t c = c0 + threadIdx.x;
-                bool look = false;
-                if (c < ncell) {
-                    const uint32_t gq = div_small(c, q.inv_wc), w = c - gq * q.WC, G = G0 + gq, kz = G / cjb, jb = G - kz * cjb;
-                    look = __ldg(sc.cand + ((size_t)(kz >> 2) * cjb + jb) * q.WC + w) != 0;
+            const uint32_t nG = G1 - G0 + 1u, nmask = nG * sc.cmw;
+            for (uint32_t c0 = 0; c0 < nmask; c0 += kClsThreads) {
+                const uint32_t mi = c0 + threadIdx.x;
+                unsigned long long bits = 0ull;
+                uint32_t gq = 0, part = 0;
+                if (mi < nmask) {
+                    gq = mi / sc.cmw; part = mi - gq * sc.cmw;
+                    const uint32_t G = G0 + gq, kz = G / cjb, jb = G - kz * cjb;
+                    bits = __ldg(sc.cand + ((size_t)(kz >> 2) * cjb + jb) * sc.cmw + part);
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, look);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    uint32_t base = 0;
-                    if (lane == leader) base = atomicAdd(&ncand_s, (uint32_t)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (look) cells[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)c;
+                const uint32_t cnt = (uint32_t)__popcll(bits);
+                uint32_t inc = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+                const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                if (total == 0u) continue;
+                uint32_t base = 0;
+                if (lane == 31) base = atomicAdd(&ncand_s, total);
+                base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+                while (bits) {
+                    const int w = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1ull;
+                    cells[base++] = (uint16_t)(gq * q.WC + part * 64u + (uint32_t)w);
                 }
             }
             __syncthreads();
@@ -1001,7 +1049,9 @@ ambiguity_kernel(const __grid_constant__ mcb_program point_prog, const Grid g, c
     if (redirected) atomicAdd(&ctr->redirected, (unsigned long long)redirected);
 }
 
-/* Exclusive scan of the per-tile totals: a few thousand tiles, one block.  Grand totals -> counters. */
+/* Exclusive scan of the per-tile totals: a few thousand tiles, one block, kTileScanPer consecutive tiles per thread.
+ * Grand totals -> counters. */
+constexpr int kTileScanPer = 8;
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const ClsScratch sc, uint32_t tiles, Counters* __restrict__ ctr) {
     __shared__ unsigned long long warp_a[32], warp_t[32];
@@ -1009,10 +1059,17 @@ tile_scan_kernel(const ClsScratch sc, uint32_t tiles, Counters* __restrict__ ctr
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) { carry_a = 0; carry_t = 0; }
     __syncthreads();
-    for (uint32_t b0 = 0; b0 < tiles; b0 += 1024) {
-        const uint32_t i = b0 + t;
-        const unsigned long long va = i < tiles ? sc.tile_a[i] : 0ull, vt = i < tiles ? sc.tile_t[i] : 0ull;
-        unsigned long long ia = va, it = vt;
+    for (uint32_t b0 = 0; b0 < tiles; b0 += 1024u * kTileScanPer) {
+        const uint32_t i0 = b0 + (uint32_t)t * kTileScanPer;
+        uint32_t va[kTileScanPer], vt[kTileScanPer];
+        unsigned long long sa = 0, st = 0;
+#pragma unroll
+        for (int q = 0; q < kTileScanPer; q++) {
+            va[q] = i0 + q < tiles ? sc.tile_a[i0 + q] : 0u;
+            vt[q] = i0 + q < tiles ? sc.tile_t[i0 + q] : 0u;
+            sa += va[q]; st += vt[q];
+        }
+        unsigned long long ia = sa, it = st;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned long long ua = __shfl_up_sync(0xffffffffu, ia, d), ut = __shfl_up_sync(0xffffffffu, it, d);
@@ -1022,7 +1079,12 @@ tile_scan_kernel(const ClsScratch sc, uint32_t tiles, Counters* __restrict__ ctr
         __syncthreads();
         unsigned long long ba = carry_a, bt = carry_t;
         for (int w2 = 0; w2 < warp; w2++) { ba += warp_a[w2]; bt += warp_t[w2]; }
-        if (i < tiles) { sc.base_a[i] = (uint32_t)(ba + ia - va); sc.base_t[i] = (uint32_t)(bt + it - vt); }
+        unsigned long long ra = ba + ia - sa, rt = bt + it - st;
+#pragma unroll
+        for (int q = 0; q < kTileScanPer; q++) {
+            if (i0 + q < tiles) { sc.base_a[i0 + q] = (uint32_t)ra; sc.base_t[i0 + q] = (uint32_t)rt; }
+            ra += va[q]; rt += vt[q];
+        }
         __syncthreads();
         if (t == 1023) { carry_a = ba + ia; carry_t = bt + it; }
         __syncthreads();
@@ -1318,7 +1380,8 @@ __device__ __forceinline__ void gradient_normal(const float* __restrict__ pa, co
     ox = nx * inv; oy = ny * inv; oz = nz * inv;
 }
 
-template <bool NORMALS, int CUBES, int THREADS, int CAP /* edge slots per chunk run */, int MINB>
+template <bool NORMALS, int CUBES, int THREADS, int CAP /* edge slots per chunk run */, int MINB,
+          bool IDX32 /* the slab's field has fewer than 2^32 values: 32-bit offsets, one IMAD.WIDE per load address */>
 __global__ void __launch_bounds__(THREADS, MINB)
 emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict__ rinv, const float* __restrict__ F,
              const ClsTables* __restrict__ gtb, const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ trioff,
@@ -1328,6 +1391,9 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
     __shared__ float4 eslot[NORMALS ? CAP : 1];     /* crossing edge: coordinate along its axis, normal */
     __shared__ float epos_only[NORMALS ? 1 : CAP];
     __shared__ float ccoord[CUBES * 6];             /* x0 x1 y0 y1 z0 z1 of the cube */
+    __shared__ float crinv[NORMALS ? CUBES * 6 : 1]; /* 1 / (c[v+1] - c[v-1]) at the same six coordinates */
+    typedef typename std::conditional<IDX32, uint32_t, unsigned long long>::type off_t; /* offsets into F */
+    __shared__ off_t cbase_s[CUBES];                /* offset of the cube's corner 0 in F */
     __shared__ uint32_t off_s[CUBES + 1];           /* first triangle of the cube */
     __shared__ uint64_t triw_s[CUBES];
     __shared__ uint32_t ijk_s[CUBES];               /* i | j << 12 */
@@ -1344,7 +1410,7 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
     if (!whole) A = cap_active; /* the host re-runs with larger buffers when counts exceed capacity */
     const unsigned long long nchunks = (A + CUBES - 1) / CUBES;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const size_t rowp = (size_t)g.P, planep = (size_t)g.NV * g.P;
+    const off_t rowp = (off_t)g.P, planep = (off_t)g.NV * (off_t)g.P;
 
     for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         __syncthreads();
@@ -1366,6 +1432,12 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
             ccoord[6 * t + 0] = __ldg(cs + i + 1); ccoord[6 * t + 1] = __ldg(cs + i + 2);
             ccoord[6 * t + 2] = __ldg(cs + j + 1); ccoord[6 * t + 3] = __ldg(cs + j + 2);
             ccoord[6 * t + 4] = __ldg(cs + k + 1); ccoord[6 * t + 5] = __ldg(cs + k + 2);
+            if (NORMALS) {
+                crinv[6 * t + 0] = __ldg(rinv + i + 1); crinv[6 * t + 1] = __ldg(rinv + i + 2);
+                crinv[6 * t + 2] = __ldg(rinv + j + 1); crinv[6 * t + 3] = __ldg(rinv + j + 2);
+                crinv[6 * t + 4] = __ldg(rinv + k + 1); crinv[6 * t + 5] = __ldg(rinv + k + 2);
+            }
+            cbase_s[t] = (off_t)(k - g.kb + 1) * planep + (off_t)(j + 1) * rowp + (off_t)(i + 1);
         }
         const uint32_t nv = __popc(emask);
         uint32_t inc = nv;
@@ -1404,25 +1476,32 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
             for (uint32_t q = q0 + t; q < q1; q += THREADS) {
                 const uint32_t wk = work_s[q];
                 const int lc = (int)(wk >> 4), e = (int)(wk & 15u);
-                const uint32_t ij = ijk_s[lc];
-                const int i = (int)(ij & 0xFFF), j = (int)(ij >> 12), k = (int)k_s[lc];
                 const int a = mcb_edge_a(e), b = mcb_edge_b(e);
                 const int oa = mcb_corner_ofs(a), ob = mcb_corner_ofs(b);
                 const int axis = e >= 8 ? 2 : (e & 1);
-                /* vertex indices into cs (apron: +1) of the two end points */
-                const int xa = i + 1 + (oa & 1), ya = j + 1 + ((oa >> 1) & 1), za = k + 1 + ((oa >> 2) & 1);
-                const int xb = i + 1 + (ob & 1), yb = j + 1 + ((ob >> 1) & 1), zb = k + 1 + ((ob >> 2) & 1);
-                const float* pa = F + (size_t)(za - g.kb) * planep + (size_t)ya * rowp + xa;
-                const float* pb = F + (size_t)(zb - g.kb) * planep + (size_t)yb * rowp + xb;
-                const float f1 = __ldg(pa), f2 = __ldg(pb);
+                const off_t c0f = cbase_s[lc]; /* corner 0 of the cube; the end points are at most one step away on each axis */
+                const off_t ia = c0f + (off_t)(oa & 1) + (((oa >> 1) & 1) ? rowp : (off_t)0) + ((oa >> 2) ? planep : (off_t)0);
+                const off_t ib = c0f + (off_t)(ob & 1) + (((ob >> 1) & 1) ? rowp : (off_t)0) + ((ob >> 2) ? planep : (off_t)0);
+                const float f1 = __ldg(F + ia), f2 = __ldg(F + ib);
                 const float tq = (g.iso - f1) / (f2 - f1); /* Marching::interp uses the surface constant itself, also in repeating-surface mode */
                 const float* cc = ccoord + 6 * lc + 2 * axis;
                 const float ca = cc[(oa >> axis) & 1], cb2 = cc[(ob >> axis) & 1];
                 const float p = interp_ref(ca, cb2, tq);
-                if (NORMALS) {
-                    float nx, ny, nz;
-                    gradient_normal(pa, pb, rowp, planep, rinv, xa, ya, za, xb, yb, zb, tq, nx, ny, nz);
-                    eslot[q - q0] = make_float4(p, nx, ny, nz);
+                if (NORMALS) { /* gradient_normal() with the reciprocals from shared memory */
+                    const float* ri = crinv + 6 * lc;
+                    const float gxa = (__ldg(F + ia + 1) - __ldg(F + ia - 1)) * ri[oa & 1];
+                    const float gya = (__ldg(F + (ia + rowp)) - __ldg(F + (ia - rowp))) * ri[2 + ((oa >> 1) & 1)];
+                    const float gza = (__ldg(F + (ia + planep)) - __ldg(F + (ia - planep))) * ri[4 + (oa >> 2)];
+                    const float gxb = (__ldg(F + ib + 1) - __ldg(F + ib - 1)) * ri[ob & 1];
+                    const float gyb = (__ldg(F + (ib + rowp)) - __ldg(F + (ib - rowp))) * ri[2 + ((ob >> 1) & 1)];
+                    const float gzb = (__ldg(F + (ib + planep)) - __ldg(F + (ib - planep))) * ri[4 + (ob >> 2)];
+                    float tt = tq;
+                    if (isinf(tt) || isnan(tt)) tt = 0.5f;
+                    const float nx = gxa + tt * (gxb - gxa);
+                    const float ny = gya + tt * (gyb - gya);
+                    const float nz = gza + tt * (gzb - gza);
+                    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+                    eslot[q - q0] = make_float4(p, nx * inv, ny * inv, nz * inv);
                 } else epos_only[q - q0] = p;
             }
             __syncthreads();

@@ -223,6 +223,70 @@ long mcref_sweep(mcref* h, int k0, int k1, uint8_t* code, uint8_t* tidx, uint8_t
     return T;
 }
 
+/* the same for cube rows [row0, row1) (row = k * M + j): lets a test spread one large layer over several threads, each with
+ * its own Evaluator + Marching pair */
+long mcref_sweep_rows(mcref* h, long row0, long row1, uint8_t* code, uint8_t* tidx, uint8_t* ntri, float* corner_vals,
+                 float* soup, long soup_cap_tris, int weld, long* n_active, long* n_ambiguous, long* n_redirected) {
+    Marching& m = h->march;
+    float step = m.grid_step_size;
+    std::vector<float> c = ref_axis(step);
+    int M = (int)c.size();
+    if (row0 < 0) row0 = 0;
+    if (row1 > (long)M * M) row1 = (long)M * M;
+    if (weld) m.reset_all_data();
+    bool any_constraint = false;
+    for (size_t i = 0; i < m.constraints.size(); i++) any_constraint |= (m.constraints[i].valid && m.constraints[i].in_use);
+    Step_Data* sd = &m.poly_data.step_data;
+    long T = 0, A = 0, AMB = 0, RED = 0, idx = 0;
+    std::vector<int> edges;
+    for (long row = row0; row < row1; row++)
+        for (int i = 0, j = (int)(row % M), k = (int)(row / M); i < M; i++, idx++) {
+                m.calculate_step(c[i], c[j], c[k]);
+                if (weld) m.add_step_to_poly_data();
+                int cc = 0, ti = 0, nt = 0;
+                bool skipped = false;
+                if (any_constraint) {
+                    for (int v = 0; v < 8 && !skipped; v++)
+                        skipped = !m.check_constraints(sd->corner_coords[3 * v], sd->corner_coords[3 * v + 1], sd->corner_coords[3 * v + 2]);
+                }
+                if (!skipped) {
+                    float iso = m.is_repeating_surface ? sd->surf_constant : m.surface_constant;
+                    for (int v = 0; v < 8; v++)
+                        if (sd->corner_values[v] > iso) cc |= (1 << v);
+                    nt = (int)sd->tri_vlist.size() / 3;
+                    ti = cc;
+                    if (cc != 0 && cc != 255) {
+                        A++;
+                        edges.clear();
+                        for (size_t t = 0; t < sd->tri_vlist.size(); t++) edges.push_back(sd->edge_list[sd->tri_vlist[t]]);
+                        int alt = ambiguity_check_and_redirect[cc][0];
+                        if (alt >= 0) AMB++;
+                        if (row_matches(tri_table[cc], edges)) ti = cc;
+                        else if (alt >= 0 && row_matches(tri_table[alt], edges)) { ti = alt; RED++; }
+                        else ti = -1; /* cannot happen; surfaces as a parity failure */
+                    }
+                    if (corner_vals)
+                        for (int v = 0; v < 8; v++) corner_vals[8 * idx + v] = sd->corner_values[v];
+                }
+                if (code) code[idx] = (uint8_t)cc;
+                if (tidx) tidx[idx] = (uint8_t)ti;
+                if (ntri) ntri[idx] = (uint8_t)nt;
+                if (soup)
+                    for (int t = 0; t < nt; t++) {
+                        if (T + t >= soup_cap_tris) break;
+                        for (int v = 0; v < 3; v++) {
+                            int li = sd->tri_vlist[3 * t + v];
+                            for (int a = 0; a < 3; a++) soup[9 * (T + t) + 3 * v + a] = sd->intersect_coord[3 * li + a];
+                        }
+                    }
+                T += nt;
+            }
+    if (n_active) *n_active = A;
+    if (n_ambiguous) *n_ambiguous = AMB;
+    if (n_redirected) *n_redirected = RED;
+    return T;
+}
+
 /* CPU baseline: nthreads independent Evaluator+Marching pairs (they share no state), each running the reference's
  * calculate_step + add_step_to_poly_data over its own contiguous share of `nrows` cube rows starting at row0
  * (row = k*M + j, M cubes each, loop order).  Returns wall seconds; *cubes / *tris = totals.  nthreads==1 with

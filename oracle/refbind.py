@@ -200,6 +200,40 @@ class Ref:
         return out
 
 
+def sweep_rows_mt(eq, step, row0, row1, nthreads=None, scale=(1.0, 1.0, 1.0), iso=0.0, force_step=True):
+    """Per-cube code / table_idx / ntri and the triangle soup of cube rows [row0, row1) (row = k*M + j) from the UNMODIFIED
+    reference, the rows spread over `nthreads` threads with one Evaluator + Marching pair each (they share no state; the
+    calls release the GIL).  Order of the outputs = the reference's loop order."""
+    import threading
+    nthreads = nthreads or min(32, os.cpu_count() or 1)
+    L = lib()
+    L.mcref_sweep_rows.restype = C.c_long
+    L.mcref_sweep_rows.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    refs = [Ref(eq, step, scale, iso, force_step=force_step) for _ in range(nthreads)]
+    M, _ = refs[0].coords()
+    cuts = [row0 + (row1 - row0) * t // nthreads for t in range(nthreads + 1)]
+    parts = [None] * nthreads
+
+    def work(t):
+        a, b = cuts[t], cuts[t + 1]
+        n = (b - a) * M
+        code, tidx, ntri = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        na, nb, nr = C.c_long(0), C.c_long(0), C.c_long(0)
+        T = L.mcref_sweep_rows(refs[t].h, a, b, _p(code), _p(tidx), _p(ntri), None, None, 0, 0, C.byref(na), C.byref(nb), C.byref(nr))
+        soup = np.zeros((max(T, 1), 3, 3), np.float32)
+        L.mcref_sweep_rows(refs[t].h, a, b, None, None, None, None, _p(soup), T, 0, None, None, None)
+        parts[t] = (code, tidx, ntri, soup[:T], int(T), na.value, nb.value, nr.value)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    return dict(M=M, code=np.concatenate([p[0] for p in parts]), table_idx=np.concatenate([p[1] for p in parts]),
+                ntri=np.concatenate([p[2] for p in parts]), soup=np.concatenate([p[3] for p in parts]), T=sum(p[4] for p in parts),
+                active=sum(p[5] for p in parts), ambiguous=sum(p[6] for p in parts), redirected=sum(p[7] for p in parts))
+
+
 def timed_rows_mt(eq, step, scale=(1.0, 1.0, 1.0), iso=0.0, row0=0, nrows=1 << 40, nthreads=1):
     """Reference CPU baseline over cube rows [row0,row0+nrows) (row = k*M+j); returns (seconds, cubes, triangles)."""
     cubes, tris = C.c_long(0), C.c_long(0)

@@ -25,6 +25,7 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline void __stcs(float* p, float v) { *p = v; }
+static inline int min(int a, int b) { return a < b ? a : b; }
 static int g_pass = 0, g_lane = 0, g_seq = 0;
 static unsigned g_masks[1024];
 static inline unsigned __ballot_sync(unsigned, bool p) {

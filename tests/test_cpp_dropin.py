@@ -24,7 +24,7 @@ def _compile(tmp_path):
     exe = str(tmp_path / "dropin_main")
     subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-o", exe, "-L", PKG, "-lmcb200",
-                           "-Wl,-rpath," + PKG])
+                           "-Wl,-rpath," + PKG, "-pthread"])
     return exe
 
 

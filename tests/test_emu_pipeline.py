@@ -91,7 +91,7 @@ def test_cpp_dropin_class_over_the_emulated_library(golden, tmp_path, mcb_emu):
     exe = str(tmp_path / "dropin_emu")
     subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-o", exe, "-L", lib_dir, "-lmcb200_emu",
-                           "-Wl,-rpath," + lib_dir])
+                           "-Wl,-rpath," + lib_dir, "-pthread"])
     meta = load_meta(golden)
     names = ["sphere_17", "eq1_gui", "gyr78_17", "gyr78_17", "eq8_ctor", "torus_33", "sphere_17", "sphere_33_iso", "sphere_33_iso"]
     args = []

@@ -72,7 +72,7 @@ def test_1024_properties(mcb):
 LIVE_1024 = [
     ("x^2+y^2+z^2-0.49", (154, 512, 870)),                       # BASELINE.json configs[2]
     ("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)", (512,)),           # configs[2], torus: `^` of a three-variable sum
-]   # (one layer of the polynomial gyroid takes the reference 100 s: it is covered at 17^3 and 257^3 instead)
+]   # (the polynomial gyroid has its own test below: its layer is spread over the host threads)
 
 
 @pytest.mark.parametrize("eq,layers", LIVE_1024)
@@ -96,4 +96,72 @@ def test_layers_against_live_reference_at_1024(mcb, refbind, eq, layers):
         assert same_bits(pos[:, :, :3], sw["soup"])
         vl, tl = c.get_indexed_mesh()
         assert np.abs(vl[tl.astype(np.int64)].astype(np.float64) - sw["soup"].astype(np.float64)).max() < 1e-6
+    c.close()
+
+
+def test_gyr78_layer_against_live_reference_at_1024(mcb, refbind):
+    """BASELINE.json configs[3] at full size: one z-layer of the 1025^3-cube grid of the polynomial gyroid — the field that
+    exercises the ambiguity redirect at scale — per cube against the UNMODIFIED reference run live (marching.cpp:456-595,
+    redirect :521-549), its 1.05 M calculate_step calls spread over the host threads: cube codes, table rows, ambiguous and
+    redirected counts and the triangle soup, bit for bit."""
+    from .helpers import same_bits
+    eq = refbind.GYR78
+    c = mcb.Context(0)
+    c.set_field_mode(mcb.FIELD_AUTO)
+    assert c.set_equation(eq) == 0 and c.set_grid_step(2.0 / 1024) == 1025
+    for k0 in (512, 3):
+        c.set_slab(k0, k0 + 1)
+        cnt = c.polygonise()
+        sw = refbind.sweep_rows_mt(eq, 2.0 / 1024, k0 * 1025, (k0 + 1) * 1025)
+        code, tidx = c.get_cases()
+        assert np.array_equal(code, sw["code"]) and np.array_equal(tidx, sw["table_idx"])
+        assert cnt.triangles == sw["T"] and cnt.triangles > 10000
+        assert (cnt.active, cnt.ambiguous, cnt.redirected) == (sw["active"], sw["ambiguous"], sw["redirected"])
+        pos, _ = c.get_mesh()
+        assert same_bits(pos[:, :, :3], sw["soup"])
+    assert cnt.ambiguous > 0
+    c.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_2048_slabs_against_live_reference(mcb, refbind, nranks):
+    """BASELINE.json configs[4]: the 2049^3-cube sphere cut into the z-slabs of an nranks-GPU run (mcb_slab_range).  A whole
+    slab is polygonised under mcb_set_slab; its first and its last cube layer — the ones next to the recomputed halo planes —
+    are compared per active cube (position, code, table row, triangle offsets) and triangle by triangle with the unmodified
+    reference run live on those layers."""
+    from .helpers import same_bits
+    eq = "x^2+y^2+z^2-0.49"
+    step = 2.0 / 2048
+    c = mcb.Context(0)
+    c.set_field_mode(mcb.FIELD_AUTO)
+    c.set_normals(0)
+    assert c.set_equation(eq) == 0 and c.set_grid_step(step) == 2049
+    M = 2049
+    r = nranks // 2                       # a slab through the sphere with neighbours on both sides
+    k0, k1 = mcb.slab_range(M, r, nranks)
+    c.set_slab(k0, k1)
+    cnt = c.polygonise()
+    assert cnt.cubes == (k1 - k0) * M * M and cnt.triangles > 0
+    rec, off = c.get_active()
+    pos, _ = c.get_mesh(normals=False)
+    layer = ((rec >> 24) & 0xFFF).astype(np.int64)
+    compared = 0
+    for k in (k0, k1 - 1):
+        sw = refbind.sweep_rows_mt(eq, step, k * M, (k + 1) * M)
+        act = np.flatnonzero((sw["code"] != 0) & (sw["code"] != 255))
+        sel = np.flatnonzero(layer == k)
+        assert len(sel) == len(act) == sw["active"]
+        if len(sel) == 0:   # the last layer of the last slab lies outside the sphere: both sides agree that it is empty
+            continue
+        compared += 1
+        lin = (rec[sel] & 0xFFF).astype(np.int64) + M * ((rec[sel] >> 12) & 0xFFF).astype(np.int64)
+        assert np.array_equal(lin, act)
+        assert np.array_equal(((rec[sel] >> 36) & 0xFF).astype(np.uint8), sw["code"][act])
+        assert np.array_equal(((rec[sel] >> 44) & 0xFF).astype(np.uint8), sw["table_idx"][act])
+        t0 = int(off[sel[0]])
+        t1 = int(off[sel[-1] + 1]) if sel[-1] + 1 < len(off) else int(cnt.triangles)
+        assert t1 - t0 == sw["T"]
+        assert np.array_equal(off[sel].astype(np.int64) - t0, np.concatenate([[0], np.cumsum(sw["ntri"][act].astype(np.int64))[:-1]]))
+        assert same_bits(pos[t0:t1, :, :3], sw["soup"])
+    assert compared >= 1
     c.close()

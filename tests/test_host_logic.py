@@ -404,7 +404,7 @@ def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, 
                            capture_output=True, text=True)
         assert r.returncode == 0, (eq, r.stderr[:2000])
         L = C.CDLL(str(so))
-        L.run_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]
+        L.run_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int]
         tables = np.zeros(3 * 64 * P + 256, np.float32)
         kpool = np.zeros(128, np.float32)
         spa = H.mcoh_tables(eq.encode(), ax[0].ctypes.data, ax[1].ctypes.data, ax[2].ctypes.data, P, tables.ctypes.data, len(tables) - 256,
@@ -417,11 +417,12 @@ def test_generated_kernel_source_executed_on_the_host_equals_the_reference(mcb, 
             want = ref > np.float32(g.iso)   # sign bit = value > iso, strict, NaN -> 0
         xs = np.arange(NV)
         nbx, nby, nbz = P // 32, (NV + 3) // 4, (NZ + 3) // 4
-        blocks = np.arange(nbx * nby * nbz, dtype=np.uint32)
+        ids = np.arange(nbx * nby * nbz)
+        blocks = ((ids % nbx) | ((ids // nbx % nby) << 8) | ((ids // (nbx * nby)) << 20)).astype(np.uint32)  # bx | by << 8 | bz << 20
         # mcb_fill_jit: every block listed; field and sign words (warp ballots emulated by the shim)
         F = np.full((NZ, NV, P), np.nan, np.float32)
         S = np.zeros((NZ, NV, 4), np.uint32)
-        L.run_fill(kpool.ctypes.data, C.byref(g), tables.ctypes.data, F.ctypes.data, S.ctypes.data, blocks.ctypes.data, len(blocks), nbx, nby, spa)
+        L.run_fill(kpool.ctypes.data, C.byref(g), tables.ctypes.data, F.ctypes.data, S.ctypes.data, blocks.ctypes.data, len(blocks), spa)
         got = F[:, :, :NV]
         assert np.all((ref.view(np.uint32) == got.view(np.uint32)) | (np.isnan(ref) & np.isnan(got))), eq
         bits = ((S[:, :, xs >> 5] >> (xs & 31).astype(np.uint32)) & 1).astype(bool)

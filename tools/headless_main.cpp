@@ -5,6 +5,7 @@
 //   mcb_headless [--eq "x^2+y^2+z^2-0.49" | --eq-file example_files/equation_1.txt] [--step 0.2 | --res 1024]
 //                [--scale sx sy sz] [--iso c] [--constraint i "lhs" "op" rhs]... [--no-normals] [--soup]
 //                [--ply out.ply] [--dump out.bin] [--repeat n] [--levels d]   (--levels: repeating-surface mode, distance d)
+//                [--devices n]   (z-slabs over GPUs 0..n-1 of this box: Marching::set_devices)
 //
 // Defaults are the reference GUI's (drawer.cpp:39-44): equation "x+y", grid 0.2, scale 1.1, iso 0.
 #include <chrono>
@@ -17,7 +18,7 @@
 
 static int usage() {
     std::fprintf(stderr, "usage: mcb_headless [--eq S | --eq-file F] [--step h | --res n] [--scale sx sy sz] [--iso c]\n"
-                         "                    [--constraint i lhs op rhs] [--no-normals] [--soup] [--ply F] [--dump F] [--repeat n] [--levels d]\n");
+                         "                    [--constraint i lhs op rhs] [--no-normals] [--soup] [--ply F] [--dump F] [--repeat n] [--levels d] [--devices n]\n");
     return 2;
 }
 
@@ -53,6 +54,7 @@ int main(int argc, char** argv) {
         else if (o == "--ply" && need(1)) ply = argv[++a];
         else if (o == "--dump" && need(1)) dump = argv[++a];
         else if (o == "--repeat" && need(1)) repeat = std::atoi(argv[++a]);
+        else if (o == "--devices" && need(1)) { if (!march_maker.set_devices(std::atoi(argv[++a]))) { std::fprintf(stderr, "bad device count\n"); return 1; } }
         else if (o == "--levels" && need(1)) { /* Marching::set_surface_repeat_step_distance + repeating_surface_mode */
             if (!march_maker.set_surface_repeat_step_distance((float)std::atof(argv[++a]))) { std::fprintf(stderr, "the level distance must be positive\n"); return 1; }
             march_maker.repeating_surface_mode(true);
