@@ -356,6 +356,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None  # nvidia-smi takes ~0.1 s to start: it runs from the warm-up on
     M, k0, k1 = configure(eq, n)
     ms_per_step, c, per, (t0, t1) = timed(step_fn, args.steps, max(3, args.warmup))
+    headline_launches = launches_total[0]  # kernels launched inside the timed region
     soak = 0
     if sampler and sampler.proc and world == 1:
         # a timed region shorter than the sampling period holds no sample: keep the same load running (untimed) until
@@ -371,7 +372,6 @@ def run_ours(args):
         clocks["window"] = "timed region" if soak == 0 else "timed region + %d untimed steps of the same load after it" % soak
     cubes, tris, active = sum_over_ranks([c.cubes, c.triangles, c.active])
     value = cubes / (ms_per_step * 1e-3) / 1e9
-    headline_launches = launches_total[0]
     layers = k1 - k0
     slabs = [int(x) for x in sum_over_ranks([k0 if r == rank else 0 for r in range(world)])] + [M] if world > 1 else [0, M]
 

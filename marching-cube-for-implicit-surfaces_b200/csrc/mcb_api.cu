@@ -592,7 +592,7 @@ int mcb_create(int device, mcb_ctx** out) {
         const char* we = std::getenv("MCB_WELD_EXACT");
         ctx->weld_exact_only = we && we[0] == '1';
         const char* ev = std::getenv("MCB_EMIT");
-        if (ev && (ev[0] == '1' || ev[0] == '2' || ev[0] == '3' || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
+        if (ev && ((ev[0] >= '1' && ev[0] <= '5') || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
     }
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
@@ -1220,6 +1220,8 @@ int Run::stage_soup() {
                             ctx->cap_tris, ctx->d_pos, nullptr);
             break;
         case 3: if (nrm) MCB_EMIT2(true, 64, 128, 512, 10, 4); else MCB_EMIT2(false, 64, 128, 512, 10, 4); break;
+        case 4: if (nrm) MCB_EMIT2(true, 128, 256, 768, 8, 2); else MCB_EMIT2(false, 128, 256, 768, 8, 2); break;
+        case 5: if (nrm) MCB_EMIT2(true, 64, 128, 384, 16, 4); else MCB_EMIT2(false, 64, 128, 384, 16, 4); break;
         case 9: if (nrm) MCB_EMIT2(true, 128, 256, 24, 2, 1); else MCB_EMIT2(false, 128, 256, 24, 2, 1); break;
         default: if (nrm) MCB_EMIT2(true, 128, 256, 1024, 6, 2); else MCB_EMIT2(false, 128, 256, 1024, 6, 2); break;
     }

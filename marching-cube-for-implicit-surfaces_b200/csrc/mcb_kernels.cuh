@@ -579,8 +579,10 @@ block_class_kernel(const __grid_constant__ mcb_program prog, const Grid g, const
             const int jb = by - (d & 1), kq = bz - (d >> 1);
             if (jb < 0 || kq < 0 || jb >= bd.cjb || kq >= bd.ckb) continue;
             unsigned long long* row = cand + ((size_t)kq * bd.cjb + jb) * cmw;
-            if (bx < bd.WC) atomicOr(row + (bx >> 6), 1ull << (bx & 63));
-            if (bx >= 1 && bx - 1 < bd.WC) atomicOr(row + ((bx - 1) >> 6), 1ull << ((bx - 1) & 63));
+            /* neighbouring blocks set the same bits: look before the atomic */
+            if (bx < bd.WC && !((*(volatile unsigned long long*)(row + (bx >> 6)) >> (bx & 63)) & 1ull)) atomicOr(row + (bx >> 6), 1ull << (bx & 63));
+            if (bx >= 1 && bx - 1 < bd.WC && !((*(volatile unsigned long long*)(row + ((bx - 1) >> 6)) >> ((bx - 1) & 63)) & 1ull))
+                atomicOr(row + ((bx - 1) >> 6), 1ull << ((bx - 1) & 63));
         }
     }
 }
@@ -604,9 +606,17 @@ decided_signs_kernel(const Grid g, const BlockDims bd, const uint32_t* __restric
         const int bx = (int)(id & 0xFFu) + lane % 3 - 1, by = (int)((id >> 8) & 0xFFFu) + (lane / 3) % 3 - 1, bz = (int)(id >> 20) + lane / 9 - 1;
         int c = 0;
         if (lane < 27 && lane != 13 && bx >= 0 && by >= 0 && bz >= 0 && bx < bd.nbx && by < bd.nby && bz < bd.nbz) {
-            c = block_class_of(cls, scls, bd, bx, by, bz);
-            if (c & 4) c = 0;                                                             /* written already */
-            else if (c != 0) cls[((size_t)bz * bd.nby + by) * bd.nbx + bx] = (uint8_t)(c | 4);
+            /* claim the block, so that exactly one warp writes its words: its class byte becomes explicit, class | 4, by a
+             * compare-and-swap on the 32-bit word that holds it (the byte is kClsInherit, 1 or 2 while unclaimed) */
+            const size_t bid = ((size_t)bz * bd.nby + by) * bd.nbx + bx;
+            unsigned* word = reinterpret_cast<unsigned*>(cls + (bid & ~(size_t)3));
+            const unsigned sh = (unsigned)(bid & 3) * 8u;
+            for (;;) {
+                const unsigned w = *(volatile unsigned*)word, b8 = (w >> sh) & 0xFFu;
+                const int cur = b8 == kClsInherit ? (int)scls[((size_t)(bz / kSuper) * bd.nsy + by / kSuper) * bd.nbx + bx] : (int)b8;
+                if (cur == 0 || (b8 != kClsInherit && (b8 & 4u))) { c = 0; break; }   /* undecided, or somebody else has it */
+                if (atomicCAS(word, w, (w & ~(0xFFu << sh)) | ((unsigned)(cur | 4) << sh)) == w) { c = cur; break; }
+            }
         }
         uint32_t todo = __ballot_sync(0xffffffffu, c != 0);
         while (todo) {
@@ -1902,7 +1912,7 @@ weld_count_kernel(const WV W, const WeldBuffers B, const Counters* __restrict__ 
  * the replay decides: a multiplication-only test on the cube's eight corner values rules it out for nearly every edge
  * (a point within 1.5e-6 of an end point has |t| h or |1 - t| h below 3e-6, with t = (iso - f_a) / (f_b - f_a)), and only
  * the edges it cannot rule out take the exact functions above.  Same vinfo words, a fraction of the work. */
-__global__ void __launch_bounds__(kWeldCubes)
+__global__ void __launch_bounds__(kWeldCubes, 12)
 weld_count_fast_kernel(const WeldView W, const WeldBuffers B, const ClsTables* __restrict__ gtb, const Counters* __restrict__ ctr,
                        unsigned long long cap_active) {
     __shared__ uint32_t warp_s[kWeldCubes / 32];

@@ -104,3 +104,24 @@ def test_cpp_dropin_class_over_the_emulated_library(golden, tmp_path, mcb_emu):
         v, t = golden[n + "/vertex_list"], golden[n + "/tri_list"]
         assert line[0] == n and line[1:3] == [str(len(v)), str(len(t))], (n, line)
         assert line[3] == fnv1a64(v.tobytes()) and line[4] == fnv1a64(t.tobytes()), n
+
+
+def test_layer_histogram_and_balanced_cut(mcb_emu, ctx, golden):
+    """mcb_layer_triangles (layer_hist_kernel) against the reference's per-cube triangle counts, whole grid and a slab; the
+    cut mcb_balance_slabs makes from it gives every rank nearly the same number of triangles"""
+    case = load_meta(golden)["sphere_33_iso"]
+    configure(ctx, case)
+    ctx.set_field_mode(mcb_emu.FIELD_AUTO)
+    ctx.set_normals(1)
+    M = case["M"]
+    want = golden["sphere_33_iso/ntri"].reshape(M, M, M).astype(np.int64).sum(axis=(1, 2))
+    ctx.polygonise()
+    assert np.array_equal(ctx.layer_triangles().astype(np.int64), want)
+    ctx.set_slab(9, 21)
+    ctx.polygonise()
+    assert np.array_equal(ctx.layer_triangles().astype(np.int64), want[9:21])
+    cuts = mcb_emu.balance_slabs(want.astype(np.uint32), 4, 1.0)
+    per = [int(want[a:b].sum()) for a, b in zip(cuts, cuts[1:])]
+    assert sum(per) == case["T"] and max(per) - min(per) <= 2 * int(want.max())
+    uniform = [int(want[(M * r) // 4:(M * (r + 1)) // 4].sum()) for r in range(4)]
+    assert max(per) < max(uniform)

@@ -108,8 +108,17 @@ def test_gyr78_layer_against_live_reference_at_1024(mcb, refbind):
     eq = refbind.GYR78
     c = mcb.Context(0)
     c.set_field_mode(mcb.FIELD_AUTO)
+    c.set_normals(0)
     assert c.set_equation(eq) == 0 and c.set_grid_step(2.0 / 1024) == 1025
-    for k0 in (512, 3):
+    # the whole grid first: which layers hold cubes whose triangles come from the redirected row 255 - code?
+    full = c.polygonise()
+    assert full.redirected > 0 and full.ambiguous >= full.redirected
+    rec, _ = c.get_active()
+    redirected = rec[((rec >> 36) & 0xFF) != ((rec >> 44) & 0xFF)]
+    assert len(redirected) == full.redirected
+    layers = sorted(set(int(k) for k in ((redirected >> 24) & 0xFFF)))
+    seen_amb = seen_red = 0
+    for k0 in (512, layers[0], layers[len(layers) // 2]):
         c.set_slab(k0, k0 + 1)
         cnt = c.polygonise()
         sw = refbind.sweep_rows_mt(eq, 2.0 / 1024, k0 * 1025, (k0 + 1) * 1025)
@@ -117,9 +126,10 @@ def test_gyr78_layer_against_live_reference_at_1024(mcb, refbind):
         assert np.array_equal(code, sw["code"]) and np.array_equal(tidx, sw["table_idx"])
         assert cnt.triangles == sw["T"] and cnt.triangles > 10000
         assert (cnt.active, cnt.ambiguous, cnt.redirected) == (sw["active"], sw["ambiguous"], sw["redirected"])
-        pos, _ = c.get_mesh()
+        pos, _ = c.get_mesh(normals=False)
         assert same_bits(pos[:, :, :3], sw["soup"])
-    assert cnt.ambiguous > 0
+        seen_amb += cnt.ambiguous; seen_red += cnt.redirected
+    assert seen_amb > 0 and seen_red > 0   # the redirect itself was exercised against the reference at full size
     c.close()
 
 

@@ -8,7 +8,7 @@ import bench
 import torch
 out = []
 for wl, n in (("sphere", 1024), ("gyr78", 1024), ("torus", 1024), ("sphere", 2048)):
-    for env in ({"MCB_EMIT": "1"}, {"MCB_EMIT": "2"}, {"MCB_EMIT": "3"}, {"MCB_EMIT": "2", "MCB_WELD_EXACT": "1"}, {"MCB_EMIT": "2", "MCB_NO_INTERVAL": "1"}):
+    for env in ({"MCB_EMIT": "1"}, {"MCB_EMIT": "2"}, {"MCB_EMIT": "3"}, {"MCB_EMIT": "4"}, {"MCB_EMIT": "5"}):
         for k in ("MCB_EMIT", "MCB_WELD_EXACT", "MCB_NO_INTERVAL"):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -20,7 +20,7 @@ for wl, n in (("sphere", 1024), ("gyr78", 1024), ("torus", 1024), ("sphere", 204
         ctx.set_grid_step(2.0 / n)
         ctx.set_normals(1)
         for mesh in (m.MESH_SOUP, m.MESH_INDEXED):
-            if mesh == m.MESH_INDEXED and env.get("MCB_EMIT") in ("1", "3"):
+            if mesh == m.MESH_INDEXED and env.get("MCB_EMIT") != "2":
                 continue
             ctx.set_mesh_mode(mesh)
             for _ in range(3):
