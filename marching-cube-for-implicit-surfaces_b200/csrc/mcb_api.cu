@@ -157,7 +157,8 @@ struct mcb_ctx {
     bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
     bool stage_timing = true;      /* mcb_set_stage_timing: CUDA events around the stages (mcb_counts::ms_*) */
     bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
-    int emit_variant = 2;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk),
+    int emit_variant = 3;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk; 3 measured
+                                      fastest on every workload, profiles/r02_ab_variants.jsonl), 4 / 5 = the same held to 32 registers (slower),
                                       9 = second generation with 24 edge slots (tests: forces chunks to be emitted in several runs) */
     uint8_t* d_fflags = nullptr;   /* [cap_fblocks] 2 = evaluated (undecided block), 1 = apron block to refill, 0 = untouched */
     uint8_t* d_bcls = nullptr;     /* [cap_fblocks] interval class of every 32 x 4 x 4 vertex block */
@@ -1219,11 +1220,11 @@ int Run::stage_soup() {
             else MCB_LAUNCH((emit_kernel<false>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
                             ctx->cap_tris, ctx->d_pos, nullptr);
             break;
-        case 3: if (nrm) MCB_EMIT2(true, 64, 128, 512, 10, 4); else MCB_EMIT2(false, 64, 128, 512, 10, 4); break;
+        case 2: if (nrm) MCB_EMIT2(true, 128, 256, 1024, 6, 2); else MCB_EMIT2(false, 128, 256, 1024, 6, 2); break;
         case 4: if (nrm) MCB_EMIT2(true, 128, 256, 768, 8, 2); else MCB_EMIT2(false, 128, 256, 768, 8, 2); break;
         case 5: if (nrm) MCB_EMIT2(true, 64, 128, 384, 16, 4); else MCB_EMIT2(false, 64, 128, 384, 16, 4); break;
         case 9: if (nrm) MCB_EMIT2(true, 128, 256, 24, 2, 1); else MCB_EMIT2(false, 128, 256, 24, 2, 1); break;
-        default: if (nrm) MCB_EMIT2(true, 128, 256, 1024, 6, 2); else MCB_EMIT2(false, 128, 256, 1024, 6, 2); break;
+        default: if (nrm) MCB_EMIT2(true, 64, 128, 512, 10, 4); else MCB_EMIT2(false, 64, 128, 512, 10, 4); break;
     }
 #undef MCB_EMIT2
 #undef MCB_EMIT2_

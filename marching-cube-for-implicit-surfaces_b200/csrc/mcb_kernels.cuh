@@ -546,10 +546,13 @@ block_class_kernel(const __grid_constant__ mcb_program prog, const Grid g, const
     const unsigned nsuper = ctr->eval_supers;
     const int lane = threadIdx.x & 31;
     const unsigned stride = gridDim.x * blockDim.x;
-    const unsigned total = (nsuper * 16u + 31u) & ~31u; /* whole warps stay in the loop: the ballot below needs them */
+    /* neighbouring threads take the same block position in neighbouring super-blocks (the list is close to x-fastest
+     * order), so the undecided blocks a warp appends are neighbours in x and the evaluation kernel's warps, which take
+     * consecutive list entries, write runs of adjacent 128-byte lines: DRAM pages stay open on dense surfaces */
+    const unsigned npad = (nsuper + 31u) & ~31u, total = npad * 16u; /* whole warps stay in the loop: the ballot below needs them */
     const int cmw = (bd.WC + 63) / 64;
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const unsigned si = t >> 4, sub = t & 15u;
+        const unsigned sub = t / npad, si = t - sub * npad;
         bool undecided = false;
         int bx = 0, by = 0, bz = 0;
         if (si < nsuper) {
