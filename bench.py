@@ -33,6 +33,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "marching-cube-for-implicit-surfaces_b200"
+_REAL_STDOUT = None
+
+
+def emit_line(obj):
+    """the one JSON line, on the process's original stdout"""
+    data = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 WORKLOADS = {
     "sphere": "x^2+y^2+z^2-0.49",
@@ -156,7 +167,7 @@ def run_reference(args):
            "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": threads, "kind": "reference", "sample": sample},
            "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.time() - t_all}
-    print(json.dumps(out))
+    emit_line(out)
     return 0
 
 
@@ -542,7 +553,7 @@ def run_ours(args):
         if rank == 0:
             out["gpu_launches"] = int(gl)
     if rank == 0:
-        print(json.dumps(out))
+        emit_line(out)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -551,6 +562,12 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries exactly one line, the JSON: whatever a library prints there (NCCL's version banner, a warning) is sent
+    # to stderr instead, and the line is written to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

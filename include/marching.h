@@ -336,7 +336,6 @@ private:
     }
     bool recalculate_on_devices() {
         reset_step_data();
-        unpin_all();
         if (!evaluator_) { poly_data.vertex_list.clear(); poly_data.tri_list.clear(); return true; }
         const int n = devices_;
         dev_ctx_.resize((size_t)n, nullptr);
@@ -398,10 +397,16 @@ private:
         std::vector<size_t> v_off((size_t)n + 1, 0);
         size_t T = 0;
         for (int r = 0; r < n; r++) { v_off[(size_t)r + 1] = v_off[(size_t)r] + (size_t)cnt[(size_t)r].vertices; T += (size_t)cnt[(size_t)r].triangles; }
+        if (v_off[(size_t)n] * 3 > poly_data.vertex_list.capacity() || T * 3 > poly_data.tri_list.capacity() ||
+            (normals_ && v_off[(size_t)n] * 3 > vertex_normals_.capacity()))
+            unpin_all(); /* a vector is about to move: its old storage must not stay page-locked */
         poly_data.vertex_list.resize(v_off[(size_t)n] * 3);
         poly_data.tri_list.resize(T * 3);
         if (normals_) vertex_normals_.resize(v_off[(size_t)n] * 3); else vertex_normals_.clear();
         soup_.clear(); normals_soup_.clear();
+        /* page-locked destinations: every device copies its part at full PCIe speed, all of them at once */
+        pin(pin_v_, poly_data.vertex_list); pin(pin_t_, poly_data.tri_list);
+        if (normals_) pin(pin_n_, vertex_normals_);
         auto fetch = [&](int r) {
             const mcb_counts& c = cnt[(size_t)r];
             if (!c.triangles) return;
