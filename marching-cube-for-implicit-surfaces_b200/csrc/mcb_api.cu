@@ -158,7 +158,7 @@ struct mcb_ctx {
     bool stage_timing = true;      /* mcb_set_stage_timing: CUDA events around the stages (mcb_counts::ms_*) */
     bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
     int emit_variant = 3;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk; 3 measured
-                                      fastest on every workload, profiles/r02_ab_variants.jsonl), 4 / 5 = 128 / 64 cubes with the cubes' field neighbourhood staged in shared memory,
+                                      fastest on every workload, profiles/r02_ab_variants.jsonl),
                                       9 = second generation with 24 edge slots (tests: forces chunks to be emitted in several runs) */
     uint8_t* d_fflags = nullptr;   /* [cap_fblocks] 2 = evaluated (undecided block), 1 = apron block to refill, 0 = untouched */
     uint8_t* d_bcls = nullptr;     /* [cap_fblocks] interval class of every 32 x 4 x 4 vertex block */
@@ -593,7 +593,7 @@ int mcb_create(int device, mcb_ctx** out) {
         const char* we = std::getenv("MCB_WELD_EXACT");
         ctx->weld_exact_only = we && we[0] == '1';
         const char* ev = std::getenv("MCB_EMIT");
-        if (ev && ((ev[0] >= '1' && ev[0] <= '5') || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
+        if (ev && ((ev[0] >= '1' && ev[0] <= '3') || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
     }
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
@@ -1207,12 +1207,11 @@ int Run::stage_seed() {
 int Run::stage_soup() {
     const float* rinv = ctx->d_cs + ctx->rinv_ofs;
     const bool idx32 = (unsigned long long)g.NZ * g.NV * g.P < (1ull << 32) - 2ull * g.NV * g.P; /* offsets +- one plane stay below 2^32 */
-#define MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, I32, STG)                                                                    \
-    MCB_LAUNCH((emit2_kernel<NRM, CUBES, THREADS, CAP, MINB, I32, STG>), eblocks * MULT, THREADS, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, \
+#define MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, I32)                                                                         \
+    MCB_LAUNCH((emit2_kernel<NRM, CUBES, THREADS, CAP, MINB, I32>), eblocks * MULT, THREADS, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, \
                ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, NRM ? ctx->d_nrm : nullptr)
-#define MCB_EMIT2S(NRM, CUBES, THREADS, CAP, MINB, MULT, STG)                                                                         \
-    do { if (idx32) MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, true, STG); else MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, false, STG); } while (0)
-#define MCB_EMIT2(NRM, CUBES, THREADS, CAP, MINB, MULT) MCB_EMIT2S(NRM, CUBES, THREADS, CAP, MINB, MULT, false)
+#define MCB_EMIT2(NRM, CUBES, THREADS, CAP, MINB, MULT)                                                                               \
+    do { if (idx32) MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, true); else MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, false); } while (0)
     const bool nrm = ctx->normals == 1;
     switch (ctx->emit_variant) {
         case 1:
@@ -1222,13 +1221,10 @@ int Run::stage_soup() {
                             ctx->cap_tris, ctx->d_pos, nullptr);
             break;
         case 2: if (nrm) MCB_EMIT2(true, 128, 256, 1024, 6, 2); else MCB_EMIT2(false, 128, 256, 1024, 6, 2); break;
-        case 4: if (nrm) MCB_EMIT2S(true, 128, 256, 1024, 5, 2, true); else MCB_EMIT2S(false, 128, 256, 1024, 5, 2, true); break;
-        case 5: if (nrm) MCB_EMIT2S(true, 64, 128, 512, 10, 4, true); else MCB_EMIT2S(false, 64, 128, 512, 10, 4, true); break;
         case 9: if (nrm) MCB_EMIT2(true, 128, 256, 24, 2, 1); else MCB_EMIT2(false, 128, 256, 24, 2, 1); break;
         default: if (nrm) MCB_EMIT2(true, 64, 128, 512, 10, 4); else MCB_EMIT2(false, 64, 128, 512, 10, 4); break;
     }
 #undef MCB_EMIT2
-#undef MCB_EMIT2S
 #undef MCB_EMIT2_
     launches++;
     return MCB_OK;

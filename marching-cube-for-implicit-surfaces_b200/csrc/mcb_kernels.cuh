@@ -1394,10 +1394,7 @@ __device__ __forceinline__ void gradient_normal(const float* __restrict__ pa, co
 }
 
 template <bool NORMALS, int CUBES, int THREADS, int CAP /* edge slots per chunk run */, int MINB,
-          bool IDX32 /* the slab's field has fewer than 2^32 values: 32-bit offsets, one IMAD.WIDE per load address */,
-          bool STAGE /* the 32 field values an active cube's edges can need (8 corners + their 24 outer neighbours) are
-                        loaded once per cube, a warp per cube and a lane per value, into shared memory: the edge threads
-                        then touch no global memory (each value is otherwise fetched by up to four edges) */>
+          bool IDX32 /* the slab's field has fewer than 2^32 values: 32-bit offsets, one IMAD.WIDE per load address */>
 __global__ void __launch_bounds__(THREADS, MINB)
 emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict__ rinv, const float* __restrict__ F,
              const ClsTables* __restrict__ gtb, const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ trioff,
@@ -1410,8 +1407,6 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
     __shared__ float crinv[NORMALS ? CUBES * 6 : 1]; /* 1 / (c[v+1] - c[v-1]) at the same six coordinates */
     typedef typename std::conditional<IDX32, uint32_t, unsigned long long>::type off_t; /* offsets into F */
     __shared__ off_t cbase_s[CUBES];                /* offset of the cube's corner 0 in F */
-    constexpr int kValStride = 33;                  /* 32 values per cube, padded against bank conflicts */
-    __shared__ float vals[STAGE ? CUBES * kValStride : 1]; /* [0..7] corner dx + 2 dy + 4 dz; [8 + 3 c + a] corner c's outer neighbour along axis a */
     __shared__ uint32_t off_s[CUBES + 1];           /* first triangle of the cube */
     __shared__ uint64_t triw_s[CUBES];
     __shared__ uint32_t ijk_s[CUBES];               /* i | j << 12 */
@@ -1429,15 +1424,6 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
     const unsigned long long nchunks = (A + CUBES - 1) / CUBES;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const off_t rowp = (off_t)g.P, planep = (off_t)g.NV * (off_t)g.P;
-    off_t stage_rel = 0; /* this lane's value of the staged neighbourhood, relative to corner 0 (unsigned wrap-around is fine) */
-    if (STAGE) {
-        const int c = lane < 8 ? lane : (lane - 8) / 3, a = lane < 8 ? -1 : (lane - 8) % 3;
-        stage_rel = (off_t)(c & 1) + (((c >> 1) & 1) ? rowp : (off_t)0) + ((c >> 2) ? planep : (off_t)0);
-        if (a >= 0) {
-            const off_t stride = a == 0 ? (off_t)1 : a == 1 ? rowp : planep;
-            stage_rel = ((c >> a) & 1) ? stage_rel + stride : stage_rel - stride;
-        }
-    }
 
     for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         __syncthreads();
@@ -1489,11 +1475,6 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
             const uint32_t first = off_s[t] - off_s[0], cnt = off_s[t + 1] - off_s[t];
             for (uint32_t q2 = 0; q2 < cnt && q2 < 5u; q2++) tri2cube[first + q2] = (uint8_t)t;
         }
-        if (STAGE) { /* ---- 1.5: a warp per cube, a lane per value: independent loads, nothing waits on them until the barrier */
-            for (int lc = warp; lc < n; lc += THREADS / 32)
-                if (NORMALS || lane < 8) vals[lc * kValStride + lane] = __ldg(F + (off_t)(cbase_s[lc] + stage_rel));
-            __syncthreads();
-        }
 
         /* runs of whole cubes whose crossing edges fit the slots (one run, except on degenerate fields) */
         for (int cb = 0; cb < n;) {
@@ -1511,38 +1492,22 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
                 const int a = mcb_edge_a(e), b = mcb_edge_b(e);
                 const int oa = mcb_corner_ofs(a), ob = mcb_corner_ofs(b);
                 const int axis = e >= 8 ? 2 : (e & 1);
-                float f1, f2, dxa = 0.f, dya = 0.f, dza = 0.f, dxb = 0.f, dyb = 0.f, dzb = 0.f; /* corner values, central differences */
-                if (STAGE) {
-                    const float* vv = vals + lc * kValStride;
-                    f1 = vv[oa]; f2 = vv[ob];
-                    if (NORMALS) { /* F[c + e_a] - F[c - e_a]: one of the two is another corner, the other the staged outer neighbour */
-#define MCB_DIFF(c, a) ((((c) >> (a)) & 1) ? vv[8 + 3 * (c) + (a)] - vv[(c) ^ (1 << (a))] : vv[(c) ^ (1 << (a))] - vv[8 + 3 * (c) + (a)])
-                        dxa = MCB_DIFF(oa, 0); dya = MCB_DIFF(oa, 1); dza = MCB_DIFF(oa, 2);
-                        dxb = MCB_DIFF(ob, 0); dyb = MCB_DIFF(ob, 1); dzb = MCB_DIFF(ob, 2);
-#undef MCB_DIFF
-                    }
-                } else {
-                    const off_t c0f = cbase_s[lc]; /* corner 0 of the cube; the end points are at most one step away on each axis */
-                    const off_t ia = c0f + (off_t)(oa & 1) + (((oa >> 1) & 1) ? rowp : (off_t)0) + ((oa >> 2) ? planep : (off_t)0);
-                    const off_t ib = c0f + (off_t)(ob & 1) + (((ob >> 1) & 1) ? rowp : (off_t)0) + ((ob >> 2) ? planep : (off_t)0);
-                    f1 = __ldg(F + ia); f2 = __ldg(F + ib);
-                    if (NORMALS) {
-                        dxa = __ldg(F + ia + 1) - __ldg(F + ia - 1);
-                        dya = __ldg(F + (ia + rowp)) - __ldg(F + (ia - rowp));
-                        dza = __ldg(F + (ia + planep)) - __ldg(F + (ia - planep));
-                        dxb = __ldg(F + ib + 1) - __ldg(F + ib - 1);
-                        dyb = __ldg(F + (ib + rowp)) - __ldg(F + (ib - rowp));
-                        dzb = __ldg(F + (ib + planep)) - __ldg(F + (ib - planep));
-                    }
-                }
+                const off_t c0f = cbase_s[lc]; /* corner 0 of the cube; the end points are at most one step away on each axis */
+                const off_t ia = c0f + (off_t)(oa & 1) + (((oa >> 1) & 1) ? rowp : (off_t)0) + ((oa >> 2) ? planep : (off_t)0);
+                const off_t ib = c0f + (off_t)(ob & 1) + (((ob >> 1) & 1) ? rowp : (off_t)0) + ((ob >> 2) ? planep : (off_t)0);
+                const float f1 = __ldg(F + ia), f2 = __ldg(F + ib);
                 const float tq = (g.iso - f1) / (f2 - f1); /* Marching::interp uses the surface constant itself, also in repeating-surface mode */
                 const float* cc = ccoord + 6 * lc + 2 * axis;
                 const float ca = cc[(oa >> axis) & 1], cb2 = cc[(ob >> axis) & 1];
                 const float p = interp_ref(ca, cb2, tq);
                 if (NORMALS) { /* gradient_normal() with the reciprocals from shared memory */
                     const float* ri = crinv + 6 * lc;
-                    const float gxa = dxa * ri[oa & 1], gya = dya * ri[2 + ((oa >> 1) & 1)], gza = dza * ri[4 + (oa >> 2)];
-                    const float gxb = dxb * ri[ob & 1], gyb = dyb * ri[2 + ((ob >> 1) & 1)], gzb = dzb * ri[4 + (ob >> 2)];
+                    const float gxa = (__ldg(F + ia + 1) - __ldg(F + ia - 1)) * ri[oa & 1];
+                    const float gya = (__ldg(F + (ia + rowp)) - __ldg(F + (ia - rowp))) * ri[2 + ((oa >> 1) & 1)];
+                    const float gza = (__ldg(F + (ia + planep)) - __ldg(F + (ia - planep))) * ri[4 + (oa >> 2)];
+                    const float gxb = (__ldg(F + ib + 1) - __ldg(F + ib - 1)) * ri[ob & 1];
+                    const float gyb = (__ldg(F + (ib + rowp)) - __ldg(F + (ib - rowp))) * ri[2 + ((ob >> 1) & 1)];
+                    const float gzb = (__ldg(F + (ib + planep)) - __ldg(F + (ib - planep))) * ri[4 + (ob >> 2)];
                     float tt = tq;
                     if (isinf(tt) || isnan(tt)) tt = 0.5f;
                     const float nx = gxa + tt * (gxb - gxa);
