@@ -231,6 +231,7 @@ def run_ours(args):
             k0, k1 = mcb.slab_range(M, rank, world)
             if not comm_up[0]:
                 ctx.comm_init(comm_id, rank, world)      # ncclCommInitRank + the uniform slab (mcb_slab_range)
+                ctx.comm_set_auto(True)                  # the all-gather is enqueued inside polygonise(), behind the emission
                 comm_up[0] = True
             else:
                 ctx.set_slab(k0, k1)
@@ -462,6 +463,7 @@ def run_ours(args):
         if world > 1:
             # the same grid on rank 0 alone, in the same run on the same box: the strong-scaling reference
             sync_all()
+            ctx.comm_set_auto(False)  # rank 0 polygonises alone now: no collective may be enqueued
             if rank == 0:
                 ctx.set_slab(0, Ms)
                 for _ in range(2):

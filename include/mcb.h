@@ -252,6 +252,11 @@ int mcb_comm_init(mcb_ctx* ctx, const void* id128, int rank, int nranks);
 /* Enqueue the all-gather of this slab's triangle count, straight from the device counters of the last mcb_polygonise,
  * on a side stream: the next polygonisation does not wait for the slowest rank.  Collective. */
 int mcb_comm_exchange(mcb_ctx* ctx);
+/* enabled != 0: mcb_polygonise enqueues that all-gather itself, right after classification, when the slab's triangle count
+ * is final — NCCL's launch cost then hides behind the emission instead of following the call; mcb_comm_exchange becomes
+ * a no-op.  Every rank must use the same setting.  (The count is the one of the call's first pass; a pass repeated
+ * because the ambiguity list overflowed — 2^18 ambiguous cubes in one slab — can change it, the next call corrects it.) */
+int mcb_comm_set_auto(mcb_ctx* ctx, int enabled);
 /* Result of the last exchange (waits for it): offset of this slab in the global triangle list, the global total, and the
  * per-rank counts (nranks values; may be NULL). */
 int mcb_comm_offsets(mcb_ctx* ctx, uint64_t* offset, uint64_t* total, uint64_t* per_rank);

@@ -107,6 +107,7 @@ def _load():
         "mcb_comm_unique_id": ([vp], i),
         "mcb_comm_init": ([vp, vp, i, i], i),
         "mcb_comm_exchange": ([vp], i),
+        "mcb_comm_set_auto": ([vp, i], i),
         "mcb_comm_offsets": ([vp, C.POINTER(u64), C.POINTER(u64), vp], i),
         "mcb_comm_balance": ([vp, C.c_double, C.POINTER(i), C.POINTER(i)], i),
         "mcb_comm_finalize": ([vp], i),
@@ -365,6 +366,10 @@ class Context:
 
     def comm_exchange(self):
         self._ck(lib.mcb_comm_exchange(self.h))
+
+    def comm_set_auto(self, enabled):
+        """polygonise() enqueues the all-gather itself as soon as the slab's triangle count is final"""
+        self._ck(lib.mcb_comm_set_auto(self.h, int(bool(enabled))))
 
     def comm_offsets(self, nranks):
         off, tot = C.c_uint64(0), C.c_uint64(0)

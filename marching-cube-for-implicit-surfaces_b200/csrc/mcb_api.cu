@@ -128,6 +128,7 @@ struct mcb_ctx {
     unsigned long long* h_comm = nullptr;   /* pinned copy of the gathered counts */
     int comm_flip = 0;
     bool comm_pending = false;
+    bool comm_auto = false;                 /* mcb_comm_set_auto: mcb_polygonise enqueues the exchange itself, as soon as the count is final */
     uint32_t* d_layer_hist = nullptr;       /* [cap_layer_hist] triangles per global cube layer */
     size_t cap_layer_hist = 0;
     uint8_t* d_mark = nullptr;
@@ -185,6 +186,8 @@ namespace {
             return e_ == cudaErrorMemoryAllocation ? MCB_E_NOMEM : MCB_E_CUDA;                               \
         }                                                                                                    \
     } while (0)
+
+int comm_enqueue(mcb_ctx* ctx); /* below, with the rest of the multi-GPU exchange */
 
 int fail(mcb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -1354,6 +1357,10 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     for (;;) { /* repeated only when an output buffer had to grow (mcb_counts::reruns) */
         if (need_classify) {
             if ((rc = run.stage_classify()) != MCB_OK) return rc;
+            /* several GPUs: this slab's triangle count is final now (tile_scan_kernel) — its all-gather is enqueued here, on
+             * the side stream, so that NCCL's launch cost hides behind the emission instead of following the call.  Once
+             * per call: a repeated pass (buffer growth) must not add a collective the other ranks do not have */
+            if (ctx->comm_auto && ctx->nccl_comm && reruns == 0 && (rc = comm_enqueue(ctx)) != MCB_OK) return rc;
             if (timing) MCB_CK(cudaEventRecord(ctx->ev[6], s));
             if (ctx->field_is_sparse && (rc = run.stage_fill()) != MCB_OK) return rc;
             if (timing) MCB_CK(cudaEventRecord(ctx->ev[7], s));
@@ -1653,6 +1660,21 @@ Nccl& nccl() {
         if (r_ != 0) return fail(ctx, MCB_E_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r_));                \
     } while (0)
 
+/* all-gather of this slab's triangle count, straight from the device counters, on the side stream */
+int comm_enqueue(mcb_ctx* ctx) {
+    /* the next polygonisation resets the live counters: the count is first copied aside, in stream order */
+    unsigned long long* stg = ctx->d_comm + ctx->comm_flip;
+    ctx->comm_flip ^= 1;
+    MCB_CK(cudaMemcpyAsync(stg, &ctx->d_ctr->triangles, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MCB_CK(cudaEventRecord(ctx->comm_ready, ctx->stream));
+    MCB_CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ready, 0));
+    MCB_NCCL(nccl().AllGather(stg, ctx->d_comm + 2, 1, kNcclUint64, ctx->nccl_comm, ctx->comm_stream));
+    MCB_CK(cudaMemcpyAsync(ctx->h_comm, ctx->d_comm + 2, (size_t)ctx->comm_nranks * 8, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    MCB_CK(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+    ctx->comm_pending = true;
+    return MCB_OK;
+}
+
 } /* namespace */
 
 extern "C" {
@@ -1745,16 +1767,13 @@ int mcb_comm_exchange(mcb_ctx* ctx) {
     int rc = enter(ctx);
     if (rc != MCB_OK) return rc;
     if (!ctx->nccl_comm) return fail(ctx, MCB_E_STATE, "mcb_comm_init has not been called");
-    /* the next polygonisation resets the live counters: the count is first copied aside, in stream order */
-    unsigned long long* stg = ctx->d_comm + ctx->comm_flip;
-    ctx->comm_flip ^= 1;
-    MCB_CK(cudaMemcpyAsync(stg, &ctx->d_ctr->triangles, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MCB_CK(cudaEventRecord(ctx->comm_ready, ctx->stream));
-    MCB_CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ready, 0));
-    MCB_NCCL(nccl().AllGather(stg, ctx->d_comm + 2, 1, kNcclUint64, ctx->nccl_comm, ctx->comm_stream));
-    MCB_CK(cudaMemcpyAsync(ctx->h_comm, ctx->d_comm + 2, (size_t)ctx->comm_nranks * 8, cudaMemcpyDeviceToHost, ctx->comm_stream));
-    MCB_CK(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
-    ctx->comm_pending = true;
+    if (ctx->comm_auto) return MCB_OK; /* mcb_polygonise has enqueued it already */
+    return comm_enqueue(ctx);
+}
+
+int mcb_comm_set_auto(mcb_ctx* ctx, int enabled) {
+    if (!ctx) return MCB_E_ARG;
+    ctx->comm_auto = enabled != 0;
     return MCB_OK;
 }
 
