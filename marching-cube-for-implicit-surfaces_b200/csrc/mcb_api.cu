@@ -1802,6 +1802,8 @@ int mcb_comm_balance(mcb_ctx* ctx, double fixed_cost_per_layer, int* k_begin, in
     if ((rc = ensure(ctx, &ctx->d_layer_hist, &ctx->cap_layer_hist, M)) != MCB_OK) return rc;
     MCB_CK(cudaMemsetAsync(ctx->d_layer_hist, 0, M * 4, ctx->stream));
     MCB_LAUNCH((layer_hist_kernel), (unsigned)ctx->sm_count * 4, 256, 0, ctx->stream, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active, ctx->d_layer_hist);
+    /* one collective at a time per communicator: an all-gather still in flight on the side stream goes first */
+    if (ctx->comm_pending) MCB_CK(cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0));
     /* every rank's layers are disjoint: the sum over ranks is the whole grid's histogram */
     MCB_NCCL(nccl().AllReduce(ctx->d_layer_hist, ctx->d_layer_hist, M, kNcclUint32, kNcclSum, ctx->nccl_comm, ctx->stream));
     std::vector<uint32_t> hist(M);
