@@ -202,6 +202,15 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_ranks(xs):
+        """[rank][len(xs)] list of every rank's values"""
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device="cuda")
+        if world == 1:
+            return [[float(x) for x in t.tolist()]]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [[float(x) for x in o.tolist()] for o in out]
+
     def sum_over_ranks(xs):
         t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -457,7 +466,11 @@ def run_ours(args):
         st = max(3, min(args.steps, 20))
         s_ms, sc_, sper, _ = timed(step_fn, st, 3)
         s_cubes, s_tris = sum_over_ranks([sc_.cubes, sc_.triangles])
-        strong = {"resolution": ns, "M": Ms, "ms_per_step": s_ms, "value": s_cubes / (s_ms * 1e-3) / 1e9, "mtriangles_per_s": s_tris / (s_ms * 1e-3) / 1e6,
+        per_rank = gather_ranks([s0, s1, sc_.triangles, sper["ms_eval"], sper["ms_classify"] + sper["ms_fill"], sper["ms_emit"],
+                                 sper["ms_tables"] + sper["ms_eval"] + sper["ms_classify"] + sper["ms_fill"] + sper["ms_emit"]])
+        strong = {"resolution": ns, "M": Ms, "ms_per_step": s_ms,
+                  "per_rank": [{"slab": [int(r[0]), int(r[1])], "triangles": int(r[2]), "ms_eval": r[3], "ms_classify": r[4], "ms_emit": r[5],
+                                "ms_kernels": r[6]} for r in per_rank], "value": s_cubes / (s_ms * 1e-3) / 1e9, "mtriangles_per_s": s_tris / (s_ms * 1e-3) / 1e6,
                   "steps": st, "triangles": s_tris, "rank0_slab": [s0, s1], "rank0_kernels_ms": sper, "scaling": "strong",
                   "slabs": "cut by measured cost (mcb_comm_balance)" if world > 1 else "one slab"}
         if world > 1:
