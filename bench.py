@@ -190,6 +190,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     launches_total = [0]
     comm_up = [False]
+    auto_on = [False]
 
     def sync_all():
         if world > 1:
@@ -241,12 +242,18 @@ def run_ours(args):
             if not comm_up[0]:
                 ctx.comm_init(comm_id, rank, world)      # ncclCommInitRank + the uniform slab (mcb_slab_range)
                 ctx.comm_set_auto(True)                  # the all-gather is enqueued inside polygonise(), behind the emission
+                auto_on[0] = True
                 comm_up[0] = True
             else:
                 ctx.set_slab(k0, k1)
             if balance:
+                ctx.set_stage_timing(True)
                 ctx.polygonise()                         # profile: triangles per layer of the uniform slab
                 k0, k1 = ctx.comm_balance()              # NCCL all-reduce of the layer histogram + the same cut on every rank
+                for _ in range(2):                       # two refinements by measured device time (mcb_comm_rebalance)
+                    ctx.polygonise()
+                    ms = sum(ctx.polygonise().ms_total for _ in range(4)) / 4
+                    k0, k1 = ctx.comm_rebalance(ms)
         return M, k0, k1
 
     def step_fn():
@@ -262,6 +269,8 @@ def run_ours(args):
         ctx.set_stage_timing(False)
         for _ in range(warm):
             c = fn()
+        if world > 1 and comm_up[0] and auto_on[0]:
+            ctx.comm_offsets(world)  # the warm-up's exchanges (NCCL sets its channels up lazily) are over before the clock starts
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
@@ -269,7 +278,7 @@ def run_ours(args):
         e0.record(stream)
         for _ in range(steps):
             c = fn()
-        if world > 1:
+        if world > 1 and auto_on[0]:
             ctx.comm_offsets(world)  # the last exchange is inside the timed region
         e1.record(stream)
         sync_all()
@@ -477,6 +486,7 @@ def run_ours(args):
             # the same grid on rank 0 alone, in the same run on the same box: the strong-scaling reference
             sync_all()
             ctx.comm_set_auto(False)  # rank 0 polygonises alone now: no collective may be enqueued
+            auto_on[0] = False
             if rank == 0:
                 ctx.set_slab(0, Ms)
                 for _ in range(2):

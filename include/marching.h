@@ -254,7 +254,7 @@ public:
     /* Several GPUs of one box: the grid is cut into z-slabs, one mcb context and one host thread per
      * device 0..n-1.  The slabs' triangle counts are all-gathered over NCCL (mcb_comm_exchange) into global offsets; the
      * first recalculate() of a configuration also measures the triangles per layer and re-cuts the slabs to equal cost
-     * (mcb_comm_balance).  Poly_Data is the slabs' welded meshes one after the other — triangles in the reference's order,
+     * (mcb_comm_balance, refined once by measured time: mcb_comm_rebalance).  Poly_Data is the slabs' welded meshes one after the other — triangles in the reference's order,
      * vertices on a plane shared by two slabs present once per slab.  Seed mode and step mode stay on device 0. */
     bool set_devices(int n) {
         if (n < 1 || n > 64) return false;
@@ -372,6 +372,9 @@ private:
             if (rebalance) { /* measured triangles per layer -> slabs of equal cost, then the real run */
                 int k0 = 0, k1 = 0;
                 good = mcb_comm_balance(c, -1.0, &k0, &k1) == MCB_OK && good;                   /* collective */
+                good = mcb_polygonise(c, &cnt[(size_t)r]) == MCB_OK && good;
+                /* one refinement by the measured device time of the balanced slabs (a failed run still takes part) */
+                good = mcb_comm_rebalance(c, good && cnt[(size_t)r].ms_total > 0.f ? (double)cnt[(size_t)r].ms_total : 1.0, &k0, &k1) == MCB_OK && good;
                 cuts_r_[(size_t)r] = k0; cuts_end_ = r == n - 1 ? k1 : cuts_end_;
                 good = mcb_polygonise(c, &cnt[(size_t)r]) == MCB_OK && good;
             }

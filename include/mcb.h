@@ -244,6 +244,10 @@ int mcb_layer_triangles(mcb_ctx* ctx, uint32_t* per_layer);
  * + fixed_cost_per_layer (< 0: the default, 0.0015 * M * M — what a layer costs before it emits anything, in
  * triangles).  cuts[0..nranks]: rank r takes layers [cuts[r], cuts[r+1]).  Every slab gets at least one layer. */
 int mcb_balance_slabs(int M, int nranks, const uint32_t* triangles_per_layer, double fixed_cost_per_layer, int* cuts);
+/* Host only: one refinement of such a cut by measured time.  cost[M] (in/out): the cost of every layer as the cut saw it
+ * (triangles + fixed cost); cuts[nranks+1] (in/out); ms[nranks]: what each slab was measured to take.  Each slab's time is
+ * spread over its layers in proportion to their cost, then the layers are cut again. */
+int mcb_rebalance_slabs(int M, int nranks, double* cost, int* cuts, const double* ms);
 /* ncclGetUniqueId into 128 bytes: call on one rank, hand the bytes to the others. */
 int mcb_comm_unique_id(void* id128);
 /* Join the communicator (ncclCommInitRank on the context's device) and take the balanced-by-layer-count slab of `rank`
@@ -265,6 +269,12 @@ int mcb_comm_offsets(mcb_ctx* ctx, uint64_t* offset, uint64_t* total, uint64_t* 
  * is returned in *k_begin / *k_end (either may be NULL).  A configuration is profiled once with the uniform slabs and
  * polygonised with the balanced ones from then on. */
 int mcb_comm_balance(mcb_ctx* ctx, double fixed_cost_per_layer, int* k_begin, int* k_end);
+/* Refine the cut of mcb_comm_balance with MEASURED time: ms_measured is what this rank's balanced slab took (e.g. the mean
+ * mcb_counts::ms_total of a few calls).  The times are all-gathered, each slab's time is spread over its layers in
+ * proportion to their modelled cost, and the layers are cut again; equal times are the fixed point, one or two passes
+ * settle it.  (fixed_cost_per_layer < 0 in mcb_comm_balance: 0.00015 M^2 in the block-field mode, 0.0015 M^2 with the
+ * dense field.)  Collective; needs mcb_comm_balance to have cut the current slabs. */
+int mcb_comm_rebalance(mcb_ctx* ctx, double ms_measured, int* k_begin, int* k_end);
 /* Leave the communicator (also done by mcb_destroy). */
 int mcb_comm_finalize(mcb_ctx* ctx);
 

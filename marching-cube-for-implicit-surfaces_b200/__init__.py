@@ -109,7 +109,9 @@ def _load():
         "mcb_comm_exchange": ([vp], i),
         "mcb_comm_set_auto": ([vp, i], i),
         "mcb_comm_offsets": ([vp, C.POINTER(u64), C.POINTER(u64), vp], i),
+        "mcb_rebalance_slabs": ([i, i, C.c_void_p, C.c_void_p, C.c_void_p], i),
         "mcb_comm_balance": ([vp, C.c_double, C.POINTER(i), C.POINTER(i)], i),
+        "mcb_comm_rebalance": ([vp, C.c_double, C.POINTER(i), C.POINTER(i)], i),
         "mcb_comm_finalize": ([vp], i),
         "mcb_host_register": ([vp, sz], i),
         "mcb_host_unregister": ([vp], i),
@@ -191,6 +193,17 @@ def balance_slabs(triangles_per_layer, nranks, fixed_cost_per_layer=-1.0):
     if rc != MCB_OK:
         raise McbError(rc)
     return [int(x) for x in cuts]
+
+
+def rebalance_slabs(cost_per_layer, cuts, ms_per_rank):
+    """Host-only: one refinement of a cut by measured time (mcb_rebalance_slabs).  Returns (new cost per layer, new cuts)."""
+    cost = np.array(cost_per_layer, np.float64)
+    c = np.array(cuts, np.int32)
+    ms = np.ascontiguousarray(ms_per_rank, np.float64)
+    rc = lib.mcb_rebalance_slabs(len(cost), len(ms), cost.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), ms.ctypes.data_as(C.c_void_p))
+    if rc != MCB_OK:
+        raise McbError(rc)
+    return cost, [int(x) for x in c]
 
 
 def comm_unique_id():
@@ -380,6 +393,12 @@ class Context:
     def comm_balance(self, fixed_cost_per_layer=-1.0):
         a, b = C.c_int(0), C.c_int(0)
         self._ck(lib.mcb_comm_balance(self.h, float(fixed_cost_per_layer), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def comm_rebalance(self, ms_measured):
+        """refine the balanced cut with the time this rank's slab was measured to take (collective)"""
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(lib.mcb_comm_rebalance(self.h, float(ms_measured), C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def get_active(self):

@@ -128,6 +128,8 @@ struct mcb_ctx {
     unsigned long long* h_comm = nullptr;   /* pinned copy of the gathered counts */
     int comm_flip = 0;
     bool comm_pending = false;
+    std::vector<double> layer_cost;         /* [M] cost of every cube layer as the last (re)balance saw it */
+    std::vector<int> comm_cuts;             /* [nranks + 1] the slabs of the last (re)balance */
     bool comm_auto = false;                 /* mcb_comm_set_auto: mcb_polygonise enqueues the exchange itself, as soon as the count is final */
     uint32_t* d_layer_hist = nullptr;       /* [cap_layer_hist] triangles per global cube layer */
     size_t cap_layer_hist = 0;
@@ -1660,6 +1662,25 @@ Nccl& nccl() {
         if (r_ != 0) return fail(ctx, MCB_E_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r_));                \
     } while (0)
 
+/* slabs of (nearly) equal cost: cuts[r] = first layer of rank r, at least one layer each */
+void cut_by_cost(int M, int nranks, const double* cost, int* cuts) {
+    double total = 0;
+    for (int k = 0; k < M; k++) total += cost[k];
+    cuts[0] = 0;
+    double run = 0;
+    int k = 0;
+    for (int r = 1; r < nranks; r++) {
+        const double want = total * (double)r / (double)nranks;
+        /* take layers while that brings the prefix closer to the target */
+        while (k < M && run + 0.5 * cost[k] <= want) { run += cost[k]; k++; }
+        int c = std::max(k, cuts[r - 1] + 1);            /* at least one layer per slab ... */
+        c = std::min(c, M - (nranks - r));               /* ... for the ranks still to come as well */
+        while (k < c) { run += cost[k]; k++; }
+        cuts[r] = c;
+    }
+    cuts[nranks] = M;
+}
+
 /* all-gather of this slab's triangle count, straight from the device counters, on the side stream */
 int comm_enqueue(mcb_ctx* ctx) {
     /* the next polygonisation resets the live counters: the count is first copied aside, in stream order */
@@ -1682,21 +1703,26 @@ extern "C" {
 int mcb_balance_slabs(int M, int nranks, const uint32_t* tri, double fixed, int* cuts) {
     if (M <= 0 || nranks <= 0 || nranks > M || !tri || !cuts) return MCB_E_ARG;
     if (fixed < 0) fixed = 0.0015 * (double)M * (double)M;
-    double total = 0;
-    for (int k = 0; k < M; k++) total += (double)tri[k] + fixed;
-    cuts[0] = 0;
-    double run = 0;
-    int k = 0;
-    for (int r = 1; r < nranks; r++) {
-        const double want = total * (double)r / (double)nranks;
-        /* take layers while that brings the prefix closer to the target */
-        while (k < M && run + 0.5 * ((double)tri[k] + fixed) <= want) { run += (double)tri[k] + fixed; k++; }
-        int c = std::max(k, cuts[r - 1] + 1);            /* at least one layer per slab ... */
-        c = std::min(c, M - (nranks - r));               /* ... for the ranks still to come as well */
-        while (k < c) { run += (double)tri[k] + fixed; k++; }
-        cuts[r] = c;
+    std::vector<double> cost((size_t)M);
+    for (int k = 0; k < M; k++) cost[(size_t)k] = (double)tri[k] + fixed;
+    cut_by_cost(M, nranks, cost.data(), cuts);
+    return MCB_OK;
+}
+
+int mcb_rebalance_slabs(int M, int nranks, double* cost, int* cuts, const double* ms) {
+    if (M <= 0 || nranks <= 0 || nranks > M || !cost || !cuts || !ms || cuts[0] != 0 || cuts[nranks] != M) return MCB_E_ARG;
+    for (int r = 0; r < nranks; r++)
+        if (!(ms[r] > 0.0) || cuts[r] >= cuts[r + 1]) return MCB_E_ARG;
+    /* the time a slab took is spread over its layers in proportion to their modelled cost; then the same cut as before.
+     * Equal times are the fixed point; what does not move with the layers (launch latencies) makes each pass undershoot a
+     * little instead of overshooting */
+    for (int r = 0; r < nranks; r++) {
+        double sum = 0;
+        for (int k = cuts[r]; k < cuts[r + 1]; k++) sum += cost[k];
+        const double scale = sum > 0 ? ms[r] / sum : 1.0;
+        for (int k = cuts[r]; k < cuts[r + 1]; k++) cost[k] = sum > 0 ? cost[k] * scale : ms[r] / (double)(cuts[r + 1] - cuts[r]);
     }
-    cuts[nranks] = M;
+    cut_by_cost(M, nranks, cost, cuts);
     return MCB_OK;
 }
 
@@ -1809,9 +1835,44 @@ int mcb_comm_balance(mcb_ctx* ctx, double fixed_cost_per_layer, int* k_begin, in
     std::vector<uint32_t> hist(M);
     MCB_CK(cudaMemcpyAsync(hist.data(), ctx->d_layer_hist, M * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<int> cuts((size_t)ctx->comm_nranks + 1);
-    if ((rc = mcb_balance_slabs((int)M, ctx->comm_nranks, hist.data(), fixed_cost_per_layer, cuts.data())) != MCB_OK) return fail(ctx, rc, "mcb_balance_slabs");
+    if (ctx->comm_nranks > (int)M) return fail(ctx, MCB_E_ARG, "fewer cube layers than ranks");
+    /* what a layer costs besides its triangles: the dense field writes every vertex of it, the block-field mode only looks
+     * at its block classes and candidate words (fitted on 2048^3 slabs: ~1.5e-4 M^2 triangle-equivalents) */
+    if (fixed_cost_per_layer < 0) fixed_cost_per_layer = (ctx->field_is_sparse ? 0.00015 : 0.0015) * (double)M * (double)M;
+    ctx->layer_cost.resize(M);
+    for (size_t k = 0; k < M; k++) ctx->layer_cost[k] = (double)hist[k] + fixed_cost_per_layer;
+    std::vector<int>& cuts = ctx->comm_cuts;
+    cuts.assign((size_t)ctx->comm_nranks + 1, 0);
+    cut_by_cost((int)M, ctx->comm_nranks, ctx->layer_cost.data(), cuts.data());
     const int k0 = cuts[(size_t)ctx->comm_rank], k1 = cuts[(size_t)ctx->comm_rank + 1];
+    if (k_begin) *k_begin = k0;
+    if (k_end) *k_end = k1;
+    return mcb_set_slab(ctx, k0, k1);
+}
+
+int mcb_comm_rebalance(mcb_ctx* ctx, double ms_measured, int* k_begin, int* k_end) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->nccl_comm) return fail(ctx, MCB_E_STATE, "mcb_comm_init has not been called");
+    const size_t M = (size_t)ctx->M;
+    const int n = ctx->comm_nranks;
+    if (ctx->layer_cost.size() != M || (int)ctx->comm_cuts.size() != n + 1 || ctx->comm_cuts[(size_t)ctx->comm_rank] != ctx->kb ||
+        ctx->comm_cuts[(size_t)ctx->comm_rank + 1] != ctx->ke)
+        return fail(ctx, MCB_E_STATE, "mcb_comm_balance has not cut the current slabs");
+    if (!(ms_measured > 0.0)) return fail(ctx, MCB_E_ARG, "the measured time must be positive");
+    /* every rank's time, as the bits of a double, through the count exchange's buffers */
+    unsigned long long bits;
+    std::memcpy(&bits, &ms_measured, 8);
+    if (ctx->comm_pending) MCB_CK(cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0));
+    MCB_CK(cudaMemcpyAsync(ctx->d_comm, &bits, 8, cudaMemcpyHostToDevice, ctx->stream));
+    MCB_NCCL(nccl().AllGather(ctx->d_comm, ctx->d_comm + 2, 1, kNcclUint64, ctx->nccl_comm, ctx->stream));
+    std::vector<unsigned long long> all((size_t)n);
+    MCB_CK(cudaMemcpyAsync(all.data(), ctx->d_comm + 2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<double> ms((size_t)n);
+    std::memcpy(ms.data(), all.data(), (size_t)n * 8);
+    if ((rc = mcb_rebalance_slabs((int)M, n, ctx->layer_cost.data(), ctx->comm_cuts.data(), ms.data())) != MCB_OK) return fail(ctx, rc, "a rank reported no time");
+    const int k0 = ctx->comm_cuts[(size_t)ctx->comm_rank], k1 = ctx->comm_cuts[(size_t)ctx->comm_rank + 1];
     if (k_begin) *k_begin = k0;
     if (k_end) *k_end = k1;
     return mcb_set_slab(ctx, k0, k1);

@@ -136,6 +136,33 @@ def test_balance_slabs_host_function(mcb):
     assert thick[0] > thick[3] and thick[-1] > thick[4]
 
 
+def test_rebalance_slabs_converges_on_a_time_model(mcb):
+    """mcb_rebalance_slabs (the host half of mcb_comm_rebalance): with slab time = launch floor + per-layer cost + per-triangle
+    cost (coefficients the first cut does not know, the triangle cost depending on z as measured on the 2048^3 sphere),
+    two refinements bring the slowest slab close to the mean."""
+    M, w = 2049, 8
+    z = (np.arange(M) + 0.5 - M / 2) / (M / 2)
+    tri = np.where(np.abs(z) < 0.7, 13500.0, 0.0)
+    per_tri = 0.145e-6 * (1.0 + 0.3 * (1 - np.abs(z)))          # ms per triangle: dearer near the equator
+    def slab_ms(cuts):
+        return [0.06 + 6e-5 * (b - a) + float((tri[a:b] * per_tri[a:b]).sum()) for a, b in zip(cuts, cuts[1:])]
+    cuts = mcb.balance_slabs(tri.astype(np.uint32), w, 0.0015 * M * M)   # a deliberately bad fixed cost
+    cost = tri + 0.0015 * M * M
+    ms0 = slab_ms(cuts)
+    spread = [max(ms0) / (sum(ms0) / w)]
+    for _ in range(3):
+        cost, cuts = mcb.rebalance_slabs(cost, cuts, slab_ms(cuts))
+        assert cuts[0] == 0 and cuts[-1] == M and all(b > a for a, b in zip(cuts, cuts[1:]))
+        ms = slab_ms(cuts)
+        spread.append(max(ms) / (sum(ms) / w))
+    assert spread[0] > 1.15 and spread[1] < 1.04 and spread[2] < 1.01 and spread[3] < 1.01 and max(slab_ms(cuts)) < 0.9 * max(ms0)
+    # bad arguments
+    with pytest.raises(mcb.McbError):
+        mcb.rebalance_slabs(cost, cuts, [0.0] * w)
+    with pytest.raises(mcb.McbError):
+        mcb.rebalance_slabs(cost, [0, 5, 5] + cuts[3:], [1.0] * w)
+
+
 def test_slab_of_matches_c_abi(mcb):
     slabs = importlib.import_module("marching-cube-for-implicit-surfaces_b200.slabs")
     for M in (9, 257, 1025, 2049):

@@ -1,5 +1,5 @@
 """Run under torchrun on N >= 2 GPUs: the z-slab path through the C ABI's own NCCL communicator (mcb_comm_*) against one
-context polygonising the whole grid.  Every rank polygonises its slab (uniform cut, then the cut balanced by measured cost),
+context polygonising the whole grid.  Every rank polygonises its slab (uniform cut, the cut balanced by measured triangles per layer, that cut refined by measured time),
 the triangle counts are all-gathered by mcb_comm_exchange, and the slabs' soups placed at the offsets mcb_comm_offsets
 returns must be, bit for bit, the soup of the full grid (rank 0 computes that one alone).  Prints one JSON line on rank 0."""
 import importlib, json, os, sys
@@ -9,6 +9,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+CUTS = ("uniform", "balanced", "rebalanced")
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
@@ -34,12 +35,14 @@ for wl, n in (("sphere", 512), ("gyr78", 256), ("torus", 384)):
         ctx.comm_init(comm_id, rank, world)
         first = False
     res = {}
-    for cut in ("uniform", "balanced"):
+    for cut in CUTS:
         if cut == "uniform":
             k0, k1 = m.slab_range(M, rank, world)
             ctx.set_slab(k0, k1)
-        else:
+        elif cut == "balanced":
             k0, k1 = ctx.comm_balance()
+        else:   # the balanced cut refined by the measured time of the balanced slabs (mcb_comm_rebalance)
+            k0, k1 = ctx.comm_rebalance(c.ms_total)
         c = ctx.polygonise()
         ctx.comm_exchange()
         off, tot, per = ctx.comm_offsets(world)
@@ -69,7 +72,7 @@ for wl, n in (("sphere", 512), ("gyr78", 256), ("torus", 384)):
         rp, rn = ref.get_mesh(normals=True)
         ref.close()
         row = {"workload": wl, "n": n, "triangles": int(rc.triangles)}
-        for cut in ("uniform", "balanced"):
+        for cut in CUTS:
             k0, k1, per, fp, fn = res[cut]
             same_p = bool(np.array_equal(fp.cpu().numpy().view(np.uint32), rp.view(np.uint32)))
             a, b = fn.cpu().numpy(), rn
