@@ -261,6 +261,13 @@ public:
         if (n != devices_) { release_devices(); devices_ = n; }
         return true;
     }
+    /* The kernels NVRTC compiles for a new equation are built on a background thread while recalculate() already
+     * delivers meshes through the bytecode interpreter (same results): this blocks until they are in place (benchmarks). */
+    bool wait_for_compiled_kernels() {
+        bool ok = ctx_ && mcb_jit_wait(ctx_) >= 0;
+        for (size_t r = 1; r < dev_ctx_.size(); r++) if (dev_ctx_[r]) ok = mcb_jit_wait(dev_ctx_[r]) >= 0 && ok;
+        return ok;
+    }
     void set_weld(bool b) { weld_ = b; }
     void set_normals(bool b) { normals_ = b; }
     /* true: get_vertex_normals() returns what CalculateNormal(get_poly_data()) would (normal.h:3-42), computed on the GPU,

@@ -186,15 +186,18 @@ int mcb_counts_device(mcb_ctx* ctx, const uint64_t** counts);
  * level sets.  distance must be > 0.  Forces MCB_FIELD_DENSE; not available together with seed mode. */
 int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance);
 
-/* Run-time specialisation of the evaluator.  The first mcb_polygonise after an equation change compiles
- * that equation's fused grid program into straight-line sm_100a kernels with NVRTC (libnvrtc.so.12, loaded on demand;
- * some tens of milliseconds, reported in mcb_counts::ms_compile) and later calls reuse them.  The kernel executes the interpreter's fp32
+/* Run-time specialisation of the evaluator.  After an equation change that equation's fused grid program is
+ * compiled into straight-line sm_100a kernels with NVRTC (libnvrtc.so.12, loaded on demand; some tens of milliseconds,
+ * reported in mcb_counts::ms_compile of the call that adopts them) and later calls reuse them.  The kernel executes the interpreter's fp32
  * operations in the interpreter's order on the interpreter's tile, so every result is bit-identical; it just has no
  * dispatch (torus 2.3 -> 1.5 ms, polynomial gyroid 1.3 -> 0.7 ms at 1024^3).  Constants, grid size and scaling are
  * kernel arguments: only a new equation compiles again.
  *   MCB_JIT_AUTO (default)  use it when NVRTC is there, the compile succeeds and the program has at most 8 `^` left after
  *                           hoisting (more: powf dominates either way and compile time grows), else the bytecode
- *                           interpreter — both are the same CUDA path with the same results; mcb_counts::jit says which ran
+ *                           interpreter — both are the same CUDA path with the same results; mcb_counts::jit says which ran.
+ *                           The compile runs on a background thread: the first mesh of a new equation does not wait for
+ *                           NVRTC, the calls made meanwhile interpret, the first call after the compile has finished
+ *                           switches over (mcb_jit_wait blocks until then; $MCB_JIT_SYNC=1 compiles inside the call)
  *   MCB_JIT_ON              require it: mcb_polygonise returns MCB_E_STATE with the log in mcb_last_error otherwise
  *   MCB_JIT_OFF             always interpret
  * One module per equation holds the kernel of the dense mode and the block kernel of the block-field mode. */
@@ -202,6 +205,10 @@ int mcb_set_repeat(mcb_ctx* ctx, int enabled, float distance);
 #define MCB_JIT_ON 1
 #define MCB_JIT_AUTO 2
 int mcb_set_jit(mcb_ctx* ctx, int mode);
+/* Block until the compile of the current surface equation's kernels has finished.  1: the next mcb_polygonise runs them;
+ * 0: it interprets (MCB_JIT_OFF, no NVRTC, too many powers, or the compile failed — mcb_last_error); < 0: MCB_JIT_ON and the
+ * compile failed. */
+int mcb_jit_wait(mcb_ctx* ctx);
 /* Host-only: generate and compile the specialised kernel for `equation` (no GPU needed).  Returns the cubin size in
  * bytes (> 0) and the generated CUDA source in `log`, or a negative status with the error / compile log in `log`. */
 int mcb_jit_check(const char* equation, char* log, size_t cap);

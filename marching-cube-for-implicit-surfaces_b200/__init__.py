@@ -94,6 +94,7 @@ def _load():
         "mcb_set_field_mode": ([vp, i], i),
         "mcb_set_stage_timing": ([vp, i], i),
         "mcb_set_jit": ([vp, i], i),
+        "mcb_jit_wait": ([vp], i),
         "mcb_jit_check": ([cp, cp, sz], i),
         "mcb_get_indexed_mesh": ([vp, vp, vp, vp, u64, u64], i),
         "mcb_get_indexed_mesh_device": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i),
@@ -297,6 +298,13 @@ class Context:
         """JIT_AUTO (default) / JIT_ON / JIT_OFF: evaluate the field with a kernel NVRTC compiles for the equation
         (bit-identical to the interpreter; compiled on first use, cached per equation)."""
         self._ck(lib.mcb_set_jit(self.h, int(mode)))
+
+    def jit_wait(self):
+        """block until the background compile of the current equation is over; True when the compiled kernels will run"""
+        rc = lib.mcb_jit_wait(self.h)
+        if rc < 0:
+            self._ck(rc)
+        return rc == 1
 
     def set_field_mode(self, mode):
         """FIELD_DENSE (whole field in device memory) or FIELD_SPARSE (signs everywhere, values only around the surface)."""

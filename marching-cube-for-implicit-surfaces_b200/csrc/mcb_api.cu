@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <future>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -112,6 +113,12 @@ struct mcb_ctx {
     struct JitKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kernel = nullptr, signs = nullptr, fill = nullptr; };
     const JitKernel* jit_cur = nullptr; /* the module the last evaluation used */
     std::map<std::string, JitKernel> jit_cache;
+    /* MCB_JIT_AUTO compiles in the background: the calls made meanwhile interpret (same results), the first call after
+     * the compile has finished loads the module.  Keyed by the generated source, like the cache. */
+    struct JitBuilt { std::string err; std::vector<char> cubin; float ms = 0.f; };
+    std::map<std::string, std::future<JitBuilt>> jit_pending;
+    std::map<std::string, std::string> jit_failed; /* source -> why its compile failed: not tried again */
+    bool jit_sync = false;         /* $MCB_JIT_SYNC=1: MCB_JIT_AUTO compiles inside the call, like MCB_JIT_ON */
     bool jit_used = false;         /* the last polygonisation ran the specialised kernel */
     float ms_compile = 0.f;        /* host time of the NVRTC compile it had to do (0 when cached) */
     bool repeat_on = false;        /* repeating-surface mode (mcb_set_repeat) */
@@ -593,6 +600,8 @@ int mcb_create(int device, mcb_ctx** out) {
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, stack_bytes) != cudaSuccess) return bail(MCB_E_CUDA);
         const char* poison = std::getenv("MCB_POISON_FIELD");
         ctx->poison_field = poison && poison[0] == '1';
+        const char* js = std::getenv("MCB_JIT_SYNC");
+        ctx->jit_sync = js && js[0] == '1';
         const char* noiv = std::getenv("MCB_NO_INTERVAL");
         ctx->decide_blocks = !(noiv && noiv[0] == '1');
         const char* we = std::getenv("MCB_WELD_EXACT");
@@ -893,35 +902,78 @@ int Run::stage_tables() {
 
 /* The module NVRTC compiled for this equation (mcb_jit.cpp), from the per-context cache or compiled now.
  * Returns MCB_OK with *out set, or a status with the reason in ctx->err. */
-int jit_module(mcb_ctx* ctx, const EqSlot& eq, const mcb_ctx::JitKernel** out) {
+constexpr int kJitDeferred = 1; /* not an error: the compile runs in the background, this call interprets */
+
+int jit_adopt(mcb_ctx* ctx, const std::string& src, const std::vector<char>& cubin, float ms, const mcb_ctx::JitKernel** out) {
+    mcb_ctx::JitKernel jk;
+    MCB_CK(cudaLibraryLoadData(&jk.lib, (void*)cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaError_t e = cudaLibraryGetKernel(&jk.kernel, jk.lib, "mcb_eval_jit");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.fill, jk.lib, "mcb_fill_jit");
+    if (e != cudaSuccess) {
+        cudaLibraryUnload(jk.lib);
+        return fail(ctx, MCB_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
+    }
+    if (ctx->jit_cache.size() >= 64) { /* a long GUI session types many equations: keep the cache bounded */
+        for (auto& kv : ctx->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+        ctx->jit_cache.clear();
+        ctx->jit_cur = nullptr;
+    }
+    *out = &ctx->jit_cache.emplace(src, jk).first->second;
+    ctx->ms_compile += ms;
+    return MCB_OK;
+}
+
+/* The module NVRTC compiled for this equation (mcb_jit.cpp): from the per-context cache, compiled now, or — MCB_JIT_AUTO,
+ * `wait` false — being compiled by a background thread, in which case kJitDeferred is returned until it is there.
+ * Returns MCB_OK with *out set, kJitDeferred, or a status with the reason in ctx->err. */
+int jit_module(mcb_ctx* ctx, const EqSlot& eq, const mcb_ctx::JitKernel** out, bool wait = false) {
     std::string err;
     bool has_pow = false;
     const std::string src = mcbjit::generate(eq.grid.code, eq.grid.n, &has_pow, &err);
     if (src.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + err);
     auto it = ctx->jit_cache.find(src);
-    if (it == ctx->jit_cache.end()) {
-        const auto t0 = std::chrono::steady_clock::now();
-        std::vector<char> cubin;
-        const std::string cerr = mcbjit::compile(src, has_pow, (int)sizeof(Grid), &cubin);
-        if (!cerr.empty()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + cerr);
-        mcb_ctx::JitKernel jk;
-        MCB_CK(cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-        cudaError_t e = cudaLibraryGetKernel(&jk.kernel, jk.lib, "mcb_eval_jit");
-        if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.fill, jk.lib, "mcb_fill_jit");
-        if (e != cudaSuccess) {
-            cudaLibraryUnload(jk.lib);
-            return fail(ctx, MCB_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
-        }
-        if (ctx->jit_cache.size() >= 64) { /* a long GUI session types many equations: keep the cache bounded */
-            for (auto& kv : ctx->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
-            ctx->jit_cache.clear();
-            ctx->jit_cur = nullptr;
-        }
-        it = ctx->jit_cache.emplace(src, jk).first;
-        ctx->ms_compile += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (it != ctx->jit_cache.end()) { *out = &it->second; return MCB_OK; }
+    auto bad = ctx->jit_failed.find(src);
+    if (bad != ctx->jit_failed.end()) return fail(ctx, MCB_E_STATE, "run-time specialisation: " + bad->second);
+    auto pend = ctx->jit_pending.find(src);
+    const bool background = ctx->jit == MCB_JIT_AUTO && !ctx->jit_sync && !wait;
+    if (pend == ctx->jit_pending.end() && background) {
+        if (ctx->jit_pending.size() >= 8) return kJitDeferred; /* equations typed faster than they compile: interpret */
+        const int grid_bytes = (int)sizeof(Grid);
+        bool started = true;
+        try {
+            ctx->jit_pending.emplace(src, std::async(std::launch::async, [src, has_pow, grid_bytes]() {
+                mcb_ctx::JitBuilt b;
+                const auto t0 = std::chrono::steady_clock::now();
+                b.err = mcbjit::compile(src, has_pow, grid_bytes, &b.cubin);
+                b.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                return b;
+            }));
+        } catch (...) { started = false; } /* a host program that cannot start threads: compile here, below */
+        if (started) return kJitDeferred;
     }
-    *out = &it->second;
-    return MCB_OK;
+    if (pend != ctx->jit_pending.end()) {
+        if (background && pend->second.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return kJitDeferred;
+        mcb_ctx::JitBuilt b = pend->second.get(); /* blocks when the caller wants the kernel now (MCB_JIT_ON, mcb_jit_wait) */
+        ctx->jit_pending.erase(pend);
+        if (!b.err.empty()) {
+            if (ctx->jit_failed.size() < 64) ctx->jit_failed.emplace(src, b.err);
+            return fail(ctx, MCB_E_STATE, "run-time specialisation: " + b.err);
+        }
+        const int rc = jit_adopt(ctx, src, b.cubin, b.ms, out);
+        if (rc != MCB_OK && ctx->jit_failed.size() < 64) ctx->jit_failed.emplace(src, ctx->err); /* not compiled over and over */
+        return rc;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    const std::string cerr = mcbjit::compile(src, has_pow, (int)sizeof(Grid), &cubin);
+    if (!cerr.empty()) {
+        if (ctx->jit_failed.size() < 64) ctx->jit_failed.emplace(src, cerr);
+        return fail(ctx, MCB_E_STATE, "run-time specialisation: " + cerr);
+    }
+    const int rc = jit_adopt(ctx, src, cubin, std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(), out);
+    if (rc != MCB_OK && ctx->jit_failed.size() < 64) ctx->jit_failed.emplace(src, ctx->err);
+    return rc;
 }
 
 /* auto: a program full of general `^` is bound by powf either way, and each inlined powf site costs compile time
@@ -984,6 +1036,7 @@ int Run::stage_eval() {
     if (jit_wanted(ctx, eq)) {
         rc = launch_eval_jit();
         if (rc == MCB_OK) ctx->jit_used = true;
+        else if (rc == kJitDeferred) ctx->jit_note = "compiling in the background";
         else if (ctx->jit == MCB_JIT_ON) return rc;      /* asked for explicitly: fail loudly */
         else ctx->jit_note = ctx->err;                   /* auto: the interpreter below does the same work */
     }
@@ -1082,6 +1135,7 @@ int Run::stage_eval_blocks() {
         const mcb_ctx::JitKernel* jk = nullptr;
         rc = jit_module(ctx, eq, &jk);
         if (rc == MCB_OK) { ctx->jit_used = true; ctx->jit_cur = jk; }
+        else if (rc == kJitDeferred) ctx->jit_note = "compiling in the background";
         else if (ctx->jit == MCB_JIT_ON) return rc;
         else ctx->jit_note = ctx->err;
     }
@@ -1478,6 +1532,19 @@ int mcb_set_jit(mcb_ctx* ctx, int enabled) {
     ctx->jit = enabled;
     ctx->have_result = false;
     return MCB_OK;
+}
+
+int mcb_jit_wait(mcb_ctx* ctx) {
+    int rc = enter(ctx);
+    if (rc != MCB_OK) return rc;
+    if (!ctx->eq[0].valid) return fail(ctx, MCB_E_STATE, "no surface equation");
+    if (!jit_wanted(ctx, ctx->eq[0])) return 0;
+    const mcb_ctx::JitKernel* jk = nullptr;
+    rc = jit_module(ctx, ctx->eq[0], &jk, true);
+    if (rc == MCB_OK) return 1;
+    if (ctx->jit == MCB_JIT_ON) return rc;
+    ctx->jit_note = ctx->err;
+    return 0;
 }
 
 int mcb_jit_check(const char* equation, char* log, size_t cap) {

@@ -45,7 +45,7 @@ def build(force=False):
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("emulated build failed: " + s)
         objs.append(o)
-    r = subprocess.run(["g++", "-shared", "-o", LIB] + objs + ["-ldl"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-o", LIB] + objs + ["-ldl", "-pthread"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("emulated link failed")

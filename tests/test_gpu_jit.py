@@ -45,7 +45,14 @@ def test_jit_equals_interpreter_on_the_golden_cases(mcb, pair, golden, name):
 
 def test_jit_compiles_once_per_equation_and_survives_parameter_changes(mcb):
     c = mcb.Context(0)
-    assert c.polygonise().jit == 1          # JIT_AUTO is the default and NVRTC is part of the image
+    # JIT_AUTO is the default and NVRTC is part of the image: the compile runs in the background, the calls made meanwhile
+    # interpret, and once it is over the compiled kernels run
+    early = c.polygonise()
+    assert c.jit_wait() is True
+    late = c.polygonise()
+    assert late.jit == 1 and (early.jit == 1 or late.ms_compile > 0)
+    assert (early.triangles, early.active) == (late.triangles, late.active)
+    assert c.polygonise().ms_compile == 0
     c.set_jit(mcb.JIT_ON)
     assert c.set_equation("x^2+y^2+z^2-0.49") == 0
     c.set_grid_step(2.0 / 64)
@@ -64,8 +71,8 @@ def test_jit_compiles_once_per_equation_and_survives_parameter_changes(mcb):
     assert (again.triangles, again.active) == (r.triangles, r.active) and same_bits(c.get_field(), ref.get_field())
     assert c.set_equation("x*y-z^3+0.1") == 0    # a new equation compiles again; a constraint does not
     assert c.set_equation("x", slot=1) == 0 and c.set_constraint(0, "<", 0.5, True) == 0
-    third = c.polygonise()
-    assert third.ms_compile > 0 and c.polygonise().ms_compile == 0
+    third = c.polygonise()              # JIT_ON: compiled inside the call
+    assert third.jit == 1 and third.ms_compile > 0 and c.polygonise().ms_compile == 0
     c.set_jit(mcb.JIT_OFF)
     assert c.polygonise().jit == 0
     c.close(); ref.close()
@@ -100,3 +107,40 @@ def test_auto_leaves_pow_heavy_programs_to_the_interpreter(mcb):
         c.close()
     assert res[0][0] == 0 and res[1][0] == 1          # 10 general powers: auto interprets, ON compiles anyway
     assert res[0][1] == res[1][1] and same_bits(res[0][2], res[1][2])
+
+
+def test_background_compile_switches_over_without_changing_a_bit(mcb):
+    """MCB_JIT_AUTO: the first mesh of a new equation does not wait for NVRTC.  Whatever ran — the interpreter before the
+    compile finished, the compiled kernels after — field, codes and soup are the same bytes."""
+    import time
+    c = mcb.Context(0)
+    c.set_field_mode(mcb.FIELD_DENSE)
+    c.set_normals(1)
+    assert c.set_equation("x*x*y-z*y*y+0.3*x*z*z-0.05") == 0   # nothing else in the suite compiles this one
+    c.set_grid_step(2.0 / 96)
+    t0 = time.perf_counter()
+    first = c.polygonise()
+    ms_first = (time.perf_counter() - t0) * 1e3
+    f0, p0 = c.get_field(), c.get_mesh(normals=True)
+    seen = [first.jit]
+    for _ in range(2000):
+        cnt = c.polygonise()
+        seen.append(cnt.jit)
+        if cnt.jit:
+            break
+        time.sleep(0.002)
+    assert seen[-1] == 1 and sorted(seen) == seen          # switches over once and stays
+    assert cnt.ms_compile > 0 or first.jit == 1
+    if first.jit == 0:
+        assert ms_first < 0.5 * cnt.ms_compile + 20           # the first call did not sit through the compile
+    f1, p1 = c.get_field(), c.get_mesh(normals=True)
+    assert (first.triangles, first.active) == (cnt.triangles, cnt.active)
+    assert same_bits(f0, f1) and same_bits(p0[0], p1[0]) and same_bits(p0[1], p1[1])
+    # a second context with the same equation while the first one's module exists: its own cache, same behaviour
+    d = mcb.Context(0)
+    assert d.set_equation("x*x*y-z*y*y+0.3*x*z*z-0.05") == 0
+    d.set_grid_step(2.0 / 96)
+    assert d.jit_wait() is True and d.polygonise().jit == 1
+    d.set_jit(mcb.JIT_OFF)
+    assert d.jit_wait() is False and d.polygonise().jit == 0
+    c.close(); d.close()

@@ -17,6 +17,7 @@ for wl, n in (("sphere", 1024), ("gyr78", 1024), ("torus", 1024), ("sphere", 204
         ctx = m.Context(0)
         ctx.set_field_mode(m.FIELD_AUTO)
         assert ctx.set_equation(bench.WORKLOADS[wl]) == 0
+        ctx.jit_wait()
         ctx.set_grid_step(2.0 / n)
         ctx.set_normals(1)
         for mesh in (m.MESH_SOUP, m.MESH_INDEXED):

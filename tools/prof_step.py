@@ -13,6 +13,7 @@ mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 field = int(sys.argv[5]) if len(sys.argv) > 5 else m.FIELD_AUTO
 ctx = m.Context(0)
 assert ctx.set_equation(eq) == 0
+ctx.jit_wait()
 ctx.set_grid_step(2.0 / n)
 ctx.set_normals(1)
 ctx.set_mesh_mode(mode)
