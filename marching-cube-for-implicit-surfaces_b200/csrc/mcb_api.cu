@@ -167,8 +167,11 @@ struct mcb_ctx {
     bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
     bool stage_timing = true;      /* mcb_set_stage_timing: CUDA events around the stages (mcb_counts::ms_*) */
     bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
-    int emit_variant = 3;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk; 3 measured
-                                      fastest on every workload, profiles/r02_ab_variants.jsonl),
+    float4* d_edge = nullptr;      /* [cap_edge] edge slots of edge_slots_kernel: 2 float4 per (record, axis) */
+    size_t cap_edge = 0;
+    int emit_variant = 4;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk),
+                                      4 (default) = 3 with every crossing grid edge computed once by its owner cube (edge_slots_kernel +
+                                      emit2<OWNED>) where the mode allows it (profiles/r02_ab_variants*.jsonl),
                                       9 = second generation with 24 edge slots (tests: forces chunks to be emitted in several runs) */
     uint8_t* d_fflags = nullptr;   /* [cap_fblocks] 2 = evaluated (undecided block), 1 = apron block to refill, 0 = untouched */
     uint8_t* d_bcls = nullptr;     /* [cap_fblocks] interval class of every 32 x 4 x 4 vertex block */
@@ -607,7 +610,7 @@ int mcb_create(int device, mcb_ctx** out) {
         const char* we = std::getenv("MCB_WELD_EXACT");
         ctx->weld_exact_only = we && we[0] == '1';
         const char* ev = std::getenv("MCB_EMIT");
-        if (ev && ((ev[0] >= '1' && ev[0] <= '3') || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
+        if (ev && ((ev[0] >= '1' && ev[0] <= '4') || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
     }
     int rc = install_equation(ctx, 0, "x+y"); /* Evaluator::Evaluator(), evaluator.cpp:6-8 */
     if (rc != MCB_OK) return bail(rc);
@@ -629,6 +632,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaFree(ctx->d_cls); cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_trioff); cudaFree(ctx->d_pos); cudaFree(ctx->d_nrm);
+    cudaFree(ctx->d_edge);
     cudaFree(ctx->d_vlist); cudaFree(ctx->d_vnrm); cudaFree(ctx->d_tlist); cudaFree(ctx->d_item); cudaFree(ctx->d_vinfo);
     cudaFree(ctx->d_chunk_new); cudaFree(ctx->d_fn); cudaFree(ctx->d_nh_count); cudaFree(ctx->d_nh_start); cudaFree(ctx->d_nh_cursor);
     cudaFree(ctx->d_nh_sums); cudaFree(ctx->d_nh_adj);
@@ -815,6 +819,11 @@ struct Run {
     int stage_soup();
     int stage_weld();
     int stage_normal_h();
+    /* K3a + emit2<OWNED>: every crossing grid edge computed once, by the cube it starts at.  The plain grid only: per-cube
+     * levels, constraints and seed mode change which cubes exist around an edge */
+    bool owned_edges() const {
+        return want_soup && ctx->normals == 1 && ctx->emit_variant == 4 && !ctx->seed_on && !any_constraint && !g.repeat;
+    }
 };
 
 int Run::prepare_buffers() {
@@ -1174,7 +1183,7 @@ int Run::stage_classify() {
         launches++;
         cw = ctx->d_cw;
     }
-    const bool need_items = want_indexed || ctx->seed_on; /* per-word record index for the weld / the seed walk */
+    const bool need_items = want_indexed || ctx->seed_on || owned_edges(); /* per-word record index for the weld / the seed walk / the edge owners */
     if (need_items && (rc = ensure_weld_scratch(ctx, g)) != MCB_OK) return rc;
     unsigned long long* items = need_items ? ctx->d_item : nullptr;
     const unsigned amb_ctas = (unsigned)ctx->sm_count * 2;
@@ -1272,6 +1281,21 @@ int Run::stage_soup() {
 #define MCB_EMIT2(NRM, CUBES, THREADS, CAP, MINB, MULT)                                                                               \
     do { if (idx32) MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, true); else MCB_EMIT2_(NRM, CUBES, THREADS, CAP, MINB, MULT, false); } while (0)
     const bool nrm = ctx->normals == 1;
+    if (owned_edges()) {
+        int rc;
+        if ((rc = ensure(ctx, &ctx->d_edge, &ctx->cap_edge, (size_t)ctx->cap_active * 6)) != MCB_OK) return rc;
+        if (idx32) {
+            MCB_LAUNCH((edge_slots_kernel<true>), eblocks * 8, kEdgeCubes, 0, s, g, rinv, ctx->d_F, ctx->d_rec, ctx->d_ctr, ctx->cap_active, ctx->d_edge);
+            MCB_LAUNCH((emit2_kernel<true, 64, 128, 512, 10, true, true>), eblocks * 4, 128, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, ctx->d_trioff,
+                       ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm, ctx->d_edge, ctx->d_item, cg.WC);
+        } else {
+            MCB_LAUNCH((edge_slots_kernel<false>), eblocks * 8, kEdgeCubes, 0, s, g, rinv, ctx->d_F, ctx->d_rec, ctx->d_ctr, ctx->cap_active, ctx->d_edge);
+            MCB_LAUNCH((emit2_kernel<true, 64, 128, 512, 10, false, true>), eblocks * 4, 128, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, ctx->d_trioff,
+                       ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, ctx->d_nrm, ctx->d_edge, ctx->d_item, cg.WC);
+        }
+        launches += 2;
+        return MCB_OK;
+    }
     switch (ctx->emit_variant) {
         case 1:
             if (nrm) MCB_LAUNCH((emit_kernel<true>), eblocks, kEmitThreads, 0, s, g, ctx->d_cs, ctx->d_F, ctx->d_rec, ctx->d_trioff, ctx->d_ctr, ctx->cap_active,
@@ -1400,7 +1424,6 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
      * from this call's own data, so a first or changed configuration is as fast as a repeated one. */
     const bool blocks = ctx->field_mode != MCB_FIELD_DENSE && !g.repeat;
     const bool timing = ctx->stage_timing;
-    ctx->ms_compile = 0.f;
     MCB_CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     if (timing) MCB_CK(cudaEventRecord(ctx->ev[0], s));
     if ((rc = run.stage_tables()) != MCB_OK) return rc;
@@ -1489,7 +1512,8 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     c.field_mode = ctx->field_is_sparse ? MCB_FIELD_SPARSE : MCB_FIELD_DENSE;
     c.field_blocks = ctx->field_is_sparse ? (uint64_t)ctx->h_ctr->field_blocks + ctx->h_ctr->eval_blocks : 0;
     c.jit = ctx->jit_used ? 1u : 0u;
-    c.ms_compile = ctx->jit_used ? ctx->ms_compile : 0.f;
+    c.ms_compile = ctx->jit_used ? ctx->ms_compile : 0.f; /* compile time of the module this call adopted (or mcb_jit_wait before it) */
+    if (ctx->jit_used) ctx->ms_compile = 0.f;
     c.vertices = run.want_indexed ? ctx->h_ctr->vertices : 0;
     c.mesh_mode = (uint32_t)ctx->mesh_mode;
     c.launches = run.launches;

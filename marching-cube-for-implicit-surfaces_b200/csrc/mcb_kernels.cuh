@@ -1228,6 +1228,20 @@ compact_kernel(const Grid g, const ClsTables* __restrict__ gtb, const uint32_t* 
  *       3  the block writes the chunk's contiguous output range, one float4 position (+ one float4 normal) per
  *          thread per step: fully coalesced 16-byte stores in the reference's emission order.
  * ------------------------------------------------------------------------------------------------------------- */
+/* The gradient normal of a crossing point is defined on the GRID EDGE, not on the cube that looks at it: blended from the
+ * lower end point to the upper one with t = (iso - f_lo) / (f_hi - f_lo) (0.5 when that is not finite).  A cube whose edge
+ * runs the other way (corner a is the upper end point) swaps the roles; fwd = corner a is the lower end point. */
+__device__ __forceinline__ void blend_edge_normal(bool fwd, float iso, float f1, float f2, float tq, float gxa, float gya, float gza, float gxb,
+                                                  float gyb, float gzb, float& nx, float& ny, float& nz) {
+    float tt = fwd ? tq : (iso - f2) / (f1 - f2);
+    if (isinf(tt) || isnan(tt)) tt = 0.5f;
+    const float lx = fwd ? gxa : gxb, ly = fwd ? gya : gyb, lz = fwd ? gza : gzb;
+    const float hx = fwd ? gxb : gxa, hy = fwd ? gyb : gya, hz = fwd ? gzb : gza;
+    nx = lx + tt * (hx - lx);
+    ny = ly + tt * (hy - ly);
+    nz = lz + tt * (hz - lz);
+}
+
 __device__ __forceinline__ float interp_ref(float xs, float xe, float t) {
     /* Marching::interp, marching.cpp:437-446, with t = (c - v_s) / (v_e - v_s) computed once: the reference calls it
      * three times per edge with the same field values, so the quotient has the same bits every time */
@@ -1323,11 +1337,8 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
                 const float gxb = (__ldg(pb + 1) - __ldg(pb - 1)) / (cs[xb + 1] - cs[xb - 1]);
                 const float gyb = (__ldg(pb + rowp) - __ldg(pb - rowp)) / (cs[yb + 1] - cs[yb - 1]);
                 const float gzb = (__ldg(pb + planep) - __ldg(pb - planep)) / (cs[zb + 1] - cs[zb - 1]);
-                float tt = tq;
-                if (isinf(tt) || isnan(tt)) tt = 0.5f;
-                const float nx = gxa + tt * (gxb - gxa);
-                const float ny = gya + tt * (gyb - gya);
-                const float nz = gza + tt * (gzb - gza);
+                float nx, ny, nz;
+                blend_edge_normal(oa < ob, g.iso, f1, f2, tq, gxa, gya, gza, gxb, gyb, gzb, nx, ny, nz);
                 const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
                 float* en = enrm + lc * kEdgeStride + 3 * e;
                 en[0] = nx * inv; en[1] = ny * inv; en[2] = nz * inv;
@@ -1393,14 +1404,118 @@ __device__ __forceinline__ void gradient_normal(const float* __restrict__ pa, co
     ox = nx * inv; oy = ny * inv; oz = nz * inv;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * K3a  edge slots.  A crossing grid edge is shared by up to four cubes, and what the emission computes for it — the two
+ *      end-point values, the gradient at both ends, the blend, the normalisation — is a function of the EDGE, not of the
+ *      cube: emit2 alone does it once per cube.  Here every active cube does it for the (up to three) crossing edges that
+ *      start at its corner 0 (+x, +y, +z): each grid edge whose lower end point is the origin of a cube of the slab has
+ *      exactly that one owner, and the owner is active because the edge crosses.  The result goes to slot
+ *      [3 * record + axis]: (f_lo, f_hi, nx, ny | nz).  emit2<OWNED> then fetches a slot per (cube, edge) — the owner is
+ *      the cube itself or its +x / +y / +z / diagonal neighbour, found through compact's per-word record index — and only
+ *      interpolates: Marching::interp in the cube's own direction from the two stored values, bit for bit what the field
+ *      holds.  Edges without an owner in the slab (far faces of the grid, last plane of the slab) are computed in place by
+ *      the same function, so a slab and the whole grid give the same bits.
+ *      The normal is defined on the edge: lower end point -> upper end point, t = (iso - f_lo) / (f_hi - f_lo).
+ * ------------------------------------------------------------------------------------------------------------- */
+template <class off_t>
+__device__ __forceinline__ void grid_edge_slot(const float* __restrict__ F, off_t ilo, int axis, off_t rowp, off_t planep, float rx, float ry,
+                                               float rz, float r_hi /* reciprocal at the upper end point along `axis` */, float iso,
+                                               float4& s0, float& s1) {
+    const off_t ihi = ilo + (axis == 0 ? (off_t)1 : axis == 1 ? rowp : planep);
+    const float f_lo = __ldg(F + ilo), f_hi = __ldg(F + ihi);
+    /* along the edge's own axis each end point's central difference uses the other end point */
+    const float xa1 = axis == 0 ? f_hi : __ldg(F + ilo + 1), xb0 = axis == 0 ? f_lo : __ldg(F + ihi - 1);
+    const float ya1 = axis == 1 ? f_hi : __ldg(F + (ilo + rowp)), yb0 = axis == 1 ? f_lo : __ldg(F + (ihi - rowp));
+    const float za1 = axis == 2 ? f_hi : __ldg(F + (ilo + planep)), zb0 = axis == 2 ? f_lo : __ldg(F + (ihi - planep));
+    const float gxa = (xa1 - __ldg(F + ilo - 1)) * rx;
+    const float gya = (ya1 - __ldg(F + (ilo - rowp))) * ry;
+    const float gza = (za1 - __ldg(F + (ilo - planep))) * rz;
+    const float gxb = (__ldg(F + ihi + 1) - xb0) * (axis == 0 ? r_hi : rx);
+    const float gyb = (__ldg(F + (ihi + rowp)) - yb0) * (axis == 1 ? r_hi : ry);
+    const float gzb = (__ldg(F + (ihi + planep)) - zb0) * (axis == 2 ? r_hi : rz);
+    float tt = (iso - f_lo) / (f_hi - f_lo);
+    if (isinf(tt) || isnan(tt)) tt = 0.5f;
+    const float nx = gxa + tt * (gxb - gxa);
+    const float ny = gya + tt * (gyb - gya);
+    const float nz = gza + tt * (gzb - gza);
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+    s0 = make_float4(f_lo, f_hi, nx * inv, ny * inv);
+    s1 = nz * inv;
+}
+
+constexpr int kEdgeCubes = 128; /* cubes per chunk = threads per block */
+
+template <bool IDX32>
+__global__ void __launch_bounds__(kEdgeCubes, 8)
+edge_slots_kernel(const Grid g, const float* __restrict__ rinv, const float* __restrict__ F, const unsigned long long* __restrict__ rec,
+                  const Counters* __restrict__ ctr, unsigned long long cap_active, float4* __restrict__ E) {
+    typedef typename std::conditional<IDX32, uint32_t, unsigned long long>::type off_t;
+    __shared__ float crinv[kEdgeCubes * 6];
+    __shared__ off_t cbase_s[kEdgeCubes];
+    __shared__ uint16_t work_s[kEdgeCubes * 3];
+    __shared__ uint32_t warp_s[kEdgeCubes / 32];
+    unsigned long long A = ctr->active;
+    if (A > cap_active) A = cap_active;
+    const unsigned long long nchunks = (A + kEdgeCubes - 1) / kEdgeCubes;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const off_t rowp = (off_t)g.P, planep = (off_t)g.NV * (off_t)g.P;
+    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();
+        const unsigned long long c0 = chunk * kEdgeCubes;
+        const int n = (int)((A - c0) < (unsigned long long)kEdgeCubes ? (A - c0) : kEdgeCubes);
+        uint32_t own = 0;
+        if (t < n) {
+            const unsigned long long r = rec[c0 + t];
+            const int code = (int)((r >> 36) & 0xFF);
+            const int i = (int)(r & 0xFFF), j = (int)((r >> 12) & 0xFFF), k = (int)((r >> 24) & 0xFFF);
+            /* corner 0 against corners 1 (+x), 3 (+y), 4 (+z): mcb_corner_ofs */
+            own = (uint32_t)(((code ^ (code >> 1)) & 1) | (((code ^ (code >> 3)) & 1) << 1) | (((code ^ (code >> 4)) & 1) << 2));
+            crinv[6 * t + 0] = __ldg(rinv + i + 1); crinv[6 * t + 1] = __ldg(rinv + i + 2);
+            crinv[6 * t + 2] = __ldg(rinv + j + 1); crinv[6 * t + 3] = __ldg(rinv + j + 2);
+            crinv[6 * t + 4] = __ldg(rinv + k + 1); crinv[6 * t + 5] = __ldg(rinv + k + 2);
+            cbase_s[t] = (off_t)(k - g.kb + 1) * planep + (off_t)(j + 1) * rowp + (off_t)(i + 1);
+        }
+        const uint32_t nv = __popc(own);
+        uint32_t inc = nv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_s[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = inc - nv, total = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kEdgeCubes / 32; w2++) { if (w2 < warp) wbase += warp_s[w2]; total += warp_s[w2]; }
+        while (own) {
+            const int a = __ffs(own) - 1;
+            own &= own - 1;
+            work_s[wbase++] = (uint16_t)((t << 2) | a);
+        }
+        __syncthreads();
+        for (uint32_t q = t; q < total; q += kEdgeCubes) {
+            const uint32_t wk = work_s[q];
+            const int lc = (int)(wk >> 2), axis = (int)(wk & 3u);
+            const float* ri = crinv + 6 * lc;
+            float4 s0;
+            float s1;
+            grid_edge_slot<off_t>(F, cbase_s[lc], axis, rowp, planep, ri[0], ri[2], ri[4], ri[2 * axis + 1], g.iso, s0, s1);
+            float4* out = E + 2 * (3 * (c0 + lc) + axis);
+            out[0] = s0;
+            out[1] = make_float4(s1, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 template <bool NORMALS, int CUBES, int THREADS, int CAP /* edge slots per chunk run */, int MINB,
-          bool IDX32 /* the slab's field has fewer than 2^32 values: 32-bit offsets, one IMAD.WIDE per load address */>
+          bool IDX32 /* the slab's field has fewer than 2^32 values: 32-bit offsets, one IMAD.WIDE per load address */,
+          bool OWNED = false /* normals and end-point values come from the edge slots of edge_slots_kernel (K3a) */>
 __global__ void __launch_bounds__(THREADS, MINB)
 emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict__ rinv, const float* __restrict__ F,
              const ClsTables* __restrict__ gtb, const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ trioff,
              const Counters* __restrict__ ctr, unsigned long long cap_active, unsigned long long cap_tris,
-             float4* __restrict__ pos, float4* __restrict__ nrm) {
+             float4* __restrict__ pos, float4* __restrict__ nrm, const float4* __restrict__ E = nullptr,
+             const unsigned long long* __restrict__ item = nullptr /* per 32-cube word: first record | active mask << 32 */,
+             uint32_t WC = 0) {
     static_assert(CAP >= 12 && CUBES <= 256 && CUBES <= THREADS, "a cube's edges fit one run; a thread per cube in phase 1");
+    static_assert(!OWNED || NORMALS, "the edge slots exist for the normals");
     __shared__ float4 eslot[NORMALS ? CAP : 1];     /* crossing edge: coordinate along its axis, normal */
     __shared__ float epos_only[NORMALS ? 1 : CAP];
     __shared__ float ccoord[CUBES * 6];             /* x0 x1 y0 y1 z0 z1 of the cube */
@@ -1495,10 +1610,43 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
                 const off_t c0f = cbase_s[lc]; /* corner 0 of the cube; the end points are at most one step away on each axis */
                 const off_t ia = c0f + (off_t)(oa & 1) + (((oa >> 1) & 1) ? rowp : (off_t)0) + ((oa >> 2) ? planep : (off_t)0);
                 const off_t ib = c0f + (off_t)(ob & 1) + (((ob >> 1) & 1) ? rowp : (off_t)0) + ((ob >> 2) ? planep : (off_t)0);
-                const float f1 = __ldg(F + ia), f2 = __ldg(F + ib);
-                const float tq = (g.iso - f1) / (f2 - f1); /* Marching::interp uses the surface constant itself, also in repeating-surface mode */
                 const float* cc = ccoord + 6 * lc + 2 * axis;
                 const float ca = cc[(oa >> axis) & 1], cb2 = cc[(ob >> axis) & 1];
+                if (OWNED) {
+                    const int lo = oa & ob; /* the end points differ in one bit: the lower one, as an offset from corner 0 */
+                    unsigned long long idx = c0 + (unsigned long long)lc;
+                    bool have = true;
+                    if (lo != 0) { /* the owner is the cube whose corner 0 is that end point */
+                        const uint32_t ij = ijk_s[lc];
+                        const int oi = (int)(ij & 0xFFF) + (lo & 1), oj = (int)(ij >> 12) + ((lo >> 1) & 1), ok = (int)k_s[lc] + (lo >> 2);
+                        have = oi < g.M && oj < g.M && ok < g.ke;
+                        if (have) {
+                            const unsigned long long info = __ldg(item + ((size_t)(ok - g.kb) * (size_t)g.M + (size_t)oj) * WC + (size_t)(oi >> 5));
+                            const uint32_t m = (uint32_t)(info >> 32);
+                            idx = (info & 0xFFFFFFFFull) + (unsigned long long)__popc(m & ((1u << (oi & 31)) - 1u));
+                            have = ((m >> (oi & 31)) & 1u) != 0u && idx < A; /* (a pass with too small buffers is repeated by the host) */
+                        }
+                    }
+                    float4 s0;
+                    float s1;
+                    if (have) {
+                        const float4* sl = E + 2 * (3 * idx + (unsigned long long)axis);
+                        s0 = __ldg(sl);
+                        s1 = __ldg(reinterpret_cast<const float*>(sl + 1));
+                    } else { /* no owner inside the slab: the same function, in place */
+                        const float* ri = crinv + 6 * lc;
+                        const off_t ilo = c0f + (off_t)(lo & 1) + (((lo >> 1) & 1) ? rowp : (off_t)0) + ((lo >> 2) ? planep : (off_t)0);
+                        grid_edge_slot<off_t>(F, ilo, axis, rowp, planep, ri[lo & 1], ri[2 + ((lo >> 1) & 1)], ri[4 + (lo >> 2)], ri[2 * axis + 1],
+                                              g.iso, s0, s1);
+                    }
+                    const bool fwd = oa == lo; /* Marching::interp runs from corner a to corner b of THIS cube's edge */
+                    const float f1 = fwd ? s0.x : s0.y, f2 = fwd ? s0.y : s0.x;
+                    const float tq = (g.iso - f1) / (f2 - f1);
+                    eslot[q - q0] = make_float4(interp_ref(ca, cb2, tq), s0.z, s0.w, s1);
+                    continue;
+                }
+                const float f1 = __ldg(F + ia), f2 = __ldg(F + ib);
+                const float tq = (g.iso - f1) / (f2 - f1); /* Marching::interp uses the surface constant itself, also in repeating-surface mode */
                 const float p = interp_ref(ca, cb2, tq);
                 if (NORMALS) { /* gradient_normal() with the reciprocals from shared memory */
                     const float* ri = crinv + 6 * lc;
@@ -1508,11 +1656,8 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
                     const float gxb = (__ldg(F + ib + 1) - __ldg(F + ib - 1)) * ri[ob & 1];
                     const float gyb = (__ldg(F + (ib + rowp)) - __ldg(F + (ib - rowp))) * ri[2 + ((ob >> 1) & 1)];
                     const float gzb = (__ldg(F + (ib + planep)) - __ldg(F + (ib - planep))) * ri[4 + (ob >> 2)];
-                    float tt = tq;
-                    if (isinf(tt) || isnan(tt)) tt = 0.5f;
-                    const float nx = gxa + tt * (gxb - gxa);
-                    const float ny = gya + tt * (gyb - gya);
-                    const float nz = gza + tt * (gzb - gza);
+                    float nx, ny, nz;
+                    blend_edge_normal(oa < ob, g.iso, f1, f2, tq, gxa, gya, gza, gxb, gyb, gzb, nx, ny, nz);
                     const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
                     eslot[q - q0] = make_float4(p, nx * inv, ny * inv, nz * inv);
                 } else epos_only[q - q0] = p;
@@ -2118,9 +2263,8 @@ weld_emit_kernel(const WV W, const WeldBuffers B, const Counters* __restrict__ c
                         const float gxb = (__ldg(pb + 1) - __ldg(pb - 1)) / (cs[xb + 1] - cs[xb - 1]);
                         const float gyb = (__ldg(pb + rowp) - __ldg(pb - rowp)) / (cs[yb + 1] - cs[yb - 1]);
                         const float gzb = (__ldg(pb + planep) - __ldg(pb - planep)) / (cs[zb + 1] - cs[zb - 1]);
-                        float tt = tq;
-                        if (isinf(tt) || isnan(tt)) tt = 0.5f;
-                        const float nx = gxa + tt * (gxb - gxa), ny = gya + tt * (gyb - gya), nz = gza + tt * (gzb - gza);
+                        float nx, ny, nz;
+                        blend_edge_normal(oa < ob, g.iso, f1, f2, tq, gxa, gya, gza, gxb, gyb, gzb, nx, ny, nz);
                         const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
                         float* on = vertex_nrm + 3ull * idx;
                         on[0] = nx * inv; on[1] = ny * inv; on[2] = nz * inv;

@@ -337,7 +337,8 @@ static void calc_cube(const mco* m, int i, int j, int k, Cube* q, int want_grad)
     if (want_grad) {
         /* Product definition of the normals (north_star "central-difference field gradients"):
          * gradient at each cube corner by central differences of the field over the grid coordinates, blended along the
-         * edge with the interpolation parameter, normalised like glm::normalize (x * (1/sqrt(dot))). */
+         * grid edge (lower end point -> upper end point) with that direction's interpolation parameter, normalised like
+         * glm::normalize (x * (1/sqrt(dot))). */
         float g[8][3];
         for (int v = 0; v < 8; v++) {
             const int o = mcb_corner_ofs(v);
@@ -350,7 +351,10 @@ static void calc_cube(const mco* m, int i, int j, int k, Cube* q, int want_grad)
             g[v][2] = (march_eval(m, 0, X, Y, m->cs[zi + 1]) - march_eval(m, 0, X, Y, m->cs[zi - 1])) * rz;
         }
         for (int n = 0; n < q->nedges; n++) {
-            const int a = mcb_edge_a(q->edges[n]), b = mcb_edge_b(q->edges[n]);
+            int a = mcb_edge_a(q->edges[n]), b = mcb_edge_b(q->edges[n]);
+            /* the normal is defined on the grid edge: blended from its lower end point to the upper one, whichever way
+             * this cube's edge runs (the up to four cubes sharing the edge get the same normal) */
+            if (mcb_corner_ofs(a) > mcb_corner_ofs(b)) { const int sw = a; a = b; b = sw; }
             float t = (m->iso - val[a]) / (val[b] - val[a]);
             if (isinf(t) || isnan(t)) t = 0.5f;
             const float nx = g[a][0] + t * (g[b][0] - g[a][0]);

@@ -39,6 +39,8 @@ def soup_gradient_normals(field_ext, cs, iso, cubes, tri_rows):
                 a, b = EDGE_A[e], EDGE_B[e]
                 if ((code >> a) ^ (code >> b)) & 1 == 0:
                     continue
+                if sum(CORNER[a]) > sum(CORNER[b]):
+                    a, b = b, a   # defined on the grid edge: from its lower end point to the upper one, for every cube sharing it
                 f1, f2 = val[a], val[b]
                 t = f32(f32(iso - f1) / f32(f2 - f1))
                 if np.isinf(t) or np.isnan(t):

@@ -8,7 +8,7 @@ import bench
 import torch
 out = []
 for wl, n in (("sphere", 1024), ("gyr78", 1024), ("torus", 1024), ("sphere", 2048)):
-    for env in ({"MCB_EMIT": "1"}, {"MCB_EMIT": "2"}, {"MCB_EMIT": "3"}):
+    for env in ({"MCB_EMIT": "2"}, {"MCB_EMIT": "3"}, {"MCB_EMIT": "4"}):
         for k in ("MCB_EMIT", "MCB_WELD_EXACT", "MCB_NO_INTERVAL"):
             os.environ.pop(k, None)
         os.environ.update(env)
