@@ -169,9 +169,9 @@ struct mcb_ctx {
     bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
     float4* d_edge = nullptr;      /* [cap_edge] edge slots of edge_slots_kernel: 2 float4 per (record, axis) */
     size_t cap_edge = 0;
-    int emit_variant = 4;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk),
-                                      4 (default) = 3 with every crossing grid edge computed once by its owner cube (edge_slots_kernel +
-                                      emit2<OWNED>) where the mode allows it (profiles/r02_ab_variants*.jsonl),
+    int emit_variant = 3;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk; 3 measured
+                                      fastest on every workload and is the default), 4 = 3 with every crossing grid edge computed once by its
+                                      owner cube (edge_slots_kernel + emit2<OWNED>): same bytes, measured slower (profiles/r02_ab_variants_owned_edges.jsonl),
                                       9 = second generation with 24 edge slots (tests: forces chunks to be emitted in several runs) */
     uint8_t* d_fflags = nullptr;   /* [cap_fblocks] 2 = evaluated (undecided block), 1 = apron block to refill, 0 = untouched */
     uint8_t* d_bcls = nullptr;     /* [cap_fblocks] interval class of every 32 x 4 x 4 vertex block */

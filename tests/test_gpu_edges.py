@@ -109,13 +109,13 @@ def test_slab_in_the_middle_equals_the_same_layers_of_the_full_grid(mcb):
                                         (None, 48, (1.0, 1.0, 1.0)), ("(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)", 64, (1.0, 1.0, 1.0)),
                                         ("x+y", 32, (1.0, 1.0, 1.0)), ("1/(x*y)-z", 24, (1.0, 1.0, 1.0))])
 def test_edges_computed_once_by_their_owner_equal_the_per_cube_computation(mcb, monkeypatch, eq, n, scale):
-    """K3a: the default emitter computes a crossing grid edge once, in the cube it starts at (edge_slots_kernel), and the up to
-    four cubes that share it fetch the result (emit2<OWNED>); $MCB_EMIT=3 is the same emitter computing it in every cube.
+    """K3a ($MCB_EMIT=4): a crossing grid edge computed once, in the cube it starts at (edge_slots_kernel), the up to four cubes
+    that share it fetching the result (emit2<OWNED>), against the default emitter, which computes it in every cube.
     Positions and normals must be the same bytes — on the whole grid, and in a slab whose boundary edges have no owner."""
     from oracle.refbind import GYR78
     eq = eq or GYR78
     res = []
-    for variant in ("3", None):
+    for variant in ("4", None):
         if variant:
             monkeypatch.setenv("MCB_EMIT", variant)
         else:
