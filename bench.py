@@ -22,6 +22,7 @@ Workloads (BASELINE.json configs):
 """
 import argparse
 import importlib
+import itertools
 import json
 import os
 import statistics
@@ -408,7 +409,7 @@ def run_ours(args):
 
     # ---- every step a NEW configuration (another iso value): nothing learnt from the previous step can help --------
     isos = [1e-4 * (1 + (i % 9)) for i in range(args.steps)]
-    it = iter(isos * 2)
+    it = itertools.cycle(isos)
 
     def changed_step():
         ctx.set_surface_constant(next(it))

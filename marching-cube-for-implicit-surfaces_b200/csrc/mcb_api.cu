@@ -1013,6 +1013,9 @@ int Run::launch_eval_jit() {
     int rg = rgpp, spa = eq.max_per_axis;
     void* args[] = {&consts, &garg, &tables, &F, &S, &rg, &spa};
     MCB_CK(cudaLaunchKernel((const void*)jk->kernel, blocks, dim3(kEvalThreads), args, 0, s));
+#ifdef __CUDACC__
+    if (mcb_debug_sync_on()) mcb_debug_sync_check("mcb_eval_jit", s);
+#endif
     ctx->jit_cur = jk;
     launches++;
     return MCB_OK;
@@ -1115,6 +1118,9 @@ int Run::launch_block_eval(const FieldBlocks& fb, const uint32_t* list, const un
         int spa = eq.max_per_axis;
         void* args[] = {&consts, &garg, &tables, &F, &S, &list, &count, &spa};
         MCB_CK(cudaLaunchKernel((const void*)ctx->jit_cur->fill, dim3(fill_ctas), dim3(kEvalThreads), args, 0, s));
+#ifdef __CUDACC__
+        if (mcb_debug_sync_on()) mcb_debug_sync_check("mcb_fill_jit", s);
+#endif
     } else {
         mcb_program launch;
         bool has_pow;

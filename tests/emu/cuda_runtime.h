@@ -15,6 +15,10 @@
  */
 #pragma once
 #include <math.h>
+#include <signal.h>
+#include <stdio.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -22,6 +26,8 @@
 
 #include <cmath>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #define MCB_EMULATED_DEVICE 1
@@ -267,10 +273,53 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     strcpy(p->name, "host emulation (tests/emu)");
     return cudaSuccess;
 }
-template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+/* $MCB_EMU_FENCE=1: every device allocation ends right before an inaccessible page (the end rounded up to 16 bytes only), so
+ * that a kernel reading or writing past its buffer faults at the instruction that does it; the handler names the kernel. */
+namespace emu {
+inline bool fence_on() { static const bool on = [] { const char* e = getenv("MCB_EMU_FENCE"); return e && e[0] == '1'; }(); return on; }
+inline const char*& current_kernel() { static const char* k = "(host)"; return k; }
+inline std::map<void*, std::pair<void*, size_t>>& fence_map() { static std::map<void*, std::pair<void*, size_t>> m; return m; }
+inline std::mutex& fence_mutex() { static std::mutex m; return m; }
+inline void fence_handler(int, siginfo_t* si, void*) {
+    char b[256];
+    const int n = snprintf(b, sizeof b, "\nemulator fence: invalid access at %p in kernel %s\n", si->si_addr, current_kernel());
+    if (n > 0) (void)!write(2, b, (size_t)n);
+    _exit(99);
+}
+inline void* fence_alloc(size_t n) {
+    static const bool installed = [] {
+        static char altstack[1 << 16];
+        stack_t ss; ss.ss_sp = altstack; ss.ss_size = sizeof altstack; ss.ss_flags = 0; sigaltstack(&ss, nullptr);
+        struct sigaction sa; memset(&sa, 0, sizeof sa); sa.sa_sigaction = fence_handler; sa.sa_flags = SA_SIGINFO | SA_ONSTACK;
+        sigaction(SIGSEGV, &sa, nullptr); sigaction(SIGBUS, &sa, nullptr);
+        return true; }();
+    (void)installed;
+    const size_t page = 4096, used = (n + 15) / 16 * 16, body = (used + page - 1) / page * page;
+    char* base = (char*)mmap(nullptr, body + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == (char*)MAP_FAILED) return nullptr;
+    mprotect(base + body, page, PROT_NONE);
+    void* p = base + (body - used);
+    memset(base, 0xA5, body); /* cudaMalloc does not clear: whoever reads before writing gets a wild index, not a convenient zero */
+    std::lock_guard<std::mutex> lk(fence_mutex());
+    fence_map()[p] = std::make_pair((void*)base, body + page);
+    return p;
+}
+inline bool fence_free(void* p) {
+    std::lock_guard<std::mutex> lk(fence_mutex());
+    auto it = fence_map().find(p);
+    if (it == fence_map().end()) return false;
+    munmap(it->second.first, it->second.second);
+    fence_map().erase(it);
+    return true;
+}
+} /* namespace emu */
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) {
+    *p = emu::fence_on() ? (T*)emu::fence_alloc(n) : (T*)aligned_alloc(256, (n + 255) / 256 * 256 + 256);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) { if (p && !emu::fence_free(p)) free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
@@ -307,5 +356,6 @@ static inline cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size
 /* launcher and dynamic shared memory as the product sources spell them (csrc/mcb_launch.h keeps the CUDA forms) */
 #define MCB_UNPAREN(...) __VA_ARGS__
 #define MCB_LAUNCH(kern, grid, block, smem, stream, ...) \
-    emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { MCB_UNPAREN kern(__VA_ARGS__); })
+    do { emu::current_kernel() = #kern; emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { MCB_UNPAREN kern(__VA_ARGS__); }); \
+         emu::current_kernel() = "(host)"; } while (0)
 #define MCB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())
