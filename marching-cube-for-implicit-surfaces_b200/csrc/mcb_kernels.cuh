@@ -2233,7 +2233,9 @@ weld_emit_kernel(const WV W, const WeldBuffers B, const Counters* __restrict__ c
             sh.mask[t] = (uint32_t)(vi >> 32);
             vb_s[t] = MCB_VINFO_BASE(vi);
         }
-        if (t == 0) off_s[n] = (c0 + n < A) ? B.trioff[c0 + n] : (A == ctr->active ? (uint32_t)T : off_s[n - 1]);
+        /* end of the chunk's output range.  In a pass with too small buffers (repeated by the host) the last cube gets no
+         * output; its offset is read from global memory, NOT from off_s[n - 1], which another warp is writing right now */
+        if (t == 0) off_s[n] = (c0 + n < A) ? B.trioff[c0 + n] : (A == ctr->active ? (uint32_t)T : B.trioff[c0 + n - 1]);
         __syncthreads();
         for (uint32_t q = t; q < total_v; q += kWeldThreads) {
             const uint32_t wk = sh.work[q];

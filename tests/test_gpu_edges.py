@@ -136,3 +136,30 @@ def test_edges_computed_once_by_their_owner_equal_the_per_cube_computation(mcb, 
         assert ta == tb and ta > 0
         assert same_bits(pa, pb)
         assert same_bits(na, nb)
+
+
+def test_truncated_passes_are_harmless(mcb):
+    """A grid that outgrows every buffer: the first pass of the call runs with too small record, soup and mesh buffers and is
+    repeated by the host.  Its kernels must stay inside their buffers whatever the truncated state looks like (weld_emit once
+    took the end of a truncated chunk from shared memory another warp was still writing: an intermittent illegal access).
+    Many fresh contexts, so that the truncated pass meets many different leftovers in shared and global memory."""
+    ref = None
+    for rep in range(24):
+        c = mcb.Context(0)
+        c.set_mesh_mode(mcb.MESH_SOUP | mcb.MESH_INDEXED)
+        c.set_normals(1)
+        c.set_field_mode(mcb.FIELD_DENSE if rep % 2 else mcb.FIELD_AUTO)
+        assert c.set_equation("x^2+y^2+z^2-0.49") == 0
+        c.set_grid_step(2.0 / (12 + rep))                 # small buffers
+        c.polygonise()
+        c.set_scaling(1.1, 0.9, 1.0)
+        c.set_surface_constant(0.01)
+        c.set_grid_step(2.0 / 257)                        # every buffer too small: truncated pass + repeat
+        cnt = c.polygonise()
+        assert cnt.reruns >= 1
+        got = (cnt.triangles, cnt.active, cnt.vertices)
+        ref = ref or got
+        assert got == ref
+        v, t, n = c.get_indexed_mesh(normals=True)
+        assert len(v) == cnt.vertices and len(t) == cnt.triangles and int(t.max()) == cnt.vertices - 1
+        c.close()
