@@ -234,12 +234,12 @@ def test_committed_bench_lines_carry_every_contract_key():
     import glob
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    ours = sorted(glob.glob(os.path.join(root, "profiles", "r01_bench_step11_n*.json")))
-    assert len(ours) >= 4
+    ours = sorted(glob.glob(os.path.join(root, "profiles", "r02_bench_n[1248].json")))
+    assert len(ours) == 4
     for path in ours:
         d = json.loads(open(path).read().strip().splitlines()[-1])
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-                  "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+                  "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "changed_param", "strong_2048"):
             assert k in d, (path, k)
         assert d["metric"] == d["unit"] == "Gvoxels/s" and d["scaling"] == "weak" and d["warmup"] >= 3 and d["gpu_launches"] > 0
         assert abs(d["config"]["cubes"] / (d["ms_per_step"] * 1e-3) / 1e9 - d["value"]) < 1e-6 * d["value"]
@@ -250,10 +250,22 @@ def test_committed_bench_lines_carry_every_contract_key():
             assert k in d["e2e"], (path, k)
         assert d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert abs(d["changed_param"]["value"] / d["value"] - 1.0) < 0.05     # a changed parameter costs what a repeat costs
+        st = d["strong_2048"]
+        assert st["resolution"] == 2048 and st["scaling"] == "strong" and len(st["per_rank"]) == d["n_gpus"]
+        assert sum(r["triangles"] for r in st["per_rank"]) == st["triangles"] == 19369064
         if d["n_gpus"] == 1:
             for k in ("value", "unit", "cores", "kind", "sample"):
                 assert k in d["cpu_baseline"], k
-    ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_step9_reference_arm.json")).read().strip().splitlines()[-1])
+            for k in ("first_call", "variants", "workloads"):
+                assert k in d, k
+            assert d["e2e"]["dropin"]["value"] > 0.9 * d["e2e"]["value"] and set(d["workloads"]) == {"gyr78", "torus"}
+            assert d["workloads"]["gyr78"]["redirected"] > 0 and d["first_call"]["ms_wall"] < 50
+        else:
+            assert 0.5 < st["efficiency_vs_n1_2048"] <= 1.0
+            ms = [r["ms_kernels"] for r in st["per_rank"]]
+            assert max(ms) / (sum(ms) / len(ms)) < 1.06               # the refined cut: every rank within a few per cent
+    ref = json.loads(open(os.path.join(root, "profiles", "r02_bench_reference_arm.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["metric"] == "Gvoxels/s" and ref["e2e"]["h2d_bytes_per_step"] == 0
     assert ref["cpu_baseline"]["kind"] == "reference" and ref["cpu_baseline"]["cores"] >= 1
 
