@@ -102,6 +102,7 @@ struct mcb_ctx {
     unsigned long long h_cap_v = 0, h_cap_t = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t seg_ev[9] = {};
+    cudaEvent_t fork_ev[2] = {};    /* evaluation stage: decided_signs runs on copy_stream next to the block evaluation */
     unsigned long long* d_bounds = nullptr;
     unsigned long long* h_bounds = nullptr; /* pinned */
     bool streamed = false;                  /* the last polygonise delivered the mesh to the registered buffers */
@@ -579,6 +580,8 @@ int mcb_create(int device, mcb_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MCB_E_CUDA);
     for (auto& e : ctx->seg_ev)
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(MCB_E_CUDA);
+    for (auto& e : ctx->fork_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(MCB_E_CUDA);
     if (cudaMalloc((void**)&ctx->d_bounds, 3 * 9 * 8) != cudaSuccess) return bail(MCB_E_NOMEM);
     if (cudaMallocHost((void**)&ctx->h_bounds, 3 * 9 * 8) != cudaSuccess) return bail(MCB_E_NOMEM);
     if (cudaMalloc((void**)&ctx->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(MCB_E_NOMEM);
@@ -639,6 +642,7 @@ void mcb_destroy(mcb_ctx* ctx) {
     cudaFree(ctx->d_mark); cudaFree(ctx->d_changed); cudaFree(ctx->d_seed_u32); cudaFree(ctx->d_rec2); cudaFree(ctx->d_trioff2);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->seg_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->fork_ev) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     mcb_comm_finalize(ctx);
     cudaFree(ctx->d_layer_hist);
@@ -1165,9 +1169,17 @@ int Run::stage_eval_blocks() {
                ctx->d_slist, ctx->d_ctr);
     MCB_LAUNCH((block_class_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->d_slist, ctx->decide_blocks ? 1 : 0,
                ctx->d_bcls, ctx->d_fflags, ctx->d_elist, ctx->d_cand, ctx->d_ctr);
-    MCB_LAUNCH((decided_signs_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, g, bd, ctx->d_elist, ctx->d_ctr, ctx->d_bcls, ctx->d_scls, ctx->d_S);
+    /* Two latency-bound kernels that touch disjoint blocks — the sign words of the decided neighbours, the field of the
+     * undecided blocks — run side by side: the first on the side stream, joined before anything reads the sign planes */
+    cudaStream_t side = ctx->copy_stream;
+    MCB_CK(cudaEventRecord(ctx->fork_ev[0], s));
+    MCB_CK(cudaStreamWaitEvent(side, ctx->fork_ev[0], 0));
+    MCB_LAUNCH((decided_signs_kernel), (unsigned)ctx->sm_count * 8, 256, 0, side, g, bd, ctx->d_elist, ctx->d_ctr, ctx->d_bcls, ctx->d_scls, ctx->d_S);
+    MCB_CK(cudaEventRecord(ctx->fork_ev[1], side));
     launches += 4;
-    if ((rc = launch_block_eval(fb, ctx->d_elist, &ctx->d_ctr->eval_blocks)) != MCB_OK) return rc;
+    rc = launch_block_eval(fb, ctx->d_elist, &ctx->d_ctr->eval_blocks);
+    MCB_CK(cudaStreamWaitEvent(s, ctx->fork_ev[1], 0)); /* joined on every path: the side stream never outlives the call */
+    if (rc != MCB_OK) return rc;
     return launch_constraints(*this);
 }
 
