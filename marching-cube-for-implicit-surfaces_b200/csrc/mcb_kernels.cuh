@@ -1386,24 +1386,6 @@ emit_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict_
  * A chunk whose crossing edges exceed the slot capacity (never on a surface; a degenerate field can) is emitted in
  * several runs of whole cubes.
  * ------------------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ void gradient_normal(const float* __restrict__ pa, const float* __restrict__ pb, size_t rowp, size_t planep,
-                                                const float* __restrict__ rinv, int xa, int ya, int za, int xb, int yb, int zb,
-                                                float tq, float& ox, float& oy, float& oz) {
-    const float gxa = (__ldg(pa + 1) - __ldg(pa - 1)) * __ldg(rinv + xa);
-    const float gya = (__ldg(pa + rowp) - __ldg(pa - rowp)) * __ldg(rinv + ya);
-    const float gza = (__ldg(pa + planep) - __ldg(pa - planep)) * __ldg(rinv + za);
-    const float gxb = (__ldg(pb + 1) - __ldg(pb - 1)) * __ldg(rinv + xb);
-    const float gyb = (__ldg(pb + rowp) - __ldg(pb - rowp)) * __ldg(rinv + yb);
-    const float gzb = (__ldg(pb + planep) - __ldg(pb - planep)) * __ldg(rinv + zb);
-    float tt = tq;
-    if (isinf(tt) || isnan(tt)) tt = 0.5f;
-    const float nx = gxa + tt * (gxb - gxa);
-    const float ny = gya + tt * (gyb - gya);
-    const float nz = gza + tt * (gzb - gza);
-    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
-    ox = nx * inv; oy = ny * inv; oz = nz * inv;
-}
-
 /* ---------------------------------------------------------------------------------------------------------------
  * K3a  edge slots.  A crossing grid edge is shared by up to four cubes, and what the emission computes for it — the two
  *      end-point values, the gradient at both ends, the blend, the normalisation — is a function of the EDGE, not of the
@@ -1648,7 +1630,7 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
                 const float f1 = __ldg(F + ia), f2 = __ldg(F + ib);
                 const float tq = (g.iso - f1) / (f2 - f1); /* Marching::interp uses the surface constant itself, also in repeating-surface mode */
                 const float p = interp_ref(ca, cb2, tq);
-                if (NORMALS) { /* gradient_normal() with the reciprocals from shared memory */
+                if (NORMALS) { /* central differences times the reciprocals kept in shared memory, blended along the grid edge */
                     const float* ri = crinv + 6 * lc;
                     const float gxa = (__ldg(F + ia + 1) - __ldg(F + ia - 1)) * ri[oa & 1];
                     const float gya = (__ldg(F + (ia + rowp)) - __ldg(F + (ia - rowp))) * ri[2 + ((oa >> 1) & 1)];

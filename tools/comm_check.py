@@ -10,6 +10,8 @@ import torch
 import torch.distributed as dist
 
 CUTS = ("uniform", "balanced", "rebalanced")
+_stdout = os.dup(1)   # NCCL prints its version banner on stdout: everything but the JSON line goes to stderr
+os.dup2(2, 1)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
@@ -83,7 +85,7 @@ for wl, n in (("sphere", 512), ("gyr78", 256), ("torus", 384)):
     dist.barrier()
 if rank == 0:
     out["ok"] = True
-    print(json.dumps(out))
+    os.write(_stdout, (json.dumps(out) + "\n").encode())
 ctx.close()
 dist.barrier()
 dist.destroy_process_group()
