@@ -1160,18 +1160,24 @@ int Run::stage_eval_blocks() {
     }
     const size_t nblocks = (size_t)bd.nbx * bd.nby * bd.nbz;
     const unsigned nsuper = (unsigned)bd.nbx * (unsigned)bd.nsy * (unsigned)bd.nsz;
-    MCB_CK(cudaMemsetAsync(ctx->d_cand, 0, (size_t)((bd.WC + 63) / 64) * bd.cjb * bd.ckb * 8, s));
-    MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nblocks, s));
-    MCB_CK(cudaMemsetAsync(ctx->d_bcls, 0xFF, nblocks, s)); /* kClsInherit: the super-block's verdict holds unless the fine pass says otherwise */
+    /* the three clears run on the side stream while the bounds and the super-block classes are computed; block_class, the
+     * first kernel that writes into the cleared arrays, waits for them */
+    cudaStream_t side = ctx->copy_stream;
+    MCB_CK(cudaEventRecord(ctx->fork_ev[0], s));
+    MCB_CK(cudaStreamWaitEvent(side, ctx->fork_ev[0], 0));
+    MCB_CK(cudaMemsetAsync(ctx->d_cand, 0, (size_t)((bd.WC + 63) / 64) * bd.cjb * bd.ckb * 8, side));
+    MCB_CK(cudaMemsetAsync(ctx->d_fflags, 0, nblocks, side));
+    MCB_CK(cudaMemsetAsync(ctx->d_bcls, 0xFF, nblocks, side)); /* kClsInherit: the super-block's verdict holds unless the fine pass says otherwise */
+    MCB_CK(cudaEventRecord(ctx->fork_ev[1], side));
     MCB_LAUNCH((axis_bounds_kernel), dim3((unsigned)((3 * bd.spa * bd.nb + 127) / 128), 2u), 128, 0, s, ctx->d_tables, g, bd, eq.c.n_axis_slots[0],
                eq.c.n_axis_slots[1], eq.c.n_axis_slots[2], ctx->d_bounds_iv);
     MCB_LAUNCH((super_class_kernel), (nsuper + 127) / 128, 128, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->decide_blocks ? 1 : 0, ctx->d_scls,
                ctx->d_slist, ctx->d_ctr);
+    MCB_CK(cudaStreamWaitEvent(s, ctx->fork_ev[1], 0));
     MCB_LAUNCH((block_class_kernel), (unsigned)ctx->sm_count * 8, 256, 0, s, eq.grid, g, bd, ctx->d_bounds_iv, ctx->d_slist, ctx->decide_blocks ? 1 : 0,
                ctx->d_bcls, ctx->d_fflags, ctx->d_elist, ctx->d_cand, ctx->d_ctr);
     /* Two latency-bound kernels that touch disjoint blocks — the sign words of the decided neighbours, the field of the
      * undecided blocks — run side by side: the first on the side stream, joined before anything reads the sign planes */
-    cudaStream_t side = ctx->copy_stream;
     MCB_CK(cudaEventRecord(ctx->fork_ev[0], s));
     MCB_CK(cudaStreamWaitEvent(side, ctx->fork_ev[0], 0));
     MCB_LAUNCH((decided_signs_kernel), (unsigned)ctx->sm_count * 8, 256, 0, side, g, bd, ctx->d_elist, ctx->d_ctr, ctx->d_bcls, ctx->d_scls, ctx->d_S);
