@@ -163,3 +163,45 @@ def test_truncated_passes_are_harmless(mcb):
         v, t, n = c.get_indexed_mesh(normals=True)
         assert len(v) == cnt.vertices and len(t) == cnt.triangles and int(t.max()) == cnt.vertices - 1
         c.close()
+
+
+def test_contexts_on_several_host_threads(mcb):
+    """One context per host thread (how Marching::set_devices drives several GPUs, and how the reference's "movie" thread
+    calls recalculate(), drawer.cpp:135): contexts share nothing but the lazily loaded NVRTC / NCCL entry points, so four
+    threads polygonising different equations at once — new equations, i.e. background compiles included — must each get
+    what a single thread gets."""
+    import threading
+    from oracle.refbind import GYR78
+    eqs = ["x^2+y^2+z^2-0.49", GYR78, "(x^2+y^2+z^2+0.25-0.0625)^2-(x^2+y^2)", "x*y*z+0.05*x-0.01"]
+    grids = [96, 64, 80, 72]
+
+    def run(eq, n, out, reps):
+        c = mcb.Context(0)
+        c.set_mesh_mode(mcb.MESH_SOUP | mcb.MESH_INDEXED)
+        c.set_normals(1)
+        assert c.set_equation(eq) == 0
+        c.set_grid_step(2.0 / n)
+        res = None
+        for r in range(reps):
+            c.set_surface_constant(0.001 * (r % 3))
+            cnt = c.polygonise()
+            if r % 3 == 0:
+                pos, nrm = c.get_mesh(normals=True)
+                v, t, vn = c.get_indexed_mesh(normals=True)
+                cur = (cnt.triangles, cnt.active, cnt.vertices, pos.tobytes(), nrm.tobytes(), v.tobytes(), t.tobytes())
+                assert res is None or cur == res      # interpreter before, compiled kernels after: the same bytes
+                res = cur
+        c.close()
+        out.append(res)
+
+    single = []
+    for eq, n in zip(eqs, grids):
+        run(eq, n, single, 1)
+    outs = [[] for _ in eqs]
+    threads = [threading.Thread(target=run, args=(eq, n, o, 30)) for eq, n, o in zip(eqs, grids, outs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for s, o in zip(single, outs):
+        assert len(o) == 1 and o[0] == s and s[0] > 0
