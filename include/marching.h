@@ -30,6 +30,7 @@
 #include <deque>
 #include <set>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -275,6 +276,10 @@ public:
     void set_reference_normals(bool b) { reference_normals_ = b; }
     bool set_slab(int k_begin, int k_end) { slab_[0] = k_begin; slab_[1] = k_end; have_slab_ = true; return true; }
     const mcb_counts& last_counts() const { return counts_; }
+    /* set_devices(n > 1): wall time of the phases of the last recalculate(), ms: the slabs' polygonisation (+ exchange),
+     * sizing and page-locking Poly_Data, the copies from the devices, the index fix-up (inside the copy threads) */
+    struct DeviceTiming { double polygonise = 0, prepare = 0, fetch = 0; };
+    const DeviceTiming& last_device_timing() const { return dev_timing_; }
     /* set_weld(false): triangle soup of the last recalculate(), 3 float4 per triangle, (x,y,z,1) and (nx,ny,nz,0) */
     const std::vector<float>& get_soup() const { return soup_; }
     const std::vector<float>& get_normals() const { return normals_soup_; }
@@ -390,12 +395,14 @@ private:
             ok[(size_t)r] = good ? 1 : 0;
         };
         cuts_r_.assign((size_t)n, 0);
+        const auto tp0 = std::chrono::steady_clock::now();
         {
             std::vector<std::thread> th;
             for (int r = 1; r < n; r++) th.emplace_back(run, r);
             run(0);
             for (auto& t : th) t.join();
         }
+        const auto tp1 = std::chrono::steady_clock::now();
         comm_ready_ = true;
         for (int r = 0; r < n; r++) if (!ok[(size_t)r]) return false;
         if (rebalance) {
@@ -417,6 +424,7 @@ private:
         /* page-locked destinations: every device copies its part at full PCIe speed, all of them at once */
         pin(pin_v_, poly_data.vertex_list); pin(pin_t_, poly_data.tri_list);
         if (normals_) pin(pin_n_, vertex_normals_);
+        const auto tp2 = std::chrono::steady_clock::now();
         auto fetch = [&](int r) {
             const mcb_counts& c = cnt[(size_t)r];
             if (!c.triangles) return;
@@ -432,6 +440,10 @@ private:
             fetch(0);
             for (auto& t : th) t.join();
         }
+        const auto tp3 = std::chrono::steady_clock::now();
+        dev_timing_.polygonise = std::chrono::duration<double, std::milli>(tp1 - tp0).count();
+        dev_timing_.prepare = std::chrono::duration<double, std::milli>(tp2 - tp1).count();
+        dev_timing_.fetch = std::chrono::duration<double, std::milli>(tp3 - tp2).count();
         counts_ = cnt[0];
         for (int r = 1; r < n; r++) {
             counts_.cubes += cnt[(size_t)r].cubes; counts_.active += cnt[(size_t)r].active; counts_.triangles += cnt[(size_t)r].triangles;
@@ -528,6 +540,7 @@ private:
     std::set<xyz> vertex_set_; /* step-by-step mode only (marching.h:149) */
     std::vector<float> soup_, normals_soup_, vertex_normals_;
     Pinned pin_v_, pin_t_, pin_n_;
+    DeviceTiming dev_timing_;
     int devices_ = 1;
     std::vector<mcb_ctx*> dev_ctx_;       /* [devices_]; [0] = ctx_ */
     bool comm_ready_ = false;

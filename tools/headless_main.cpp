@@ -89,6 +89,12 @@ int main(int argc, char** argv) {
                 (unsigned long long)c.triangles, pData->vertex_list.size() / 3, (unsigned long long)c.ambiguous,
                 (unsigned long long)c.redirected, c.ms_eval, c.ms_classify, c.ms_emit, c.ms_weld, c.ms_total, best_ms,
                 steady_n ? steady_sum / steady_n : best_ms, first_ms, repeat);
+    {
+        const Marching::DeviceTiming& dt = march_maker.last_device_timing();
+        if (dt.polygonise > 0)
+            std::fprintf(stderr, "devices: polygonise+exchange %.3f ms, size+page-lock Poly_Data %.3f ms, copies+index fix-up %.3f ms (last call)\n",
+                         dt.polygonise, dt.prepare, dt.fetch);
+    }
     if (!ply.empty()) {
         setenv("MCB_MESH_FILE", ply.c_str(), 1);
         if (!march_maker.save_poly_to_file()) { std::fprintf(stderr, "nothing to save / cannot write %s\n", ply.c_str()); return 1; }
