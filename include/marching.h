@@ -429,10 +429,9 @@ private:
             const mcb_counts& c = cnt[(size_t)r];
             if (!c.triangles) return;
             unsigned* tl = poly_data.tri_list.data() + 3 * (size_t)tri_off[(size_t)r];
+            mcb_set_index_base(dev_ctx_[(size_t)r], (uint32_t)v_off[(size_t)r]); /* the slab's indices are shifted on the device */
             if (mcb_get_indexed_mesh(dev_ctx_[(size_t)r], poly_data.vertex_list.data() + 3 * v_off[(size_t)r], tl,
                                      normals_ ? vertex_normals_.data() + 3 * v_off[(size_t)r] : nullptr, c.vertices, c.triangles) != MCB_OK) { ok[(size_t)r] = 0; return; }
-            const unsigned base = (unsigned)v_off[(size_t)r];
-            if (base) for (size_t q = 0; q < 3 * (size_t)c.triangles; q++) tl[q] += base;
         };
         {
             std::vector<std::thread> th;

@@ -226,6 +226,10 @@ int mcb_set_mesh_mode(mcb_ctx* ctx, int mode);
  * normals = 3*vertices floats (gradient normals per welded vertex; needs mcb_set_normals(1)).  Any may be NULL. */
 int mcb_get_indexed_mesh(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, float* normals, uint64_t cap_vertices,
                          uint64_t cap_triangles);
+/* A mesh assembled from several slabs (one context each) numbers the vertices of slab r from the sum of the earlier slabs'
+ * vertex counts: `base` is added, on the device, to every index mcb_get_indexed_mesh delivers from then on (default 0;
+ * the streamed host output of mcb_set_host_output and mcb_get_indexed_mesh_device are not shifted). */
+int mcb_set_index_base(mcb_ctx* ctx, uint32_t base);
 int mcb_get_indexed_mesh_device(mcb_ctx* ctx, const float** vertex_list, const uint32_t** tri_list, const float** normals);
 /* Register host buffers (pinned memory for real overlap) as the destination of the indexed mesh.  While they are
  * registered, mcb_polygonise in MCB_MESH_INDEXED mode streams vertex_list / normals / tri_list out range by range

@@ -93,6 +93,7 @@ def _load():
         "mcb_set_mesh_mode": ([vp, i], i),
         "mcb_set_field_mode": ([vp, i], i),
         "mcb_set_stage_timing": ([vp, i], i),
+        "mcb_set_index_base": ([vp, C.c_uint32], i),
         "mcb_set_jit": ([vp, i], i),
         "mcb_jit_wait": ([vp], i),
         "mcb_jit_check": ([cp, cp, sz], i),
@@ -298,6 +299,10 @@ class Context:
         """JIT_AUTO (default) / JIT_ON / JIT_OFF: evaluate the field with a kernel NVRTC compiles for the equation
         (bit-identical to the interpreter; compiled on first use, cached per equation)."""
         self._ck(lib.mcb_set_jit(self.h, int(mode)))
+
+    def set_index_base(self, base):
+        """added on the device to every index get_indexed_mesh delivers (slab r of a mesh assembled from several slabs)"""
+        self._ck(lib.mcb_set_index_base(self.h, int(base)))
 
     def jit_wait(self):
         """block until the background compile of the current equation is over; True when the compiled kernels will run"""

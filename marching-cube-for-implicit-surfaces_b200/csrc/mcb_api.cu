@@ -168,6 +168,8 @@ struct mcb_ctx {
     bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
     bool stage_timing = true;      /* mcb_set_stage_timing: CUDA events around the stages (mcb_counts::ms_*) */
     bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
+    uint32_t index_base = 0;        /* mcb_set_index_base: added to every index mcb_get_indexed_mesh delivers */
+    uint32_t index_base_applied = 0; /* what d_tlist currently carries (0 after every polygonisation) */
     float4* d_edge = nullptr;      /* [cap_edge] edge slots of edge_slots_kernel: 2 float4 per (record, axis) */
     size_t cap_edge = 0;
     int emit_variant = 3;          /* $MCB_EMIT: 1 = first-generation emit kernel, 2 / 3 = second generation (128 / 64 cubes per chunk; 3 measured
@@ -1538,6 +1540,7 @@ int mcb_polygonise(mcb_ctx* ctx, mcb_counts* out) {
     c.jit = ctx->jit_used ? 1u : 0u;
     c.ms_compile = ctx->jit_used ? ctx->ms_compile : 0.f; /* compile time of the module this call adopted (or mcb_jit_wait before it) */
     if (ctx->jit_used) ctx->ms_compile = 0.f;
+    if (run.want_indexed) ctx->index_base_applied = 0; /* weld_emit has just rewritten tri_list from zero */
     c.vertices = run.want_indexed ? ctx->h_ctr->vertices : 0;
     c.mesh_mode = (uint32_t)ctx->mesh_mode;
     c.launches = run.launches;
@@ -1639,8 +1642,21 @@ int mcb_get_indexed_mesh(mcb_ctx* ctx, float* vertex_list, uint32_t* tri_list, f
     if (normals && !ctx->normals) return fail(ctx, MCB_E_STATE, "normals are switched off");
     if (vertex_list && Vn) MCB_CK(cudaMemcpyAsync(vertex_list, ctx->d_vlist, Vn * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (normals && Vn) MCB_CK(cudaMemcpyAsync(normals, ctx->d_vnrm, Vn * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (tri_list && T) MCB_CK(cudaMemcpyAsync(tri_list, ctx->d_tlist, T * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (tri_list && T) {
+        if (ctx->index_base != ctx->index_base_applied) { /* the slab's indices moved to their place in the assembled mesh, on the device */
+            MCB_LAUNCH((add_index_base_kernel), (unsigned)ctx->sm_count * 8, 256, 0, ctx->stream, ctx->d_tlist, (unsigned long long)T * 3ull,
+                       ctx->index_base - ctx->index_base_applied);
+            ctx->index_base_applied = ctx->index_base;
+        }
+        MCB_CK(cudaMemcpyAsync(tri_list, ctx->d_tlist, T * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     MCB_CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_set_index_base(mcb_ctx* ctx, uint32_t base) {
+    if (!ctx) return MCB_E_ARG;
+    ctx->index_base = base;
     return MCB_OK;
 }
 

@@ -631,6 +631,13 @@ decided_signs_kernel(const Grid g, const BlockDims bd, const uint32_t* __restric
         }
     }
 }
+/* tri_list of a slab shifted to its place in a mesh assembled from several slabs: index += delta (mcb_set_index_base) */
+__global__ void __launch_bounds__(256)
+add_index_base_kernel(uint32_t* __restrict__ tri_list, unsigned long long n, uint32_t delta) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) tri_list[q] += delta;
+}
+
 /* the parity hook mcb_get_cases reads every sign word: write those of all decided blocks */
 __global__ void __launch_bounds__(256)
 decided_signs_all_kernel(const Grid g, const BlockDims bd, uint8_t* __restrict__ cls, const uint8_t* __restrict__ scls, uint32_t* __restrict__ S) {

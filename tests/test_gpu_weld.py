@@ -175,3 +175,24 @@ def test_streamed_host_output_equals_the_plain_copy(mcb):
     assert same_bits(v1, v0) and np.array_equal(t1, t0)
     c.set_host_output(0, 0, 0, 0, 0)
     c.close()
+
+
+def test_index_base_shifts_tri_list_on_the_device(mcb):
+    """mcb_set_index_base: the slab's tri_list as it sits in a mesh assembled from several slabs (Marching::set_devices) —
+    shifted once on the device, idempotent over repeated reads, reset by the next polygonisation."""
+    c = mcb.Context(0)
+    c.set_mesh_mode(mcb.MESH_INDEXED)
+    assert c.set_equation("x^2+y^2+z^2-0.49") == 0 and c.set_grid_step(2.0 / 40) > 0
+    c.polygonise()
+    v0, t0 = c.get_indexed_mesh()
+    c.set_index_base(1000)
+    for _ in range(2):
+        v1, t1 = c.get_indexed_mesh()
+        assert np.array_equal(t1.astype(np.int64), t0.astype(np.int64) + 1000) and np.array_equal(v0.view(np.uint32), v1.view(np.uint32))
+    c.set_index_base(7)
+    assert np.array_equal(c.get_indexed_mesh()[1].astype(np.int64), t0.astype(np.int64) + 7)
+    c.polygonise()                                    # tri_list rewritten from zero: the base is applied to the new one
+    assert np.array_equal(c.get_indexed_mesh()[1].astype(np.int64), t0.astype(np.int64) + 7)
+    c.set_index_base(0)
+    assert np.array_equal(c.get_indexed_mesh()[1], t0)
+    c.close()
