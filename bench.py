@@ -8,9 +8,12 @@ One "step" = one full polygonisation of the workload through the C ABI: axis tab
 blocks -> field + sign planes where undecided -> classify/scan/compact -> emit (positions + normals), inputs (bytecode,
 coordinates) already resident in HBM, and the 48-byte counts read back.  Nothing is carried over from one step to the
 next: a first or changed configuration runs the same path (`changed_param`, `first_call` in the line).
-For N>1 each rank owns a z-slab, cut so that every rank carries the same cost (mcb_comm_balance), and the
-step ends with the all-gather of the per-slab triangle counts (NCCL, behind the C ABI: mcb_comm_exchange) that gives
-every slab its global output offset.
+MCB_JIT_AUTO compiles a new equation's kernels on a background thread; the timed loops start after mcb_jit_wait (the steady
+state), `first_call` shows the first mesh of a new equation (interpreter) and when the compiled kernels were in place.
+For N>1 each rank owns a z-slab, cut so that every rank carries the same cost (mcb_comm_balance, refined
+twice by measured time: mcb_comm_rebalance; `strong_2048.per_rank` shows every rank's slab and kernel times), and every
+step includes the all-gather of the per-slab triangle counts (NCCL, behind the C ABI, enqueued inside mcb_polygonise on a
+side stream: mcb_comm_set_auto) that gives every slab its global output offset.
 
 Workloads (BASELINE.json configs):
   headline   sphere x^2+y^2+z^2-0.49, configs[2]; N=1 -> 1024^3 (M=1025 cubes per axis in the reference's loop semantics);
