@@ -168,6 +168,7 @@ struct mcb_ctx {
     bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
     bool stage_timing = true;      /* mcb_set_stage_timing: CUDA events around the stages (mcb_counts::ms_*) */
     bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
+    int emit_blocks_per_sm = 16;    /* grid of the default emitter, blocks per SM ($MCB_EMIT_BLOCKS_PER_SM, A/B runs) */
     uint32_t index_base = 0;        /* mcb_set_index_base: added to every index mcb_get_indexed_mesh delivers */
     uint32_t index_base_applied = 0; /* what d_tlist currently carries (0 after every polygonisation) */
     float4* d_edge = nullptr;      /* [cap_edge] edge slots of edge_slots_kernel: 2 float4 per (record, axis) */
@@ -614,6 +615,8 @@ int mcb_create(int device, mcb_ctx** out) {
         ctx->decide_blocks = !(noiv && noiv[0] == '1');
         const char* we = std::getenv("MCB_WELD_EXACT");
         ctx->weld_exact_only = we && we[0] == '1';
+        const char* eb = std::getenv("MCB_EMIT_BLOCKS_PER_SM");
+        if (eb && std::atoi(eb) >= 1 && std::atoi(eb) <= 64) ctx->emit_blocks_per_sm = std::atoi(eb);
         const char* ev = std::getenv("MCB_EMIT");
         if (ev && ((ev[0] >= '1' && ev[0] <= '4') || ev[0] == '9') && ev[1] == 0) ctx->emit_variant = ev[0] - '0';
     }
@@ -1331,7 +1334,16 @@ int Run::stage_soup() {
             break;
         case 2: if (nrm) MCB_EMIT2(true, 128, 256, 1024, 6, 2); else MCB_EMIT2(false, 128, 256, 1024, 6, 2); break;
         case 9: if (nrm) MCB_EMIT2(true, 128, 256, 24, 2, 1); else MCB_EMIT2(false, 128, 256, 24, 2, 1); break;
-        default: if (nrm) MCB_EMIT2(true, 64, 128, 512, 10, 4); else MCB_EMIT2(false, 64, 128, 512, 10, 4); break;
+        default: {
+            const unsigned grid = (unsigned)ctx->sm_count * (unsigned)ctx->emit_blocks_per_sm;
+#define MCB_EMIT3(NRM, I32)                                                                                                           \
+    MCB_LAUNCH((emit2_kernel<NRM, 64, 128, 512, 10, I32>), grid, 128, 0, s, g, ctx->d_cs, rinv, ctx->d_F, ctx->d_cls, ctx->d_rec, ctx->d_trioff, \
+               ctx->d_ctr, ctx->cap_active, ctx->cap_tris, ctx->d_pos, NRM ? ctx->d_nrm : nullptr)
+            if (nrm) { if (idx32) MCB_EMIT3(true, true); else MCB_EMIT3(true, false); }
+            else { if (idx32) MCB_EMIT3(false, true); else MCB_EMIT3(false, false); }
+#undef MCB_EMIT3
+            break;
+        }
     }
 #undef MCB_EMIT2
 #undef MCB_EMIT2_
