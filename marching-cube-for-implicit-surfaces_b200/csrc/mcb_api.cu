@@ -168,7 +168,7 @@ struct mcb_ctx {
     bool decide_blocks = true;     /* $MCB_NO_INTERVAL=1: treat every block as undecided, i.e. evaluate them all (tests) */
     bool stage_timing = true;      /* mcb_set_stage_timing: CUDA events around the stages (mcb_counts::ms_*) */
     bool weld_exact_only = false;  /* $MCB_WELD_EXACT=1: weld_count_kernel (a thread per crossing edge) on the plain grid too (tests) */
-    int emit_blocks_per_sm = 16;    /* grid of the default emitter, blocks per SM ($MCB_EMIT_BLOCKS_PER_SM, A/B runs) */
+    int emit_blocks_per_sm = 10;    /* grid of the default emitter: one resident wave, 10 blocks per SM ($MCB_EMIT_BLOCKS_PER_SM: A/B runs) */
     uint32_t index_base = 0;        /* mcb_set_index_base: added to every index mcb_get_indexed_mesh delivers */
     uint32_t index_base_applied = 0; /* what d_tlist currently carries (0 after every polygonisation) */
     float4* d_edge = nullptr;      /* [cap_edge] edge slots of edge_slots_kernel: 2 float4 per (record, axis) */

@@ -99,6 +99,7 @@ struct Counters {
     unsigned long long nh_vertices, nh_triangles; /* what the normal.h stage works on: the mesh, or nothing when it is truncated */
     /* ---- everything above is reset before every classify pass; what follows belongs to the evaluation stage ---- */
     unsigned int eval_blocks, eval_supers; /* block-field mode: 32 x 4 x 4 vertex blocks / 32 x 16 x 16 super-blocks the interval test could not decide */
+    unsigned int emit_next, emit_done;     /* emit2: next chunk to hand out / blocks that have finished (the last one resets both) */
 };
 constexpr size_t kCountersClassifyBytes = offsetof(Counters, eval_blocks);
 
@@ -1499,7 +1500,7 @@ template <bool NORMALS, int CUBES, int THREADS, int CAP /* edge slots per chunk 
 __global__ void __launch_bounds__(THREADS, MINB)
 emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict__ rinv, const float* __restrict__ F,
              const ClsTables* __restrict__ gtb, const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ trioff,
-             const Counters* __restrict__ ctr, unsigned long long cap_active, unsigned long long cap_tris,
+             Counters* ctr, unsigned long long cap_active, unsigned long long cap_tris,
              float4* __restrict__ pos, float4* __restrict__ nrm, const float4* __restrict__ E = nullptr,
              const unsigned long long* __restrict__ item = nullptr /* per 32-cube word: first record | active mask << 32 */,
              uint32_t WC = 0) {
@@ -1529,8 +1530,16 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const off_t rowp = (off_t)g.P, planep = (off_t)g.NV * (off_t)g.P;
 
-    for (unsigned long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    /* Chunks are handed out by an atomic counter: a chunk's work varies with its crossing edges, and the grid is one
+     * resident wave (a static stride leaves the blocks of a partial last wave running alone).  The last block to finish
+     * resets the counters, so a repeated launch within the call starts from zero again. */
+    __shared__ unsigned int chunk_s;
+    for (;;) {
         __syncthreads();
+        if (t == 0) chunk_s = atomicAdd(&ctr->emit_next, 1u);
+        __syncthreads();
+        const unsigned long long chunk = chunk_s;
+        if (chunk >= nchunks) break;
         const unsigned long long c0 = chunk * CUBES;
         const int n = (int)((A - c0) < (unsigned long long)CUBES ? (A - c0) : CUBES);
 
@@ -1680,6 +1689,10 @@ emit2_kernel(const Grid g, const float* __restrict__ cs, const float* __restrict
             cb = ce;
             if (cb < n) __syncthreads(); /* the slots are reused by the next run */
         }
+    }
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(&ctr->emit_done, 1u) == gridDim.x - 1u) { ctr->emit_next = 0u; ctr->emit_done = 0u; }
     }
 }
 
