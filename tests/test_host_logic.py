@@ -260,7 +260,9 @@ def test_committed_bench_lines_carry_every_contract_key():
             for k in ("first_call", "variants", "workloads"):
                 assert k in d, k
             assert d["e2e"]["dropin"]["value"] > 0.9 * d["e2e"]["value"] and set(d["workloads"]) == {"gyr78", "torus"}
-            assert d["workloads"]["gyr78"]["redirected"] > 0 and d["first_call"]["ms_wall"] < 50
+            assert d["workloads"]["gyr78"]["redirected"] > 0
+            fc = d["first_call"]   # the first mesh of a new equation came from the interpreter, before the compile had finished
+            assert fc["jit_first_call"] == 0 and fc["ms_wall"] < fc["ms_until_compiled_wall"] and fc["ms_compile"] > 0
         else:
             assert 0.5 < st["efficiency_vs_n1_2048"] <= 1.0
             ms = [r["ms_kernels"] for r in st["per_rank"]]
